@@ -1,0 +1,218 @@
+/*
+ * lcsim_b200.h — C ABI of the B200-native per-tick agent-stepping path of LCSim.
+ *
+ * The reference (tsinghua-fib-lab/LCSim) is pure Python and has no FFI of its own; its callers
+ * reach the hot path through Python methods.  Every entry point below names the reference
+ * method(s) it replaces (paths relative to the reference root).  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add to route those methods here.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative lcsim_b200_status; the message is read
+ *    with lcsim_b200_last_error().  No exception crosses this boundary.
+ *  - pointers documented "device" are CUDA device pointers of the engine's device; pointers
+ *    documented "host" are ordinary host pointers.  `stream` is a cudaStream_t passed as void*.
+ *  - the engine owns every persistent device buffer; lcsim_b200_views() lends them out.  Outputs
+ *    of build_obs / rewards are caller-owned buffers borrowed for the call.
+ *  - no host synchronisation and no allocation happen inside step / rollout / rewards / build_obs /
+ *    set_ref_trajectory / episode_stats: the work is only enqueued on `stream` (graph-capturable).
+ *  - a handle is not thread-safe: one host thread drives one handle.
+ *  - there is no CPU fallback: on a machine without a usable CUDA device create() fails.
+ */
+#ifndef LCSIM_B200_H
+#define LCSIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCSIM_B200_ABI_VERSION 1
+
+/* reference: lcsim/entity/agent/agent.py:89-90 */
+#define LCSIM_B200_H_STEPS 11 /* NUM_HISTORICAL_STEPS */
+#define LCSIM_B200_ROUTE_LEN 10 /* ROUTE_LENGTH */
+#define LCSIM_B200_N_REWARD_TERMS 6 /* forward, route_progress, smooth, collision, offroad, destination */
+#define LCSIM_B200_N_STATS 8
+
+typedef enum {
+    LCSIM_B200_OK = 0,
+    LCSIM_B200_ERR_ARG = -1, /* bad argument / shape */
+    LCSIM_B200_ERR_CUDA = -2, /* a CUDA runtime call failed (message holds cudaGetErrorString) */
+    LCSIM_B200_ERR_STATE = -3, /* call order (e.g. step before upload_static) */
+    LCSIM_B200_ERR_NOMEM = -4
+} lcsim_b200_status;
+
+/* reference: lcsim/entity/agent/agent.py:29-33 Agent.Status */
+enum { LCSIM_B200_WAITING = 0, LCSIM_B200_ACTIVE = 1, LCSIM_B200_FINISHED = 2, LCSIM_B200_IDLE = 3 };
+/* reference: lcsim/entity/agent/policy/type.py:79-84 Action.ActionType (0 = "no external action") */
+enum { LCSIM_B200_ACT_NONE = 0, LCSIM_B200_ACT_BICYCLE = 1, LCSIM_B200_ACT_DELTA = 2, LCSIM_B200_ACT_STATE = 3 };
+
+/* per-scenario episode statistics (int64), summed over ranks by the caller (one NCCL all-reduce);
+ * the distributed form of AgentManager.get_collision_rate / get_offroad_rate, manager.py:329-345 */
+enum {
+    LCSIM_B200_STAT_AGENT_STEPS = 0, /* sum over ticks of len(active_agents) at update time */
+    LCSIM_B200_STAT_ACTIVE_SUM = 1, /* sum over ticks of len(active_agents) after the tick */
+    LCSIM_B200_STAT_COLLISION_SUM = 2, /* sum over ticks of check_collision_all().sum() */
+    LCSIM_B200_STAT_OFFROAD_SUM = 3, /* sum over ticks of check_offroads().sum() */
+    LCSIM_B200_STAT_ARRIVALS = 4, /* agents that went FINISHED -> IDLE */
+    LCSIM_B200_STAT_DEPARTURES = 5, /* agents that went WAITING -> ACTIVE */
+    LCSIM_B200_STAT_TICKS = 6,
+    LCSIM_B200_STAT_RESERVED = 7
+};
+
+typedef struct lcsim_b200_engine lcsim_b200_engine;
+
+/* Shape and control of one batch of independent scenarios.
+ * reference: the `control` block of lcsim/config/example.yml read at lcsim/engine/engine.py:59-86 */
+typedef struct {
+    int32_t abi_version; /* LCSIM_B200_ABI_VERSION */
+    int32_t S; /* scenarios in this batch (this rank's shard) */
+    int32_t A; /* max agents per scenario (<= 1024) */
+    int32_t T; /* max reference-trajectory length */
+    int32_t E; /* max resampled road-edge points per scenario */
+    double start, interval; /* control.step.start / interval */
+    int32_t total_steps; /* control.step.total */
+    int32_t reactive; /* control.reactive: TrajIDM instead of StateExpert (agent.py:167-171) */
+    int32_t no_static; /* control.no_static (manager.py:76-77) */
+    int32_t allow_new_obj; /* control.allow_new_obj (engine.py:208-210) */
+    int32_t device; /* CUDA device ordinal */
+    int32_t with_metrics; /* 1: every tick also fills collision counts / nearest edge / off-road */
+    float grid_cell; /* road-edge hash-grid cell in metres; <= 0 selects the default (8 m) */
+} lcsim_b200_batch_desc;
+
+/* Packed static inputs, host pointers, C-contiguous, exactly the arrays of
+ * lcsim_b200.packer.StaticBatch.  What Engine.__init__ derives from map.pb / agents.pb
+ * (reference: engine.py:84-130, agent/agent.py:106-171, junction/junction.py:59-78,374-380). */
+typedef struct {
+    const int32_t* n_agents; /* [S] */
+    const int32_t* ads_index; /* [S] */
+    const int32_t* agent_type; /* [S][A] */
+    const double* length; /* [S][A] */
+    const double* width; /* [S][A] */
+    const uint8_t* dynamic; /* [S][A] Agent.dynamic_flag */
+    const int32_t* traj_len; /* [S][A] */
+    const int32_t* depart_tick; /* [S][A] first tick j with departure_time <= t_j (float64 clock) */
+    const int32_t* wait_order; /* [S][A] agent indices sorted by departure time (stable) */
+    const double* home_xy; /* [S][A][2] */
+    const double* traj_xy; /* [S][A][T][2] */
+    const double* traj_vel; /* [S][A][T][2] */
+    const double* traj_h; /* [S][A][T] */
+    const int32_t* n_edge; /* [S] */
+    const double* edge_xy; /* [S][E][2] resampled road-edge points, pb order */
+    const double* edge_dir; /* [S][E][2] unit direction of the segment ending at the point */
+    const double* origin; /* [S][2] origin of the scenario-local fp32 frame */
+} lcsim_b200_static_host;
+
+/* Borrowed device pointers into the engine's state (valid until destroy).  A_stride >= A is the
+ * padded agent pitch of every per-agent array.
+ * reference: Agent.runtime / Agent.history_states / Trajectory cursor (agent.py:35-84, type.py:10-71),
+ * AgentManager.active_agents (manager.py:22), and the metric aggregates (manager.py:313-345). */
+typedef struct {
+    int32_t S, A, A_stride, T, E, H;
+    int32_t* tick; /* [S] Engine.current_step */
+    int32_t* n_active; /* [S] */
+    int32_t* active; /* [S][A_stride] active_agents, list order */
+    int32_t* status; /* [S][A_stride] */
+    int32_t* cursor; /* [S][A_stride] Trajectory.index */
+    int32_t* ring_count; /* [S][A_stride] valid history entries (<= H) */
+    int32_t* ring_head; /* [S][A_stride] next slot to write (circular) */
+    double* pose64; /* [S][A_stride][4] x, y, heading, v (world frame, master state) */
+    float* pose32; /* [S][A_stride][4] x - origin_x, y - origin_y, heading, v */
+    double* ring; /* [S][A_stride][H][5] x, y, vx, vy, heading; circular, oldest at ring_head */
+    uint8_t* lead_valid; /* [S][A_stride] Observation.ahead_vehicle is not None */
+    double* lead_dis; /* [S][A_stride] */
+    double* lead_v; /* [S][A_stride] */
+    int32_t* coll_count; /* [S][A_stride] check_collision_all() count, 0 for inactive */
+    int32_t* nearest_edge; /* [S][A_stride] index into the concatenated edge points, -1 inactive */
+    uint8_t* offroad; /* [S][A_stride] */
+    int32_t* traj_len; /* [S][A_stride] current (after re-plans) */
+    double* traj_xy; /* [S][A_stride][T][2] */
+    double* traj_vel; /* [S][A_stride][T][2] */
+    double* traj_h; /* [S][A_stride][T] */
+    int64_t* stats; /* [S][LCSIM_B200_N_STATS] */
+    double* origin; /* [S][2] */
+} lcsim_b200_state_views;
+
+int lcsim_b200_abi_version(void);
+
+/* Allocates the device state for a batch.  Replaces constructing S `Engine(config)` objects
+ * (engine.py:53-130).  Fails with LCSIM_B200_ERR_CUDA when no CUDA device is usable. */
+int lcsim_b200_create(const lcsim_b200_batch_desc* desc, lcsim_b200_engine** out);
+
+/* Uploads the packed scenarios, builds the fp32 filter copies and the road-edge hash grid, and
+ * resets every scenario.  Replaces the map / agent construction in Engine.__init__
+ * (engine.py:90-130).  Synchronous (init-time). */
+int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_static_host* st);
+
+/* Engine.reset (engine.py:132-143) for the scenarios whose byte in reset_mask (device, [S]) is
+ * non-zero; NULL resets all. */
+int lcsim_b200_reset(lcsim_b200_engine* e, const uint8_t* reset_mask, void* stream);
+
+/* Engine.step(actions) (engine.py:145-158) for every scenario: update -> departures/arrivals ->
+ * prepare_obs -> clock, plus (desc.with_metrics) check_collision_all / check_offroads
+ * (manager.py:313-345).  External actions (device pointers, may be NULL when K == 0):
+ *   act_agent [S][K] agent index inside the scenario (-1 = unused entry)
+ *   act_type  [S][K] LCSIM_B200_ACT_*
+ *   act_data  [S][K][5] BICYCLE: acc, steer | DELTA: dx, dy, dheading | STATE: x, y, vx, vy, heading
+ * Agents without an entry use their own policy (manager.py:111-115). */
+int lcsim_b200_step(lcsim_b200_engine* e, const int32_t* act_agent, const int32_t* act_type, const double* act_data,
+                    int K, void* stream);
+
+/* n_ticks consecutive steps without external actions (one kernel launch per tick). */
+int lcsim_b200_rollout(lcsim_b200_engine* e, int n_ticks, void* stream);
+
+/* Agent.set_ref_trajectory (agent.py:462-466) as called from Engine._plan_trajectory
+ * (engine.py:286-297): n (scenario, agent) pairs receive float32 (T,2) xy, (T,2) vel, (T,) heading
+ * straight from device memory; cursor <- 0.  All pointers device. */
+int lcsim_b200_set_ref_trajectory(lcsim_b200_engine* e, const int32_t* scenario, const int32_t* agent, const float* xy,
+                                  const float* vel, const float* heading, int n, int T, void* stream);
+
+/* Engine._compute_rewards (engine.py:301-357) + Agent.get_route (agent.py:468-480) +
+ * AgentManager.check_collision / Agent.is_offroad for one agent per scenario (agent [S] device,
+ * NULL = the ADS).  Outputs (device, any may be NULL):
+ *   terms [S][6] float64, terminated [S] u8, truncated [S] u8 (engine.py:197-200),
+ *   route [S][10][2] float64, reward [S] float64 = sum coef6[k] * terms[k] (coef6 host, may be NULL). */
+int lcsim_b200_rewards(lcsim_b200_engine* e, const int32_t* agent, const double* coef6, double* reward, double* terms,
+                       uint8_t* terminated, uint8_t* truncated, double* route, void* stream);
+
+/* Ego-centric neighbour gather feeding lcsim.envs observations: the radius sets of
+ * motion_diff/modules/agent_encoder.py:208-215,235-241 (torch_cluster.radius / radius_graph call-site
+ * contract: strict d^2 < r^2, ascending source index, at most max_nbr per query) for one ego per
+ * scenario, optionally as a distance-sorted top-k, plus the (N,11,.) history gather of
+ * junction/junction.py:280-336.  See lcsim_b200_obs_desc. */
+typedef struct {
+    const int32_t* ego; /* [S] device, NULL = the ADS */
+    double radius; /* 50.0 in the reference */
+    int32_t k_agents; /* capacity of the agent-neighbour list per ego */
+    int32_t k_polys; /* capacity of the polyline-neighbour list per ego */
+    int32_t sort_by_distance; /* 0: ascending index (torch_cluster order); 1: nearest first */
+    /* outputs, device, caller-owned */
+    int32_t* nbr_agent; /* [S][k_agents] agent index or -1 */
+    float* nbr_agent_feat; /* [S][k_agents][4] ego-frame dx, dy, wrap(dheading), v */
+    int32_t* n_nbr_agent; /* [S] */
+    int32_t* nbr_poly; /* [S][k_polys] polyline-centre index or -1 */
+    float* nbr_poly_feat; /* [S][k_polys][3] ego-frame dx, dy, wrap(dheading) */
+    int32_t* n_nbr_poly; /* [S] */
+    float* history; /* [S][A_stride][H][6] x, y, vx, vy, heading, valid in shift-register order */
+} lcsim_b200_obs_desc;
+
+/* polyline centres (junction/junction.py:117-184, polygon.py:11-75): host [S][P][3] x, y, heading */
+int lcsim_b200_upload_polylines(lcsim_b200_engine* e, const int32_t* n_poly, const double* poly_xyh, int P);
+int lcsim_b200_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_desc* obs, void* stream);
+
+int lcsim_b200_views(lcsim_b200_engine* e, lcsim_b200_state_views* out);
+
+/* Sums the per-scenario statistics into stats_device[LCSIM_B200_N_STATS] (int64, device). */
+int lcsim_b200_episode_stats(lcsim_b200_engine* e, int64_t* stats_device, void* stream);
+
+/* number of tick-kernel launches since create (bench.py's gpu_launches) */
+int64_t lcsim_b200_launch_count(const lcsim_b200_engine* e);
+
+const char* lcsim_b200_last_error(const lcsim_b200_engine* e);
+void lcsim_b200_destroy(lcsim_b200_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCSIM_B200_H */

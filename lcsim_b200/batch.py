@@ -1,0 +1,174 @@
+"""Batched engine: S independent scenarios stepped by one CUDA launch per tick.
+
+This is the host-side owner of one ``lcsim_b200_engine`` handle (include/lcsim_b200.h).  It mirrors,
+for a whole batch at once, the reference's ``Engine.reset / step`` (lcsim/engine/engine.py:132-158),
+``AgentManager.check_collision_all / get_collision_rate / get_offroad_rate``
+(lcsim/entity/agent/manager.py:313-345), ``Engine._compute_rewards`` (engine.py:301-357),
+``Agent.get_route / set_ref_trajectory`` (lcsim/entity/agent/agent.py:462-480).  The per-scenario
+facade with the reference's class names lives in ``lcsim_b200/engine.py``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import native
+from .packer import StaticBatch
+
+
+class BatchEngine:
+    def __init__(self, static: StaticBatch, reactive: bool = False, no_static: bool = False,
+                 allow_new_obj: bool = True, with_metrics: bool = True, device: int = 0, grid_cell: float = 0.0,
+                 backend=None):
+        self.backend = backend if backend is not None else native.TorchCudaBackend(device)
+        self.lib = self.backend.lib
+        self.static = static
+        self.S, self.A, self.T, self.E = static.S, static.A, static.T, static.E
+        self.reactive, self.no_static, self.allow_new_obj = bool(reactive), bool(no_static), bool(allow_new_obj)
+        self.with_metrics = bool(with_metrics)
+        d = native.BatchDesc()
+        d.abi_version = native.ABI_VERSION
+        d.S, d.A, d.T, d.E = static.S, static.A, static.T, static.E
+        d.start, d.interval, d.total_steps = static.start, static.interval, static.total_steps
+        d.reactive, d.no_static, d.allow_new_obj = int(reactive), int(no_static), int(allow_new_obj)
+        d.device = getattr(self.backend, "device_index", 0)
+        d.with_metrics = int(with_metrics)
+        d.grid_cell = float(grid_cell)
+        self._h = C.c_void_p()
+        rc = self.lib.lcsim_b200_create(C.byref(d), C.byref(self._h))
+        if rc != 0:
+            msg = self.lib.lcsim_b200_last_error(self._h).decode() if self._h else "create failed"
+            self._destroy()
+            raise native.NativeLibraryError(f"lcsim_b200_create: {rc}: {msg}")
+        sh = native.StaticHost()
+        keep = []
+        for name, dt in native.STATIC_FIELDS:
+            arr = np.ascontiguousarray(getattr(static, name), dtype=dt)
+            keep.append(arr)
+            setattr(sh, name, arr.ctypes.data)
+        self._check(self.lib.lcsim_b200_upload_static(self._h, C.byref(sh)), "upload_static")
+        del keep
+        v = native.StateViews()
+        self._check(self.lib.lcsim_b200_views(self._h, C.byref(v)), "views")
+        self.A_stride = int(v.A_stride)
+        S, Ap, T, H = self.S, self.A_stride, self.T, native.H_STEPS
+        shapes = {"tick": (S,), "n_active": (S,), "active": (S, Ap), "status": (S, Ap), "cursor": (S, Ap),
+                  "ring_count": (S, Ap), "ring_head": (S, Ap), "pose64": (S, Ap, 4), "pose32": (S, Ap, 4),
+                  "ring": (S, Ap, H, 5), "lead_valid": (S, Ap), "lead_dis": (S, Ap), "lead_v": (S, Ap),
+                  "coll_count": (S, Ap), "nearest_edge": (S, Ap), "offroad": (S, Ap), "traj_len": (S, Ap),
+                  "traj_xy": (S, Ap, T, 2), "traj_vel": (S, Ap, T, 2), "traj_h": (S, Ap, T),
+                  "stats": (S, native.N_STATS), "origin": (S, 2)}
+        # zero-copy views of the engine's buffers; per-agent arrays are sliced to the logical A
+        for name, typestr in native.VIEW_FIELDS:
+            t = self.backend.view(getattr(v, name), shapes[name], typestr)
+            if len(shapes[name]) >= 2 and shapes[name][1] == Ap and name not in ("stats", "origin"):
+                t = t[:, : self.A]
+            setattr(self, name, t)
+        self._stats_out = self.backend.empty((native.N_STATS,), np.int64)
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise native.NativeLibraryError(f"lcsim_b200_{what}: {rc}: {self.lib.lcsim_b200_last_error(self._h).decode()}")
+
+    def _destroy(self):
+        if getattr(self, "_h", None):
+            self.lib.lcsim_b200_destroy(self._h)
+            self._h = None
+
+    def close(self):
+        self._destroy()
+
+    def __del__(self):
+        try:
+            self._destroy()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.lcsim_b200_launch_count(self._h))
+
+    def sync(self):
+        self.backend.sync()
+
+    # ------------------------------------------------------------------ Engine.reset / step
+    def reset(self, mask=None):
+        """Engine.reset for the scenarios selected by ``mask`` ((S,) bool/uint8; None = all)."""
+        if mask is None:
+            self._check(self.lib.lcsim_b200_reset(self._h, None, self.backend.stream()), "reset")
+            return
+        m = self.backend.to_device(mask, np.uint8)
+        self._check(self.lib.lcsim_b200_reset(self._h, self.backend.ptr(m), self.backend.stream()), "reset")
+        self._keep = m
+
+    def step(self, act_agent=None, act_type=None, act_data=None):
+        """Engine.step(actions).  act_agent/act_type: (S,K) int32, act_data: (S,K,5) float64 (device tensors or
+        arrays); None lets every agent use its own policy."""
+        if act_agent is None:
+            self._check(self.lib.lcsim_b200_step(self._h, None, None, None, 0, self.backend.stream()), "step")
+            return
+        aa = self.backend.to_device(act_agent, np.int32)
+        at = self.backend.to_device(act_type, np.int32)
+        ad = self.backend.to_device(act_data, np.float64)
+        K = int(aa.shape[1])
+        assert tuple(aa.shape) == tuple(at.shape) == (self.S, K) and tuple(ad.shape) == (self.S, K, 5)
+        self._check(self.lib.lcsim_b200_step(self._h, self.backend.ptr(aa), self.backend.ptr(at), self.backend.ptr(ad),
+                                             K, self.backend.stream()), "step")
+        self._keep = (aa, at, ad)  # the launch is asynchronous: keep the buffers alive until the next call
+
+    def rollout(self, n_ticks: int):
+        self._check(self.lib.lcsim_b200_rollout(self._h, int(n_ticks), self.backend.stream()), "rollout")
+
+    # ------------------------------------------------------------------ diffusion-action ingest
+    def set_ref_trajectory(self, scenario, agent, xy, vel, heading):
+        """Agent.set_ref_trajectory for n (scenario, agent) pairs: xy/vel (n,T,2), heading (n,T) float32."""
+        sc = self.backend.to_device(scenario, np.int32)
+        ag = self.backend.to_device(agent, np.int32)
+        xy = self.backend.to_device(xy, np.float32)
+        vel = self.backend.to_device(vel, np.float32)
+        hd = self.backend.to_device(heading, np.float32)
+        n, T = int(hd.shape[0]), int(hd.shape[1])
+        assert tuple(xy.shape) == tuple(vel.shape) == (n, T, 2) and tuple(sc.shape) == tuple(ag.shape) == (n,)
+        self._check(self.lib.lcsim_b200_set_ref_trajectory(
+            self._h, self.backend.ptr(sc), self.backend.ptr(ag), self.backend.ptr(xy), self.backend.ptr(vel),
+            self.backend.ptr(hd), n, T, self.backend.stream()), "set_ref_trajectory")
+        self._keep = (sc, ag, xy, vel, hd)
+
+    # ------------------------------------------------------------------ rewards / route
+    def rewards(self, agent=None, coef: Optional[dict] = None):
+        """Engine._compute_rewards + get_route for one agent per scenario (None = the ADS).
+        Returns dict(terms (S,6), terminated (S,), truncated (S,), route (S,10,2), reward (S,))."""
+        b = self.backend
+        out = dict(terms=b.empty((self.S, native.N_REWARD_TERMS), np.float64), terminated=b.empty((self.S,), np.uint8),
+                   truncated=b.empty((self.S,), np.uint8), route=b.empty((self.S, native.ROUTE_LEN, 2), np.float64),
+                   reward=b.empty((self.S,), np.float64))
+        ag = None if agent is None else b.to_device(agent, np.int32)
+        cf = None
+        if coef is not None:
+            cf = np.asarray([float(coef.get(k, 0.0)) for k in native.REWARD_KEYS], np.float64)
+        self._check(self.lib.lcsim_b200_rewards(
+            self._h, None if ag is None else b.ptr(ag), None if cf is None else cf.ctypes.data,
+            b.ptr(out["reward"]), b.ptr(out["terms"]), b.ptr(out["terminated"]), b.ptr(out["truncated"]),
+            b.ptr(out["route"]), b.stream()), "rewards")
+        self._keep = ag
+        return out
+
+    # ------------------------------------------------------------------ aggregates
+    def episode_stats(self):
+        """(8,) int64 device tensor: this rank's sums (see native.STAT_KEYS)."""
+        self._check(self.lib.lcsim_b200_episode_stats(self._h, self.backend.ptr(self._stats_out), self.backend.stream()),
+                    "episode_stats")
+        return self._stats_out
+
+    def ring_ordered(self):
+        """History ring in the reference's shift-register order (oldest first, newest last), (S,A,11,5)."""
+        H = native.H_STEPS
+        xp = self.backend.torch if hasattr(self.backend, "torch") else None
+        if xp is not None:
+            idx = (self.ring_head.long().unsqueeze(-1) + xp.arange(H, device=self.ring.device)) % H
+            return xp.gather(self.ring, 2, idx.unsqueeze(-1).expand(-1, -1, -1, 5))
+        idx = (self.ring_head.astype(np.int64)[..., None] + np.arange(H)) % H
+        return np.take_along_axis(self.ring, idx[..., None], axis=2)

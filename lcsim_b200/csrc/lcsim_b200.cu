@@ -1,0 +1,838 @@
+// lcsim_b200.cu — kernels and C ABI (include/lcsim_b200.h) of the B200-native agent-stepping path.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// (lcsim_b200/native.py:build()).  With -DLCSIM_HOSTEMU the same file compiles as plain C++ in which
+// "device memory" is host memory and a launch is a loop; tests/hostemu uses that to exercise the
+// ABI and the kernel control flow on a machine without a GPU.  The package never loads that build.
+#include "../../include/lcsim_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <thread>
+#include <vector>
+
+#ifdef LCSIM_HOSTEMU
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+#define cudaSuccess 0
+static const char* cudaGetErrorString(cudaError_t) { return "hostemu"; }
+static cudaError_t cudaMalloc(void** p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 2; }
+static cudaError_t cudaFree(void* p) { free(p); return 0; }
+enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToDevice = 3 };
+static cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { memcpy(d, s, n); return 0; }
+static cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return 0; }
+static cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
+static cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
+static cudaError_t cudaSetDevice(int) { return 0; }
+static cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
+static cudaError_t cudaDeviceSynchronize() { return 0; }
+static cudaError_t cudaGetLastError() { return 0; }
+#define __global__
+#else
+#include <cuda_runtime.h>
+#endif
+
+#include "lcsim_core.cuh"
+
+// ------------------------------------------------------------------------------------ kernels
+
+#ifndef LCSIM_HOSTEMU
+// One CTA per scenario, one thread per agent; the whole tick in one launch (reference:
+// engine.py:145-158 Engine.step, plus manager.py:313-345 when with_metrics).
+__global__ void __launch_bounds__(1024) lcs_tick_kernel(const LcsParams p) {
+    extern __shared__ __align__(16) unsigned char lcs_smem_raw[];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    if (p.mode == 1 && p.reset_mask && !p.reset_mask[s]) return;
+    LcsSmem sm;
+    lcs_smem_carve(sm, lcs_smem_raw, p.Ap);
+    lcs_phase_update(p, sm, s, tid);
+    __syncthreads();
+    bool fin, pop, act;
+    int aw;
+    lcs_phase_depart_flags(p, sm, s, tid, &fin, &pop, &act, &aw);
+    __syncthreads();
+    lcs_phase_depart_place(p, sm, s, tid, fin, act, aw);
+    __syncthreads();
+    lcs_phase_depart_fill(p, sm, s, tid, fin);
+    __syncthreads();
+    lcs_phase_publish(p, sm, s, tid);
+    __syncthreads();
+    if (p.reactive) lcs_phase_lead(p, sm, s, tid);
+    if (p.with_metrics) {
+        lcs_phase_collision(p, sm, s, tid);
+        int off;
+        lcs_phase_offroad(p, sm, s, tid, &off);
+        __syncthreads();
+        lcs_phase_metrics_out(p, sm, s, tid, off);
+        __syncthreads();
+        lcs_phase_stats_out(p, sm, s, tid);
+    }
+}
+#endif
+
+static void lcs_launch_tick(const LcsParams& p, cudaStream_t stream) {
+#ifndef LCSIM_HOSTEMU
+    lcs_tick_kernel<<<p.S, p.Ap, lcs_smem_bytes(p.Ap), stream>>>(p);
+#else
+    const int Ap = p.Ap;
+    std::vector<unsigned char> raw(lcs_smem_bytes(Ap) + 16);
+    std::vector<char> fin(Ap), pop(Ap), act(Ap);
+    std::vector<int> aw(Ap), off(Ap);
+    for (int s = 0; s < p.S; s++) {
+        if (p.mode == 1 && p.reset_mask && !p.reset_mask[s]) continue;
+        LcsSmem sm;
+        lcs_smem_carve(sm, (unsigned char*)(((uintptr_t)raw.data() + 15) & ~(uintptr_t)15), Ap);
+        for (int t = 0; t < Ap; t++) lcs_phase_update(p, sm, s, t);
+        for (int t = 0; t < Ap; t++) {
+            bool f, q, a;
+            lcs_phase_depart_flags(p, sm, s, t, &f, &q, &a, &aw[t]);
+            fin[t] = f; pop[t] = q; act[t] = a;
+        }
+        for (int t = 0; t < Ap; t++) lcs_phase_depart_place(p, sm, s, t, fin[t], act[t], aw[t]);
+        for (int t = 0; t < Ap; t++) lcs_phase_depart_fill(p, sm, s, t, fin[t]);
+        for (int t = 0; t < Ap; t++) lcs_phase_publish(p, sm, s, t);
+        if (p.reactive)
+            for (int t = 0; t < Ap; t++) lcs_phase_lead(p, sm, s, t);
+        if (p.with_metrics) {
+            for (int t = 0; t < Ap; t++) lcs_phase_collision(p, sm, s, t);
+            for (int t = 0; t < Ap; t++) lcs_phase_offroad(p, sm, s, t, &off[t]);
+            for (int t = 0; t < Ap; t++) lcs_phase_metrics_out(p, sm, s, t, off[t]);
+            for (int t = 0; t < Ap; t++) lcs_phase_stats_out(p, sm, s, t);
+        }
+    }
+#endif
+}
+
+// ---- set_ref_trajectory: one CTA (64 threads) per (scenario, agent) entry
+struct LcsReplanArgs {
+    const int32_t *scenario, *agent;
+    const float *xy, *vel, *heading;
+    int n, Tn;
+};
+LCS_D void lcs_replan_stale(const LcsParams& p, const LcsReplanArgs& r, int e) {
+    const int s = r.scenario[e], a = r.agent[e];
+    const size_t ia = (size_t)s * p.Ap + a;
+    if (p.status[ia] == LCS_ACTIVE && !p.stale_valid[ia]) {
+        double wp[5];
+        const bool f = lcs_policy_waypoint(p, ia, p.cursor[ia], p.traj_len[ia], wp);
+        for (int k = 0; k < 5; k++) p.stale_wp[5 * ia + k] = wp[k];
+        p.stale_f32[ia] = f ? 1 : 0;
+        p.stale_valid[ia] = 1;
+    }
+}
+LCS_D void lcs_replan_copy(const LcsParams& p, const LcsReplanArgs& r, int e, int k) {
+    const int s = r.scenario[e], a = r.agent[e];
+    const size_t ia = (size_t)s * p.Ap + a;
+    const int Tn = r.Tn < p.T ? r.Tn : p.T;
+    const size_t f = ((size_t)s * p.T + k) * p.Ap + a;
+    if (k < Tn) {
+        const size_t t = ia * p.T + k, q = (size_t)e * r.Tn + k;
+        const double x = (double)r.xy[2 * q], y = (double)r.xy[2 * q + 1];
+        p.traj_xy[2 * t] = x;
+        p.traj_xy[2 * t + 1] = y;
+        p.traj_vel[2 * t] = (double)r.vel[2 * q];
+        p.traj_vel[2 * t + 1] = (double)r.vel[2 * q + 1];
+        p.traj_h[t] = (double)r.heading[q];
+        lcs_f2 v;
+        v.x = (float)(x - p.origin[2 * s]);
+        v.y = (float)(y - p.origin[2 * s + 1]);
+        p.tf_xy[f] = v;
+    } else if (k < p.T) {
+        lcs_f2 v;
+        v.x = LCS_FAR;
+        v.y = LCS_FAR;
+        p.tf_xy[f] = v;
+    }
+    if (k == 0) {
+        p.traj_len[ia] = Tn;
+        p.traj_f32[ia] = 1;
+        p.cursor[ia] = 0;
+    }
+}
+#ifndef LCSIM_HOSTEMU
+__global__ void lcs_replan_kernel(const LcsParams p, const LcsReplanArgs r) {
+    const int e = blockIdx.x;
+    if (threadIdx.x == 0) lcs_replan_stale(p, r, e);
+    __syncthreads();
+    for (int k = threadIdx.x; k < p.T; k += blockDim.x) lcs_replan_copy(p, r, e, k);
+}
+#endif
+
+// ---- rewards / route for one agent per scenario (thread per scenario)
+struct LcsRewardArgs {
+    const int32_t* agent; // [S] or null (ADS)
+    double coef[LCSIM_B200_N_REWARD_TERMS];
+    int has_coef;
+    double *reward, *terms, *route;
+    uint8_t *terminated, *truncated;
+    const double* s_tab0; // [S][Ap][T] np.sum(seg[:k]) of the pristine trajectories
+};
+
+// numpy's pairwise summation for n < 128 (np.add.reduce on a contiguous 1-D array): 8 running
+// partial sums, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail added in order.
+template <typename F>
+LCS_D F lcs_np_sum_small(const F* a, int n) {
+    if (n < 8) {
+        F r = 0;
+        for (int i = 0; i < n; i++) r = r + a[i];
+        return r;
+    }
+    F r[8];
+    int i;
+    for (i = 0; i < 8; i++) r[i] = a[i];
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; j++) r[j] = r[j] + a[i + j];
+    F res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res = res + a[i];
+    return res;
+}
+
+// np.sum(seg[:k]) of a re-planned (float32) trajectory, evaluated in float32 like the reference does
+// (polygon.py:287-292 on float32 arrays).  T <= 128 is enforced at create() for this path.
+LCS_D double lcs_seg_sum_f32(const double* xy, int n_seg, int k) {
+    if (k > n_seg) k = n_seg;
+    if (k <= 0) return 0.0;
+    float sg[128];
+    for (int i = 0; i < k; i++) {
+        const float dx = (float)xy[2 * (i + 1)] - (float)xy[2 * i], dy = (float)xy[2 * (i + 1) + 1] - (float)xy[2 * i + 1];
+        sg[i] = sqrtf(dx * dx + dy * dy);
+    }
+    return (double)lcs_np_sum_small<float>(sg, k);
+}
+
+// first-index argmin of sqrt(dx^2+dy^2) in float64 (polygon.py:285)
+LCS_D int lcs_argmin_exact(const double* pts, int n, double px, double py) {
+    int best = 0;
+    double bd = lcs_inf_d();
+    for (int k = 0; k < n; k++) {
+        const double d = lcs_norm2_axis(lcs_dsub(pts[2 * k], px), lcs_dsub(pts[2 * k + 1], py));
+        if (d < bd) { bd = d; best = k; }
+    }
+    return best;
+}
+
+// reference: engine.py:301-357 _compute_rewards, agent.py:468-480 get_route, manager.py:289-311
+// check_collision (lane=None agents: all active), agent.py:482-494 is_offroad
+LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s) {
+    const int a = r.agent ? r.agent[s] : p.ads_index[s];
+    const size_t ia = (size_t)s * p.Ap + a;
+    double terms[6] = {0, 0, 0, 0, 0, 0};
+    const double* ps = p.pose64 + 4 * ia;
+    const double x = ps[0], y = ps[1], h = ps[2];
+    const double* xy = p.traj_xy + ia * p.T * 2;
+    const int n = p.traj_len[ia];
+    const int status = p.status[ia];
+    const bool f32 = p.traj_f32[ia] != 0;
+    if (p.ring_count[ia] > 1) {
+        const int head = p.ring_head[ia];
+        const double* p1 = p.ring + (ia * LCS_H + (head + LCS_H - 1) % LCS_H) * 5;
+        const double* p0 = p.ring + (ia * LCS_H + (head + LCS_H - 2) % LCS_H) * 5;
+        const double cur_v = lcs_norm2_vec(p1[2], p1[3]);
+        const int i0 = lcs_argmin_exact(xy, n, p0[0], p0[1]), i1 = lcs_argmin_exact(xy, n, p1[0], p1[1]);
+        const double d0 = lcs_norm2_vec(lcs_dsub(p0[0], xy[2 * i0]), lcs_dsub(p0[1], xy[2 * i0 + 1]));
+        const double d1 = lcs_norm2_vec(lcs_dsub(p1[0], xy[2 * i1]), lcs_dsub(p1[1], xy[2 * i1 + 1]));
+        if (f32) {
+            const double s0 = lcs_seg_sum_f32(xy, n - 1, i0), s1 = lcs_seg_sum_f32(xy, n - 1, i1);
+            terms[0] = lcs_dsub((double)((float)s1 - (float)s0), lcs_dsub(d1, d0));
+            terms[1] = (double)((float)s1 / (float)lcs_seg_sum_f32(xy, n - 1, n - 1));
+        } else {
+            const double* st = r.s_tab0 + ia * p.T;
+            const double s0 = st[i0], s1 = st[i1];
+            terms[0] = lcs_dsub(lcs_dsub(s1, s0), lcs_dsub(d1, d0));
+            terms[1] = s1 / st[n - 1];
+        }
+        double steer = lcs_wrap_angle(lcs_dsub(p1[4], p0[4])) / lcs_norm2_vec(lcs_dsub(p1[0], p0[0]), lcs_dsub(p1[1], p0[1]));
+        steer = lcs_npclip(steer, -0.3, 0.3);
+        const double sm = lcs_dsub(1.0 / cur_v, fabs(steer));
+        terms[2] = sm < 0 ? sm : 0.0; // min(0, x): NaN -> 0
+    }
+    // collision of this agent against every other active agent
+    bool collision = false;
+    if (status == LCS_ACTIVE) {
+        double ea[8], eo[8];
+        ea[0] = x; ea[1] = y; ea[2] = ps[3];
+        lcs_sincos(h, &ea[4], &ea[3]);
+        ea[5] = p.length[ia]; ea[6] = p.width[ia]; ea[7] = h;
+        const float rad_a = 0.5f * sqrtf((float)(ea[5] * ea[5] + ea[6] * ea[6])) * 1.0001f + 1e-3f;
+        const int na = p.n_active[s];
+        for (int j = 0; j < na && !collision; j++) {
+            const int o = p.active[(size_t)s * p.Ap + j];
+            if (o == a) continue;
+            const size_t io = (size_t)s * p.Ap + o;
+            const double* po = p.pose64 + 4 * io;
+            const double L = p.length[io], W = p.width[io];
+            const float rad_o = 0.5f * sqrtf((float)(L * L + W * W)) * 1.0001f + 1e-3f;
+            const double dx = po[0] - x, dy = po[1] - y;
+            const double rr = (double)(rad_a + rad_o);
+            if (dx * dx + dy * dy > rr * rr * 1.0001) continue; // bounding circles apart: SAT cannot overlap
+            eo[0] = po[0]; eo[1] = po[1]; eo[2] = po[3];
+            lcs_sincos(po[2], &eo[4], &eo[3]);
+            eo[5] = L; eo[6] = W; eo[7] = po[2];
+            collision = lcs_collide(ea, eo);
+        }
+    }
+    terms[3] = collision ? -1.0 : 0.0;
+    bool off;
+    lcs_nearest_edge(p, s, x, y, &off);
+    terms[4] = off ? -1.0 : 0.0;
+    if (status == LCS_IDLE || status == LCS_FINISHED) {
+        const double dis = lcs_norm2_vec(lcs_dsub(xy[2 * (n - 1)], x), lcs_dsub(xy[2 * (n - 1) + 1], y));
+        terms[5] = dis < 2.5 ? 10.0 : -5.0;
+    }
+    if (r.terms)
+        for (int k = 0; k < 6; k++) r.terms[6 * (size_t)s + k] = terms[k];
+    if (r.terminated) r.terminated[s] = (collision || off) ? 1 : 0;
+    // engine.py:197-200: current_step >= total_steps or the agent finished (clock already advanced)
+    if (r.truncated) r.truncated[s] = (p.tick[s] >= p.total_steps || status == LCS_IDLE || status == LCS_FINISHED) ? 1 : 0;
+    if (r.reward) {
+        double acc = 0.0;
+        if (r.has_coef)
+            for (int k = 0; k < 6; k++)
+                if (r.coef[k] != 0.0) acc = lcs_dadd(acc, lcs_dmul(terms[k], r.coef[k]));
+        r.reward[s] = acc;
+    }
+    if (r.route) {
+        double* out = r.route + (size_t)s * LCS_ROUTE * 2;
+        double sn, c;
+        lcs_sincos(h, &sn, &c);
+        const int cur = p.cursor[ia];
+        for (int q = 0; q < LCS_ROUTE; q++) {
+            const int k = cur + 1 + q;
+            if (k < n) {
+                const double dx = lcs_dsub(xy[2 * k], x), dy = lcs_dsub(xy[2 * k + 1], y);
+                out[2 * q] = lcs_dot2(dx, c, dy, sn);
+                out[2 * q + 1] = lcs_dot2(dx, -sn, dy, c);
+            } else {
+                out[2 * q] = 0.0;
+                out[2 * q + 1] = 0.0;
+            }
+        }
+    }
+}
+#ifndef LCSIM_HOSTEMU
+__global__ void lcs_rewards_kernel(const LcsParams p, const LcsRewardArgs r) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < p.S) lcs_rewards_one(p, r, s);
+}
+__global__ void lcs_stats_kernel(const int64_t* stats, int S, int64_t* out) {
+    __shared__ long long acc[LCS_NSTAT];
+    if (threadIdx.x < LCS_NSTAT) acc[threadIdx.x] = 0;
+    __syncthreads();
+    long long loc[LCS_NSTAT];
+    for (int k = 0; k < LCS_NSTAT; k++) loc[k] = 0;
+    for (int s = threadIdx.x; s < S; s += blockDim.x)
+        for (int k = 0; k < LCS_NSTAT; k++) loc[k] += stats[(size_t)s * LCS_NSTAT + k];
+    for (int k = 0; k < LCS_NSTAT; k++)
+        if (loc[k]) atomicAdd((unsigned long long*)&acc[k], (unsigned long long)loc[k]);
+    __syncthreads();
+    if (threadIdx.x < LCS_NSTAT) out[threadIdx.x] = acc[threadIdx.x];
+}
+#endif
+
+// ------------------------------------------------------------------------------------ engine
+
+struct lcsim_b200_engine {
+    lcsim_b200_batch_desc desc;
+    LcsParams p;
+    std::vector<void*> allocs;
+    double* s_tab0 = nullptr;
+    bool uploaded = false;
+    int64_t launches = 0;
+    std::string err;
+};
+
+static int lcs_fail(lcsim_b200_engine* e, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf;
+    return code;
+}
+#define LCS_CUDA(e, call)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t _st = (call);                                                                           \
+        if (_st != cudaSuccess) return lcs_fail(e, LCSIM_B200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_st)); \
+    } while (0)
+
+template <typename Tp>
+static int lcs_alloc(lcsim_b200_engine* e, Tp** out, size_t count) {
+    void* ptr = nullptr;
+    cudaError_t st = cudaMalloc(&ptr, std::max<size_t>(count, 1) * sizeof(Tp));
+    if (st != cudaSuccess) return lcs_fail(e, LCSIM_B200_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(Tp), cudaGetErrorString(st));
+    st = cudaMemset(ptr, 0, std::max<size_t>(count, 1) * sizeof(Tp));
+    if (st != cudaSuccess) return lcs_fail(e, LCSIM_B200_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(st));
+    e->allocs.push_back(ptr);
+    *out = (Tp*)ptr;
+    return 0;
+}
+#define LCS_ALLOC(e, field, count)                                            \
+    do {                                                                      \
+        int _rc = lcs_alloc(e, (decltype(field)*)&(field), (size_t)(count)); \
+        if (_rc) return _rc;                                                  \
+    } while (0)
+
+extern "C" int lcsim_b200_abi_version(void) { return LCSIM_B200_ABI_VERSION; }
+
+extern "C" const char* lcsim_b200_last_error(const lcsim_b200_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+extern "C" int64_t lcsim_b200_launch_count(const lcsim_b200_engine* e) { return e ? e->launches : 0; }
+
+extern "C" void lcsim_b200_destroy(lcsim_b200_engine* e) {
+    if (!e) return;
+    for (void* q : e->allocs) cudaFree(q);
+    delete e;
+}
+
+extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engine** out) {
+    if (!d || !out) return LCSIM_B200_ERR_ARG;
+    *out = nullptr;
+    if (d->abi_version != LCSIM_B200_ABI_VERSION) return LCSIM_B200_ERR_ARG;
+    if (d->S < 1 || d->A < 1 || d->A > 1024 || d->T < 1 || d->E < 0) return LCSIM_B200_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || d->device < 0 || d->device >= ndev) return LCSIM_B200_ERR_CUDA;
+    if (cudaSetDevice(d->device) != cudaSuccess) return LCSIM_B200_ERR_CUDA;
+    lcsim_b200_engine* e = new lcsim_b200_engine();
+    e->desc = *d;
+    LcsParams& p = e->p;
+    memset(&p, 0, sizeof p);
+    p.S = d->S;
+    p.A = d->A;
+    p.Ap = (d->A + 31) / 32 * 32;
+    p.T = d->T;
+    p.E = std::max(d->E, 1);
+    p.dt = d->interval;
+    p.total_steps = d->total_steps;
+    p.reactive = d->reactive;
+    p.no_static = d->no_static;
+    p.allow_new_obj = d->allow_new_obj;
+    p.with_metrics = d->with_metrics;
+    *out = e; // returned even on failure below so the caller can read last_error and destroy
+    const size_t S = p.S, SA = S * p.Ap, SAT = SA * p.T, SE = S * p.E;
+    LCS_ALLOC(e, p.n_agents, S);
+    LCS_ALLOC(e, p.ads_index, S);
+    LCS_ALLOC(e, p.origin, S * 2);
+    LCS_ALLOC(e, p.eta_pts, S);
+    LCS_ALLOC(e, p.depart_tick, SA);
+    LCS_ALLOC(e, p.wait_order, SA);
+    LCS_ALLOC(e, p.dynamic, SA);
+    LCS_ALLOC(e, p.length, SA);
+    LCS_ALLOC(e, p.width, SA);
+    LCS_ALLOC(e, p.home_xy, SA * 2);
+    LCS_ALLOC(e, p.traj_len0, SA);
+    LCS_ALLOC(e, p.traj_xy0, SAT * 2);
+    LCS_ALLOC(e, p.traj_vel0, SAT * 2);
+    LCS_ALLOC(e, p.traj_h0, SAT);
+    LCS_ALLOC(e, p.tf_xy0, SAT);
+    LCS_ALLOC(e, p.traj_len, SA);
+    LCS_ALLOC(e, p.traj_xy, SAT * 2);
+    LCS_ALLOC(e, p.traj_vel, SAT * 2);
+    LCS_ALLOC(e, p.traj_h, SAT);
+    LCS_ALLOC(e, p.tf_xy, SAT);
+    LCS_ALLOC(e, p.traj_f32, SA);
+    LCS_ALLOC(e, p.stale_valid, SA);
+    LCS_ALLOC(e, p.stale_f32, SA);
+    LCS_ALLOC(e, p.stale_wp, SA * 5);
+    LCS_ALLOC(e, p.n_edge, S);
+    LCS_ALLOC(e, p.edge_xy, SE * 2);
+    LCS_ALLOC(e, p.edge_dir, SE * 2);
+    LCS_ALLOC(e, p.grid_geom, S * 4);
+    LCS_ALLOC(e, p.grid_dim, S * 2);
+    LCS_ALLOC(e, p.ge_xy, SE);
+    LCS_ALLOC(e, p.ge_idx, SE);
+    LCS_ALLOC(e, p.tick, S);
+    LCS_ALLOC(e, p.n_active, S);
+    LCS_ALLOC(e, p.wait_ptr, S);
+    LCS_ALLOC(e, p.stats, S * LCS_NSTAT);
+    LCS_ALLOC(e, p.active, SA);
+    LCS_ALLOC(e, p.status, SA);
+    LCS_ALLOC(e, p.cursor, SA);
+    LCS_ALLOC(e, p.ring_count, SA);
+    LCS_ALLOC(e, p.ring_head, SA);
+    LCS_ALLOC(e, p.pose64, SA * 4);
+    LCS_ALLOC(e, p.pose32, SA);
+    LCS_ALLOC(e, p.ring, SA * LCS_H * 5);
+    LCS_ALLOC(e, p.lead_valid, SA);
+    LCS_ALLOC(e, p.lead_dis, SA);
+    LCS_ALLOC(e, p.lead_v, SA);
+    LCS_ALLOC(e, p.coll_count, SA);
+    LCS_ALLOC(e, p.nearest_edge, SA);
+    LCS_ALLOC(e, p.offroad, SA);
+    LCS_ALLOC(e, e->s_tab0, SAT);
+    return 0;
+}
+
+// ---- host-side preparation of the static arrays ------------------------------------------------
+
+namespace {
+
+struct Staging {
+    std::vector<int32_t> depart_tick, wait_order, traj_len, ge_idx, grid_dim, grid_start;
+    std::vector<uint8_t> dynamic;
+    std::vector<double> length, width, home_xy, traj_xy, traj_vel, traj_h, s_tab, edge_xy, edge_dir;
+    std::vector<lcs_f2> tf_xy, ge_xy;
+    std::vector<float> grid_geom, eta;
+};
+
+// np.sum(seg[:k]) for every k of one trajectory, numpy pairwise order (n < 128 path is exact for any T
+// <= 128; longer prefixes fall back to the recursive split below).
+double np_sum_rec(const double* a, int64_t n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int64_t i = 0; i < n; i++) r += a[i];
+        return r;
+    } else if (n <= 128) {
+        double r[8];
+        int64_t i;
+        for (i = 0; i < 8; i++) r[i] = a[i];
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int j = 0; j < 8; j++) r[j] += a[i + j];
+        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; i++) res += a[i];
+        return res;
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_sum_rec(a, n2) + np_sum_rec(a + n2, n - n2);
+}
+
+} // namespace
+
+static void lcs_parallel_range(int n, const std::function<void(int, int)>& fn) {
+    int nt = (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 32) nt = 32;
+    if (nt > n) nt = n;
+    if (nt <= 1) {
+        fn(0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back(fn, (int)((int64_t)n * t / nt), (int)((int64_t)n * (t + 1) / nt));
+    for (auto& t : th) t.join();
+}
+
+extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_static_host* st) {
+    if (!e || !st) return LCSIM_B200_ERR_ARG;
+    LcsParams& p = e->p;
+    const int S = p.S, A = p.A, Ap = p.Ap, T = p.T, E = e->desc.E;
+    const size_t SA = (size_t)S * Ap, SAT = SA * T;
+    for (int s = 0; s < S; s++) {
+        if (st->n_agents[s] < 0 || st->n_agents[s] > A) return lcs_fail(e, LCSIM_B200_ERR_ARG, "scenario %d: n_agents %d out of [0,%d]", s, st->n_agents[s], A);
+        if (st->n_edge[s] < 0 || st->n_edge[s] > E) return lcs_fail(e, LCSIM_B200_ERR_ARG, "scenario %d: n_edge %d out of [0,%d]", s, st->n_edge[s], E);
+        if (st->n_agents[s] > 0 && (st->ads_index[s] < 0 || st->ads_index[s] >= st->n_agents[s]))
+            return lcs_fail(e, LCSIM_B200_ERR_ARG, "scenario %d: ads_index %d out of range", s, st->ads_index[s]);
+        int prev = -1;
+        for (int i = 0; i < st->n_agents[s]; i++) {
+            const int a = st->wait_order[(size_t)s * A + i];
+            if (a < 0 || a >= st->n_agents[s]) return lcs_fail(e, LCSIM_B200_ERR_ARG, "scenario %d: wait_order[%d]=%d out of range", s, i, a);
+            const int tl = st->traj_len[(size_t)s * A + a];
+            if (tl < 1 || tl > T) return lcs_fail(e, LCSIM_B200_ERR_ARG, "scenario %d agent %d: traj_len %d out of [1,%d]", s, a, tl, T);
+            const int dtk = st->depart_tick[(size_t)s * A + a];
+            if (dtk < prev) return lcs_fail(e, LCSIM_B200_ERR_ARG, "scenario %d: depart_tick not sorted along wait_order", s);
+            prev = dtk;
+        }
+    }
+    Staging g;
+    g.depart_tick.assign(SA, 0x7fffffff);
+    g.wait_order.assign(SA, 0);
+    g.traj_len.assign(SA, 1);
+    g.dynamic.assign(SA, 0);
+    g.length.assign(SA, 0.0);
+    g.width.assign(SA, 0.0);
+    g.home_xy.assign(SA * 2, 0.0);
+    g.traj_xy.assign(SAT * 2, 0.0);
+    g.traj_vel.assign(SAT * 2, 0.0);
+    g.traj_h.assign(SAT, 0.0);
+    g.s_tab.assign(SAT, 0.0);
+    lcs_f2 far;
+    far.x = LCS_FAR;
+    far.y = LCS_FAR;
+    g.tf_xy.assign(SAT, far);
+    const size_t Ed = (size_t)p.E;
+    g.edge_xy.assign((size_t)S * Ed * 2, 0.0);
+    g.edge_dir.assign((size_t)S * Ed * 2, 0.0);
+    g.ge_xy.assign((size_t)S * Ed, far);
+    g.ge_idx.assign((size_t)S * Ed, 0);
+    g.grid_geom.assign((size_t)S * 4, 0.f);
+    g.grid_dim.assign((size_t)S * 2, 1);
+    g.eta.assign(S, 0.f);
+    const float cell = e->desc.grid_cell > 0 ? e->desc.grid_cell : 8.0f;
+    std::vector<std::vector<int32_t>> cell_starts(S);
+
+    lcs_parallel_range(S, [&](int s0, int s1) {
+        std::vector<double> seg(T);
+        std::vector<std::pair<std::pair<double, double>, int>> keyed;
+        for (int s = s0; s < s1; s++) {
+            const double ox = st->origin[2 * s], oy = st->origin[2 * s + 1];
+            double eta = 0.0;
+            auto to_f32 = [&](double x, double y) {
+                lcs_f2 v;
+                v.x = (float)(x - ox);
+                v.y = (float)(y - oy);
+                const double ex = (double)v.x - (x - ox), ey = (double)v.y - (y - oy);
+                eta = std::max(eta, std::sqrt(ex * ex + ey * ey));
+                return v;
+            };
+            for (int a = 0; a < st->n_agents[s]; a++) {
+                const size_t src = (size_t)s * A + a, dst = (size_t)s * Ap + a;
+                g.depart_tick[dst] = st->depart_tick[src];
+                g.dynamic[dst] = st->dynamic[src];
+                g.length[dst] = st->length[src];
+                g.width[dst] = st->width[src];
+                g.home_xy[2 * dst] = st->home_xy[2 * src];
+                g.home_xy[2 * dst + 1] = st->home_xy[2 * src + 1];
+                const int n = st->traj_len[src];
+                g.traj_len[dst] = n;
+                const double* xy = st->traj_xy + src * T * 2;
+                memcpy(&g.traj_xy[dst * T * 2], xy, sizeof(double) * 2 * n);
+                memcpy(&g.traj_vel[dst * T * 2], st->traj_vel + src * T * 2, sizeof(double) * 2 * n);
+                memcpy(&g.traj_h[dst * T], st->traj_h + src * T, sizeof(double) * n);
+                // a point that repeats an earlier one exactly can never be the FIRST argmin: drop it from
+                // the filter copy (the float64 arrays keep it)
+                keyed.clear();
+                for (int k = 0; k < n; k++) keyed.push_back({{xy[2 * k], xy[2 * k + 1]}, k});
+                std::sort(keyed.begin(), keyed.end());
+                for (int q = 0; q < n; q++) {
+                    const bool dup = q > 0 && keyed[q].first == keyed[q - 1].first;
+                    const int k = keyed[q].second;
+                    if (!dup) g.tf_xy[((size_t)s * T + k) * Ap + a] = to_f32(xy[2 * k], xy[2 * k + 1]);
+                }
+                // Trajectory.s table: s_tab[k] = np.sum(seg[:k]) (polygon.py:287-292)
+                for (int k = 0; k + 1 < n; k++) {
+                    const double dx = xy[2 * (k + 1)] - xy[2 * k], dy = xy[2 * (k + 1) + 1] - xy[2 * k + 1];
+                    seg[k] = std::sqrt(dx * dx + dy * dy);
+                }
+                for (int k = 0; k < n; k++) g.s_tab[dst * T + k] = np_sum_rec(seg.data(), k);
+            }
+            for (int i = 0; i < A; i++) g.wait_order[(size_t)s * Ap + i] = st->wait_order[(size_t)s * A + i];
+            // ---- road edges: exact arrays + hash grid over the de-duplicated float32 points
+            const int ne = st->n_edge[s];
+            const double* exy = st->edge_xy + (size_t)s * E * 2;
+            memcpy(&g.edge_xy[(size_t)s * Ed * 2], exy, sizeof(double) * 2 * ne);
+            memcpy(&g.edge_dir[(size_t)s * Ed * 2], st->edge_dir + (size_t)s * E * 2, sizeof(double) * 2 * ne);
+            keyed.clear();
+            for (int k = 0; k < ne; k++) keyed.push_back({{exy[2 * k], exy[2 * k + 1]}, k});
+            std::sort(keyed.begin(), keyed.end());
+            std::vector<int> keep;
+            for (int q = 0; q < ne; q++)
+                if (!(q > 0 && keyed[q].first == keyed[q - 1].first)) keep.push_back(keyed[q].second);
+            std::sort(keep.begin(), keep.end());
+            std::vector<lcs_f2> pts(keep.size());
+            float minx = 0, miny = 0, maxx = 0, maxy = 0;
+            for (size_t q = 0; q < keep.size(); q++) {
+                pts[q] = to_f32(exy[2 * keep[q]], exy[2 * keep[q] + 1]);
+                if (q == 0) {
+                    minx = maxx = pts[q].x;
+                    miny = maxy = pts[q].y;
+                } else {
+                    minx = std::min(minx, pts[q].x); maxx = std::max(maxx, pts[q].x);
+                    miny = std::min(miny, pts[q].y); maxy = std::max(maxy, pts[q].y);
+                }
+            }
+            const float inv = 1.0f / cell;
+            const float gx0 = minx, gy0 = miny;
+            int W = 1, H = 1;
+            if (!keep.empty()) {
+                W = (int)floorf((maxx - gx0) * inv) + 1;
+                H = (int)floorf((maxy - gy0) * inv) + 1;
+            }
+            g.grid_geom[4 * s] = gx0; g.grid_geom[4 * s + 1] = gy0; g.grid_geom[4 * s + 2] = inv; g.grid_geom[4 * s + 3] = cell;
+            g.grid_dim[2 * s] = W; g.grid_dim[2 * s + 1] = H;
+            std::vector<int32_t>& cs = cell_starts[s];
+            cs.assign((size_t)W * H + 1, 0);
+            std::vector<int> cell_of(keep.size());
+            for (size_t q = 0; q < keep.size(); q++) {
+                // the same float32 expression the kernel uses to locate a query (lcs_nearest_edge)
+                int cx = (int)floorf((pts[q].x - gx0) * inv), cy = (int)floorf((pts[q].y - gy0) * inv);
+                cx = std::min(std::max(cx, 0), W - 1);
+                cy = std::min(std::max(cy, 0), H - 1);
+                cell_of[q] = cy * W + cx;
+                cs[cell_of[q] + 1]++;
+            }
+            for (size_t c = 0; c < (size_t)W * H; c++) cs[c + 1] += cs[c];
+            std::vector<int32_t> fill(cs.begin(), cs.end() - 1);
+            for (size_t q = 0; q < keep.size(); q++) { // ascending original index inside each cell
+                const int pos = fill[cell_of[q]]++;
+                g.ge_xy[(size_t)s * Ed + pos] = pts[q];
+                g.ge_idx[(size_t)s * Ed + pos] = keep[q];
+            }
+            g.eta[s] = (float)(eta * 1.0001) + 1e-12f;
+        }
+    });
+    int GC = 2;
+    for (int s = 0; s < S; s++) GC = std::max<int>(GC, (int)cell_starts[s].size());
+    g.grid_start.assign((size_t)S * GC, 0);
+    for (int s = 0; s < S; s++) {
+        std::copy(cell_starts[s].begin(), cell_starts[s].end(), g.grid_start.begin() + (size_t)s * GC);
+        for (size_t c = cell_starts[s].size(); c < (size_t)GC; c++) g.grid_start[(size_t)s * GC + c] = cell_starts[s].back();
+    }
+    if (p.grid_start) { /* re-upload: keep the old block alive until destroy */ }
+    p.GC = GC;
+    LCS_ALLOC(e, p.grid_start, (size_t)S * GC);
+
+#define LCS_UP(dst, vec) LCS_CUDA(e, cudaMemcpy((void*)(dst), (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice))
+    LCS_CUDA(e, cudaMemcpy((void*)p.n_agents, st->n_agents, sizeof(int32_t) * S, cudaMemcpyHostToDevice));
+    LCS_CUDA(e, cudaMemcpy((void*)p.ads_index, st->ads_index, sizeof(int32_t) * S, cudaMemcpyHostToDevice));
+    LCS_CUDA(e, cudaMemcpy((void*)p.origin, st->origin, sizeof(double) * 2 * S, cudaMemcpyHostToDevice));
+    LCS_CUDA(e, cudaMemcpy((void*)p.n_edge, st->n_edge, sizeof(int32_t) * S, cudaMemcpyHostToDevice));
+    LCS_UP(p.eta_pts, g.eta);
+    LCS_UP(p.depart_tick, g.depart_tick);
+    LCS_UP(p.wait_order, g.wait_order);
+    LCS_UP(p.dynamic, g.dynamic);
+    LCS_UP(p.length, g.length);
+    LCS_UP(p.width, g.width);
+    LCS_UP(p.home_xy, g.home_xy);
+    LCS_UP(p.traj_len0, g.traj_len);
+    LCS_UP(p.traj_xy0, g.traj_xy);
+    LCS_UP(p.traj_vel0, g.traj_vel);
+    LCS_UP(p.traj_h0, g.traj_h);
+    LCS_UP(p.tf_xy0, g.tf_xy);
+    LCS_UP(p.traj_len, g.traj_len);
+    LCS_UP(p.traj_xy, g.traj_xy);
+    LCS_UP(p.traj_vel, g.traj_vel);
+    LCS_UP(p.traj_h, g.traj_h);
+    LCS_UP(p.tf_xy, g.tf_xy);
+    LCS_UP(e->s_tab0, g.s_tab);
+    LCS_UP(p.edge_xy, g.edge_xy);
+    LCS_UP(p.edge_dir, g.edge_dir);
+    LCS_UP(p.grid_geom, g.grid_geom);
+    LCS_UP(p.grid_dim, g.grid_dim);
+    LCS_UP(p.grid_start, g.grid_start);
+    LCS_UP(p.ge_xy, g.ge_xy);
+    LCS_UP(p.ge_idx, g.ge_idx);
+#undef LCS_UP
+    LCS_CUDA(e, cudaMemset(p.traj_f32, 0, SA));
+    LCS_CUDA(e, cudaMemset(p.stale_valid, 0, SA));
+    e->uploaded = true;
+    int rc = lcsim_b200_reset(e, nullptr, nullptr);
+    if (rc) return rc;
+    LCS_CUDA(e, cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int lcsim_b200_reset(lcsim_b200_engine* e, const uint8_t* reset_mask, void* stream) {
+    if (!e) return LCSIM_B200_ERR_ARG;
+    if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "reset before upload_static");
+    LcsParams q = e->p;
+    q.mode = 1;
+    q.reset_mask = reset_mask;
+    q.K = 0;
+    lcs_launch_tick(q, (cudaStream_t)stream);
+    e->launches++;
+    LCS_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lcsim_b200_step(lcsim_b200_engine* e, const int32_t* act_agent, const int32_t* act_type,
+                               const double* act_data, int K, void* stream) {
+    if (!e) return LCSIM_B200_ERR_ARG;
+    if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "step before upload_static");
+    if (K < 0 || (K > 0 && (!act_agent || !act_type || !act_data))) return lcs_fail(e, LCSIM_B200_ERR_ARG, "K=%d with null action arrays", K);
+    LcsParams q = e->p;
+    q.mode = 0;
+    q.act_agent = act_agent;
+    q.act_type = act_type;
+    q.act_data = act_data;
+    q.K = K;
+    lcs_launch_tick(q, (cudaStream_t)stream);
+    e->launches++;
+    LCS_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lcsim_b200_rollout(lcsim_b200_engine* e, int n_ticks, void* stream) {
+    if (!e || n_ticks < 0) return LCSIM_B200_ERR_ARG;
+    for (int k = 0; k < n_ticks; k++) {
+        int rc = lcsim_b200_step(e, nullptr, nullptr, nullptr, 0, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+extern "C" int lcsim_b200_set_ref_trajectory(lcsim_b200_engine* e, const int32_t* scenario, const int32_t* agent,
+                                             const float* xy, const float* vel, const float* heading, int n, int T,
+                                             void* stream) {
+    if (!e) return LCSIM_B200_ERR_ARG;
+    if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "set_ref_trajectory before upload_static");
+    if (n < 0 || T < 1 || (n > 0 && (!scenario || !agent || !xy || !vel || !heading))) return lcs_fail(e, LCSIM_B200_ERR_ARG, "bad re-plan arguments");
+    if (T > 128) return lcs_fail(e, LCSIM_B200_ERR_ARG, "re-plan length %d > 128", T);
+    if (n == 0) return 0;
+    LcsReplanArgs r{scenario, agent, xy, vel, heading, n, T};
+#ifndef LCSIM_HOSTEMU
+    lcs_replan_kernel<<<n, 64, 0, (cudaStream_t)stream>>>(e->p, r);
+    LCS_CUDA(e, cudaGetLastError());
+#else
+    for (int i = 0; i < n; i++) {
+        lcs_replan_stale(e->p, r, i);
+        for (int k = 0; k < e->p.T; k++) lcs_replan_copy(e->p, r, i, k);
+    }
+#endif
+    return 0;
+}
+
+extern "C" int lcsim_b200_rewards(lcsim_b200_engine* e, const int32_t* agent, const double* coef6, double* reward,
+                                  double* terms, uint8_t* terminated, uint8_t* truncated, double* route, void* stream) {
+    if (!e) return LCSIM_B200_ERR_ARG;
+    if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "rewards before upload_static");
+    LcsRewardArgs r;
+    memset(&r, 0, sizeof r);
+    r.agent = agent;
+    r.has_coef = coef6 != nullptr;
+    if (coef6) memcpy(r.coef, coef6, sizeof r.coef);
+    r.reward = reward;
+    r.terms = terms;
+    r.route = route;
+    r.terminated = terminated;
+    r.truncated = truncated;
+    r.s_tab0 = e->s_tab0;
+#ifndef LCSIM_HOSTEMU
+    lcs_rewards_kernel<<<(e->p.S + 63) / 64, 64, 0, (cudaStream_t)stream>>>(e->p, r);
+    LCS_CUDA(e, cudaGetLastError());
+#else
+    for (int s = 0; s < e->p.S; s++) lcs_rewards_one(e->p, r, s);
+#endif
+    return 0;
+}
+
+extern "C" int lcsim_b200_upload_polylines(lcsim_b200_engine* e, const int32_t*, const double*, int) {
+    return lcs_fail(e, LCSIM_B200_ERR_STATE, "upload_polylines: not built yet");
+}
+extern "C" int lcsim_b200_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_desc*, void*) {
+    return lcs_fail(e, LCSIM_B200_ERR_STATE, "build_obs: not built yet");
+}
+
+extern "C" int lcsim_b200_views(lcsim_b200_engine* e, lcsim_b200_state_views* v) {
+    if (!e || !v) return LCSIM_B200_ERR_ARG;
+    const LcsParams& p = e->p;
+    v->S = p.S; v->A = p.A; v->A_stride = p.Ap; v->T = p.T; v->E = p.E; v->H = LCS_H;
+    v->tick = p.tick; v->n_active = p.n_active; v->active = p.active; v->status = p.status; v->cursor = p.cursor;
+    v->ring_count = p.ring_count; v->ring_head = p.ring_head; v->pose64 = p.pose64; v->pose32 = (float*)p.pose32;
+    v->ring = p.ring; v->lead_valid = p.lead_valid; v->lead_dis = p.lead_dis; v->lead_v = p.lead_v;
+    v->coll_count = p.coll_count; v->nearest_edge = p.nearest_edge; v->offroad = p.offroad;
+    v->traj_len = p.traj_len; v->traj_xy = p.traj_xy; v->traj_vel = p.traj_vel; v->traj_h = p.traj_h;
+    v->stats = p.stats; v->origin = (double*)p.origin;
+    return 0;
+}
+
+extern "C" int lcsim_b200_episode_stats(lcsim_b200_engine* e, int64_t* stats_device, void* stream) {
+    if (!e || !stats_device) return LCSIM_B200_ERR_ARG;
+#ifndef LCSIM_HOSTEMU
+    lcs_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(e->p.stats, e->p.S, stats_device);
+    LCS_CUDA(e, cudaGetLastError());
+#else
+    for (int k = 0; k < LCS_NSTAT; k++) {
+        int64_t acc = 0;
+        for (int s = 0; s < e->p.S; s++) acc += e->p.stats[(size_t)s * LCS_NSTAT + k];
+        stats_device[k] = acc;
+    }
+#endif
+    return 0;
+}

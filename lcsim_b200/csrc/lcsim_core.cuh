@@ -1,0 +1,893 @@
+// lcsim_core.cuh — device code of the per-tick agent-stepping path (one CTA per scenario,
+// one thread per agent).  Included by lcsim_b200.cu (nvcc, sm_100a).  The same text also
+// compiles as plain C++ with -DLCSIM_HOSTEMU, where a "kernel launch" is a loop over
+// (scenario, phase, thread); that build exists only under tests/hostemu to debug the
+// control flow on machines without a GPU and is never loaded by the package.
+//
+// Numerics contract: every decision the reference takes in float64 is taken
+// here in float64, operation for operation, with the roundings pinned by explicit
+// __dmul_rn/__dadd_rn/__fma_rn (no compiler contraction).  float32 is used only as a
+// conservative FILTER in front of those decisions: a float32 scan may discard a candidate
+// only when a rigorous error bound proves it cannot win; survivors are re-evaluated in
+// float64.  Integer outputs are therefore those of the float64 algorithm.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef LCSIM_HOSTEMU
+#include <string.h>
+#define LCS_D static inline
+struct lcs_f2 { float x, y; };
+struct alignas(16) lcs_f4 { float x, y, z, w; };
+LCS_D double lcs_dmul(double a, double b) { return a * b; } // built with -ffp-contract=off
+LCS_D double lcs_dadd(double a, double b) { return a + b; }
+LCS_D double lcs_dsub(double a, double b) { return a - b; }
+LCS_D double lcs_dfma(double a, double b, double c) { return fma(a, b, c); }
+LCS_D void lcs_sincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
+LCS_D int lcs_popc(uint32_t x) { return __builtin_popcount(x); }
+LCS_D int lcs_atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
+#else
+#define LCS_D __device__ __forceinline__
+typedef float2 lcs_f2;
+typedef float4 lcs_f4;
+LCS_D double lcs_dmul(double a, double b) { return __dmul_rn(a, b); }
+LCS_D double lcs_dadd(double a, double b) { return __dadd_rn(a, b); }
+LCS_D double lcs_dsub(double a, double b) { return __dsub_rn(a, b); }
+LCS_D double lcs_dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+LCS_D void lcs_sincos(double a, double* s, double* c) { sincos(a, s, c); }
+LCS_D int lcs_popc(uint32_t x) { return __popc(x); }
+LCS_D int lcs_atomic_add(int* p, int v) { return atomicAdd(p, v); }
+#endif
+
+#define LCS_WAITING 0
+#define LCS_ACTIVE 1
+#define LCS_FINISHED 2
+#define LCS_IDLE 3
+#define LCS_ACT_NONE 0
+#define LCS_ACT_BICYCLE 1
+#define LCS_ACT_DELTA 2
+#define LCS_ACT_STATE 3
+#define LCS_H 11
+#define LCS_ROUTE 10
+#define LCS_NSTAT 8
+#define LCS_CAND 8 // private candidate list length per thread in the all-pairs phases
+#define LCS_PI 3.14159265358979323846
+#define LCS_FAR 3.0e18f // filter coordinate of "no point here" (its square stays finite in float32)
+
+LCS_D float lcs_inf_f() {
+#ifdef LCSIM_HOSTEMU
+    return INFINITY;
+#else
+    return __int_as_float(0x7f800000);
+#endif
+}
+LCS_D double lcs_inf_d() {
+#ifdef LCSIM_HOSTEMU
+    return (double)INFINITY;
+#else
+    return __longlong_as_double(0x7ff0000000000000LL);
+#endif
+}
+
+// Everything a tick needs, as raw device pointers.  Layouts: DESIGN.md §3.
+struct LcsParams {
+    int32_t S, A, Ap, T, E;
+    double dt;
+    int32_t total_steps, reactive, no_static, allow_new_obj, with_metrics;
+    // ---- static, per scenario
+    const int32_t *n_agents, *ads_index;
+    const double* origin; // [S][2]
+    const float* eta_pts; // [S] bound on |fl32(p - origin) - (p - origin)| over all static points
+    // ---- static, per agent [S][Ap]
+    const int32_t *depart_tick, *wait_order;
+    const uint8_t* dynamic;
+    const double *length, *width; // [S][Ap]
+    const double* home_xy; // [S][Ap][2]
+    // pristine trajectories (reset restores re-planned ones from here)
+    const int32_t* traj_len0;
+    const double *traj_xy0, *traj_vel0, *traj_h0; // [S][Ap][T][2], [S][Ap][T][2], [S][Ap][T]
+    const lcs_f2* tf_xy0; // [S][T][Ap] float32 filter copy, relative to origin, duplicates -> LCS_FAR
+    // ---- current trajectories (set_ref_trajectory overwrites)
+    int32_t* traj_len;
+    double *traj_xy, *traj_vel, *traj_h;
+    lcs_f2* tf_xy;
+    uint8_t* traj_f32; // 1: arrays came from a float32 re-plan (engine.py:290-297)
+    uint8_t *stale_valid, *stale_f32; // obs.ref_trajectory still points at the old Trajectory
+    double* stale_wp; // [S][Ap][5]
+    // ---- road edges
+    const int32_t* n_edge; // [S]
+    const double *edge_xy, *edge_dir; // [S][E][2] original order (exact phase)
+    // hash grid over the de-duplicated edge points of a scenario
+    const float* grid_geom; // [S][4] gx0, gy0, inv_cell, cell
+    const int32_t* grid_dim; // [S][2] W, H
+    const int32_t* grid_start; // [S][GC] CSR offsets (W*H+1 used), cells row-major
+    int32_t GC;
+    const lcs_f2* ge_xy; // [S][E] points sorted by cell, float32 relative to origin
+    const int32_t* ge_idx; // [S][E] original index of each sorted point
+    // ---- state, per scenario
+    int32_t *tick, *n_active, *wait_ptr;
+    int64_t* stats; // [S][LCS_NSTAT]
+    // ---- state, per agent
+    int32_t *active; // [S][Ap]
+    int32_t *status, *cursor, *ring_count, *ring_head;
+    double* pose64; // [S][Ap][4]
+    lcs_f4* pose32; // [S][Ap]
+    double* ring; // [S][Ap][H][5]
+    uint8_t* lead_valid;
+    double *lead_dis, *lead_v;
+    int32_t *coll_count, *nearest_edge;
+    uint8_t* offroad;
+    // ---- external actions of this launch
+    const int32_t *act_agent, *act_type; // [S][K]
+    const double* act_data; // [S][K][5]
+    int32_t K;
+    // ---- launch mode
+    int32_t mode; // 0 = step, 1 = reset
+    const uint8_t* reset_mask; // [S] or null
+};
+
+// Shared memory of one CTA (Ap threads).  Carved from one dynamic allocation.
+struct LcsSmem {
+    double* ex; // [Ap][8]  x, y, v, cos h, sin h, L, W, h  (agent index)
+    lcs_f4* rec; // [Ap]     x32, y32, filter radius (-1 inactive), coordinate slack   (agent index)
+    int32_t* status; // [Ap] (agent index)
+    int32_t* act; // [Ap] active list (slot index)
+    int32_t* act2; // [Ap] new active list
+    int32_t* dlist; // [Ap] agents activated this tick, in waiting-list order
+    int32_t* cnt; // [Ap] collision counts
+    uint16_t* cand; // [LCS_CAND][Ap]
+    uint32_t* mask; // [3][32] ballot words: finished, popped, activated
+    int32_t* misc; // [8] n_old, n_new, ...
+};
+
+#ifdef LCSIM_HOSTEMU
+static inline
+#else
+__host__ __device__ inline
+#endif
+size_t lcs_smem_bytes(int Ap) {
+    return (size_t)Ap * (8 * 8 + 16 + 4 * 5 + 2 * LCS_CAND) + 3 * 32 * 4 + 8 * 4 + 64;
+}
+
+LCS_D void lcs_smem_carve(LcsSmem& sm, unsigned char* base, int Ap) {
+    unsigned char* p = base;
+    sm.ex = (double*)p; p += (size_t)Ap * 64;
+    sm.rec = (lcs_f4*)p; p += (size_t)Ap * 16;
+    sm.status = (int32_t*)p; p += (size_t)Ap * 4;
+    sm.act = (int32_t*)p; p += (size_t)Ap * 4;
+    sm.act2 = (int32_t*)p; p += (size_t)Ap * 4;
+    sm.dlist = (int32_t*)p; p += (size_t)Ap * 4;
+    sm.cnt = (int32_t*)p; p += (size_t)Ap * 4;
+    sm.mask = (uint32_t*)p; p += 3 * 32 * 4;
+    sm.misc = (int32_t*)p; p += 8 * 4;
+    sm.cand = (uint16_t*)p;
+}
+
+// ------------------------------------------------------------------ small float64 helpers
+
+// reference: utils/polygon.py:191-192 wrap_angle = (a + pi) % (2*pi) - pi with the floored
+// modulo of Python/NumPy.  fmod is exact in IEEE arithmetic on both sides.
+LCS_D double lcs_wrap_angle(double a) {
+    const double two_pi = 2 * LCS_PI;
+    double t = lcs_dadd(a, LCS_PI);
+    double r = fmod(t, two_pi);
+    if (r != 0.0) {
+        if (r < 0.0) r = lcs_dadd(r, two_pi);
+    } else {
+        r = 0.0;
+    }
+    return lcs_dsub(r, LCS_PI);
+}
+// two-term dot product the way BLAS evaluates np.dot / np.matmul / 1-D np.linalg.norm: a0*b0 then fma
+LCS_D double lcs_dot2(double a0, double b0, double a1, double b1) { return lcs_dfma(a1, b1, lcs_dmul(a0, b0)); }
+// np.linalg.norm over a trailing axis of length 2 (unfused)
+LCS_D double lcs_norm2_axis(double dx, double dy) { return sqrt(lcs_dadd(lcs_dmul(dx, dx), lcs_dmul(dy, dy))); }
+// np.linalg.norm of a 1-D 2-vector (BLAS ddot)
+LCS_D double lcs_norm2_vec(double dx, double dy) { return sqrt(lcs_dot2(dx, dx, dy, dy)); }
+LCS_D double lcs_pymax(double a, double b) { return b > a ? b : a; }
+LCS_D double lcs_pymin(double a, double b) { return b < a ? b : a; }
+LCS_D double lcs_npclip(double x, double lo, double hi) {
+    if (x != x) return x;
+    double m = x < lo ? lo : x;
+    return m > hi ? hi : m;
+}
+
+// float32 candidate threshold: every point whose float64 distance can equal the minimum has a
+// filter value <= thr when the best filter value is m.  eta bounds the error of
+// the float32 coordinates (points + query).
+// eta: static points carry at most eta_pts (measured at upload); the query and any re-planned
+// (float32-sourced) point near it carry at most half an ulp of their local coordinate.
+LCS_D float lcs_filter_eta(float eta_pts, float fqx, float fqy, float m) {
+    return eta_pts + 1.2e-7f * (fabsf(fqx) + fabsf(fqy)) + 1.2e-7f * (sqrtf(m) + 1.0f);
+}
+LCS_D float lcs_filter_thr(float m, float eta) {
+    float r = sqrtf(m) * 1.000001f + 2.1f * eta + 1e-7f;
+    r *= 1.000001f;
+    return r * r * 1.000001f;
+}
+
+// ------------------------------------------------------------------ ballot-word scans
+
+// flag of "thread" tid -> bit tid of words[]
+LCS_D void lcs_set_flag(uint32_t* words, int tid, bool f) {
+#ifdef LCSIM_HOSTEMU
+    if (f) words[tid >> 5] |= 1u << (tid & 31);
+#else
+    uint32_t b = __ballot_sync(0xffffffffu, f);
+    if ((tid & 31) == 0) words[tid >> 5] = b;
+#endif
+}
+LCS_D int lcs_prefix(const uint32_t* words, int tid) { // number of set flags below tid
+    int w = tid >> 5, r = lcs_popc(words[w] & ((1u << (tid & 31)) - 1u));
+    for (int k = 0; k < w; k++) r += lcs_popc(words[k]);
+    return r;
+}
+LCS_D int lcs_total(const uint32_t* words, int nwords) {
+    int r = 0;
+    for (int k = 0; k < nwords; k++) r += lcs_popc(words[k]);
+    return r;
+}
+
+// ------------------------------------------------------------------ cursor: Trajectory.next
+
+// reference: agent/policy/type.py:42-48 Trajectory.next -> utils/polygon.py:271-293
+// frenet_projection: index = first argmin_k sqrt((x_k-px)^2 + (y_k-py)^2) over ALL len points.
+// Filter scan over the float32 copy (coalesced: [T][Ap]), exact float64 only on near-ties.
+LCS_D int lcs_cursor_argmin(const LcsParams& p, int s, int a, int len, double qx, double qy) {
+    const lcs_f2* tf = p.tf_xy + (size_t)s * p.T * p.Ap + a;
+    const double ox = p.origin[2 * s], oy = p.origin[2 * s + 1];
+    const float fqx = (float)(qx - ox), fqy = (float)(qy - oy);
+    float m = lcs_inf_f(), m2 = lcs_inf_f();
+    int j = 0;
+#pragma unroll 4
+    for (int k = 0; k < len; k++) {
+        lcs_f2 pt = tf[(size_t)k * p.Ap];
+        float dx = pt.x - fqx, dy = pt.y - fqy;
+        float d = dx * dx + dy * dy;
+        bool c = d < m;
+        m2 = c ? m : fminf(m2, d);
+        j = c ? k : j;
+        m = c ? d : m;
+    }
+    const float eta = lcs_filter_eta(p.eta_pts[s], fqx, fqy, m);
+    const float thr = lcs_filter_thr(m, eta);
+    if (m2 > thr) return j;
+    // near-tie: float64 evaluation of every candidate, first minimum wins (np.argmin)
+    const double* t64 = p.traj_xy + ((size_t)s * p.Ap + a) * p.T * 2;
+    double bd = lcs_inf_d();
+    int best = j;
+    for (int k = 0; k < len; k++) {
+        lcs_f2 pt = tf[(size_t)k * p.Ap];
+        float dx = pt.x - fqx, dy = pt.y - fqy;
+        float d = dx * dx + dy * dy;
+        if (d <= thr) {
+            double e = lcs_norm2_axis(lcs_dsub(t64[2 * k], qx), lcs_dsub(t64[2 * k + 1], qy));
+            if (e < bd) { bd = e; best = k; }
+        }
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------ nearest road-edge point
+
+// reference: junction/junction.py:365-385 check_offroad: k* = first argmin over the concatenated,
+// resampled edge points; offroad = cross(pts[k*] - pos, dir[k*]) < 0.
+// The points live in a uniform hash grid (cells row-major, CSR); a (2r+1)^2 window around the
+// query is scanned row by row (one contiguous span per row), r grows until the window provably
+// contains every point that can be the float64 argmin.
+LCS_D int lcs_nearest_edge(const LcsParams& p, int s, double qx, double qy, bool* offroad) {
+    *offroad = false;
+    const int ne = p.n_edge[s];
+    if (ne == 0) return -1;
+    const double ox = p.origin[2 * s], oy = p.origin[2 * s + 1];
+    const float fqx = (float)(qx - ox), fqy = (float)(qy - oy);
+    const float gx0 = p.grid_geom[4 * s], gy0 = p.grid_geom[4 * s + 1], inv = p.grid_geom[4 * s + 2];
+    const int W = p.grid_dim[2 * s], H = p.grid_dim[2 * s + 1];
+    const int32_t* cs = p.grid_start + (size_t)s * p.GC;
+    const lcs_f2* gp = p.ge_xy + (size_t)s * p.E;
+    // cell of the query; clamped far outside the grid so the integer math below cannot overflow
+    float fcx = floorf((fqx - gx0) * inv), fcy = floorf((fqy - gy0) * inv);
+    fcx = fminf(fmaxf(fcx, -1.0e6f), 1.0e6f);
+    fcy = fminf(fmaxf(fcy, -1.0e6f), 1.0e6f);
+    const int cx = (int)fcx, cy = (int)fcy;
+    int x0 = cx - 1, x1 = cx + 1, y0 = cy - 1, y1 = cy + 1;
+    float m, m2, thr;
+    int j;
+    for (;;) {
+        const int wx0 = x0 < 0 ? 0 : x0, wx1 = x1 > W - 1 ? W - 1 : x1;
+        const int wy0 = y0 < 0 ? 0 : y0, wy1 = y1 > H - 1 ? H - 1 : y1;
+        m = lcs_inf_f();
+        m2 = lcs_inf_f();
+        j = -1;
+        if (wx0 <= wx1) {
+            for (int y = wy0; y <= wy1; y++) {
+                const int b = cs[y * W + wx0], e = cs[y * W + wx1 + 1];
+                for (int k = b; k < e; k++) {
+                    lcs_f2 pt = gp[k];
+                    float dx = pt.x - fqx, dy = pt.y - fqy;
+                    float d = dx * dx + dy * dy;
+                    bool c = d < m;
+                    m2 = c ? m : fminf(m2, d);
+                    j = c ? k : j;
+                    m = c ? d : m;
+                }
+            }
+        }
+        const bool covers_all = x0 <= 0 && y0 <= 0 && x1 >= W - 1 && y1 >= H - 1;
+        if (j >= 0) {
+            thr = lcs_filter_thr(m, lcs_filter_eta(p.eta_pts[s], fqx, fqy, m));
+            // every candidate lies within D of the query in each axis; the extra 1e-3 m absorbs the
+            // float32 rounding of the cell arithmetic (grid points were binned with the same formula)
+            const float D = sqrtf(thr) * 1.000001f + 1e-3f + 4e-7f * (fabsf(fqx) + fabsf(fqy) + fabsf(gx0) + fabsf(gy0));
+            const int nx0 = (int)fmaxf(floorf((fqx - D - gx0) * inv), -1.0e6f);
+            const int nx1 = (int)fminf(floorf((fqx + D - gx0) * inv), 1.0e6f);
+            const int ny0 = (int)fmaxf(floorf((fqy - D - gy0) * inv), -1.0e6f);
+            const int ny1 = (int)fminf(floorf((fqy + D - gy0) * inv), 1.0e6f);
+            if (covers_all || (nx0 >= x0 && nx1 <= x1 && ny0 >= y0 && ny1 <= y1)) break;
+            x0 = nx0 < x0 ? nx0 : x0;
+            x1 = nx1 > x1 ? nx1 : x1;
+            y0 = ny0 < y0 ? ny0 : y0;
+            y1 = ny1 > y1 ? ny1 : y1;
+        } else {
+            if (covers_all) return -1; // cannot happen with ne > 0
+            const int r = (x1 - x0); // grow geometrically while the window is empty
+            x0 -= r; x1 += r; y0 -= r; y1 += r;
+        }
+    }
+    const double* e64 = p.edge_xy + (size_t)s * p.E * 2;
+    const int32_t* gi = p.ge_idx + (size_t)s * p.E;
+    int best = gi[j];
+    if (m2 <= thr) {
+        // near-tie: float64 evaluation of every candidate in the window; (distance, index) lexicographic
+        const int wx0 = x0 < 0 ? 0 : x0, wx1 = x1 > W - 1 ? W - 1 : x1;
+        const int wy0 = y0 < 0 ? 0 : y0, wy1 = y1 > H - 1 ? H - 1 : y1;
+        double bd = lcs_inf_d();
+        best = 0x7fffffff;
+        for (int y = wy0; y <= wy1; y++) {
+            const int b = cs[y * W + wx0], e = cs[y * W + wx1 + 1];
+            for (int k = b; k < e; k++) {
+                lcs_f2 pt = gp[k];
+                float dx = pt.x - fqx, dy = pt.y - fqy;
+                float d = dx * dx + dy * dy;
+                if (d <= thr) {
+                    const int idx = gi[k];
+                    double ee = lcs_norm2_axis(lcs_dsub(e64[2 * idx], qx), lcs_dsub(e64[2 * idx + 1], qy));
+                    if (ee < bd || (ee == bd && idx < best)) { bd = ee; best = idx; }
+                }
+            }
+        }
+    }
+    const double* d64 = p.edge_dir + (size_t)s * p.E * 2;
+    const double ax = lcs_dsub(e64[2 * best], qx), ay = lcs_dsub(e64[2 * best + 1], qy);
+    const double cross = lcs_dsub(lcs_dmul(ax, d64[2 * best + 1]), lcs_dmul(ay, d64[2 * best])); // np.cross, 2-vectors
+    *offroad = cross < 0;
+    return best;
+}
+
+// ------------------------------------------------------------------ oriented-box SAT (exact)
+
+// reference: utils/polygon.py:238-268 corners_from_bboxes
+LCS_D void lcs_corners(const double* ex /* x,y,v,c,s,L,W,h */, double* X, double* Y) {
+    const double x = ex[0], y = ex[1], c = ex[3], s = ex[4];
+    const double hl = ex[5] / 2, hw = ex[6] / 2;
+    const double lc = lcs_dmul(hl, c), ls = lcs_dmul(hl, s), wc = lcs_dmul(hw, c), ws = lcs_dmul(hw, s);
+    X[0] = lcs_dadd(lcs_dadd(x, lc), ws);
+    X[1] = lcs_dadd(lcs_dsub(x, lc), ws);
+    X[2] = lcs_dsub(lcs_dsub(x, lc), ws);
+    X[3] = lcs_dsub(lcs_dadd(x, lc), ws);
+    Y[0] = lcs_dsub(lcs_dadd(y, ls), wc);
+    Y[1] = lcs_dsub(lcs_dsub(y, ls), wc);
+    Y[2] = lcs_dadd(lcs_dsub(y, ls), wc);
+    Y[3] = lcs_dadd(lcs_dadd(y, ls), wc);
+}
+// reference: utils/polygon.py:206-230 _overlap_a_over_b (projection on `first`'s two axes, strict > 0)
+LCS_D bool lcs_overlap_a_over_b(const double* fX, const double* fY, double c, double s, const double* sX, const double* sY) {
+    for (int axis = 0; axis < 2; axis++) {
+        const double n0 = axis == 0 ? c : -s, n1 = axis == 0 ? s : c;
+        double min_a = lcs_inf_d(), max_a = -lcs_inf_d(), min_b = lcs_inf_d(), max_b = -lcs_inf_d();
+        for (int k = 0; k < 4; k++) {
+            const double pa = lcs_dot2(fX[k], n0, fY[k], n1);
+            const double pb = lcs_dot2(sX[k], n0, sY[k], n1);
+            min_a = pa < min_a ? pa : min_a;
+            max_a = pa > max_a ? pa : max_a;
+            min_b = pb < min_b ? pb : min_b;
+            max_b = pb > max_b ? pb : max_b;
+        }
+        const double hi = max_a < max_b ? max_a : max_b, lo = min_a > min_b ? min_a : min_b;
+        if (!(lcs_dsub(hi, lo) > 0)) return false;
+    }
+    return true;
+}
+LCS_D bool lcs_collide(const double* ea, const double* eb) {
+    double aX[4], aY[4], bX[4], bY[4];
+    lcs_corners(ea, aX, aY);
+    lcs_corners(eb, bX, bY);
+    return lcs_overlap_a_over_b(aX, aY, ea[3], ea[4], bX, bY) && lcs_overlap_a_over_b(bX, bY, eb[3], eb[4], aX, aY);
+}
+
+// ------------------------------------------------------------------ lead vehicle (exact part)
+
+// reference: agent/agent.py:249-299, one (ego, other) pair.  cos/sin of the relative heading come
+// from the per-agent cos/sin by the angle-difference identity instead of
+// cos(wrap(h_o - h)); the two agree to ~2 ulp, which moves no integer output.
+LCS_D bool lcs_lead_pair(const double* eg, const double* eo, double* dis, double* vlead) {
+    const double ch = eg[3], sh = eg[4], L = eg[5], W = eg[6];
+    const double dx = lcs_dsub(eo[0], eg[0]), dy = lcs_dsub(eo[1], eg[1]);
+    const double rx = lcs_dot2(dx, ch, dy, sh);
+    const double ry = lcs_dot2(dx, -sh, dy, ch);
+    const double la = eo[5], wa = eo[6];
+    const double c = lcs_dfma(eo[4], sh, lcs_dmul(eo[3], ch)); // cos(ho - h)
+    const double sn = lcs_dsub(lcs_dmul(eo[4], ch), lcs_dmul(eo[3], sh)); // sin(ho - h)
+    const double ls = lcs_dmul(la / 2.0, sn), wc = lcs_dmul(wa / 2.0, c);
+    const double y0 = lcs_dsub(lcs_dadd(ry, ls), wc), y1 = lcs_dadd(lcs_dadd(ry, ls), wc);
+    const double y2 = lcs_dadd(lcs_dsub(ry, ls), wc), y3 = lcs_dsub(lcs_dsub(ry, ls), wc);
+    const double ymax = fmax(fmax(y0, y1), fmax(y2, y3)), ymin = fmin(fmin(y0, y1), fmin(y2, y3));
+    if (ymax < -W / 2.0 || ymin > W / 2.0) return false;
+    const double lc = lcs_dmul(la / 2.0, c), ws = lcs_dmul(wa / 2.0, sn);
+    const double x0 = lcs_dadd(lcs_dadd(rx, lc), ws), x1 = lcs_dsub(lcs_dadd(rx, lc), ws);
+    const double x2 = lcs_dsub(lcs_dsub(rx, lc), ws), x3 = lcs_dadd(lcs_dsub(rx, lc), ws);
+    const double xmin = fmin(fmin(x0, x1), fmin(x2, x3));
+    if (xmin < L / 2.0) return false;
+    *dis = lcs_dsub(xmin, L / 2.0);
+    *vlead = lcs_dmul(eo[2], c);
+    return true;
+}
+
+// ------------------------------------------------------------------ policies
+
+// reference: policy/idm_policy.py:226-245 TrajIDM._get_acc with the class constants
+LCS_D double lcs_idm_acc(double self_v, double target_v, double ahead_v, double distance) {
+    const double min_gap = 10.0, headway = 2.0, max_a = 2.0, max_brake = -2.0;
+    double acc;
+    if (lcs_dsub(distance, min_gap) < 0) {
+        acc = -lcs_inf_d();
+    } else {
+        // 2*sqrt(-usual_brake*max_a) = 2*sqrt(4) = 4 exactly
+        const double t = lcs_dadd(lcs_dmul(self_v, headway), lcs_dmul(self_v, lcs_dsub(self_v, ahead_v)) / 4.0);
+        const double s_star = lcs_dadd(min_gap, lcs_pymax(t, 0.0));
+        const double r1 = self_v / target_v, r2 = s_star / distance;
+        const double r1_2 = lcs_dmul(r1, r1);
+        acc = lcs_dmul(max_a, lcs_dsub(lcs_dsub(1.0, lcs_dmul(r1_2, r1_2)), lcs_dmul(r2, r2)));
+    }
+    return lcs_pymax(max_brake, lcs_pymin(max_a, acc));
+}
+
+// obs.ref_trajectory.next_waypoint() as the policy sees it (type.py:32-40); after a re-plan the
+// observation still holds the OLD trajectory until the next prepare_obs (agent.py:247,250 vs :462-466)
+LCS_D bool lcs_policy_waypoint(const LcsParams& p, size_t ia, int cursor, int len, double* wp) {
+    if (p.stale_valid[ia]) {
+        for (int k = 0; k < 5; k++) wp[k] = p.stale_wp[5 * ia + k];
+        return p.stale_f32[ia] != 0;
+    }
+    const int w = len == 1 ? cursor : cursor + 1;
+    const size_t t0 = ia * p.T + w;
+    wp[0] = p.traj_xy[2 * t0];
+    wp[1] = p.traj_xy[2 * t0 + 1];
+    wp[2] = p.traj_vel[2 * t0];
+    wp[3] = p.traj_vel[2 * t0 + 1];
+    wp[4] = p.traj_h[t0];
+    return p.traj_f32[ia] != 0;
+}
+
+// reference: agent/agent.py:67-84 HistoryState.update + :419-426; circular instead of shifting
+LCS_D void lcs_ring_push(const LcsParams& p, size_t ia, double x, double y, double h, double v, double ch, double sh, bool f32) {
+    int head = p.ring_head[ia];
+    double* r = p.ring + (ia * LCS_H + head) * 5;
+    r[0] = x;
+    r[1] = y;
+    if (f32) { // runtime.v / heading are np.float32 after a STATE action read from a float32 re-plan
+        r[2] = (double)((float)v * cosf((float)h));
+        r[3] = (double)((float)v * sinf((float)h));
+    } else {
+        r[2] = lcs_dmul(v, ch);
+        r[3] = lcs_dmul(v, sh);
+    }
+    r[4] = h;
+    p.ring_head[ia] = head + 1 == LCS_H ? 0 : head + 1;
+    int c = p.ring_count[ia];
+    if (c < LCS_H) p.ring_count[ia] = c + 1;
+}
+
+// ------------------------------------------------------------------ the tick, phase by phase
+// Phases are separated by __syncthreads() in the kernel (lcsim_b200.cu) and by loop boundaries
+// in the host emulation.  tid = agent index a (phases A, C, D, E) or list slot i (phase B).
+
+// Phase A: Engine.update (engine.py:221-225 -> manager.py:105-115 -> agent.py:310-426) or, in reset
+// mode, Agent.__init__ / Engine.reset (agent.py:106-171, engine.py:132-143).
+LCS_D void lcs_phase_update(const LcsParams& p, LcsSmem& sm, int s, int tid) {
+    const int a = tid;
+    const size_t ia = (size_t)s * p.Ap + a;
+    const int n_ag = p.n_agents[s];
+    for (int k = tid; k < 96; k += p.Ap) sm.mask[k] = 0;
+    if (tid == 0) {
+        sm.misc[0] = p.mode == 1 ? 0 : p.n_active[s]; // n_old
+        sm.misc[1] = 0; // n_new
+        sm.misc[2] = 0; // collision sum
+        sm.misc[3] = 0; // off-road sum
+        sm.misc[4] = p.mode == 1 ? 0 : p.tick[s];
+        sm.misc[5] = p.mode == 1 ? 0 : p.wait_ptr[s];
+    }
+    sm.cnt[a] = 0;
+    sm.act[a] = p.mode == 1 ? -1 : p.active[ia];
+    double x = 0, y = 0, h = 0, v = 0, ch = 1, sh = 0;
+    int status = LCS_IDLE;
+    if (a < n_ag) {
+        if (p.mode == 1) {
+            // ---- reset: restore a re-planned trajectory, home pose, first history entry
+            if (p.traj_f32[ia]) {
+                p.traj_len[ia] = p.traj_len0[ia];
+                for (int k = 0; k < p.T; k++) {
+                    const size_t t = ia * p.T + k;
+                    p.traj_xy[2 * t] = p.traj_xy0[2 * t];
+                    p.traj_xy[2 * t + 1] = p.traj_xy0[2 * t + 1];
+                    p.traj_vel[2 * t] = p.traj_vel0[2 * t];
+                    p.traj_vel[2 * t + 1] = p.traj_vel0[2 * t + 1];
+                    p.traj_h[t] = p.traj_h0[t];
+                    const size_t f = ((size_t)s * p.T + k) * p.Ap + a;
+                    p.tf_xy[f] = p.tf_xy0[f];
+                }
+                p.traj_f32[ia] = 0;
+            }
+            p.stale_valid[ia] = 0;
+            const double vx = p.traj_vel[2 * ia * p.T], vy = p.traj_vel[2 * ia * p.T + 1];
+            x = p.home_xy[2 * ia];
+            y = p.home_xy[2 * ia + 1];
+            v = sqrt(lcs_dadd(lcs_dmul(vx, vx), lcs_dmul(vy, vy))); // agent.py:144-146
+            h = p.traj_h[ia * p.T];
+            lcs_sincos(h, &sh, &ch);
+            status = LCS_WAITING;
+            p.cursor[ia] = 0;
+            p.ring_head[ia] = 0;
+            p.ring_count[ia] = 0;
+            for (int k = 0; k < LCS_H * 5; k++) p.ring[ia * LCS_H * 5 + k] = 0.0;
+            lcs_ring_push(p, ia, x, y, h, v, ch, sh, false); // agent.py:159-165
+            p.lead_valid[ia] = 0;
+            p.lead_dis[ia] = lcs_inf_d();
+            p.lead_v[ia] = 0.0;
+        } else {
+            status = p.status[ia];
+            const double* ps = p.pose64 + 4 * ia;
+            x = ps[0];
+            y = ps[1];
+            h = ps[2];
+            v = ps[3];
+            if (status == LCS_ACTIVE) {
+                const int len = p.traj_len[ia];
+                int cursor = p.cursor[ia];
+                // ---- which action (manager.py:111-115)
+                int type = LCS_ACT_NONE;
+                double d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0;
+                bool f32 = false;
+                for (int k = 0; k < p.K; k++) {
+                    const size_t q = (size_t)s * p.K + k;
+                    if (p.act_agent[q] == a && p.act_type[q] != LCS_ACT_NONE) {
+                        type = p.act_type[q];
+                        d0 = p.act_data[5 * q];
+                        d1 = p.act_data[5 * q + 1];
+                        d2 = p.act_data[5 * q + 2];
+                        d3 = p.act_data[5 * q + 3];
+                        d4 = p.act_data[5 * q + 4];
+                    }
+                }
+                if (type == LCS_ACT_NONE) {
+                    double wp[5];
+                    const bool wp_f32 = lcs_policy_waypoint(p, ia, cursor, len, wp);
+                    if (p.reactive) {
+                        // ---- TrajIDM.get_action (idm_policy.py:196-224), dt = 0.1 default argument
+                        const double pdt = 0.1;
+                        double vn = lcs_norm2_vec(wp[2], wp[3]);
+                        if (wp_f32) {
+                            const float fvx = (float)wp[2], fvy = (float)wp[3];
+                            vn = (double)sqrtf(fmaf(fvy, fvy, fvx * fvx));
+                        }
+                        double acc = lcs_npclip(lcs_dsub(vn, v) / pdt, -3.0, 3.0);
+                        const double dh = lcs_wrap_angle(lcs_dsub(wp[4], h));
+                        double steer;
+                        if (v < 0.6 || vn < 0.6)
+                            steer = 0.0;
+                        else
+                            steer = dh / lcs_dadd(lcs_dmul(v, pdt), lcs_dmul(lcs_dmul(0.5, acc), lcs_dmul(pdt, pdt)));
+                        steer = lcs_npclip(steer, -0.3, 0.3);
+                        if (p.lead_valid[ia]) {
+                            const double idm = lcs_idm_acc(v, 40.0, p.lead_v[ia], p.lead_dis[ia]);
+                            acc = lcs_pymax(lcs_pymin(acc, idm), -3.0);
+                        }
+                        type = LCS_ACT_BICYCLE;
+                        d0 = acc;
+                        d1 = steer;
+                    } else {
+                        // ---- StateExpert.get_action (expert_policy.py:18-33)
+                        type = LCS_ACT_STATE;
+                        d0 = wp[0]; d1 = wp[1]; d2 = wp[2]; d3 = wp[3]; d4 = wp[4];
+                        f32 = wp_f32;
+                    }
+                }
+                // ---- update_runtime_by_action (agent.py:377-416)
+                double qx = x, qy = y; // position fed to Trajectory.next
+                bool ring_f32 = false;
+                const double dt = p.dt;
+                if (type == LCS_ACT_STATE) {
+                    x = d0;
+                    y = d1;
+                    if (f32) {
+                        const float fvx = (float)d2, fvy = (float)d3;
+                        v = (double)sqrtf(fvx * fvx + fvy * fvy);
+                        ring_f32 = true;
+                    } else {
+                        v = sqrt(lcs_dadd(lcs_dmul(d2, d2), lcs_dmul(d3, d3)));
+                    }
+                    h = d4;
+                    qx = x;
+                    qy = y;
+                    lcs_sincos(h, &sh, &ch);
+                } else if (type == LCS_ACT_BICYCLE) {
+                    const double acc = d0, steer = d1;
+                    const double delta = lcs_dadd(lcs_dmul(v, dt), lcs_dmul(lcs_dmul(0.5, acc), lcs_dmul(dt, dt)));
+                    const double nh = lcs_wrap_angle(lcs_dadd(h, lcs_dmul(steer, delta)));
+                    lcs_sincos(nh, &sh, &ch);
+                    x = lcs_dadd(x, lcs_dmul(delta, ch));
+                    y = lcs_dadd(y, lcs_dmul(delta, sh));
+                    v = lcs_dadd(v, lcs_dmul(acc, dt));
+                    h = nh;
+                } else { // DELTA
+                    x = lcs_dadd(x, d0);
+                    y = lcs_dadd(y, d1);
+                    h = lcs_wrap_angle(lcs_dadd(h, d2));
+                    lcs_sincos(h, &sh, &ch);
+                }
+                cursor = lcs_cursor_argmin(p, s, a, len, qx, qy);
+                p.cursor[ia] = cursor;
+                if (cursor >= len - 1) status = LCS_FINISHED; // type.py:50-51 reach_end
+                lcs_ring_push(p, ia, x, y, h, v, ch, sh, ring_f32);
+            } else {
+                lcs_sincos(h, &sh, &ch);
+            }
+        }
+        if (p.mode == 1 || (status != LCS_IDLE && status != LCS_WAITING)) {
+        double* ps = p.pose64 + 4 * ia;
+        ps[0] = x;
+        ps[1] = y;
+        ps[2] = h;
+        ps[3] = v;
+        lcs_f4 p32;
+        p32.x = (float)(x - p.origin[2 * s]);
+        p32.y = (float)(y - p.origin[2 * s + 1]);
+        p32.z = (float)h;
+        p32.w = (float)v;
+        p.pose32[ia] = p32;
+        }
+    } else if (p.mode == 1) {
+        // padding agents: inert but defined
+        double* ps = p.pose64 + 4 * ia;
+        ps[0] = ps[1] = ps[2] = ps[3] = 0.0;
+        lcs_f4 z;
+        z.x = z.y = z.z = z.w = 0.f;
+        p.pose32[ia] = z;
+        p.cursor[ia] = 0;
+        p.ring_head[ia] = 0;
+        p.ring_count[ia] = 0;
+        p.lead_valid[ia] = 0;
+        p.stale_valid[ia] = 0;
+    }
+    double* ex = sm.ex + 8 * a;
+    ex[0] = x; ex[1] = y; ex[2] = v; ex[3] = ch; ex[4] = sh;
+    ex[5] = a < n_ag ? p.length[ia] : 0.0;
+    ex[6] = a < n_ag ? p.width[ia] : 0.0;
+    ex[7] = h;
+    sm.status[a] = status;
+}
+
+// Phase B1: AgentManager.check_departure_and_arrival (manager.py:50-96), flags.  tid = list slot /
+// waiting-list offset.
+LCS_D void lcs_phase_depart_flags(const LcsParams& p, LcsSmem& sm, int s, int tid, bool* fin_out, bool* pop_out, bool* act_out, int* aw_out) {
+    const int n = sm.misc[0];
+    const int tick = sm.misc[4];
+    const bool allow = p.mode == 1 ? true : (p.allow_new_obj != 0);
+    bool fin = false;
+    if (tid < n) {
+        const int a = sm.act[tid];
+        if (sm.status[a] == LCS_FINISHED) {
+            fin = true;
+            sm.status[a] = LCS_IDLE; // single-trip schedules: next_trip() is False (schedule.py:22-40)
+        }
+    }
+    bool pop = false, act = false;
+    int aw = -1;
+    const int wp = sm.misc[5];
+    if (allow && wp + tid < p.n_agents[s]) {
+        aw = p.wait_order[(size_t)s * p.Ap + wp + tid];
+        pop = p.depart_tick[(size_t)s * p.Ap + aw] <= tick;
+        act = pop && !(p.no_static && !p.dynamic[(size_t)s * p.Ap + aw] && aw != p.ads_index[s]);
+    }
+    lcs_set_flag(sm.mask, tid, fin);
+    lcs_set_flag(sm.mask + 32, tid, pop);
+    lcs_set_flag(sm.mask + 64, tid, act);
+    *fin_out = fin; *pop_out = pop; *act_out = act; *aw_out = aw;
+}
+
+// Phase B2: build the new active list (slot reuse in order, else append; leftover finished slots
+// are dropped preserving order).
+LCS_D void lcs_phase_depart_place(const LcsParams& p, LcsSmem& sm, int s, int tid, bool fin, bool act, int aw) {
+    const int nw = (p.Ap + 31) >> 5;
+    const int n = sm.misc[0];
+    const int n_arr = lcs_total(sm.mask, nw), m = lcs_total(sm.mask + 64, nw);
+    if (tid < n) {
+        const int r = lcs_prefix(sm.mask, tid);
+        if (!fin) {
+            const int removed_before = r > m ? r - m : 0;
+            sm.act2[tid - removed_before] = sm.act[tid];
+        }
+    }
+    if (act) {
+        const int q = lcs_prefix(sm.mask + 64, tid);
+        sm.status[aw] = LCS_ACTIVE;
+        sm.dlist[q] = aw;
+        if (q >= n_arr) sm.act2[n + (q - n_arr)] = aw;
+    }
+}
+LCS_D void lcs_phase_depart_fill(const LcsParams& p, LcsSmem& sm, int s, int tid, bool fin) {
+    const int nw = (p.Ap + 31) >> 5;
+    const int n = sm.misc[0];
+    const int n_arr = lcs_total(sm.mask, nw), n_pop = lcs_total(sm.mask + 32, nw), m = lcs_total(sm.mask + 64, nw);
+    if (tid < n && fin) {
+        const int r = lcs_prefix(sm.mask, tid);
+        if (r < m) sm.act2[tid] = sm.dlist[r]; // no slot before this one was dropped when r < m
+    }
+    if (tid == 0) {
+        const int n_new = n - n_arr + m;
+        sm.misc[1] = n_new;
+        p.wait_ptr[s] = sm.misc[5] + n_pop;
+        p.n_active[s] = n_new;
+        int64_t* st = p.stats + (size_t)s * LCS_NSTAT;
+        if (p.mode == 1) {
+            for (int k = 0; k < LCS_NSTAT; k++) st[k] = 0;
+            st[5] = m;
+            p.tick[s] = 0;
+        } else {
+            st[0] += n;
+            st[1] += n_new;
+            st[4] += n_arr;
+            st[5] += m;
+            st[6] += 1;
+            p.tick[s] = sm.misc[4] + 1;
+        }
+    }
+}
+
+// Phase C: publish the list and the filter records; clear the per-agent metric outputs.
+LCS_D void lcs_phase_publish(const LcsParams& p, LcsSmem& sm, int s, int tid) {
+    const int a = tid;
+    const size_t ia = (size_t)s * p.Ap + a;
+    const int n_new = sm.misc[1];
+    p.active[ia] = tid < n_new ? sm.act2[tid] : -1;
+    const int status = sm.status[a];
+    p.status[ia] = status;
+    p.stale_valid[ia] = 0; // prepare_obs refreshed every observation (manager.py:98-103)
+    const double* ex = sm.ex + 8 * a;
+    const double ox = p.origin[2 * s], oy = p.origin[2 * s + 1];
+    lcs_f4 r;
+    r.x = (float)(ex[0] - ox);
+    r.y = (float)(ex[1] - oy);
+    // half diagonal rounded up + float32 coordinate error; negative = not in the active list
+    const float hl = (float)ex[5], hw = (float)ex[6];
+    const float slack = 5e-5f + 1.2e-7f * (fabsf(r.x) + fabsf(r.y)); // float32 coordinate error
+    const float rad = 0.5f * sqrtf(hl * hl + hw * hw) * 1.00001f + slack;
+    r.z = status == LCS_ACTIVE ? rad : -1.0f;
+    r.w = slack;
+    sm.rec[a] = r;
+    if (p.with_metrics) {
+        p.nearest_edge[ia] = -1;
+        p.offroad[ia] = 0;
+    }
+}
+
+// Phase D: TrajIDM branch of Agent.prepare_obs (agent.py:249-299): lead vehicle of every active
+// agent over the NEW active list, in list order (strict < keeps the first on ties).
+LCS_D void lcs_phase_lead(const LcsParams& p, LcsSmem& sm, int s, int tid) {
+    const int a = tid;
+    if (sm.status[a] != LCS_ACTIVE) return;
+    const size_t ia = (size_t)s * p.Ap + a;
+    const int n_new = sm.misc[1];
+    const double* eg = sm.ex + 8 * a;
+    const lcs_f4 me = sm.rec[a];
+    const float c32 = (float)eg[3], s32 = (float)eg[4];
+    const float hl = 0.5f * (float)eg[5], hw = 0.5f * (float)eg[6];
+    double best = lcs_inf_d(), best_v = 0.0;
+    int nc = 0;
+    for (int j = 0; j <= n_new; j++) {
+        bool flush = j == n_new;
+        if (!flush) {
+            const int o = sm.act2[j];
+            const lcs_f4 ot = sm.rec[o];
+            const float dx = ot.x - me.x, dy = ot.y - me.y;
+            const float rx = dx * c32 + dy * s32, ry = dy * c32 - dx * s32;
+            // error of rx, ry: coordinate rounding (inside ot.z / me.z) + float32 trig/arithmetic
+            const float err = ot.w + me.w + 1e-6f * (fabsf(dx) + fabsf(dy));
+            // corners lie within the other's half diagonal of its centre; min corner x <= centre x
+            if (o != a && fabsf(ry) <= hw + ot.z + err && rx >= hl - err) {
+                sm.cand[nc * p.Ap + a] = (uint16_t)o;
+                nc++;
+                flush = nc == LCS_CAND;
+            }
+        }
+        if (flush) {
+            for (int k = 0; k < nc; k++) {
+                const int o = sm.cand[k * p.Ap + a];
+                double dis, vl;
+                if (lcs_lead_pair(eg, sm.ex + 8 * o, &dis, &vl) && dis < best) {
+                    best = dis;
+                    best_v = vl;
+                }
+            }
+            nc = 0;
+        }
+    }
+    p.lead_valid[ia] = best != lcs_inf_d();
+    p.lead_dis[ia] = best;
+    p.lead_v[ia] = best_v;
+}
+
+// Phase E1: check_collision_all (manager.py:313-327 -> polygon.py:195-235): bounding-circle
+// broadphase in float32 over agent pairs (o > a), exact SAT on survivors, counts to both.
+LCS_D void lcs_phase_collision(const LcsParams& p, LcsSmem& sm, int s, int tid) {
+    const int a = tid;
+    if (sm.status[a] != LCS_ACTIVE) return;
+    const lcs_f4 me = sm.rec[a];
+    const double* ea = sm.ex + 8 * a;
+    int nc = 0;
+    for (int o = a + 1; o <= p.Ap; o++) {
+        bool flush = o == p.Ap;
+        if (!flush) {
+            const lcs_f4 ot = sm.rec[o];
+            const float dx = ot.x - me.x, dy = ot.y - me.y;
+            const float rr = ot.z + me.z; // both radii already include their coordinate slack
+            if (ot.z >= 0.f && dx * dx + dy * dy <= rr * rr * 1.00001f) {
+                sm.cand[nc * p.Ap + a] = (uint16_t)o;
+                nc++;
+                flush = nc == LCS_CAND;
+            }
+        }
+        if (flush) {
+            for (int k = 0; k < nc; k++) {
+                const int o2 = sm.cand[k * p.Ap + a];
+                if (lcs_collide(ea, sm.ex + 8 * o2)) {
+                    lcs_atomic_add(&sm.cnt[a], 1);
+                    lcs_atomic_add(&sm.cnt[o2], 1);
+                }
+            }
+            nc = 0;
+        }
+    }
+}
+
+// Phase E2: off-road / nearest edge of every active agent (manager.py:337-345 -> junction.py:387-409)
+LCS_D void lcs_phase_offroad(const LcsParams& p, LcsSmem& sm, int s, int tid, int* off_flag) {
+    const int a = tid;
+    *off_flag = 0;
+    if (sm.status[a] != LCS_ACTIVE) return;
+    const size_t ia = (size_t)s * p.Ap + a;
+    bool off;
+    const int k = lcs_nearest_edge(p, s, sm.ex[8 * a], sm.ex[8 * a + 1], &off);
+    p.nearest_edge[ia] = k;
+    p.offroad[ia] = off ? 1 : 0;
+    *off_flag = off ? 1 : 0;
+}
+
+// Phase F: write the collision counts and the per-scenario sums.
+LCS_D void lcs_phase_metrics_out(const LcsParams& p, LcsSmem& sm, int s, int tid, int off_flag) {
+    const size_t ia = (size_t)s * p.Ap + tid;
+    const int c = sm.cnt[tid];
+    p.coll_count[ia] = c;
+    if (c) lcs_atomic_add(&sm.misc[2], c);
+    if (off_flag) lcs_atomic_add(&sm.misc[3], 1);
+}
+LCS_D void lcs_phase_stats_out(const LcsParams& p, LcsSmem& sm, int s, int tid) {
+    if (tid == 0 && p.mode == 0) {
+        int64_t* st = p.stats + (size_t)s * LCS_NSTAT;
+        st[2] += sm.misc[2];
+        st[3] += sm.misc[3];
+    }
+}
+
+// The whole tick of one scenario, phases in order.  SYNC is __syncthreads() on the device; the host
+// emulation runs each phase for every tid before the next (see lcs_tick_emulate in lcsim_b200.cu).

@@ -1,0 +1,199 @@
+"""ctypes binding of the C ABI in ``include/lcsim_b200.h`` (``lcsim_b200/csrc/lcsim_b200.cu``).
+
+The product path is CUDA only: :func:`load` returns the sm_100a library or raises
+:class:`NativeLibraryError`; nothing in this package computes on the CPU when the library
+(or a GPU) is missing.  PyTorch appears only as the owner of streams and as a zero-copy
+view onto the engine's device buffers (``__cuda_array_interface__``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+SRC = os.path.join(_HERE, "csrc", "lcsim_b200.cu")
+HDRS = [os.path.join(_HERE, "csrc", "lcsim_core.cuh"), os.path.join(ROOT, "include", "lcsim_b200.h")]
+LIB_PATH = os.path.join(_HERE, "liblcsim_b200.so")
+
+ABI_VERSION = 1
+H_STEPS, ROUTE_LEN, N_REWARD_TERMS, N_STATS = 11, 10, 6, 8
+WAITING, ACTIVE, FINISHED, IDLE = 0, 1, 2, 3
+ACT_NONE, ACT_BICYCLE, ACT_DELTA, ACT_STATE = 0, 1, 2, 3
+REWARD_KEYS = ("forward", "route_progress", "smooth", "collision", "offroad", "destination")
+STAT_KEYS = ("agent_steps", "active_sum", "collision_sum", "offroad_sum", "arrivals", "departures", "ticks", "reserved")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def _nvcc() -> str | None:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compiles the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [SRC] + HDRS
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    nvcc = _nvcc()
+    if nvcc is None:
+        raise NativeLibraryError("nvcc not found: cannot build lcsim_b200/liblcsim_b200.so")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", LIB_PATH + ".tmp"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise NativeLibraryError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+class BatchDesc(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("S", C.c_int32), ("A", C.c_int32), ("T", C.c_int32), ("E", C.c_int32),
+                ("start", C.c_double), ("interval", C.c_double), ("total_steps", C.c_int32),
+                ("reactive", C.c_int32), ("no_static", C.c_int32), ("allow_new_obj", C.c_int32),
+                ("device", C.c_int32), ("with_metrics", C.c_int32), ("grid_cell", C.c_float)]
+
+
+STATIC_FIELDS = (("n_agents", np.int32), ("ads_index", np.int32), ("agent_type", np.int32), ("length", np.float64),
+                 ("width", np.float64), ("dynamic", np.uint8), ("traj_len", np.int32), ("depart_tick", np.int32),
+                 ("wait_order", np.int32), ("home_xy", np.float64), ("traj_xy", np.float64), ("traj_vel", np.float64),
+                 ("traj_h", np.float64), ("n_edge", np.int32), ("edge_xy", np.float64), ("edge_dir", np.float64),
+                 ("origin", np.float64))
+
+
+class StaticHost(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n, _ in STATIC_FIELDS]
+
+
+VIEW_FIELDS = (("tick", "<i4"), ("n_active", "<i4"), ("active", "<i4"), ("status", "<i4"), ("cursor", "<i4"),
+               ("ring_count", "<i4"), ("ring_head", "<i4"), ("pose64", "<f8"), ("pose32", "<f4"), ("ring", "<f8"),
+               ("lead_valid", "|u1"), ("lead_dis", "<f8"), ("lead_v", "<f8"), ("coll_count", "<i4"),
+               ("nearest_edge", "<i4"), ("offroad", "|u1"), ("traj_len", "<i4"), ("traj_xy", "<f8"),
+               ("traj_vel", "<f8"), ("traj_h", "<f8"), ("stats", "<i8"), ("origin", "<f8"))
+
+
+class StateViews(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("S", "A", "A_stride", "T", "E", "H")] + [(n, C.c_void_p) for n, _ in VIEW_FIELDS]
+
+
+class ObsDesc(C.Structure):
+    _fields_ = [("ego", C.c_void_p), ("radius", C.c_double), ("k_agents", C.c_int32), ("k_polys", C.c_int32),
+                ("sort_by_distance", C.c_int32), ("nbr_agent", C.c_void_p), ("nbr_agent_feat", C.c_void_p),
+                ("n_nbr_agent", C.c_void_p), ("nbr_poly", C.c_void_p), ("nbr_poly_feat", C.c_void_p),
+                ("n_nbr_poly", C.c_void_p), ("history", C.c_void_p)]
+
+
+EXPORTS = ("lcsim_b200_abi_version", "lcsim_b200_create", "lcsim_b200_upload_static", "lcsim_b200_reset",
+           "lcsim_b200_step", "lcsim_b200_rollout", "lcsim_b200_set_ref_trajectory", "lcsim_b200_rewards",
+           "lcsim_b200_upload_polylines", "lcsim_b200_build_obs", "lcsim_b200_views", "lcsim_b200_episode_stats",
+           "lcsim_b200_launch_count", "lcsim_b200_last_error", "lcsim_b200_destroy")
+
+
+def bind(path: str) -> C.CDLL:
+    """dlopen + prototypes.  Raises if a symbol declared in include/lcsim_b200.h is missing."""
+    lib = C.CDLL(path)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise NativeLibraryError(f"{path}: missing export {name}")
+    vp, i32 = C.c_void_p, C.c_int
+    lib.lcsim_b200_abi_version.restype = i32
+    lib.lcsim_b200_create.argtypes = [C.POINTER(BatchDesc), C.POINTER(vp)]
+    lib.lcsim_b200_upload_static.argtypes = [vp, C.POINTER(StaticHost)]
+    lib.lcsim_b200_reset.argtypes = [vp, vp, vp]
+    lib.lcsim_b200_step.argtypes = [vp, vp, vp, vp, i32, vp]
+    lib.lcsim_b200_rollout.argtypes = [vp, i32, vp]
+    lib.lcsim_b200_set_ref_trajectory.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.lcsim_b200_rewards.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.lcsim_b200_upload_polylines.argtypes = [vp, vp, vp, i32]
+    lib.lcsim_b200_build_obs.argtypes = [vp, C.POINTER(ObsDesc), vp]
+    lib.lcsim_b200_views.argtypes = [vp, C.POINTER(StateViews)]
+    lib.lcsim_b200_episode_stats.argtypes = [vp, vp, vp]
+    lib.lcsim_b200_launch_count.argtypes = [vp]
+    lib.lcsim_b200_launch_count.restype = C.c_int64
+    lib.lcsim_b200_last_error.argtypes = [vp]
+    lib.lcsim_b200_last_error.restype = C.c_char_p
+    lib.lcsim_b200_destroy.argtypes = [vp]
+    lib.lcsim_b200_destroy.restype = None
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("lcsim_b200_abi_version",):
+            fn.restype = i32
+    if lib.lcsim_b200_abi_version() != ABI_VERSION:
+        raise NativeLibraryError(f"{path}: ABI version {lib.lcsim_b200_abi_version()} != {ABI_VERSION}")
+    return lib
+
+
+_LIB = None
+
+
+def load() -> C.CDLL:
+    """The CUDA library.  Built on first use when nvcc is present; otherwise it must already be in-tree."""
+    global _LIB
+    if _LIB is None:
+        if _nvcc() is not None:
+            build()
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                f"{LIB_PATH} is missing and nvcc is unavailable: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "lcsim_b200 has no CPU fallback.")
+        _LIB = bind(LIB_PATH)
+    return _LIB
+
+
+class _CudaArray:
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2}
+
+
+class TorchCudaBackend:
+    """Device memory and streams through PyTorch (plumbing only)."""
+
+    name = "cuda"
+
+    def __init__(self, device: int = 0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise NativeLibraryError("no CUDA device visible: lcsim_b200 runs on the GPU only (no CPU fallback)")
+        self.torch = torch
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.lib = load()
+
+    def view(self, ptr: int, shape, typestr: str):
+        return self.torch.as_tensor(_CudaArray(ptr, shape, typestr), device=self.device)
+
+    def stream(self) -> int:
+        return int(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def to_device(self, arr, dtype):
+        t = self.torch
+        if isinstance(arr, t.Tensor):
+            return arr.to(device=self.device, dtype=getattr(t, np.dtype(dtype).name)).contiguous()
+        return t.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(self.device)
+
+    def empty(self, shape, dtype):
+        return self.torch.empty(tuple(shape), dtype=getattr(self.torch, np.dtype(dtype).name), device=self.device)
+
+    def ptr(self, x) -> int:
+        return int(x.data_ptr())
+
+    def to_numpy(self, x) -> np.ndarray:
+        return x.detach().cpu().numpy()
+
+    def sync(self):
+        self.torch.cuda.synchronize(self.device)
