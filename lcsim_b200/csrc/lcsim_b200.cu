@@ -180,7 +180,7 @@ template <typename F>
 LCS_D F lcs_np_sum_small(const F* a, int n) {
     if (n < 8) {
         F r = 0;
-        for (int i = 0; i < n; i++) r = r + a[i];
+        for (int i = 0; i < n; i++) r = r + a[i]; // additions only: nothing to contract
         return r;
     }
     F r[8];
@@ -201,7 +201,7 @@ LCS_D double lcs_seg_sum_f32(const double* xy, int n_seg, int k) {
     float sg[128];
     for (int i = 0; i < k; i++) {
         const float dx = (float)xy[2 * (i + 1)] - (float)xy[2 * i], dy = (float)xy[2 * (i + 1) + 1] - (float)xy[2 * i + 1];
-        sg[i] = sqrtf(dx * dx + dy * dy);
+        sg[i] = sqrtf(lcs_fadd(lcs_fmul(dx, dx), lcs_fmul(dy, dy)));
     }
     return (double)lcs_np_sum_small<float>(sg, k);
 }

@@ -24,6 +24,8 @@ LCS_D double lcs_dadd(double a, double b) { return a + b; }
 LCS_D double lcs_dsub(double a, double b) { return a - b; }
 LCS_D double lcs_dfma(double a, double b, double c) { return fma(a, b, c); }
 LCS_D void lcs_sincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
+LCS_D float lcs_fmul(float a, float b) { return a * b; }
+LCS_D float lcs_fadd(float a, float b) { return a + b; }
 LCS_D int lcs_popc(uint32_t x) { return __builtin_popcount(x); }
 LCS_D int lcs_atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
 #else
@@ -35,6 +37,8 @@ LCS_D double lcs_dadd(double a, double b) { return __dadd_rn(a, b); }
 LCS_D double lcs_dsub(double a, double b) { return __dsub_rn(a, b); }
 LCS_D double lcs_dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
 LCS_D void lcs_sincos(double a, double* s, double* c) { sincos(a, s, c); }
+LCS_D float lcs_fmul(float a, float b) { return __fmul_rn(a, b); }
+LCS_D float lcs_fadd(float a, float b) { return __fadd_rn(a, b); }
 LCS_D int lcs_popc(uint32_t x) { return __popc(x); }
 LCS_D int lcs_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 #endif
@@ -510,7 +514,7 @@ LCS_D void lcs_phase_update(const LcsParams& p, LcsSmem& sm, int s, int tid) {
     sm.cnt[a] = 0;
     sm.act[a] = p.mode == 1 ? -1 : p.active[ia];
     double x = 0, y = 0, h = 0, v = 0, ch = 1, sh = 0;
-    int status = LCS_IDLE;
+    int status = LCS_WAITING; // padding agents stay WAITING forever
     if (a < n_ag) {
         if (p.mode == 1) {
             // ---- reset: restore a re-planned trajectory, home pose, first history entry
@@ -578,7 +582,7 @@ LCS_D void lcs_phase_update(const LcsParams& p, LcsSmem& sm, int s, int tid) {
                         double vn = lcs_norm2_vec(wp[2], wp[3]);
                         if (wp_f32) {
                             const float fvx = (float)wp[2], fvy = (float)wp[3];
-                            vn = (double)sqrtf(fmaf(fvy, fvy, fvx * fvx));
+                            vn = (double)sqrtf(fmaf(fvy, fvy, lcs_fmul(fvx, fvx))); // float32 BLAS-style dot
                         }
                         double acc = lcs_npclip(lcs_dsub(vn, v) / pdt, -3.0, 3.0);
                         const double dh = lcs_wrap_angle(lcs_dsub(wp[4], h));
@@ -611,7 +615,7 @@ LCS_D void lcs_phase_update(const LcsParams& p, LcsSmem& sm, int s, int tid) {
                     y = d1;
                     if (f32) {
                         const float fvx = (float)d2, fvy = (float)d3;
-                        v = (double)sqrtf(fvx * fvx + fvy * fvy);
+                        v = (double)sqrtf(lcs_fadd(lcs_fmul(fvx, fvx), lcs_fmul(fvy, fvy))); // np.sqrt(vx**2+vy**2) in float32
                         ring_f32 = true;
                     } else {
                         v = sqrt(lcs_dadd(lcs_dmul(d2, d2), lcs_dmul(d3, d3)));
