@@ -42,69 +42,77 @@ static cudaError_t cudaGetLastError() { return 0; }
 
 // ------------------------------------------------------------------------------------ kernels
 
-#ifndef LCSIM_HOSTEMU
-// One CTA per scenario, one thread per agent; the whole tick in one launch (reference:
+// One CTA per scenario, one thread per active-list slot; the whole tick in one launch (reference:
 // engine.py:145-158 Engine.step, plus manager.py:313-345 when with_metrics).
-__global__ void __launch_bounds__(1024) lcs_tick_kernel(const LcsParams p) {
+#define LCS_TICK_BODY(SYNC, FOR_T)                                                  \
+    FOR_T lcs_phase_update(p, sm, s, tid, TH);                                      \
+    SYNC;                                                                           \
+    FOR_T lcs_phase_depart_flags(p, sm, s, tid, TH);                                \
+    SYNC;                                                                           \
+    FOR_T lcs_phase_depart_place(p, sm, s, tid, TH);                                \
+    SYNC;                                                                           \
+    FOR_T lcs_phase_depart_fill(p, sm, s, tid, TH);                                 \
+    SYNC;                                                                           \
+    FOR_T lcs_phase_publish(p, sm, s, tid);                                         \
+    SYNC;                                                                           \
+    if (p.reactive) {                                                               \
+        FOR_T lcs_phase_lead_filter(p, sm, s, tid);                                 \
+        SYNC;                                                                       \
+        FOR_T lcs_phase_lead_drain(p, sm, s, tid);                                  \
+        SYNC;                                                                       \
+        FOR_T lcs_phase_lead_out(p, sm, s, tid);                                    \
+        SYNC;                                                                       \
+    }                                                                               \
+    if (p.with_metrics) {                                                           \
+        FOR_T lcs_phase_collision_filter(p, sm, s, tid);                            \
+        FOR_T lcs_phase_offroad(p, sm, s, tid, TH);                                 \
+        SYNC;                                                                       \
+        FOR_T lcs_phase_collision_drain(p, sm, s, tid);                             \
+        SYNC;                                                                       \
+        FOR_T lcs_phase_metrics_out(p, sm, s, tid, TH);                             \
+        SYNC;                                                                       \
+        FOR_T lcs_phase_stats_out(p, sm, s, tid);                                   \
+    }
+
+#ifndef LCSIM_HOSTEMU
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT) lcs_tick_kernel(const LcsParams p) {
     extern __shared__ __align__(16) unsigned char lcs_smem_raw[];
     const int s = blockIdx.x, tid = threadIdx.x;
     if (p.mode == 1 && p.reset_mask && !p.reset_mask[s]) return;
     LcsSmem sm;
     lcs_smem_carve(sm, lcs_smem_raw, p.Ap);
-    lcs_phase_update(p, sm, s, tid);
-    __syncthreads();
-    bool fin, pop, act;
-    int aw;
-    lcs_phase_depart_flags(p, sm, s, tid, &fin, &pop, &act, &aw);
-    __syncthreads();
-    lcs_phase_depart_place(p, sm, s, tid, fin, act, aw);
-    __syncthreads();
-    lcs_phase_depart_fill(p, sm, s, tid, fin);
-    __syncthreads();
-    lcs_phase_publish(p, sm, s, tid);
-    __syncthreads();
-    if (p.reactive) lcs_phase_lead(p, sm, s, tid);
-    if (p.with_metrics) {
-        lcs_phase_collision(p, sm, s, tid);
-        int off;
-        lcs_phase_offroad(p, sm, s, tid, &off);
-        __syncthreads();
-        lcs_phase_metrics_out(p, sm, s, tid, off);
-        __syncthreads();
-        lcs_phase_stats_out(p, sm, s, tid);
-    }
+    LcsThread th;
+#define TH th
+    LCS_TICK_BODY(__syncthreads(), )
+#undef TH
 }
 #endif
 
 static void lcs_launch_tick(const LcsParams& p, cudaStream_t stream) {
 #ifndef LCSIM_HOSTEMU
-    lcs_tick_kernel<<<p.S, p.Ap, lcs_smem_bytes(p.Ap), stream>>>(p);
+    const size_t smem = lcs_smem_bytes(p.Ap);
+    if (p.Ap <= 128)
+        lcs_tick_kernel<128><<<p.S, p.Ap, smem, stream>>>(p);
+    else if (p.Ap <= 256)
+        lcs_tick_kernel<256><<<p.S, p.Ap, smem, stream>>>(p);
+    else if (p.Ap <= 512)
+        lcs_tick_kernel<512><<<p.S, p.Ap, smem, stream>>>(p);
+    else
+        lcs_tick_kernel<1024><<<p.S, p.Ap, smem, stream>>>(p);
 #else
     const int Ap = p.Ap;
     std::vector<unsigned char> raw(lcs_smem_bytes(Ap) + 16);
-    std::vector<char> fin(Ap), pop(Ap), act(Ap);
-    std::vector<int> aw(Ap), off(Ap);
+    std::vector<LcsThread> ths(Ap);
     for (int s = 0; s < p.S; s++) {
         if (p.mode == 1 && p.reset_mask && !p.reset_mask[s]) continue;
         LcsSmem sm;
         lcs_smem_carve(sm, (unsigned char*)(((uintptr_t)raw.data() + 15) & ~(uintptr_t)15), Ap);
-        for (int t = 0; t < Ap; t++) lcs_phase_update(p, sm, s, t);
-        for (int t = 0; t < Ap; t++) {
-            bool f, q, a;
-            lcs_phase_depart_flags(p, sm, s, t, &f, &q, &a, &aw[t]);
-            fin[t] = f; pop[t] = q; act[t] = a;
-        }
-        for (int t = 0; t < Ap; t++) lcs_phase_depart_place(p, sm, s, t, fin[t], act[t], aw[t]);
-        for (int t = 0; t < Ap; t++) lcs_phase_depart_fill(p, sm, s, t, fin[t]);
-        for (int t = 0; t < Ap; t++) lcs_phase_publish(p, sm, s, t);
-        if (p.reactive)
-            for (int t = 0; t < Ap; t++) lcs_phase_lead(p, sm, s, t);
-        if (p.with_metrics) {
-            for (int t = 0; t < Ap; t++) lcs_phase_collision(p, sm, s, t);
-            for (int t = 0; t < Ap; t++) lcs_phase_offroad(p, sm, s, t, &off[t]);
-            for (int t = 0; t < Ap; t++) lcs_phase_metrics_out(p, sm, s, t, off[t]);
-            for (int t = 0; t < Ap; t++) lcs_phase_stats_out(p, sm, s, t);
-        }
+#define TH ths[tid]
+#define LCS_FOR_T for (int tid = 0; tid < Ap; tid++)
+        LCS_TICK_BODY((void)0, LCS_FOR_T)
+#undef LCS_FOR_T
+#undef TH
     }
 #endif
 }
@@ -130,7 +138,7 @@ LCS_D void lcs_replan_copy(const LcsParams& p, const LcsReplanArgs& r, int e, in
     const int s = r.scenario[e], a = r.agent[e];
     const size_t ia = (size_t)s * p.Ap + a;
     const int Tn = r.Tn < p.T ? r.Tn : p.T;
-    const size_t f = ((size_t)s * p.T + k) * p.Ap + a;
+    const size_t f = lcs_tf_index(p, s, k, a); // k < 2 * T2
     if (k < Tn) {
         const size_t t = ia * p.T + k, q = (size_t)e * r.Tn + k;
         const double x = (double)r.xy[2 * q], y = (double)r.xy[2 * q + 1];
@@ -143,7 +151,7 @@ LCS_D void lcs_replan_copy(const LcsParams& p, const LcsReplanArgs& r, int e, in
         v.x = (float)(x - p.origin[2 * s]);
         v.y = (float)(y - p.origin[2 * s + 1]);
         p.tf_xy[f] = v;
-    } else if (k < p.T) {
+    } else {
         lcs_f2 v;
         v.x = LCS_FAR;
         v.y = LCS_FAR;
@@ -160,7 +168,7 @@ __global__ void lcs_replan_kernel(const LcsParams p, const LcsReplanArgs r) {
     const int e = blockIdx.x;
     if (threadIdx.x == 0) lcs_replan_stale(p, r, e);
     __syncthreads();
-    for (int k = threadIdx.x; k < p.T; k += blockDim.x) lcs_replan_copy(p, r, e, k);
+    for (int k = threadIdx.x; k < 2 * p.T2; k += blockDim.x) lcs_replan_copy(p, r, e, k);
 }
 #endif
 
@@ -407,6 +415,7 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     p.A = d->A;
     p.Ap = (d->A + 31) / 32 * 32;
     p.T = d->T;
+    p.T2 = (d->T + 1) / 2;
     p.E = std::max(d->E, 1);
     p.dt = d->interval;
     p.total_steps = d->total_steps;
@@ -430,12 +439,12 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     LCS_ALLOC(e, p.traj_xy0, SAT * 2);
     LCS_ALLOC(e, p.traj_vel0, SAT * 2);
     LCS_ALLOC(e, p.traj_h0, SAT);
-    LCS_ALLOC(e, p.tf_xy0, SAT);
+    LCS_ALLOC(e, p.tf_xy0, SA * p.T2 * 2);
     LCS_ALLOC(e, p.traj_len, SA);
     LCS_ALLOC(e, p.traj_xy, SAT * 2);
     LCS_ALLOC(e, p.traj_vel, SAT * 2);
     LCS_ALLOC(e, p.traj_h, SAT);
-    LCS_ALLOC(e, p.tf_xy, SAT);
+    LCS_ALLOC(e, p.tf_xy, SA * p.T2 * 2);
     LCS_ALLOC(e, p.traj_f32, SA);
     LCS_ALLOC(e, p.stale_valid, SA);
     LCS_ALLOC(e, p.stale_f32, SA);
@@ -555,7 +564,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     lcs_f2 far;
     far.x = LCS_FAR;
     far.y = LCS_FAR;
-    g.tf_xy.assign(SAT, far);
+    g.tf_xy.assign(SA * p.T2 * 2, far);
     const size_t Ed = (size_t)p.E;
     g.edge_xy.assign((size_t)S * Ed * 2, 0.0);
     g.edge_dir.assign((size_t)S * Ed * 2, 0.0);
@@ -603,7 +612,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
                 for (int q = 0; q < n; q++) {
                     const bool dup = q > 0 && keyed[q].first == keyed[q - 1].first;
                     const int k = keyed[q].second;
-                    if (!dup) g.tf_xy[((size_t)s * T + k) * Ap + a] = to_f32(xy[2 * k], xy[2 * k + 1]);
+                    if (!dup) g.tf_xy[lcs_tf_index(p, s, k, a)] = to_f32(xy[2 * k], xy[2 * k + 1]);
                 }
                 // Trajectory.s table: s_tab[k] = np.sum(seg[:k]) (polygon.py:287-292)
                 for (int k = 0; k + 1 < n; k++) {
@@ -772,7 +781,7 @@ extern "C" int lcsim_b200_set_ref_trajectory(lcsim_b200_engine* e, const int32_t
 #else
     for (int i = 0; i < n; i++) {
         lcs_replan_stale(e->p, r, i);
-        for (int k = 0; k < e->p.T; k++) lcs_replan_copy(e->p, r, i, k);
+        for (int k = 0; k < 2 * e->p.T2; k++) lcs_replan_copy(e->p, r, i, k);
     }
 #endif
     return 0;

@@ -17,6 +17,7 @@
 #ifdef LCSIM_HOSTEMU
 #include <string.h>
 #define LCS_D static inline
+#define LCS_HD static inline
 struct lcs_f2 { float x, y; };
 struct alignas(16) lcs_f4 { float x, y, z, w; };
 LCS_D double lcs_dmul(double a, double b) { return a * b; } // built with -ffp-contract=off
@@ -28,8 +29,11 @@ LCS_D float lcs_fmul(float a, float b) { return a * b; }
 LCS_D float lcs_fadd(float a, float b) { return a + b; }
 LCS_D int lcs_popc(uint32_t x) { return __builtin_popcount(x); }
 LCS_D int lcs_atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
+LCS_D void lcs_atomic_min_u64(unsigned long long* p, unsigned long long v) { if (v < *p) *p = v; }
+LCS_D unsigned long long lcs_d2u(double d) { unsigned long long u; memcpy(&u, &d, 8); return u; }
 #else
 #define LCS_D __device__ __forceinline__
+#define LCS_HD __host__ __device__ __forceinline__
 typedef float2 lcs_f2;
 typedef float4 lcs_f4;
 LCS_D double lcs_dmul(double a, double b) { return __dmul_rn(a, b); }
@@ -41,6 +45,8 @@ LCS_D float lcs_fmul(float a, float b) { return __fmul_rn(a, b); }
 LCS_D float lcs_fadd(float a, float b) { return __fadd_rn(a, b); }
 LCS_D int lcs_popc(uint32_t x) { return __popc(x); }
 LCS_D int lcs_atomic_add(int* p, int v) { return atomicAdd(p, v); }
+LCS_D void lcs_atomic_min_u64(unsigned long long* p, unsigned long long v) { atomicMin(p, v); }
+LCS_D unsigned long long lcs_d2u(double d) { return (unsigned long long)__double_as_longlong(d); }
 #endif
 
 #define LCS_WAITING 0
@@ -54,7 +60,6 @@ LCS_D int lcs_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 #define LCS_H 11
 #define LCS_ROUTE 10
 #define LCS_NSTAT 8
-#define LCS_CAND 8 // private candidate list length per thread in the all-pairs phases
 #define LCS_PI 3.14159265358979323846
 #define LCS_FAR 3.0e18f // filter coordinate of "no point here" (its square stays finite in float32)
 
@@ -75,7 +80,7 @@ LCS_D double lcs_inf_d() {
 
 // Everything a tick needs, as raw device pointers.  Layouts: DESIGN.md §3.
 struct LcsParams {
-    int32_t S, A, Ap, T, E;
+    int32_t S, A, Ap, T, T2, E;
     double dt;
     int32_t total_steps, reactive, no_static, allow_new_obj, with_metrics;
     // ---- static, per scenario
@@ -90,7 +95,8 @@ struct LcsParams {
     // pristine trajectories (reset restores re-planned ones from here)
     const int32_t* traj_len0;
     const double *traj_xy0, *traj_vel0, *traj_h0; // [S][Ap][T][2], [S][Ap][T][2], [S][Ap][T]
-    const lcs_f2* tf_xy0; // [S][T][Ap] float32 filter copy, relative to origin, duplicates -> LCS_FAR
+    const lcs_f2* tf_xy0; // [S][T2][Ap][2] float32 filter copy (two consecutive points per 16 B), relative to
+                          // the origin, exact duplicates -> LCS_FAR; T2 = ceil(T/2)
     // ---- current trajectories (set_ref_trajectory overwrites)
     int32_t* traj_len;
     double *traj_xy, *traj_vel, *traj_h;
@@ -131,17 +137,18 @@ struct LcsParams {
 };
 
 // Shared memory of one CTA (Ap threads).  Carved from one dynamic allocation.
+#define LCS_QPER 8 // pair-queue capacity per thread (queue = LCS_QPER * Ap candidate pairs)
 struct LcsSmem {
-    double* ex; // [Ap][8]  x, y, v, cos h, sin h, L, W, h  (agent index)
-    lcs_f4* rec; // [Ap]     x32, y32, filter radius (-1 inactive), coordinate slack   (agent index)
-    int32_t* status; // [Ap] (agent index)
-    int32_t* act; // [Ap] active list (slot index)
-    int32_t* act2; // [Ap] new active list
+    double* ex; // [Ap][8]  x, y, v, cos h, sin h, L, W, h          (agent index)
+    unsigned long long* lead_key; // [Ap] packed (distance, slot) minimum per ego   (slot index)
+    lcs_f4* crec; // [Ap]  x32, y32, filter radius, coordinate slack   (slot index, new list)
+    int32_t* act; // [Ap] active list at tick start (slot index)
+    int32_t* act2; // [Ap] active list after departures / arrivals
     int32_t* dlist; // [Ap] agents activated this tick, in waiting-list order
-    int32_t* cnt; // [Ap] collision counts
-    uint16_t* cand; // [LCS_CAND][Ap]
+    int32_t* cnt; // [Ap] collision counts (slot index)
+    uint32_t* queue; // [LCS_QPER * Ap] candidate pairs (slot_i << 16 | slot_j)
     uint32_t* mask; // [3][32] ballot words: finished, popped, activated
-    int32_t* misc; // [8] n_old, n_new, ...
+    int32_t* misc; // [8] n_old, n_new, collision sum, off-road sum, tick, wait_ptr, queue length
 };
 
 #ifdef LCSIM_HOSTEMU
@@ -150,21 +157,21 @@ static inline
 __host__ __device__ inline
 #endif
 size_t lcs_smem_bytes(int Ap) {
-    return (size_t)Ap * (8 * 8 + 16 + 4 * 5 + 2 * LCS_CAND) + 3 * 32 * 4 + 8 * 4 + 64;
+    return (size_t)Ap * (64 + 8 + 16 + 4 * 4 + 4 * LCS_QPER) + 3 * 32 * 4 + 8 * 4 + 64;
 }
 
 LCS_D void lcs_smem_carve(LcsSmem& sm, unsigned char* base, int Ap) {
     unsigned char* p = base;
     sm.ex = (double*)p; p += (size_t)Ap * 64;
-    sm.rec = (lcs_f4*)p; p += (size_t)Ap * 16;
-    sm.status = (int32_t*)p; p += (size_t)Ap * 4;
+    sm.lead_key = (unsigned long long*)p; p += (size_t)Ap * 8;
+    sm.crec = (lcs_f4*)p; p += (size_t)Ap * 16;
     sm.act = (int32_t*)p; p += (size_t)Ap * 4;
     sm.act2 = (int32_t*)p; p += (size_t)Ap * 4;
     sm.dlist = (int32_t*)p; p += (size_t)Ap * 4;
     sm.cnt = (int32_t*)p; p += (size_t)Ap * 4;
+    sm.queue = (uint32_t*)p; p += (size_t)Ap * 4 * LCS_QPER;
     sm.mask = (uint32_t*)p; p += 3 * 32 * 4;
-    sm.misc = (int32_t*)p; p += 8 * 4;
-    sm.cand = (uint16_t*)p;
+    sm.misc = (int32_t*)p;
 }
 
 // ------------------------------------------------------------------ small float64 helpers
@@ -237,35 +244,48 @@ LCS_D int lcs_total(const uint32_t* words, int nwords) {
 // reference: agent/policy/type.py:42-48 Trajectory.next -> utils/polygon.py:271-293
 // frenet_projection: index = first argmin_k sqrt((x_k-px)^2 + (y_k-py)^2) over ALL len points.
 // Filter scan over the float32 copy (coalesced: [T][Ap]), exact float64 only on near-ties.
+// float2 index of filter point k of agent a in scenario s
+LCS_HD size_t lcs_tf_index(const LcsParams& p, int s, int k, int a) {
+    return ((((size_t)s * p.T2 + (k >> 1)) * p.Ap + a) << 1) + (k & 1);
+}
+
+#define LCS_SCAN_POINT(PX, PY, K)            \
+    {                                        \
+        const float dx = (PX)-fqx, dy = (PY)-fqy; \
+        const float d = dx * dx + dy * dy;   \
+        const bool c = d < m;                \
+        m2 = c ? m : fminf(m2, d);           \
+        j = c ? (K) : j;                     \
+        m = c ? d : m;                       \
+    }
+
 LCS_D int lcs_cursor_argmin(const LcsParams& p, int s, int a, int len, double qx, double qy) {
-    const lcs_f2* tf = p.tf_xy + (size_t)s * p.T * p.Ap + a;
+    const lcs_f4* tf = (const lcs_f4*)p.tf_xy + (size_t)s * p.T2 * p.Ap + a;
     const double ox = p.origin[2 * s], oy = p.origin[2 * s + 1];
     const float fqx = (float)(qx - ox), fqy = (float)(qy - oy);
     float m = lcs_inf_f(), m2 = lcs_inf_f();
     int j = 0;
-#pragma unroll 4
-    for (int k = 0; k < len; k++) {
-        lcs_f2 pt = tf[(size_t)k * p.Ap];
-        float dx = pt.x - fqx, dy = pt.y - fqy;
-        float d = dx * dx + dy * dy;
-        bool c = d < m;
-        m2 = c ? m : fminf(m2, d);
-        j = c ? k : j;
-        m = c ? d : m;
+    const int n2 = (len + 1) >> 1; // entries past len hold LCS_FAR
+#pragma unroll 8
+    for (int k2 = 0; k2 < n2; k2++) {
+        const lcs_f4 v = tf[(size_t)k2 * p.Ap];
+        LCS_SCAN_POINT(v.x, v.y, 2 * k2)
+        LCS_SCAN_POINT(v.z, v.w, 2 * k2 + 1)
     }
     const float eta = lcs_filter_eta(p.eta_pts[s], fqx, fqy, m);
     const float thr = lcs_filter_thr(m, eta);
     if (m2 > thr) return j;
     // near-tie: float64 evaluation of every candidate, first minimum wins (np.argmin)
     const double* t64 = p.traj_xy + ((size_t)s * p.Ap + a) * p.T * 2;
+    const lcs_f2* tf2 = p.tf_xy;
     double bd = lcs_inf_d();
     int best = j;
     for (int k = 0; k < len; k++) {
-        lcs_f2 pt = tf[(size_t)k * p.Ap];
-        float dx = pt.x - fqx, dy = pt.y - fqy;
-        float d = dx * dx + dy * dy;
+        const lcs_f2 pt = tf2[lcs_tf_index(p, s, k, a)];
+        const float dx = pt.x - fqx, dy = pt.y - fqy;
+        const float d = dx * dx + dy * dy;
         if (d <= thr) {
-            double e = lcs_norm2_axis(lcs_dsub(t64[2 * k], qx), lcs_dsub(t64[2 * k + 1], qy));
+            const double e = lcs_norm2_axis(lcs_dsub(t64[2 * k], qx), lcs_dsub(t64[2 * k + 1], qy));
             if (e < bd) { bd = e; best = k; }
         }
     }
@@ -492,248 +512,280 @@ LCS_D void lcs_ring_push(const LcsParams& p, size_t ia, double x, double y, doub
     if (c < LCS_H) p.ring_count[ia] = c + 1;
 }
 
-// ------------------------------------------------------------------ the tick, phase by phase
-// Phases are separated by __syncthreads() in the kernel (lcsim_b200.cu) and by loop boundaries
-// in the host emulation.  tid = agent index a (phases A, C, D, E) or list slot i (phase B).
 
-// Phase A: Engine.update (engine.py:221-225 -> manager.py:105-115 -> agent.py:310-426) or, in reset
-// mode, Agent.__init__ / Engine.reset (agent.py:106-171, engine.py:132-143).
-LCS_D void lcs_phase_update(const LcsParams& p, LcsSmem& sm, int s, int tid) {
-    const int a = tid;
+// ------------------------------------------------------------------ float32 SAT pre-test
+
+// Classic OBB separating-axis test in float32 on coordinates relative to box a (all magnitudes
+// of a few metres, absolute error ~1e-6 m).  Equivalent to the reference's corner-projection test
+// (polygon.py:206-230: min(max_a,max_b) - max(min_a,min_b) > 0 on the four box axes) whenever the
+// largest signed axis gap is farther than LCS_SAT_MARGIN from zero; returns -1 otherwise and the
+// caller falls back to the float64 restatement (lcs_collide).
+#define LCS_SAT_MARGIN 1.0e-4f
+LCS_D int lcs_sat_f32(const double* ea, const double* eb) {
+    const float dx = (float)(eb[0] - ea[0]), dy = (float)(eb[1] - ea[1]);
+    const float ca = (float)ea[3], sa = (float)ea[4], cb = (float)eb[3], sb = (float)eb[4];
+    const float hla = 0.5f * (float)ea[5], hwa = 0.5f * (float)ea[6], hlb = 0.5f * (float)eb[5], hwb = 0.5f * (float)eb[6];
+    const float ac = fabsf(ca * cb + sa * sb), as = fabsf(sb * ca - cb * sa);
+    const float t1 = fabsf(dx * ca + dy * sa) - (hla + hlb * ac + hwb * as);
+    const float t2 = fabsf(dy * ca - dx * sa) - (hwa + hlb * as + hwb * ac);
+    const float t3 = fabsf(dx * cb + dy * sb) - (hlb + hla * ac + hwa * as);
+    const float t4 = fabsf(dy * cb - dx * sb) - (hwb + hla * as + hwa * ac);
+    const float tmax = fmaxf(fmaxf(t1, t2), fmaxf(t3, t4));
+    if (tmax > LCS_SAT_MARGIN) return 0;
+    if (tmax < -LCS_SAT_MARGIN) return 1;
+    return -1;
+}
+
+// ------------------------------------------------------------------ the tick, phase by phase
+// Phases are separated by __syncthreads() in the kernel (lcsim_b200.cu) and by loop boundaries in
+// the host emulation.  Threads map to LIST SLOTS (dense lanes: slot i < n_active), except in reset
+// mode where phase A maps thread -> agent index.  Per-agent float64 records travel between phases
+// through shared memory indexed by agent (sm.ex); the new list gets a slot-indexed float32 filter
+// record (sm.crec).
+
+struct LcsThread { // per-thread values that live across phases (registers on the device)
+    bool fin, pop, act;
+    int aw, off;
+};
+
+LCS_D void lcs_store_ex(LcsSmem& sm, int a, double x, double y, double v, double ch, double sh, double L, double W, double h) {
+    double* ex = sm.ex + 8 * a;
+    ex[0] = x; ex[1] = y; ex[2] = v; ex[3] = ch; ex[4] = sh; ex[5] = L; ex[6] = W; ex[7] = h;
+}
+LCS_D void lcs_store_pose(const LcsParams& p, int s, size_t ia, double x, double y, double h, double v) {
+    double* ps = p.pose64 + 4 * ia;
+    ps[0] = x; ps[1] = y; ps[2] = h; ps[3] = v;
+    lcs_f4 p32;
+    p32.x = (float)(x - p.origin[2 * s]);
+    p32.y = (float)(y - p.origin[2 * s + 1]);
+    p32.z = (float)h;
+    p32.w = (float)v;
+    p.pose32[ia] = p32;
+}
+
+// Agent.__init__ / Engine.reset for agent a (agent.py:106-171, engine.py:132-143)
+LCS_D void lcs_reset_agent(const LcsParams& p, int s, int a) {
     const size_t ia = (size_t)s * p.Ap + a;
-    const int n_ag = p.n_agents[s];
+    p.status[ia] = LCS_WAITING;
+    p.cursor[ia] = 0;
+    p.ring_head[ia] = 0;
+    p.ring_count[ia] = 0;
+    p.lead_valid[ia] = 0;
+    p.lead_dis[ia] = lcs_inf_d();
+    p.lead_v[ia] = 0.0;
+    p.stale_valid[ia] = 0;
+    p.coll_count[ia] = 0;
+    p.nearest_edge[ia] = -1;
+    p.offroad[ia] = 0;
+    for (int k = 0; k < LCS_H * 5; k++) p.ring[ia * LCS_H * 5 + k] = 0.0;
+    if (a >= p.n_agents[s]) { // padding agents: inert but defined
+        lcs_store_pose(p, s, ia, 0.0, 0.0, 0.0, 0.0);
+        return;
+    }
+    if (p.traj_f32[ia]) { // restore a re-planned trajectory
+        p.traj_len[ia] = p.traj_len0[ia];
+        for (int k = 0; k < p.T; k++) {
+            const size_t t = ia * p.T + k;
+            p.traj_xy[2 * t] = p.traj_xy0[2 * t];
+            p.traj_xy[2 * t + 1] = p.traj_xy0[2 * t + 1];
+            p.traj_vel[2 * t] = p.traj_vel0[2 * t];
+            p.traj_vel[2 * t + 1] = p.traj_vel0[2 * t + 1];
+            p.traj_h[t] = p.traj_h0[t];
+            const size_t f = lcs_tf_index(p, s, k, a);
+            p.tf_xy[f] = p.tf_xy0[f];
+        }
+        p.traj_f32[ia] = 0;
+    }
+    const double vx = p.traj_vel[2 * ia * p.T], vy = p.traj_vel[2 * ia * p.T + 1];
+    const double x = p.home_xy[2 * ia], y = p.home_xy[2 * ia + 1];
+    const double v = sqrt(lcs_dadd(lcs_dmul(vx, vx), lcs_dmul(vy, vy))); // agent.py:144-146
+    const double h = p.traj_h[ia * p.T];
+    double sh, ch;
+    lcs_sincos(h, &sh, &ch);
+    lcs_ring_push(p, ia, x, y, h, v, ch, sh, false); // agent.py:159-165
+    lcs_store_pose(p, s, ia, x, y, h, v);
+}
+
+// Engine.update for the agent in list slot `slot` (engine.py:221-225 -> manager.py:105-115 ->
+// agent.py:310-426).  Returns true when the agent reached the end of its trajectory.
+LCS_D bool lcs_update_agent(const LcsParams& p, LcsSmem& sm, int s, int a) {
+    const size_t ia = (size_t)s * p.Ap + a;
+    const double* ps = p.pose64 + 4 * ia;
+    double x = ps[0], y = ps[1], h = ps[2], v = ps[3], ch, sh;
+    const int len = p.traj_len[ia];
+    int cursor = p.cursor[ia];
+    // ---- which action (manager.py:111-115)
+    int type = LCS_ACT_NONE;
+    double d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0;
+    bool f32 = false;
+    for (int k = 0; k < p.K; k++) {
+        const size_t q = (size_t)s * p.K + k;
+        if (p.act_agent[q] == a && p.act_type[q] != LCS_ACT_NONE) {
+            type = p.act_type[q];
+            d0 = p.act_data[5 * q];
+            d1 = p.act_data[5 * q + 1];
+            d2 = p.act_data[5 * q + 2];
+            d3 = p.act_data[5 * q + 3];
+            d4 = p.act_data[5 * q + 4];
+        }
+    }
+    if (type == LCS_ACT_NONE) {
+        double wp[5];
+        const bool wp_f32 = lcs_policy_waypoint(p, ia, cursor, len, wp);
+        if (p.reactive) {
+            // ---- TrajIDM.get_action (idm_policy.py:196-224), dt = 0.1 default argument
+            const double pdt = 0.1;
+            double vn = lcs_norm2_vec(wp[2], wp[3]);
+            if (wp_f32) {
+                const float fvx = (float)wp[2], fvy = (float)wp[3];
+                vn = (double)sqrtf(fmaf(fvy, fvy, lcs_fmul(fvx, fvx))); // float32 BLAS-style dot
+            }
+            double acc = lcs_npclip(lcs_dsub(vn, v) / pdt, -3.0, 3.0);
+            const double dh = lcs_wrap_angle(lcs_dsub(wp[4], h));
+            double steer;
+            if (v < 0.6 || vn < 0.6)
+                steer = 0.0;
+            else
+                steer = dh / lcs_dadd(lcs_dmul(v, pdt), lcs_dmul(lcs_dmul(0.5, acc), lcs_dmul(pdt, pdt)));
+            steer = lcs_npclip(steer, -0.3, 0.3);
+            if (p.lead_valid[ia]) {
+                const double idm = lcs_idm_acc(v, 40.0, p.lead_v[ia], p.lead_dis[ia]);
+                acc = lcs_pymax(lcs_pymin(acc, idm), -3.0);
+            }
+            type = LCS_ACT_BICYCLE;
+            d0 = acc;
+            d1 = steer;
+        } else {
+            // ---- StateExpert.get_action (expert_policy.py:18-33)
+            type = LCS_ACT_STATE;
+            d0 = wp[0]; d1 = wp[1]; d2 = wp[2]; d3 = wp[3]; d4 = wp[4];
+            f32 = wp_f32;
+        }
+    }
+    // ---- update_runtime_by_action (agent.py:377-416)
+    double qx = x, qy = y; // position fed to Trajectory.next
+    bool ring_f32 = false;
+    const double dt = p.dt;
+    if (type == LCS_ACT_STATE) {
+        x = d0;
+        y = d1;
+        if (f32) {
+            const float fvx = (float)d2, fvy = (float)d3;
+            v = (double)sqrtf(lcs_fadd(lcs_fmul(fvx, fvx), lcs_fmul(fvy, fvy))); // np.sqrt(vx**2+vy**2) in float32
+            ring_f32 = true;
+        } else {
+            v = sqrt(lcs_dadd(lcs_dmul(d2, d2), lcs_dmul(d3, d3)));
+        }
+        h = d4;
+        qx = x;
+        qy = y;
+        lcs_sincos(h, &sh, &ch);
+    } else if (type == LCS_ACT_BICYCLE) {
+        const double acc = d0, steer = d1;
+        const double delta = lcs_dadd(lcs_dmul(v, dt), lcs_dmul(lcs_dmul(0.5, acc), lcs_dmul(dt, dt)));
+        const double nh = lcs_wrap_angle(lcs_dadd(h, lcs_dmul(steer, delta)));
+        lcs_sincos(nh, &sh, &ch);
+        x = lcs_dadd(x, lcs_dmul(delta, ch));
+        y = lcs_dadd(y, lcs_dmul(delta, sh));
+        v = lcs_dadd(v, lcs_dmul(acc, dt));
+        h = nh;
+    } else { // DELTA
+        x = lcs_dadd(x, d0);
+        y = lcs_dadd(y, d1);
+        h = lcs_wrap_angle(lcs_dadd(h, d2));
+        lcs_sincos(h, &sh, &ch);
+    }
+    cursor = lcs_cursor_argmin(p, s, a, len, qx, qy);
+    p.cursor[ia] = cursor;
+    lcs_ring_push(p, ia, x, y, h, v, ch, sh, ring_f32);
+    lcs_store_pose(p, s, ia, x, y, h, v);
+    lcs_store_ex(sm, a, x, y, v, ch, sh, p.length[ia], p.width[ia], h);
+    const bool fin = cursor >= len - 1; // type.py:50-51 reach_end
+    if (fin) {
+        // FINISHED now, IDLE after this tick's check_departure_and_arrival (single-trip schedules:
+        // schedule.py:22-40 next_trip() is False); the agent leaves the list, its metric outputs reset
+        p.status[ia] = LCS_IDLE;
+        if (p.with_metrics) {
+            p.coll_count[ia] = 0;
+            p.nearest_edge[ia] = -1;
+            p.offroad[ia] = 0;
+        }
+    }
+    return fin;
+}
+
+// Phase A: shared-memory init + update (step mode: thread = old list slot) or reset (thread = agent)
+LCS_D void lcs_phase_update(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
     for (int k = tid; k < 96; k += p.Ap) sm.mask[k] = 0;
+    const int n_old = p.mode == 1 ? 0 : p.n_active[s];
     if (tid == 0) {
-        sm.misc[0] = p.mode == 1 ? 0 : p.n_active[s]; // n_old
+        sm.misc[0] = n_old;
         sm.misc[1] = 0; // n_new
         sm.misc[2] = 0; // collision sum
         sm.misc[3] = 0; // off-road sum
         sm.misc[4] = p.mode == 1 ? 0 : p.tick[s];
         sm.misc[5] = p.mode == 1 ? 0 : p.wait_ptr[s];
+        sm.misc[6] = 0; // pair-queue length
     }
-    sm.cnt[a] = 0;
-    sm.act[a] = p.mode == 1 ? -1 : p.active[ia];
-    double x = 0, y = 0, h = 0, v = 0, ch = 1, sh = 0;
-    int status = LCS_WAITING; // padding agents stay WAITING forever
-    if (a < n_ag) {
-        if (p.mode == 1) {
-            // ---- reset: restore a re-planned trajectory, home pose, first history entry
-            if (p.traj_f32[ia]) {
-                p.traj_len[ia] = p.traj_len0[ia];
-                for (int k = 0; k < p.T; k++) {
-                    const size_t t = ia * p.T + k;
-                    p.traj_xy[2 * t] = p.traj_xy0[2 * t];
-                    p.traj_xy[2 * t + 1] = p.traj_xy0[2 * t + 1];
-                    p.traj_vel[2 * t] = p.traj_vel0[2 * t];
-                    p.traj_vel[2 * t + 1] = p.traj_vel0[2 * t + 1];
-                    p.traj_h[t] = p.traj_h0[t];
-                    const size_t f = ((size_t)s * p.T + k) * p.Ap + a;
-                    p.tf_xy[f] = p.tf_xy0[f];
-                }
-                p.traj_f32[ia] = 0;
-            }
-            p.stale_valid[ia] = 0;
-            const double vx = p.traj_vel[2 * ia * p.T], vy = p.traj_vel[2 * ia * p.T + 1];
-            x = p.home_xy[2 * ia];
-            y = p.home_xy[2 * ia + 1];
-            v = sqrt(lcs_dadd(lcs_dmul(vx, vx), lcs_dmul(vy, vy))); // agent.py:144-146
-            h = p.traj_h[ia * p.T];
-            lcs_sincos(h, &sh, &ch);
-            status = LCS_WAITING;
-            p.cursor[ia] = 0;
-            p.ring_head[ia] = 0;
-            p.ring_count[ia] = 0;
-            for (int k = 0; k < LCS_H * 5; k++) p.ring[ia * LCS_H * 5 + k] = 0.0;
-            lcs_ring_push(p, ia, x, y, h, v, ch, sh, false); // agent.py:159-165
-            p.lead_valid[ia] = 0;
-            p.lead_dis[ia] = lcs_inf_d();
-            p.lead_v[ia] = 0.0;
-        } else {
-            status = p.status[ia];
-            const double* ps = p.pose64 + 4 * ia;
-            x = ps[0];
-            y = ps[1];
-            h = ps[2];
-            v = ps[3];
-            if (status == LCS_ACTIVE) {
-                const int len = p.traj_len[ia];
-                int cursor = p.cursor[ia];
-                // ---- which action (manager.py:111-115)
-                int type = LCS_ACT_NONE;
-                double d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0;
-                bool f32 = false;
-                for (int k = 0; k < p.K; k++) {
-                    const size_t q = (size_t)s * p.K + k;
-                    if (p.act_agent[q] == a && p.act_type[q] != LCS_ACT_NONE) {
-                        type = p.act_type[q];
-                        d0 = p.act_data[5 * q];
-                        d1 = p.act_data[5 * q + 1];
-                        d2 = p.act_data[5 * q + 2];
-                        d3 = p.act_data[5 * q + 3];
-                        d4 = p.act_data[5 * q + 4];
-                    }
-                }
-                if (type == LCS_ACT_NONE) {
-                    double wp[5];
-                    const bool wp_f32 = lcs_policy_waypoint(p, ia, cursor, len, wp);
-                    if (p.reactive) {
-                        // ---- TrajIDM.get_action (idm_policy.py:196-224), dt = 0.1 default argument
-                        const double pdt = 0.1;
-                        double vn = lcs_norm2_vec(wp[2], wp[3]);
-                        if (wp_f32) {
-                            const float fvx = (float)wp[2], fvy = (float)wp[3];
-                            vn = (double)sqrtf(fmaf(fvy, fvy, lcs_fmul(fvx, fvx))); // float32 BLAS-style dot
-                        }
-                        double acc = lcs_npclip(lcs_dsub(vn, v) / pdt, -3.0, 3.0);
-                        const double dh = lcs_wrap_angle(lcs_dsub(wp[4], h));
-                        double steer;
-                        if (v < 0.6 || vn < 0.6)
-                            steer = 0.0;
-                        else
-                            steer = dh / lcs_dadd(lcs_dmul(v, pdt), lcs_dmul(lcs_dmul(0.5, acc), lcs_dmul(pdt, pdt)));
-                        steer = lcs_npclip(steer, -0.3, 0.3);
-                        if (p.lead_valid[ia]) {
-                            const double idm = lcs_idm_acc(v, 40.0, p.lead_v[ia], p.lead_dis[ia]);
-                            acc = lcs_pymax(lcs_pymin(acc, idm), -3.0);
-                        }
-                        type = LCS_ACT_BICYCLE;
-                        d0 = acc;
-                        d1 = steer;
-                    } else {
-                        // ---- StateExpert.get_action (expert_policy.py:18-33)
-                        type = LCS_ACT_STATE;
-                        d0 = wp[0]; d1 = wp[1]; d2 = wp[2]; d3 = wp[3]; d4 = wp[4];
-                        f32 = wp_f32;
-                    }
-                }
-                // ---- update_runtime_by_action (agent.py:377-416)
-                double qx = x, qy = y; // position fed to Trajectory.next
-                bool ring_f32 = false;
-                const double dt = p.dt;
-                if (type == LCS_ACT_STATE) {
-                    x = d0;
-                    y = d1;
-                    if (f32) {
-                        const float fvx = (float)d2, fvy = (float)d3;
-                        v = (double)sqrtf(lcs_fadd(lcs_fmul(fvx, fvx), lcs_fmul(fvy, fvy))); // np.sqrt(vx**2+vy**2) in float32
-                        ring_f32 = true;
-                    } else {
-                        v = sqrt(lcs_dadd(lcs_dmul(d2, d2), lcs_dmul(d3, d3)));
-                    }
-                    h = d4;
-                    qx = x;
-                    qy = y;
-                    lcs_sincos(h, &sh, &ch);
-                } else if (type == LCS_ACT_BICYCLE) {
-                    const double acc = d0, steer = d1;
-                    const double delta = lcs_dadd(lcs_dmul(v, dt), lcs_dmul(lcs_dmul(0.5, acc), lcs_dmul(dt, dt)));
-                    const double nh = lcs_wrap_angle(lcs_dadd(h, lcs_dmul(steer, delta)));
-                    lcs_sincos(nh, &sh, &ch);
-                    x = lcs_dadd(x, lcs_dmul(delta, ch));
-                    y = lcs_dadd(y, lcs_dmul(delta, sh));
-                    v = lcs_dadd(v, lcs_dmul(acc, dt));
-                    h = nh;
-                } else { // DELTA
-                    x = lcs_dadd(x, d0);
-                    y = lcs_dadd(y, d1);
-                    h = lcs_wrap_angle(lcs_dadd(h, d2));
-                    lcs_sincos(h, &sh, &ch);
-                }
-                cursor = lcs_cursor_argmin(p, s, a, len, qx, qy);
-                p.cursor[ia] = cursor;
-                if (cursor >= len - 1) status = LCS_FINISHED; // type.py:50-51 reach_end
-                lcs_ring_push(p, ia, x, y, h, v, ch, sh, ring_f32);
-            } else {
-                lcs_sincos(h, &sh, &ch);
-            }
-        }
-        if (p.mode == 1 || (status != LCS_IDLE && status != LCS_WAITING)) {
-        double* ps = p.pose64 + 4 * ia;
-        ps[0] = x;
-        ps[1] = y;
-        ps[2] = h;
-        ps[3] = v;
-        lcs_f4 p32;
-        p32.x = (float)(x - p.origin[2 * s]);
-        p32.y = (float)(y - p.origin[2 * s + 1]);
-        p32.z = (float)h;
-        p32.w = (float)v;
-        p.pose32[ia] = p32;
-        }
-    } else if (p.mode == 1) {
-        // padding agents: inert but defined
-        double* ps = p.pose64 + 4 * ia;
-        ps[0] = ps[1] = ps[2] = ps[3] = 0.0;
-        lcs_f4 z;
-        z.x = z.y = z.z = z.w = 0.f;
-        p.pose32[ia] = z;
-        p.cursor[ia] = 0;
-        p.ring_head[ia] = 0;
-        p.ring_count[ia] = 0;
-        p.lead_valid[ia] = 0;
-        p.stale_valid[ia] = 0;
+    sm.cnt[tid] = 0;
+    sm.lead_key[tid] = ~0ull;
+    t.fin = false;
+    t.off = 0;
+    int a = -1;
+    if (p.mode == 1) {
+        lcs_reset_agent(p, s, tid);
+    } else if (tid < n_old) {
+        a = p.active[(size_t)s * p.Ap + tid];
+        t.fin = lcs_update_agent(p, sm, s, a);
     }
-    double* ex = sm.ex + 8 * a;
-    ex[0] = x; ex[1] = y; ex[2] = v; ex[3] = ch; ex[4] = sh;
-    ex[5] = a < n_ag ? p.length[ia] : 0.0;
-    ex[6] = a < n_ag ? p.width[ia] : 0.0;
-    ex[7] = h;
-    sm.status[a] = status;
+    sm.act[tid] = a;
 }
 
-// Phase B1: AgentManager.check_departure_and_arrival (manager.py:50-96), flags.  tid = list slot /
-// waiting-list offset.
-LCS_D void lcs_phase_depart_flags(const LcsParams& p, LcsSmem& sm, int s, int tid, bool* fin_out, bool* pop_out, bool* act_out, int* aw_out) {
-    const int n = sm.misc[0];
-    const int tick = sm.misc[4];
+// Phase B1: AgentManager.check_departure_and_arrival (manager.py:50-96), flags.  tid = list slot and,
+// independently, offset into the waiting list (sorted by departure time, manager.py:33-35).
+LCS_D void lcs_phase_depart_flags(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
+    const int tick = sm.misc[4], wp = sm.misc[5];
     const bool allow = p.mode == 1 ? true : (p.allow_new_obj != 0);
-    bool fin = false;
-    if (tid < n) {
-        const int a = sm.act[tid];
-        if (sm.status[a] == LCS_FINISHED) {
-            fin = true;
-            sm.status[a] = LCS_IDLE; // single-trip schedules: next_trip() is False (schedule.py:22-40)
-        }
-    }
-    bool pop = false, act = false;
-    int aw = -1;
-    const int wp = sm.misc[5];
+    t.pop = t.act = false;
+    t.aw = -1;
     if (allow && wp + tid < p.n_agents[s]) {
-        aw = p.wait_order[(size_t)s * p.Ap + wp + tid];
-        pop = p.depart_tick[(size_t)s * p.Ap + aw] <= tick;
-        act = pop && !(p.no_static && !p.dynamic[(size_t)s * p.Ap + aw] && aw != p.ads_index[s]);
+        const int aw = p.wait_order[(size_t)s * p.Ap + wp + tid];
+        t.aw = aw;
+        t.pop = p.depart_tick[(size_t)s * p.Ap + aw] <= tick;
+        t.act = t.pop && !(p.no_static && !p.dynamic[(size_t)s * p.Ap + aw] && aw != p.ads_index[s]);
     }
-    lcs_set_flag(sm.mask, tid, fin);
-    lcs_set_flag(sm.mask + 32, tid, pop);
-    lcs_set_flag(sm.mask + 64, tid, act);
-    *fin_out = fin; *pop_out = pop; *act_out = act; *aw_out = aw;
+    lcs_set_flag(sm.mask, tid, t.fin);
+    lcs_set_flag(sm.mask + 32, tid, t.pop);
+    lcs_set_flag(sm.mask + 64, tid, t.act);
 }
 
-// Phase B2: build the new active list (slot reuse in order, else append; leftover finished slots
-// are dropped preserving order).
-LCS_D void lcs_phase_depart_place(const LcsParams& p, LcsSmem& sm, int s, int tid, bool fin, bool act, int aw) {
+// Phase B2: new active list — departures reuse the finished slots in order, else append; leftover
+// finished slots are dropped preserving order.  Departing agents publish their record.
+LCS_D void lcs_phase_depart_place(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
     const int nw = (p.Ap + 31) >> 5;
     const int n = sm.misc[0];
     const int n_arr = lcs_total(sm.mask, nw), m = lcs_total(sm.mask + 64, nw);
-    if (tid < n) {
+    if (tid < n && !t.fin) {
         const int r = lcs_prefix(sm.mask, tid);
-        if (!fin) {
-            const int removed_before = r > m ? r - m : 0;
-            sm.act2[tid - removed_before] = sm.act[tid];
-        }
+        sm.act2[tid - (r > m ? r - m : 0)] = sm.act[tid];
     }
-    if (act) {
-        const int q = lcs_prefix(sm.mask + 64, tid);
-        sm.status[aw] = LCS_ACTIVE;
+    if (t.act) {
+        const int q = lcs_prefix(sm.mask + 64, tid), aw = t.aw;
+        const size_t ia = (size_t)s * p.Ap + aw;
+        p.status[ia] = LCS_ACTIVE;
         sm.dlist[q] = aw;
         if (q >= n_arr) sm.act2[n + (q - n_arr)] = aw;
+        const double* ps = p.pose64 + 4 * ia;
+        double sh, ch;
+        lcs_sincos(ps[2], &sh, &ch);
+        lcs_store_ex(sm, aw, ps[0], ps[1], ps[3], ch, sh, p.length[ia], p.width[ia], ps[2]);
     }
 }
-LCS_D void lcs_phase_depart_fill(const LcsParams& p, LcsSmem& sm, int s, int tid, bool fin) {
+LCS_D void lcs_phase_depart_fill(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
     const int nw = (p.Ap + 31) >> 5;
     const int n = sm.misc[0];
     const int n_arr = lcs_total(sm.mask, nw), n_pop = lcs_total(sm.mask + 32, nw), m = lcs_total(sm.mask + 64, nw);
-    if (tid < n && fin) {
+    if (tid < n && t.fin) {
         const int r = lcs_prefix(sm.mask, tid);
         if (r < m) sm.act2[tid] = sm.dlist[r]; // no slot before this one was dropped when r < m
     }
@@ -758,132 +810,145 @@ LCS_D void lcs_phase_depart_fill(const LcsParams& p, LcsSmem& sm, int s, int tid
     }
 }
 
-// Phase C: publish the list and the filter records; clear the per-agent metric outputs.
+// Phase C: publish the list; slot-indexed float32 filter records of the new list.
 LCS_D void lcs_phase_publish(const LcsParams& p, LcsSmem& sm, int s, int tid) {
-    const int a = tid;
-    const size_t ia = (size_t)s * p.Ap + a;
+    const size_t is = (size_t)s * p.Ap + tid;
     const int n_new = sm.misc[1];
-    p.active[ia] = tid < n_new ? sm.act2[tid] : -1;
-    const int status = sm.status[a];
-    p.status[ia] = status;
-    p.stale_valid[ia] = 0; // prepare_obs refreshed every observation (manager.py:98-103)
-    const double* ex = sm.ex + 8 * a;
-    const double ox = p.origin[2 * s], oy = p.origin[2 * s + 1];
-    lcs_f4 r;
-    r.x = (float)(ex[0] - ox);
-    r.y = (float)(ex[1] - oy);
-    // half diagonal rounded up + float32 coordinate error; negative = not in the active list
-    const float hl = (float)ex[5], hw = (float)ex[6];
-    const float slack = 5e-5f + 1.2e-7f * (fabsf(r.x) + fabsf(r.y)); // float32 coordinate error
-    const float rad = 0.5f * sqrtf(hl * hl + hw * hw) * 1.00001f + slack;
-    r.z = status == LCS_ACTIVE ? rad : -1.0f;
-    r.w = slack;
-    sm.rec[a] = r;
-    if (p.with_metrics) {
-        p.nearest_edge[ia] = -1;
-        p.offroad[ia] = 0;
+    p.stale_valid[is] = 0; // prepare_obs refreshed every observation (manager.py:98-103)
+    if (tid >= n_new) {
+        p.active[is] = -1;
+        return;
     }
+    const int a = sm.act2[tid];
+    p.active[is] = a;
+    const double* ex = sm.ex + 8 * a;
+    lcs_f4 r;
+    r.x = (float)(ex[0] - p.origin[2 * s]);
+    r.y = (float)(ex[1] - p.origin[2 * s + 1]);
+    const float L = (float)ex[5], W = (float)ex[6];
+    r.w = 5e-5f + 1.2e-7f * (fabsf(r.x) + fabsf(r.y)); // float32 coordinate error
+    r.z = 0.5f * sqrtf(L * L + W * W) * 1.00001f + r.w; // half diagonal, rounded up
+    sm.crec[tid] = r;
 }
 
-// Phase D: TrajIDM branch of Agent.prepare_obs (agent.py:249-299): lead vehicle of every active
-// agent over the NEW active list, in list order (strict < keeps the first on ties).
-LCS_D void lcs_phase_lead(const LcsParams& p, LcsSmem& sm, int s, int tid) {
-    const int a = tid;
-    if (sm.status[a] != LCS_ACTIVE) return;
-    const size_t ia = (size_t)s * p.Ap + a;
-    const int n_new = sm.misc[1];
-    const double* eg = sm.ex + 8 * a;
-    const lcs_f4 me = sm.rec[a];
+LCS_D void lcs_push_pair(LcsSmem& sm, int cap, int i, int j, bool* overflow) {
+    const int q = lcs_atomic_add(&sm.misc[6], 1);
+    *overflow = q >= cap;
+    if (q < cap) sm.queue[q] = ((uint32_t)i << 16) | (uint32_t)j;
+}
+
+// lead candidate (ego slot i, other slot j): exact evaluation, packed (distance, slot) minimum.
+// The low 10 bits of the float64 distance make room for the slot: distances that agree to 2^-42
+// relative are ordered by list position, exact ties included (reference: strict <, list order).
+LCS_D void lcs_lead_eval(LcsSmem& sm, int i, int j) {
+    double dis, vl;
+    if (lcs_lead_pair(sm.ex + 8 * sm.act2[i], sm.ex + 8 * sm.act2[j], &dis, &vl))
+        lcs_atomic_min_u64(&sm.lead_key[i], (lcs_d2u(dis) & ~0x3ffull) | (unsigned long long)j);
+}
+
+// Phase D1: TrajIDM branch of Agent.prepare_obs (agent.py:249-299), float32 filter over all ordered pairs
+LCS_D void lcs_phase_lead_filter(const LcsParams& p, LcsSmem& sm, int s, int tid) {
+    const int n_new = sm.misc[1], cap = LCS_QPER * p.Ap;
+    if (tid >= n_new) return;
+    const double* eg = sm.ex + 8 * sm.act2[tid];
+    const lcs_f4 me = sm.crec[tid];
     const float c32 = (float)eg[3], s32 = (float)eg[4];
     const float hl = 0.5f * (float)eg[5], hw = 0.5f * (float)eg[6];
-    double best = lcs_inf_d(), best_v = 0.0;
-    int nc = 0;
-    for (int j = 0; j <= n_new; j++) {
-        bool flush = j == n_new;
-        if (!flush) {
-            const int o = sm.act2[j];
-            const lcs_f4 ot = sm.rec[o];
-            const float dx = ot.x - me.x, dy = ot.y - me.y;
-            const float rx = dx * c32 + dy * s32, ry = dy * c32 - dx * s32;
-            // error of rx, ry: coordinate rounding (inside ot.z / me.z) + float32 trig/arithmetic
-            const float err = ot.w + me.w + 1e-6f * (fabsf(dx) + fabsf(dy));
-            // corners lie within the other's half diagonal of its centre; min corner x <= centre x
-            if (o != a && fabsf(ry) <= hw + ot.z + err && rx >= hl - err) {
-                sm.cand[nc * p.Ap + a] = (uint16_t)o;
-                nc++;
-                flush = nc == LCS_CAND;
-            }
-        }
-        if (flush) {
-            for (int k = 0; k < nc; k++) {
-                const int o = sm.cand[k * p.Ap + a];
-                double dis, vl;
-                if (lcs_lead_pair(eg, sm.ex + 8 * o, &dis, &vl) && dis < best) {
-                    best = dis;
-                    best_v = vl;
-                }
-            }
-            nc = 0;
-        }
-    }
-    p.lead_valid[ia] = best != lcs_inf_d();
-    p.lead_dis[ia] = best;
-    p.lead_v[ia] = best_v;
-}
-
-// Phase E1: check_collision_all (manager.py:313-327 -> polygon.py:195-235): bounding-circle
-// broadphase in float32 over agent pairs (o > a), exact SAT on survivors, counts to both.
-LCS_D void lcs_phase_collision(const LcsParams& p, LcsSmem& sm, int s, int tid) {
-    const int a = tid;
-    if (sm.status[a] != LCS_ACTIVE) return;
-    const lcs_f4 me = sm.rec[a];
-    const double* ea = sm.ex + 8 * a;
-    int nc = 0;
-    for (int o = a + 1; o <= p.Ap; o++) {
-        bool flush = o == p.Ap;
-        if (!flush) {
-            const lcs_f4 ot = sm.rec[o];
-            const float dx = ot.x - me.x, dy = ot.y - me.y;
-            const float rr = ot.z + me.z; // both radii already include their coordinate slack
-            if (ot.z >= 0.f && dx * dx + dy * dy <= rr * rr * 1.00001f) {
-                sm.cand[nc * p.Ap + a] = (uint16_t)o;
-                nc++;
-                flush = nc == LCS_CAND;
-            }
-        }
-        if (flush) {
-            for (int k = 0; k < nc; k++) {
-                const int o2 = sm.cand[k * p.Ap + a];
-                if (lcs_collide(ea, sm.ex + 8 * o2)) {
-                    lcs_atomic_add(&sm.cnt[a], 1);
-                    lcs_atomic_add(&sm.cnt[o2], 1);
-                }
-            }
-            nc = 0;
+    for (int j = 0; j < n_new; j++) {
+        const lcs_f4 ot = sm.crec[j];
+        const float dx = ot.x - me.x, dy = ot.y - me.y;
+        const float rx = dx * c32 + dy * s32, ry = dy * c32 - dx * s32;
+        // error of rx, ry: coordinate rounding (slack) + float32 trig / arithmetic
+        const float err = ot.w + me.w + 1e-6f * (fabsf(dx) + fabsf(dy));
+        // every corner lies within the other's half diagonal of its centre; min corner x <= centre x
+        if (j != tid && fabsf(ry) <= hw + ot.z + err && rx >= hl - err) {
+            bool overflow;
+            lcs_push_pair(sm, cap, tid, j, &overflow);
+            if (overflow) lcs_lead_eval(sm, tid, j);
         }
     }
 }
+LCS_D void lcs_phase_lead_drain(const LcsParams& p, LcsSmem& sm, int s, int tid) {
+    const int cap = LCS_QPER * p.Ap;
+    const int n = sm.misc[6] < cap ? sm.misc[6] : cap;
+    for (int q = tid; q < n; q += p.Ap) {
+        const uint32_t e = sm.queue[q];
+        lcs_lead_eval(sm, (int)(e >> 16), (int)(e & 0xffff));
+    }
+}
+LCS_D void lcs_phase_lead_out(const LcsParams& p, LcsSmem& sm, int s, int tid) {
+    if (tid == 0) sm.misc[6] = 0; // the queue is reused by the collision phase
+    if (tid >= sm.misc[1]) return;
+    const size_t ia = (size_t)s * p.Ap + sm.act2[tid];
+    const unsigned long long key = sm.lead_key[tid];
+    double dis = lcs_inf_d(), vl = 0.0;
+    bool valid = false;
+    if (key != ~0ull) valid = lcs_lead_pair(sm.ex + 8 * sm.act2[tid], sm.ex + 8 * sm.act2[(int)(key & 0x3ffull)], &dis, &vl);
+    p.lead_valid[ia] = valid ? 1 : 0;
+    p.lead_dis[ia] = valid ? dis : lcs_inf_d();
+    p.lead_v[ia] = valid ? vl : 0.0;
+}
 
-// Phase E2: off-road / nearest edge of every active agent (manager.py:337-345 -> junction.py:387-409)
-LCS_D void lcs_phase_offroad(const LcsParams& p, LcsSmem& sm, int s, int tid, int* off_flag) {
-    const int a = tid;
-    *off_flag = 0;
-    if (sm.status[a] != LCS_ACTIVE) return;
+LCS_D void lcs_collide_eval(LcsSmem& sm, int i, int j) {
+    const double *ea = sm.ex + 8 * sm.act2[i], *eb = sm.ex + 8 * sm.act2[j];
+    int r = lcs_sat_f32(ea, eb);
+    if (r < 0) r = lcs_collide(ea, eb) ? 1 : 0;
+    if (r) {
+        lcs_atomic_add(&sm.cnt[i], 1);
+        lcs_atomic_add(&sm.cnt[j], 1);
+    }
+}
+
+// Phase E1: check_collision_all (manager.py:313-327 -> polygon.py:195-235), bounding-circle broadphase.
+// Every unordered pair of slots is visited once: slot i tests i+1 .. i+n/2 (mod n).
+LCS_D void lcs_phase_collision_filter(const LcsParams& p, LcsSmem& sm, int s, int tid) {
+    const int n = sm.misc[1], cap = LCS_QPER * p.Ap;
+    if (tid >= n) return;
+    const lcs_f4 me = sm.crec[tid];
+    const int half = n >> 1;
+    for (int d = 1; d <= half; d++) {
+        int j = tid + d;
+        if (j >= n) j -= n;
+        const lcs_f4 ot = sm.crec[j];
+        const float dx = ot.x - me.x, dy = ot.y - me.y;
+        const float rr = ot.z + me.z; // both radii already include their coordinate slack
+        if (dx * dx + dy * dy <= rr * rr * 1.00001f && !(2 * d == n && tid >= half)) {
+            bool overflow;
+            lcs_push_pair(sm, cap, tid, j, &overflow);
+            if (overflow) lcs_collide_eval(sm, tid, j);
+        }
+    }
+}
+// Phase E2: narrowphase over the queued pairs (float32 SAT, float64 SAT when within the margin)
+LCS_D void lcs_phase_collision_drain(const LcsParams& p, LcsSmem& sm, int s, int tid) {
+    const int cap = LCS_QPER * p.Ap;
+    const int n = sm.misc[6] < cap ? sm.misc[6] : cap;
+    for (int q = tid; q < n; q += p.Ap) {
+        const uint32_t e = sm.queue[q];
+        lcs_collide_eval(sm, (int)(e >> 16), (int)(e & 0xffff));
+    }
+}
+
+// Phase E3: off-road / nearest edge of every active agent (manager.py:337-345 -> junction.py:387-409)
+LCS_D void lcs_phase_offroad(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
+    t.off = 0;
+    if (tid >= sm.misc[1]) return;
+    const int a = sm.act2[tid];
     const size_t ia = (size_t)s * p.Ap + a;
     bool off;
     const int k = lcs_nearest_edge(p, s, sm.ex[8 * a], sm.ex[8 * a + 1], &off);
     p.nearest_edge[ia] = k;
     p.offroad[ia] = off ? 1 : 0;
-    *off_flag = off ? 1 : 0;
+    t.off = off ? 1 : 0;
 }
 
-// Phase F: write the collision counts and the per-scenario sums.
-LCS_D void lcs_phase_metrics_out(const LcsParams& p, LcsSmem& sm, int s, int tid, int off_flag) {
-    const size_t ia = (size_t)s * p.Ap + tid;
+// Phase F: collision counts out, per-scenario sums.
+LCS_D void lcs_phase_metrics_out(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
+    if (tid >= sm.misc[1]) return;
     const int c = sm.cnt[tid];
-    p.coll_count[ia] = c;
+    p.coll_count[(size_t)s * p.Ap + sm.act2[tid]] = c;
     if (c) lcs_atomic_add(&sm.misc[2], c);
-    if (off_flag) lcs_atomic_add(&sm.misc[3], 1);
+    if (t.off) lcs_atomic_add(&sm.misc[3], 1);
 }
 LCS_D void lcs_phase_stats_out(const LcsParams& p, LcsSmem& sm, int s, int tid) {
     if (tid == 0 && p.mode == 0) {
@@ -892,6 +957,3 @@ LCS_D void lcs_phase_stats_out(const LcsParams& p, LcsSmem& sm, int s, int tid) 
         st[3] += sm.misc[3];
     }
 }
-
-// The whole tick of one scenario, phases in order.  SYNC is __syncthreads() on the device; the host
-// emulation runs each phase for every tid before the next (see lcs_tick_emulate in lcsim_b200.cu).
