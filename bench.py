@@ -150,7 +150,7 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     S = args.scenarios
     sb = workload.synthetic_batch(rank * S, S, args.agents, workers=max(1, min(32, (os.cpu_count() or 1) // world)))
-    be = BatchEngine(sb, reactive=(args.mode == "reactive"), with_metrics=True, device=local)
+    be = BatchEngine(sb, reactive=(args.mode == "reactive"), with_metrics=not args.no_metrics, device=local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -314,6 +314,7 @@ def main():
     ap.add_argument("--scenarios", type=int, default=1024, help="scenarios per GPU")
     ap.add_argument("--agents", type=int, default=128)
     ap.add_argument("--mode", default="replay", choices=["replay", "reactive"], help="control mode of the timed rollout")
+    ap.add_argument("--no-metrics", action="store_true", help="experiment: skip the fused collision/off-road phases")
     ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and CPU legs (profiling runs)")
     ap.add_argument("--cpu-scenarios", type=int, default=0, help="bounded CPU sample (scenarios per rollout); "
                     "0 = max(64, 2 x host cores)")

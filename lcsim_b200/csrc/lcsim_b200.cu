@@ -44,9 +44,7 @@ static cudaError_t cudaGetLastError() { return 0; }
 
 // One CTA per scenario, one thread per active-list slot; the whole tick in one launch (reference:
 // engine.py:145-158 Engine.step, plus manager.py:313-345 when with_metrics).
-#define LCS_TICK_BODY(SYNC, FOR_T)                                                  \
-    FOR_T lcs_phase_update(p, sm, s, tid, TH);                                      \
-    SYNC;                                                                           \
+#define LCS_TICK_REST(SYNC, FOR_T)                                                  \
     FOR_T lcs_phase_depart_flags(p, sm, s, tid, TH);                                \
     SYNC;                                                                           \
     FOR_T lcs_phase_depart_place(p, sm, s, tid, TH);                                \
@@ -75,31 +73,219 @@ static cudaError_t cudaGetLastError() { return 0; }
     }
 
 #ifndef LCSIM_HOSTEMU
-template <int MAXT>
+// ---- TMA (cp.async.bulk) + mbarrier plumbing for the filter-tile ring
+LCS_D uint32_t lcs_saddr(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
+LCS_D void lcs_mbar_init(uint64_t* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lcs_saddr(b)), "r"(count) : "memory");
+}
+LCS_D void lcs_mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lcs_saddr(b)), "r"(bytes) : "memory");
+}
+LCS_D void lcs_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(lcs_saddr(dst)),
+                 "l"(src), "r"(bytes), "r"(lcs_saddr(b))
+                 : "memory");
+}
+LCS_D void lcs_mbar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(lcs_saddr(b)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// The float32 filter tile of a scenario ([T2][Ap] x 16 B, contiguous) streams through a ring of NST
+// stages of ROWS tile rows each; one elected thread issues the bulk copies, every thread consumes its
+// own column from shared memory.  The first NST chunks are in flight before the tick's dependent
+// global loads start.
+template <int MAXT, int ROWS, int NST>
 __global__ void __launch_bounds__(MAXT) lcs_tick_kernel(const LcsParams p) {
-    extern __shared__ __align__(16) unsigned char lcs_smem_raw[];
+    extern __shared__ __align__(128) unsigned char lcs_smem_raw[];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    if (p.mode == 1 && p.reset_mask && !p.reset_mask[s]) return;
+    const size_t stage_bytes = (size_t)ROWS * p.Ap * 16;
+    lcs_f4* ring = (lcs_f4*)lcs_smem_raw;
+    uint64_t* full = (uint64_t*)(lcs_smem_raw + NST * stage_bytes);
+    LcsSmem sm;
+    lcs_smem_carve(sm, lcs_smem_raw + NST * stage_bytes + 64, p.Ap);
+    const bool scan = p.mode == 0;
+    const int n_chunks = scan ? (p.T2 + ROWS - 1) / ROWS : 0;
+    const lcs_f4* tile = (const lcs_f4*)p.tf_xy + (size_t)s * p.T2 * p.Ap;
+    auto issue = [&](int g) { // chunk g of this scenario -> stage g % NST
+        const int r0 = g * ROWS;
+        const int rows = p.T2 - r0 < ROWS ? p.T2 - r0 : ROWS;
+        const uint32_t bytes = (uint32_t)rows * p.Ap * 16;
+        uint64_t* bar = full + (g % NST);
+        lcs_mbar_expect_tx(bar, bytes);
+        lcs_bulk_g2s((unsigned char*)ring + (size_t)(g % NST) * stage_bytes, tile + (size_t)r0 * p.Ap, bytes, bar);
+    };
+    if (tid == 0) {
+        for (int k = 0; k < NST; k++) lcs_mbar_init(full + k, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int g = 0; g < NST && g < n_chunks; g++) issue(g);
+    }
+    LcsThread th;
+    LcsUpd u;
+    LcsScan sc;
+    const int a = lcs_phase_init(p, sm, s, tid, th);
+    int n2 = 0;
+    if (a >= 0) {
+        lcs_update_pre(p, s, a, u);
+        lcs_scan_begin(p, s, u.qx, u.qy, sc);
+        n2 = (u.len + 1) >> 1;
+    }
+    __syncthreads(); // barrier inits visible to every waiter
+    for (int g = 0; g < n_chunks; g++) {
+        lcs_mbar_wait(full + (g % NST), (uint32_t)(g / NST) & 1u);
+        if (a >= 0) {
+            const lcs_f4* st = ring + (size_t)(g % NST) * ROWS * p.Ap + a;
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                const int k2 = g * ROWS + r;
+                if (k2 < n2) lcs_scan_pair(sc, st[(size_t)r * p.Ap], 2 * k2);
+            }
+        }
+        __syncthreads(); // every reader is done with this stage before it is refilled
+        if (tid == 0 && g + NST < n_chunks) issue(g + NST);
+    }
+    if (a >= 0) th.fin = lcs_update_post(p, sm, s, a, u, sc);
+    __syncthreads();
+#define TH th
+    LCS_TICK_REST(__syncthreads(), )
+#undef TH
+}
+
+// Variant without the ring: every thread scans its filter column straight from global memory
+// (16-byte loads, 8 in flight per thread).  Smaller shared-memory footprint -> more CTAs per SM.
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? 8 : 1)) lcs_tick_kernel_ldg(const LcsParams p) {
+    extern __shared__ __align__(128) unsigned char lcs_smem_raw[];
     const int s = blockIdx.x, tid = threadIdx.x;
     if (p.mode == 1 && p.reset_mask && !p.reset_mask[s]) return;
     LcsSmem sm;
     lcs_smem_carve(sm, lcs_smem_raw, p.Ap);
     LcsThread th;
+    lcs_phase_update(p, sm, s, tid, th);
+    __syncthreads();
 #define TH th
-    LCS_TICK_BODY(__syncthreads(), )
+    LCS_TICK_REST(__syncthreads(), )
 #undef TH
 }
+
+// Instrumented copy of the plain kernel (LCSIM_B200_CLOCKS=1): thread 0 stamps clock64() at every phase
+// boundary into p.dbg[s][*]; used only by profiles/phase_clocks.py.
+__global__ void __launch_bounds__(128) lcs_tick_kernel_clk(const LcsParams p) {
+    extern __shared__ __align__(128) unsigned char lcs_smem_raw[];
+    const int s = blockIdx.x, tid = threadIdx.x;
+    if (p.mode == 1) return;
+    LcsSmem sm;
+    lcs_smem_carve(sm, lcs_smem_raw, p.Ap);
+    LcsThread th;
+    long long* dbg = p.dbg + (size_t)s * 16;
+    int k = 0;
+#define STAMP() do { if (tid == 0) dbg[k] = clock64(); k++; } while (0)
+    STAMP();
+    const int a = lcs_phase_init(p, sm, s, tid, th);
+    LcsUpd u;
+    LcsScan sc;
+    if (a >= 0) lcs_update_pre(p, s, a, u);
+    __syncthreads();
+    STAMP(); // 1: pre done
+    if (a >= 0) {
+        lcs_scan_begin(p, s, u.qx, u.qy, sc);
+        lcs_scan_global(p, s, a, u.len, sc);
+    }
+    __syncthreads();
+    STAMP(); // 2: scan done
+    if (a >= 0) th.fin = lcs_update_post(p, sm, s, a, u, sc);
+    __syncthreads();
+    STAMP(); // 3: post done
+    lcs_phase_depart_flags(p, sm, s, tid, th);
+    __syncthreads();
+    lcs_phase_depart_place(p, sm, s, tid, th);
+    __syncthreads();
+    lcs_phase_depart_fill(p, sm, s, tid, th);
+    __syncthreads();
+    lcs_phase_publish(p, sm, s, tid);
+    __syncthreads();
+    STAMP(); // 4: departures + publish
+    if (p.reactive) {
+        lcs_phase_lead_filter(p, sm, s, tid);
+        __syncthreads();
+        lcs_phase_lead_drain(p, sm, s, tid);
+        __syncthreads();
+        lcs_phase_lead_out(p, sm, s, tid);
+        __syncthreads();
+    }
+    STAMP(); // 5: lead
+    if (p.with_metrics) {
+        lcs_phase_collision_filter(p, sm, s, tid);
+        __syncthreads();
+        STAMP(); // 6: collision filter
+        lcs_phase_offroad(p, sm, s, tid, th);
+        __syncthreads();
+        STAMP(); // 7: offroad
+        lcs_phase_collision_drain(p, sm, s, tid);
+        __syncthreads();
+        STAMP(); // 8: collision drain
+        lcs_phase_metrics_out(p, sm, s, tid, th);
+        __syncthreads();
+        lcs_phase_stats_out(p, sm, s, tid);
+    }
+    STAMP(); // 9: end
+#undef STAMP
+}
+
+template <int MAXT, int ROWS, int NST>
+static cudaError_t lcs_tick_configure() {
+    return cudaFuncSetAttribute(lcs_tick_kernel<MAXT, ROWS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+static size_t lcs_tick_smem(int Ap, int rows, int nst) { return (size_t)nst * rows * Ap * 16 + 64 + lcs_smem_bytes(Ap); }
 #endif
+
+static cudaError_t lcs_configure_kernels() {
+#ifndef LCSIM_HOSTEMU
+    cudaError_t e;
+    if ((e = lcs_tick_configure<128, 4, 4>()) != cudaSuccess) return e;
+    if ((e = lcs_tick_configure<256, 2, 4>()) != cudaSuccess) return e;
+    if ((e = lcs_tick_configure<512, 2, 2>()) != cudaSuccess) return e;
+    if ((e = lcs_tick_configure<1024, 1, 2>()) != cudaSuccess) return e;
+#endif
+    return cudaSuccess;
+}
+
+static int lcs_use_ring = 0; // LCSIM_B200_RING=1 selects the TMA-ring variant of the tick kernel
 
 static void lcs_launch_tick(const LcsParams& p, cudaStream_t stream) {
 #ifndef LCSIM_HOSTEMU
-    const size_t smem = lcs_smem_bytes(p.Ap);
+    if (p.dbg && p.Ap == 128 && p.mode == 0) {
+        lcs_tick_kernel_clk<<<p.S, p.Ap, lcs_smem_bytes(p.Ap), stream>>>(p);
+        return;
+    }
+    if (!lcs_use_ring) {
+        const size_t smem = lcs_smem_bytes(p.Ap);
+        if (p.Ap <= 128)
+            lcs_tick_kernel_ldg<128><<<p.S, p.Ap, smem, stream>>>(p);
+        else if (p.Ap <= 256)
+            lcs_tick_kernel_ldg<256><<<p.S, p.Ap, smem, stream>>>(p);
+        else if (p.Ap <= 512)
+            lcs_tick_kernel_ldg<512><<<p.S, p.Ap, smem, stream>>>(p);
+        else
+            lcs_tick_kernel_ldg<1024><<<p.S, p.Ap, smem, stream>>>(p);
+        return;
+    }
     if (p.Ap <= 128)
-        lcs_tick_kernel<128><<<p.S, p.Ap, smem, stream>>>(p);
+        lcs_tick_kernel<128, 4, 4><<<p.S, p.Ap, lcs_tick_smem(p.Ap, 4, 4), stream>>>(p);
     else if (p.Ap <= 256)
-        lcs_tick_kernel<256><<<p.S, p.Ap, smem, stream>>>(p);
+        lcs_tick_kernel<256, 2, 4><<<p.S, p.Ap, lcs_tick_smem(p.Ap, 2, 4), stream>>>(p);
     else if (p.Ap <= 512)
-        lcs_tick_kernel<512><<<p.S, p.Ap, smem, stream>>>(p);
+        lcs_tick_kernel<512, 2, 2><<<p.S, p.Ap, lcs_tick_smem(p.Ap, 2, 2), stream>>>(p);
     else
-        lcs_tick_kernel<1024><<<p.S, p.Ap, smem, stream>>>(p);
+        lcs_tick_kernel<1024, 1, 2><<<p.S, p.Ap, lcs_tick_smem(p.Ap, 1, 2), stream>>>(p);
 #else
     const int Ap = p.Ap;
     std::vector<unsigned char> raw(lcs_smem_bytes(Ap) + 16);
@@ -110,7 +296,8 @@ static void lcs_launch_tick(const LcsParams& p, cudaStream_t stream) {
         lcs_smem_carve(sm, (unsigned char*)(((uintptr_t)raw.data() + 15) & ~(uintptr_t)15), Ap);
 #define TH ths[tid]
 #define LCS_FOR_T for (int tid = 0; tid < Ap; tid++)
-        LCS_TICK_BODY((void)0, LCS_FOR_T)
+        LCS_FOR_T lcs_phase_update(p, sm, s, tid, TH);
+        LCS_TICK_REST((void)0, LCS_FOR_T)
 #undef LCS_FOR_T
 #undef TH
     }
@@ -407,6 +594,16 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || d->device < 0 || d->device >= ndev) return LCSIM_B200_ERR_CUDA;
     if (cudaSetDevice(d->device) != cudaSuccess) return LCSIM_B200_ERR_CUDA;
+    if (lcs_configure_kernels() != cudaSuccess) return LCSIM_B200_ERR_CUDA;
+    {
+        const char* env = getenv("LCSIM_B200_RING");
+        lcs_use_ring = env && env[0] == '1';
+    }
+    int prefetch_env = 0;
+    {
+        const char* env = getenv("LCSIM_B200_PREFETCH");
+        prefetch_env = env && env[0] == '1';
+    }
     lcsim_b200_engine* e = new lcsim_b200_engine();
     e->desc = *d;
     LcsParams& p = e->p;
@@ -423,6 +620,7 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     p.no_static = d->no_static;
     p.allow_new_obj = d->allow_new_obj;
     p.with_metrics = d->with_metrics;
+    p.prefetch = prefetch_env;
     *out = e; // returned even on failure below so the caller can read last_error and destroy
     const size_t S = p.S, SA = S * p.Ap, SAT = SA * p.T, SE = S * p.E;
     LCS_ALLOC(e, p.n_agents, S);
@@ -475,6 +673,10 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     LCS_ALLOC(e, p.nearest_edge, SA);
     LCS_ALLOC(e, p.offroad, SA);
     LCS_ALLOC(e, e->s_tab0, SAT);
+    {
+        const char* env = getenv("LCSIM_B200_CLOCKS");
+        if (env && env[0] == '1') LCS_ALLOC(e, p.dbg, S * 16);
+    }
     return 0;
 }
 
@@ -845,3 +1047,6 @@ extern "C" int lcsim_b200_episode_stats(lcsim_b200_engine* e, int64_t* stats_dev
 #endif
     return 0;
 }
+
+// not part of the public ABI: device pointer of the phase-clock buffer ([S][16] int64) or NULL
+extern "C" void* lcsim_b200_debug_clocks(lcsim_b200_engine* e) { return e ? (void*)e->p.dbg : nullptr; }

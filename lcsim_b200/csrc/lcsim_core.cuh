@@ -132,6 +132,8 @@ struct LcsParams {
     const double* act_data; // [S][K][5]
     int32_t K;
     // ---- launch mode
+    long long* dbg; // [S][16] phase clocks (debug builds of the launch only)
+    int32_t prefetch; // experiment switch: L2 prefetch of the filter columns
     int32_t mode; // 0 = step, 1 = reset
     const uint8_t* reset_mask; // [S] or null
 };
@@ -259,27 +261,44 @@ LCS_HD size_t lcs_tf_index(const LcsParams& p, int s, int k, int a) {
         m = c ? d : m;                       \
     }
 
-LCS_D int lcs_cursor_argmin(const LcsParams& p, int s, int a, int len, double qx, double qy) {
+// Running state of one filter scan: best and second-best float32 squared distance, index of the best.
+struct LcsScan {
+    float fqx, fqy, m, m2;
+    int j;
+};
+LCS_D void lcs_scan_begin(const LcsParams& p, int s, double qx, double qy, LcsScan& sc) {
+    sc.fqx = (float)(qx - p.origin[2 * s]);
+    sc.fqy = (float)(qy - p.origin[2 * s + 1]);
+    sc.m = sc.m2 = lcs_inf_f();
+    sc.j = 0;
+}
+// one 16-byte filter entry = points k and k+1
+LCS_D void lcs_scan_pair(LcsScan& sc, const lcs_f4 v, int k) {
+    const float fqx = sc.fqx, fqy = sc.fqy;
+    float m = sc.m, m2 = sc.m2;
+    int j = sc.j;
+    LCS_SCAN_POINT(v.x, v.y, k)
+    LCS_SCAN_POINT(v.z, v.w, k + 1)
+    sc.m = m; sc.m2 = m2; sc.j = j;
+}
+// scan straight from global memory (host emulation, and the fallback when the ring is not used)
+LCS_D void lcs_scan_global(const LcsParams& p, int s, int a, int len, LcsScan& sc) {
     const lcs_f4* tf = (const lcs_f4*)p.tf_xy + (size_t)s * p.T2 * p.Ap + a;
-    const double ox = p.origin[2 * s], oy = p.origin[2 * s + 1];
-    const float fqx = (float)(qx - ox), fqy = (float)(qy - oy);
-    float m = lcs_inf_f(), m2 = lcs_inf_f();
-    int j = 0;
     const int n2 = (len + 1) >> 1; // entries past len hold LCS_FAR
 #pragma unroll 8
-    for (int k2 = 0; k2 < n2; k2++) {
-        const lcs_f4 v = tf[(size_t)k2 * p.Ap];
-        LCS_SCAN_POINT(v.x, v.y, 2 * k2)
-        LCS_SCAN_POINT(v.z, v.w, 2 * k2 + 1)
-    }
-    const float eta = lcs_filter_eta(p.eta_pts[s], fqx, fqy, m);
-    const float thr = lcs_filter_thr(m, eta);
-    if (m2 > thr) return j;
-    // near-tie: float64 evaluation of every candidate, first minimum wins (np.argmin)
+    for (int k2 = 0; k2 < n2; k2++) lcs_scan_pair(sc, tf[(size_t)k2 * p.Ap], 2 * k2);
+}
+// the cursor from a finished scan: unique candidate -> done; near-tie -> float64 on every candidate,
+// first minimum wins (np.argmin)
+LCS_D int lcs_scan_finish(const LcsParams& p, int s, int a, int len, double qx, double qy, const LcsScan& sc) {
+    const float fqx = sc.fqx, fqy = sc.fqy;
+    const float eta = lcs_filter_eta(p.eta_pts[s], fqx, fqy, sc.m);
+    const float thr = lcs_filter_thr(sc.m, eta);
+    if (sc.m2 > thr) return sc.j;
     const double* t64 = p.traj_xy + ((size_t)s * p.Ap + a) * p.T * 2;
     const lcs_f2* tf2 = p.tf_xy;
     double bd = lcs_inf_d();
-    int best = j;
+    int best = sc.j;
     for (int k = 0; k < len; k++) {
         const lcs_f2 pt = tf2[lcs_tf_index(p, s, k, a)];
         const float dx = pt.x - fqx, dy = pt.y - fqy;
@@ -606,14 +625,22 @@ LCS_D void lcs_reset_agent(const LcsParams& p, int s, int a) {
     lcs_store_pose(p, s, ia, x, y, h, v);
 }
 
-// Engine.update for the agent in list slot `slot` (engine.py:221-225 -> manager.py:105-115 ->
-// agent.py:310-426).  Returns true when the agent reached the end of its trajectory.
-LCS_D bool lcs_update_agent(const LcsParams& p, LcsSmem& sm, int s, int a) {
+// Engine.update for one agent (engine.py:221-225 -> manager.py:105-115 -> agent.py:310-426), in three
+// parts so the Trajectory.next scan in the middle can run off the shared-memory ring:
+//   pre  : action selection + state update, leaves the new state and the scan query in LcsUpd
+//   scan : float32 filter scan (lcs_scan_*)
+//   post : cursor, history ring, stores; returns true when the agent reached the end of its trajectory
+struct LcsUpd {
+    double x, y, h, v, ch, sh, qx, qy;
+    int len;
+    bool ring_f32;
+};
+LCS_D void lcs_update_pre(const LcsParams& p, int s, int a, LcsUpd& u) {
     const size_t ia = (size_t)s * p.Ap + a;
     const double* ps = p.pose64 + 4 * ia;
     double x = ps[0], y = ps[1], h = ps[2], v = ps[3], ch, sh;
     const int len = p.traj_len[ia];
-    int cursor = p.cursor[ia];
+    const int cursor = p.cursor[ia];
     // ---- which action (manager.py:111-115)
     int type = LCS_ACT_NONE;
     double d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0;
@@ -695,12 +722,18 @@ LCS_D bool lcs_update_agent(const LcsParams& p, LcsSmem& sm, int s, int a) {
         h = lcs_wrap_angle(lcs_dadd(h, d2));
         lcs_sincos(h, &sh, &ch);
     }
-    cursor = lcs_cursor_argmin(p, s, a, len, qx, qy);
+    u.x = x; u.y = y; u.h = h; u.v = v; u.ch = ch; u.sh = sh; u.qx = qx; u.qy = qy;
+    u.len = len;
+    u.ring_f32 = ring_f32;
+}
+LCS_D bool lcs_update_post(const LcsParams& p, LcsSmem& sm, int s, int a, const LcsUpd& u, const LcsScan& sc) {
+    const size_t ia = (size_t)s * p.Ap + a;
+    const int cursor = lcs_scan_finish(p, s, a, u.len, u.qx, u.qy, sc);
     p.cursor[ia] = cursor;
-    lcs_ring_push(p, ia, x, y, h, v, ch, sh, ring_f32);
-    lcs_store_pose(p, s, ia, x, y, h, v);
-    lcs_store_ex(sm, a, x, y, v, ch, sh, p.length[ia], p.width[ia], h);
-    const bool fin = cursor >= len - 1; // type.py:50-51 reach_end
+    lcs_ring_push(p, ia, u.x, u.y, u.h, u.v, u.ch, u.sh, u.ring_f32);
+    lcs_store_pose(p, s, ia, u.x, u.y, u.h, u.v);
+    lcs_store_ex(sm, a, u.x, u.y, u.v, u.ch, u.sh, p.length[ia], p.width[ia], u.h);
+    const bool fin = cursor >= u.len - 1; // type.py:50-51 reach_end
     if (fin) {
         // FINISHED now, IDLE after this tick's check_departure_and_arrival (single-trip schedules:
         // schedule.py:22-40 next_trip() is False); the agent leaves the list, its metric outputs reset
@@ -714,8 +747,9 @@ LCS_D bool lcs_update_agent(const LcsParams& p, LcsSmem& sm, int s, int a) {
     return fin;
 }
 
-// Phase A: shared-memory init + update (step mode: thread = old list slot) or reset (thread = agent)
-LCS_D void lcs_phase_update(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
+// Phase A: shared-memory init + update (step mode: thread = old list slot) or reset (thread = agent).
+// lcs_phase_init returns the agent this thread updates (-1: none).
+LCS_D int lcs_phase_init(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
     for (int k = tid; k < 96; k += p.Ap) sm.mask[k] = 0;
     const int n_old = p.mode == 1 ? 0 : p.n_active[s];
     if (tid == 0) {
@@ -732,13 +766,28 @@ LCS_D void lcs_phase_update(const LcsParams& p, LcsSmem& sm, int s, int tid, Lcs
     t.fin = false;
     t.off = 0;
     int a = -1;
-    if (p.mode == 1) {
+    if (p.mode == 1)
         lcs_reset_agent(p, s, tid);
-    } else if (tid < n_old) {
+    else if (tid < n_old)
         a = p.active[(size_t)s * p.Ap + tid];
-        t.fin = lcs_update_agent(p, sm, s, a);
-    }
     sm.act[tid] = a;
+    return a;
+}
+LCS_D void lcs_phase_update(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
+    const int a = lcs_phase_init(p, sm, s, tid, t);
+    if (a < 0) return;
+#ifndef LCSIM_HOSTEMU
+    if (p.prefetch) { // pull this agent's filter column towards L2 while the dependent state loads run
+        const lcs_f4* tf = (const lcs_f4*)p.tf_xy + (size_t)s * p.T2 * p.Ap + a;
+        for (int k2 = 0; k2 < p.T2; k2++) asm volatile("prefetch.global.L2 [%0];" ::"l"(tf + (size_t)k2 * p.Ap));
+    }
+#endif
+    LcsUpd u;
+    LcsScan sc;
+    lcs_update_pre(p, s, a, u);
+    lcs_scan_begin(p, s, u.qx, u.qy, sc);
+    lcs_scan_global(p, s, a, u.len, sc);
+    t.fin = lcs_update_post(p, sm, s, a, u, sc);
 }
 
 // Phase B1: AgentManager.check_departure_and_arrival (manager.py:50-96), flags.  tid = list slot and,
