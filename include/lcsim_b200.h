@@ -78,7 +78,7 @@ typedef struct {
     int32_t allow_new_obj; /* control.allow_new_obj (engine.py:208-210) */
     int32_t device; /* CUDA device ordinal */
     int32_t with_metrics; /* 1: every tick also fills collision counts / nearest edge / off-road */
-    float grid_cell; /* road-edge hash-grid cell in metres; <= 0 selects the default (8 m) */
+    float grid_cell; /* road-edge hash-grid cell in metres; <= 0 selects the default (4 m) */
 } lcsim_b200_batch_desc;
 
 /* Packed static inputs, host pointers, C-contiguous, exactly the arrays of

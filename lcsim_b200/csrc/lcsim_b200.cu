@@ -73,94 +73,6 @@ static cudaError_t cudaGetLastError() { return 0; }
     }
 
 #ifndef LCSIM_HOSTEMU
-// ---- TMA (cp.async.bulk) + mbarrier plumbing for the filter-tile ring
-LCS_D uint32_t lcs_saddr(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
-LCS_D void lcs_mbar_init(uint64_t* b, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lcs_saddr(b)), "r"(count) : "memory");
-}
-LCS_D void lcs_mbar_expect_tx(uint64_t* b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lcs_saddr(b)), "r"(bytes) : "memory");
-}
-LCS_D void lcs_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(lcs_saddr(dst)),
-                 "l"(src), "r"(bytes), "r"(lcs_saddr(b))
-                 : "memory");
-}
-LCS_D void lcs_mbar_wait(uint64_t* b, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-            : "=r"(ok)
-            : "r"(lcs_saddr(b)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-
-// The float32 filter tile of a scenario ([T2][Ap] x 16 B, contiguous) streams through a ring of NST
-// stages of ROWS tile rows each; one elected thread issues the bulk copies, every thread consumes its
-// own column from shared memory.  The first NST chunks are in flight before the tick's dependent
-// global loads start.
-template <int MAXT, int ROWS, int NST>
-__global__ void __launch_bounds__(MAXT) lcs_tick_kernel(const LcsParams p) {
-    extern __shared__ __align__(128) unsigned char lcs_smem_raw[];
-    const int s = blockIdx.x, tid = threadIdx.x;
-    if (p.mode == 1 && p.reset_mask && !p.reset_mask[s]) return;
-    const size_t stage_bytes = (size_t)ROWS * p.Ap * 16;
-    lcs_f4* ring = (lcs_f4*)lcs_smem_raw;
-    uint64_t* full = (uint64_t*)(lcs_smem_raw + NST * stage_bytes);
-    LcsSmem sm;
-    lcs_smem_carve(sm, lcs_smem_raw + NST * stage_bytes + 64, p.Ap);
-    const bool scan = p.mode == 0;
-    const int n_chunks = scan ? (p.T2 + ROWS - 1) / ROWS : 0;
-    const lcs_f4* tile = (const lcs_f4*)p.tf_xy + (size_t)s * p.T2 * p.Ap;
-    auto issue = [&](int g) { // chunk g of this scenario -> stage g % NST
-        const int r0 = g * ROWS;
-        const int rows = p.T2 - r0 < ROWS ? p.T2 - r0 : ROWS;
-        const uint32_t bytes = (uint32_t)rows * p.Ap * 16;
-        uint64_t* bar = full + (g % NST);
-        lcs_mbar_expect_tx(bar, bytes);
-        lcs_bulk_g2s((unsigned char*)ring + (size_t)(g % NST) * stage_bytes, tile + (size_t)r0 * p.Ap, bytes, bar);
-    };
-    if (tid == 0) {
-        for (int k = 0; k < NST; k++) lcs_mbar_init(full + k, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int g = 0; g < NST && g < n_chunks; g++) issue(g);
-    }
-    LcsThread th;
-    LcsUpd u;
-    LcsScan sc;
-    const int a = lcs_phase_init(p, sm, s, tid, th);
-    int n2 = 0;
-    if (a >= 0) {
-        lcs_update_pre(p, s, a, u);
-        lcs_scan_begin(p, s, u.qx, u.qy, sc);
-        n2 = (u.len + 1) >> 1;
-    }
-    __syncthreads(); // barrier inits visible to every waiter
-    for (int g = 0; g < n_chunks; g++) {
-        lcs_mbar_wait(full + (g % NST), (uint32_t)(g / NST) & 1u);
-        if (a >= 0) {
-            const lcs_f4* st = ring + (size_t)(g % NST) * ROWS * p.Ap + a;
-#pragma unroll
-            for (int r = 0; r < ROWS; r++) {
-                const int k2 = g * ROWS + r;
-                if (k2 < n2) lcs_scan_pair(sc, st[(size_t)r * p.Ap], 2 * k2);
-            }
-        }
-        __syncthreads(); // every reader is done with this stage before it is refilled
-        if (tid == 0 && g + NST < n_chunks) issue(g + NST);
-    }
-    if (a >= 0) th.fin = lcs_update_post(p, sm, s, a, u, sc);
-    __syncthreads();
-#define TH th
-    LCS_TICK_REST(__syncthreads(), )
-#undef TH
-}
-
-// Variant without the ring: every thread scans its filter column straight from global memory
-// (16-byte loads, 8 in flight per thread).  Smaller shared-memory footprint -> more CTAs per SM.
 template <int MAXT>
 __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? 8 : 1)) lcs_tick_kernel_ldg(const LcsParams p) {
     extern __shared__ __align__(128) unsigned char lcs_smem_raw[];
@@ -239,26 +151,9 @@ __global__ void __launch_bounds__(128) lcs_tick_kernel_clk(const LcsParams p) {
     STAMP(); // 9: end
 #undef STAMP
 }
-
-template <int MAXT, int ROWS, int NST>
-static cudaError_t lcs_tick_configure() {
-    return cudaFuncSetAttribute(lcs_tick_kernel<MAXT, ROWS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-}
-static size_t lcs_tick_smem(int Ap, int rows, int nst) { return (size_t)nst * rows * Ap * 16 + 64 + lcs_smem_bytes(Ap); }
 #endif
 
-static cudaError_t lcs_configure_kernels() {
-#ifndef LCSIM_HOSTEMU
-    cudaError_t e;
-    if ((e = lcs_tick_configure<128, 4, 4>()) != cudaSuccess) return e;
-    if ((e = lcs_tick_configure<256, 2, 4>()) != cudaSuccess) return e;
-    if ((e = lcs_tick_configure<512, 2, 2>()) != cudaSuccess) return e;
-    if ((e = lcs_tick_configure<1024, 1, 2>()) != cudaSuccess) return e;
-#endif
-    return cudaSuccess;
-}
-
-static int lcs_use_ring = 0; // LCSIM_B200_RING=1 selects the TMA-ring variant of the tick kernel
+static cudaError_t lcs_configure_kernels() { return cudaSuccess; }
 
 static void lcs_launch_tick(const LcsParams& p, cudaStream_t stream) {
 #ifndef LCSIM_HOSTEMU
@@ -266,26 +161,15 @@ static void lcs_launch_tick(const LcsParams& p, cudaStream_t stream) {
         lcs_tick_kernel_clk<<<p.S, p.Ap, lcs_smem_bytes(p.Ap), stream>>>(p);
         return;
     }
-    if (!lcs_use_ring) {
-        const size_t smem = lcs_smem_bytes(p.Ap);
-        if (p.Ap <= 128)
-            lcs_tick_kernel_ldg<128><<<p.S, p.Ap, smem, stream>>>(p);
-        else if (p.Ap <= 256)
-            lcs_tick_kernel_ldg<256><<<p.S, p.Ap, smem, stream>>>(p);
-        else if (p.Ap <= 512)
-            lcs_tick_kernel_ldg<512><<<p.S, p.Ap, smem, stream>>>(p);
-        else
-            lcs_tick_kernel_ldg<1024><<<p.S, p.Ap, smem, stream>>>(p);
-        return;
-    }
+    const size_t smem = lcs_smem_bytes(p.Ap);
     if (p.Ap <= 128)
-        lcs_tick_kernel<128, 4, 4><<<p.S, p.Ap, lcs_tick_smem(p.Ap, 4, 4), stream>>>(p);
+        lcs_tick_kernel_ldg<128><<<p.S, p.Ap, smem, stream>>>(p);
     else if (p.Ap <= 256)
-        lcs_tick_kernel<256, 2, 4><<<p.S, p.Ap, lcs_tick_smem(p.Ap, 2, 4), stream>>>(p);
+        lcs_tick_kernel_ldg<256><<<p.S, p.Ap, smem, stream>>>(p);
     else if (p.Ap <= 512)
-        lcs_tick_kernel<512, 2, 2><<<p.S, p.Ap, lcs_tick_smem(p.Ap, 2, 2), stream>>>(p);
+        lcs_tick_kernel_ldg<512><<<p.S, p.Ap, smem, stream>>>(p);
     else
-        lcs_tick_kernel<1024, 1, 2><<<p.S, p.Ap, lcs_tick_smem(p.Ap, 1, 2), stream>>>(p);
+        lcs_tick_kernel_ldg<1024><<<p.S, p.Ap, smem, stream>>>(p);
 #else
     const int Ap = p.Ap;
     std::vector<unsigned char> raw(lcs_smem_bytes(Ap) + 16);
@@ -325,7 +209,7 @@ LCS_D void lcs_replan_copy(const LcsParams& p, const LcsReplanArgs& r, int e, in
     const int s = r.scenario[e], a = r.agent[e];
     const size_t ia = (size_t)s * p.Ap + a;
     const int Tn = r.Tn < p.T ? r.Tn : p.T;
-    const size_t f = lcs_tf_index(p, s, k, a); // k < 2 * T2
+    const size_t f = lcs_tf_index(p, s, k, a); // k < Tp
     if (k < Tn) {
         const size_t t = ia * p.T + k, q = (size_t)e * r.Tn + k;
         const double x = (double)r.xy[2 * q], y = (double)r.xy[2 * q + 1];
@@ -355,7 +239,7 @@ __global__ void lcs_replan_kernel(const LcsParams p, const LcsReplanArgs r) {
     const int e = blockIdx.x;
     if (threadIdx.x == 0) lcs_replan_stale(p, r, e);
     __syncthreads();
-    for (int k = threadIdx.x; k < 2 * p.T2; k += blockDim.x) lcs_replan_copy(p, r, e, k);
+    for (int k = threadIdx.x; k < p.Tp; k += blockDim.x) lcs_replan_copy(p, r, e, k);
 }
 #endif
 
@@ -595,15 +479,7 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || d->device < 0 || d->device >= ndev) return LCSIM_B200_ERR_CUDA;
     if (cudaSetDevice(d->device) != cudaSuccess) return LCSIM_B200_ERR_CUDA;
     if (lcs_configure_kernels() != cudaSuccess) return LCSIM_B200_ERR_CUDA;
-    {
-        const char* env = getenv("LCSIM_B200_RING");
-        lcs_use_ring = env && env[0] == '1';
-    }
-    int prefetch_env = 0;
-    {
-        const char* env = getenv("LCSIM_B200_PREFETCH");
-        prefetch_env = env && env[0] == '1';
-    }
+
     lcsim_b200_engine* e = new lcsim_b200_engine();
     e->desc = *d;
     LcsParams& p = e->p;
@@ -612,15 +488,14 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     p.A = d->A;
     p.Ap = (d->A + 31) / 32 * 32;
     p.T = d->T;
-    p.T2 = (d->T + 1) / 2;
-    p.E = std::max(d->E, 1);
+    p.Tp = (d->T + 3) / 4 * 4;
+    p.E = (std::max(d->E, 1) + 3) / 4 * 4; // 32-byte blocks of 4 points
     p.dt = d->interval;
     p.total_steps = d->total_steps;
     p.reactive = d->reactive;
     p.no_static = d->no_static;
     p.allow_new_obj = d->allow_new_obj;
     p.with_metrics = d->with_metrics;
-    p.prefetch = prefetch_env;
     *out = e; // returned even on failure below so the caller can read last_error and destroy
     const size_t S = p.S, SA = S * p.Ap, SAT = SA * p.T, SE = S * p.E;
     LCS_ALLOC(e, p.n_agents, S);
@@ -637,12 +512,12 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     LCS_ALLOC(e, p.traj_xy0, SAT * 2);
     LCS_ALLOC(e, p.traj_vel0, SAT * 2);
     LCS_ALLOC(e, p.traj_h0, SAT);
-    LCS_ALLOC(e, p.tf_xy0, SA * p.T2 * 2);
+    LCS_ALLOC(e, p.tf_xy0, SA * p.Tp);
     LCS_ALLOC(e, p.traj_len, SA);
     LCS_ALLOC(e, p.traj_xy, SAT * 2);
     LCS_ALLOC(e, p.traj_vel, SAT * 2);
     LCS_ALLOC(e, p.traj_h, SAT);
-    LCS_ALLOC(e, p.tf_xy, SA * p.T2 * 2);
+    LCS_ALLOC(e, p.tf_xy, SA * p.Tp);
     LCS_ALLOC(e, p.traj_f32, SA);
     LCS_ALLOC(e, p.stale_valid, SA);
     LCS_ALLOC(e, p.stale_f32, SA);
@@ -671,6 +546,8 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     LCS_ALLOC(e, p.lead_v, SA);
     LCS_ALLOC(e, p.coll_count, SA);
     LCS_ALLOC(e, p.nearest_edge, SA);
+    LCS_ALLOC(e, p.edge_hint, SA);
+    LCS_ALLOC(e, p.home_edge, SA);
     LCS_ALLOC(e, p.offroad, SA);
     LCS_ALLOC(e, e->s_tab0, SAT);
     {
@@ -685,7 +562,7 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
 namespace {
 
 struct Staging {
-    std::vector<int32_t> depart_tick, wait_order, traj_len, ge_idx, grid_dim, grid_start;
+    std::vector<int32_t> depart_tick, wait_order, traj_len, ge_idx, grid_dim, grid_start, home_edge;
     std::vector<uint8_t> dynamic;
     std::vector<double> length, width, home_xy, traj_xy, traj_vel, traj_h, s_tab, edge_xy, edge_dir;
     std::vector<lcs_f2> tf_xy, ge_xy;
@@ -766,7 +643,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     lcs_f2 far;
     far.x = LCS_FAR;
     far.y = LCS_FAR;
-    g.tf_xy.assign(SA * p.T2 * 2, far);
+    g.tf_xy.assign(SA * p.Tp, far);
     const size_t Ed = (size_t)p.E;
     g.edge_xy.assign((size_t)S * Ed * 2, 0.0);
     g.edge_dir.assign((size_t)S * Ed * 2, 0.0);
@@ -775,7 +652,8 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     g.grid_geom.assign((size_t)S * 4, 0.f);
     g.grid_dim.assign((size_t)S * 2, 1);
     g.eta.assign(S, 0.f);
-    const float cell = e->desc.grid_cell > 0 ? e->desc.grid_cell : 8.0f;
+    g.home_edge.assign(SA, -1);
+    const float cell = e->desc.grid_cell > 0 ? e->desc.grid_cell : 4.0f;
     std::vector<std::vector<int32_t>> cell_starts(S);
 
     lcs_parallel_range(S, [&](int s0, int s1) {
@@ -876,6 +754,18 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
                 g.ge_idx[(size_t)s * Ed + pos] = keep[q];
             }
             g.eta[s] = (float)(eta * 1.0001) + 1e-12f;
+            // hint for the first off-road query of every agent: the nearest edge point of its home pose
+            // (first index among exact ties; any edge point would be a valid hint, the nearest is the tightest)
+            for (int a = 0; a < st->n_agents[s]; a++) {
+                const double hx = st->home_xy[2 * ((size_t)s * A + a)], hy = st->home_xy[2 * ((size_t)s * A + a) + 1];
+                double bd = 1e300;
+                int bi = -1;
+                for (int k : keep) {
+                    const double dx = exy[2 * k] - hx, dy = exy[2 * k + 1] - hy, d = dx * dx + dy * dy;
+                    if (d < bd) { bd = d; bi = k; }
+                }
+                g.home_edge[(size_t)s * Ap + a] = bi;
+            }
         }
     });
     int GC = 2;
@@ -919,6 +809,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     LCS_UP(p.grid_start, g.grid_start);
     LCS_UP(p.ge_xy, g.ge_xy);
     LCS_UP(p.ge_idx, g.ge_idx);
+    LCS_UP(p.home_edge, g.home_edge);
 #undef LCS_UP
     LCS_CUDA(e, cudaMemset(p.traj_f32, 0, SA));
     LCS_CUDA(e, cudaMemset(p.stale_valid, 0, SA));
@@ -983,7 +874,7 @@ extern "C" int lcsim_b200_set_ref_trajectory(lcsim_b200_engine* e, const int32_t
 #else
     for (int i = 0; i < n; i++) {
         lcs_replan_stale(e->p, r, i);
-        for (int k = 0; k < 2 * e->p.T2; k++) lcs_replan_copy(e->p, r, i, k);
+        for (int k = 0; k < e->p.Tp; k++) lcs_replan_copy(e->p, r, i, k);
     }
 #endif
     return 0;

@@ -80,7 +80,7 @@ LCS_D double lcs_inf_d() {
 
 // Everything a tick needs, as raw device pointers.  Layouts: DESIGN.md §3.
 struct LcsParams {
-    int32_t S, A, Ap, T, T2, E;
+    int32_t S, A, Ap, T, Tp, E; // Tp = T rounded up to 4 points (32-byte filter entries)
     double dt;
     int32_t total_steps, reactive, no_static, allow_new_obj, with_metrics;
     // ---- static, per scenario
@@ -95,8 +95,8 @@ struct LcsParams {
     // pristine trajectories (reset restores re-planned ones from here)
     const int32_t* traj_len0;
     const double *traj_xy0, *traj_vel0, *traj_h0; // [S][Ap][T][2], [S][Ap][T][2], [S][Ap][T]
-    const lcs_f2* tf_xy0; // [S][T2][Ap][2] float32 filter copy (two consecutive points per 16 B), relative to
-                          // the origin, exact duplicates -> LCS_FAR; T2 = ceil(T/2)
+    const lcs_f2* tf_xy0; // [S][Ap][Tp] float32 filter copy, contiguous per agent, relative to the origin;
+                          // exact duplicates and the padding past traj_len -> LCS_FAR
     // ---- current trajectories (set_ref_trajectory overwrites)
     int32_t* traj_len;
     double *traj_xy, *traj_vel, *traj_h;
@@ -126,6 +126,8 @@ struct LcsParams {
     uint8_t* lead_valid;
     double *lead_dis, *lead_v;
     int32_t *coll_count, *nearest_edge;
+    int32_t* edge_hint; // [S][Ap] last known nearest edge point (reset: the one of the home pose)
+    const int32_t* home_edge; // [S][Ap] nearest edge point of the home pose (computed at upload)
     uint8_t* offroad;
     // ---- external actions of this launch
     const int32_t *act_agent, *act_type; // [S][K]
@@ -133,7 +135,6 @@ struct LcsParams {
     int32_t K;
     // ---- launch mode
     long long* dbg; // [S][16] phase clocks (debug builds of the launch only)
-    int32_t prefetch; // experiment switch: L2 prefetch of the filter columns
     int32_t mode; // 0 = step, 1 = reset
     const uint8_t* reset_mask; // [S] or null
 };
@@ -144,6 +145,7 @@ struct LcsSmem {
     double* ex; // [Ap][8]  x, y, v, cos h, sin h, L, W, h          (agent index)
     unsigned long long* lead_key; // [Ap] packed (distance, slot) minimum per ego   (slot index)
     lcs_f4* crec; // [Ap]  x32, y32, filter radius, coordinate slack   (slot index, new list)
+    lcs_f4* crec2; // [Ap] cos h, sin h, half length, half width in float32 (slot index)
     int32_t* act; // [Ap] active list at tick start (slot index)
     int32_t* act2; // [Ap] active list after departures / arrivals
     int32_t* dlist; // [Ap] agents activated this tick, in waiting-list order
@@ -159,7 +161,7 @@ static inline
 __host__ __device__ inline
 #endif
 size_t lcs_smem_bytes(int Ap) {
-    return (size_t)Ap * (64 + 8 + 16 + 4 * 4 + 4 * LCS_QPER) + 3 * 32 * 4 + 8 * 4 + 64;
+    return (size_t)Ap * (64 + 8 + 32 + 4 * 4 + 4 * LCS_QPER) + 3 * 32 * 4 + 8 * 4 + 64;
 }
 
 LCS_D void lcs_smem_carve(LcsSmem& sm, unsigned char* base, int Ap) {
@@ -167,6 +169,7 @@ LCS_D void lcs_smem_carve(LcsSmem& sm, unsigned char* base, int Ap) {
     sm.ex = (double*)p; p += (size_t)Ap * 64;
     sm.lead_key = (unsigned long long*)p; p += (size_t)Ap * 8;
     sm.crec = (lcs_f4*)p; p += (size_t)Ap * 16;
+    sm.crec2 = (lcs_f4*)p; p += (size_t)Ap * 16;
     sm.act = (int32_t*)p; p += (size_t)Ap * 4;
     sm.act2 = (int32_t*)p; p += (size_t)Ap * 4;
     sm.dlist = (int32_t*)p; p += (size_t)Ap * 4;
@@ -247,8 +250,21 @@ LCS_D int lcs_total(const uint32_t* words, int nwords) {
 // frenet_projection: index = first argmin_k sqrt((x_k-px)^2 + (y_k-py)^2) over ALL len points.
 // Filter scan over the float32 copy (coalesced: [T][Ap]), exact float64 only on near-ties.
 // float2 index of filter point k of agent a in scenario s
-LCS_HD size_t lcs_tf_index(const LcsParams& p, int s, int k, int a) {
-    return ((((size_t)s * p.T2 + (k >> 1)) * p.Ap + a) << 1) + (k & 1);
+LCS_HD size_t lcs_tf_index(const LcsParams& p, int s, int k, int a) { return ((size_t)s * p.Ap + a) * p.Tp + k; }
+
+// 32-byte load (4 filter points).  Thread-per-agent scans are uncoalesced by nature; one 32-byte sector per
+// lane per request keeps the L1 line-lookup rate (one 128-byte line per cycle) from becoming the limit.
+struct alignas(32) lcs_f8 { float v[8]; };
+LCS_D lcs_f8 lcs_ld32(const lcs_f8* q) {
+#ifdef LCSIM_HOSTEMU
+    return *q;
+#else
+    lcs_f8 r;
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(q));
+    return r;
+#endif
 }
 
 #define LCS_SCAN_POINT(PX, PY, K)            \
@@ -272,21 +288,23 @@ LCS_D void lcs_scan_begin(const LcsParams& p, int s, double qx, double qy, LcsSc
     sc.m = sc.m2 = lcs_inf_f();
     sc.j = 0;
 }
-// one 16-byte filter entry = points k and k+1
-LCS_D void lcs_scan_pair(LcsScan& sc, const lcs_f4 v, int k) {
+// one 32-byte filter entry = points k .. k+3
+LCS_D void lcs_scan_quad(LcsScan& sc, const lcs_f8 v, int k) {
     const float fqx = sc.fqx, fqy = sc.fqy;
     float m = sc.m, m2 = sc.m2;
     int j = sc.j;
-    LCS_SCAN_POINT(v.x, v.y, k)
-    LCS_SCAN_POINT(v.z, v.w, k + 1)
+    LCS_SCAN_POINT(v.v[0], v.v[1], k)
+    LCS_SCAN_POINT(v.v[2], v.v[3], k + 1)
+    LCS_SCAN_POINT(v.v[4], v.v[5], k + 2)
+    LCS_SCAN_POINT(v.v[6], v.v[7], k + 3)
     sc.m = m; sc.m2 = m2; sc.j = j;
 }
-// scan straight from global memory (host emulation, and the fallback when the ring is not used)
+// the agent's own contiguous filter row; only ceil(len/4) sectors are touched (entries past len hold LCS_FAR)
 LCS_D void lcs_scan_global(const LcsParams& p, int s, int a, int len, LcsScan& sc) {
-    const lcs_f4* tf = (const lcs_f4*)p.tf_xy + (size_t)s * p.T2 * p.Ap + a;
-    const int n2 = (len + 1) >> 1; // entries past len hold LCS_FAR
-#pragma unroll 8
-    for (int k2 = 0; k2 < n2; k2++) lcs_scan_pair(sc, tf[(size_t)k2 * p.Ap], 2 * k2);
+    const lcs_f8* tf = (const lcs_f8*)(p.tf_xy + lcs_tf_index(p, s, 0, a));
+    const int n4 = (len + 3) >> 2;
+#pragma unroll 4
+    for (int k4 = 0; k4 < n4; k4++) lcs_scan_quad(sc, lcs_ld32(tf + k4), 4 * k4);
 }
 // the cursor from a finished scan: unique candidate -> done; near-tie -> float64 on every candidate,
 // first minimum wins (np.argmin)
@@ -318,92 +336,211 @@ LCS_D int lcs_scan_finish(const LcsParams& p, int s, int a, int len, double qx, 
 // The points live in a uniform hash grid (cells row-major, CSR); a (2r+1)^2 window around the
 // query is scanned row by row (one contiguous span per row), r grows until the window provably
 // contains every point that can be the float64 argmin.
-LCS_D int lcs_nearest_edge(const LcsParams& p, int s, double qx, double qy, bool* offroad) {
-    *offroad = false;
-    const int ne = p.n_edge[s];
-    if (ne == 0) return -1;
-    const double ox = p.origin[2 * s], oy = p.origin[2 * s + 1];
-    const float fqx = (float)(qx - ox), fqy = (float)(qy - oy);
-    const float gx0 = p.grid_geom[4 * s], gy0 = p.grid_geom[4 * s + 1], inv = p.grid_geom[4 * s + 2];
-    const int W = p.grid_dim[2 * s], H = p.grid_dim[2 * s + 1];
-    const int32_t* cs = p.grid_start + (size_t)s * p.GC;
-    const lcs_f2* gp = p.ge_xy + (size_t)s * p.E;
+// The search is written per LANE so that one thread (nlanes = 1: rewards kernel) or a whole warp
+// (nlanes = 32: tick kernel, coalesced loads + warp-shuffle argmin) can run it.
+struct LcsEdgeQ {
+    float fqx, fqy, gx0, gy0, inv, eta0;
+    int W, H, x0, x1, y0, y1;
+    const int32_t* cs;
+    const lcs_f2* gp;
+};
+LCS_D void lcs_edge_begin(const LcsParams& p, int s, double qx, double qy, LcsEdgeQ& q) {
+    q.fqx = (float)(qx - p.origin[2 * s]);
+    q.fqy = (float)(qy - p.origin[2 * s + 1]);
+    q.gx0 = p.grid_geom[4 * s];
+    q.gy0 = p.grid_geom[4 * s + 1];
+    q.inv = p.grid_geom[4 * s + 2];
+    q.eta0 = p.eta_pts[s];
+    q.W = p.grid_dim[2 * s];
+    q.H = p.grid_dim[2 * s + 1];
+    q.cs = p.grid_start + (size_t)s * p.GC;
+    q.gp = p.ge_xy + (size_t)s * p.E;
     // cell of the query; clamped far outside the grid so the integer math below cannot overflow
-    float fcx = floorf((fqx - gx0) * inv), fcy = floorf((fqy - gy0) * inv);
+    float fcx = floorf((q.fqx - q.gx0) * q.inv), fcy = floorf((q.fqy - q.gy0) * q.inv);
     fcx = fminf(fmaxf(fcx, -1.0e6f), 1.0e6f);
     fcy = fminf(fmaxf(fcy, -1.0e6f), 1.0e6f);
     const int cx = (int)fcx, cy = (int)fcy;
-    int x0 = cx - 1, x1 = cx + 1, y0 = cy - 1, y1 = cy + 1;
-    float m, m2, thr;
-    int j;
-    for (;;) {
-        const int wx0 = x0 < 0 ? 0 : x0, wx1 = x1 > W - 1 ? W - 1 : x1;
-        const int wy0 = y0 < 0 ? 0 : y0, wy1 = y1 > H - 1 ? H - 1 : y1;
-        m = lcs_inf_f();
-        m2 = lcs_inf_f();
-        j = -1;
-        if (wx0 <= wx1) {
-            for (int y = wy0; y <= wy1; y++) {
-                const int b = cs[y * W + wx0], e = cs[y * W + wx1 + 1];
-                for (int k = b; k < e; k++) {
-                    lcs_f2 pt = gp[k];
-                    float dx = pt.x - fqx, dy = pt.y - fqy;
-                    float d = dx * dx + dy * dy;
-                    bool c = d < m;
-                    m2 = c ? m : fminf(m2, d);
-                    j = c ? k : j;
-                    m = c ? d : m;
-                }
-            }
-        }
-        const bool covers_all = x0 <= 0 && y0 <= 0 && x1 >= W - 1 && y1 >= H - 1;
-        if (j >= 0) {
-            thr = lcs_filter_thr(m, lcs_filter_eta(p.eta_pts[s], fqx, fqy, m));
-            // every candidate lies within D of the query in each axis; the extra 1e-3 m absorbs the
-            // float32 rounding of the cell arithmetic (grid points were binned with the same formula)
-            const float D = sqrtf(thr) * 1.000001f + 1e-3f + 4e-7f * (fabsf(fqx) + fabsf(fqy) + fabsf(gx0) + fabsf(gy0));
-            const int nx0 = (int)fmaxf(floorf((fqx - D - gx0) * inv), -1.0e6f);
-            const int nx1 = (int)fminf(floorf((fqx + D - gx0) * inv), 1.0e6f);
-            const int ny0 = (int)fmaxf(floorf((fqy - D - gy0) * inv), -1.0e6f);
-            const int ny1 = (int)fminf(floorf((fqy + D - gy0) * inv), 1.0e6f);
-            if (covers_all || (nx0 >= x0 && nx1 <= x1 && ny0 >= y0 && ny1 <= y1)) break;
-            x0 = nx0 < x0 ? nx0 : x0;
-            x1 = nx1 > x1 ? nx1 : x1;
-            y0 = ny0 < y0 ? ny0 : y0;
-            y1 = ny1 > y1 ? ny1 : y1;
-        } else {
-            if (covers_all) return -1; // cannot happen with ne > 0
-            const int r = (x1 - x0); // grow geometrically while the window is empty
-            x0 -= r; x1 += r; y0 -= r; y1 += r;
+    q.x0 = cx - 1; q.x1 = cx + 1; q.y0 = cy - 1; q.y1 = cy + 1;
+}
+// this lane's share of the window: points lane, lane + nlanes, ... of every row span
+LCS_D void lcs_edge_lane_scan(const LcsEdgeQ& q, int lane, int nlanes, float& m, float& m2, int& j) {
+    const float fqx = q.fqx, fqy = q.fqy;
+    m = lcs_inf_f();
+    m2 = lcs_inf_f();
+    j = -1;
+    const int wx0 = q.x0 < 0 ? 0 : q.x0, wx1 = q.x1 > q.W - 1 ? q.W - 1 : q.x1;
+    const int wy0 = q.y0 < 0 ? 0 : q.y0, wy1 = q.y1 > q.H - 1 ? q.H - 1 : q.y1;
+    if (wx0 > wx1) return;
+    for (int y = wy0; y <= wy1; y++) {
+        const int b = q.cs[y * q.W + wx0], e = q.cs[y * q.W + wx1 + 1];
+        for (int k = b + lane; k < e; k += nlanes) {
+            const lcs_f2 pt = q.gp[k];
+            LCS_SCAN_POINT(pt.x, pt.y, k)
         }
     }
+}
+// after the lanes' results were merged into (M, J): 1 = window final (thr valid), 0 = window grown, scan again,
+// -1 = the scenario has no edge point at all
+LCS_D int lcs_edge_step(LcsEdgeQ& q, float M, int J, float& thr) {
+    const bool covers_all = q.x0 <= 0 && q.y0 <= 0 && q.x1 >= q.W - 1 && q.y1 >= q.H - 1;
+    if (J >= 0) {
+        thr = lcs_filter_thr(M, lcs_filter_eta(q.eta0, q.fqx, q.fqy, M));
+        // every candidate lies within D of the query in each axis; the extra 1e-3 m absorbs the float32
+        // rounding of the cell arithmetic (grid points were binned with the same formula)
+        const float D = sqrtf(thr) * 1.000001f + 1e-3f + 4e-7f * (fabsf(q.fqx) + fabsf(q.fqy) + fabsf(q.gx0) + fabsf(q.gy0));
+        const int nx0 = (int)fmaxf(floorf((q.fqx - D - q.gx0) * q.inv), -1.0e6f);
+        const int nx1 = (int)fminf(floorf((q.fqx + D - q.gx0) * q.inv), 1.0e6f);
+        const int ny0 = (int)fmaxf(floorf((q.fqy - D - q.gy0) * q.inv), -1.0e6f);
+        const int ny1 = (int)fminf(floorf((q.fqy + D - q.gy0) * q.inv), 1.0e6f);
+        if (covers_all || (nx0 >= q.x0 && nx1 <= q.x1 && ny0 >= q.y0 && ny1 <= q.y1)) return 1;
+        q.x0 = nx0 < q.x0 ? nx0 : q.x0;
+        q.x1 = nx1 > q.x1 ? nx1 : q.x1;
+        q.y0 = ny0 < q.y0 ? ny0 : q.y0;
+        q.y1 = ny1 > q.y1 ? ny1 : q.y1;
+        return 0;
+    }
+    if (covers_all) return -1;
+    const int r = q.x1 - q.x0; // grow geometrically while the window is empty
+    q.x0 -= r; q.x1 += r; q.y0 -= r; q.y1 += r;
+    return 0;
+}
+// near-tie: float64 evaluation of this lane's candidates; (distance, original index) lexicographic minimum
+LCS_D void lcs_edge_lane_exact(const LcsParams& p, int s, const LcsEdgeQ& q, double qx, double qy, float thr, int lane,
+                               int nlanes, double& bd, int& bi) {
     const double* e64 = p.edge_xy + (size_t)s * p.E * 2;
     const int32_t* gi = p.ge_idx + (size_t)s * p.E;
-    int best = gi[j];
+    bd = lcs_inf_d();
+    bi = 0x7fffffff;
+    const int wx0 = q.x0 < 0 ? 0 : q.x0, wx1 = q.x1 > q.W - 1 ? q.W - 1 : q.x1;
+    const int wy0 = q.y0 < 0 ? 0 : q.y0, wy1 = q.y1 > q.H - 1 ? q.H - 1 : q.y1;
+    for (int y = wy0; y <= wy1; y++) {
+        const int b = q.cs[y * q.W + wx0], e = q.cs[y * q.W + wx1 + 1];
+        for (int k = b + lane; k < e; k += nlanes) {
+            const lcs_f2 pt = q.gp[k];
+            const float dx = pt.x - q.fqx, dy = pt.y - q.fqy;
+            if (dx * dx + dy * dy <= thr) {
+                const int idx = gi[k];
+                const double ee = lcs_norm2_axis(lcs_dsub(e64[2 * idx], qx), lcs_dsub(e64[2 * idx + 1], qy));
+                if (ee < bd || (ee == bd && idx < bi)) { bd = ee; bi = idx; }
+            }
+        }
+    }
+}
+// off-road side test at the nearest point (junction.py:383-385)
+LCS_D bool lcs_edge_side(const LcsParams& p, int s, double qx, double qy, int best) {
+    const double* e64 = p.edge_xy + (size_t)s * p.E * 2;
+    const double* d64 = p.edge_dir + (size_t)s * p.E * 2;
+    const double ax = lcs_dsub(e64[2 * best], qx), ay = lcs_dsub(e64[2 * best + 1], qy);
+    const double cross = lcs_dsub(lcs_dmul(ax, d64[2 * best + 1]), lcs_dmul(ay, d64[2 * best])); // np.cross, 2-vectors
+    return cross < 0;
+}
+// merge of two lanes' filter results (best, second best, index of best)
+LCS_D void lcs_edge_merge(float& m, float& m2, int& j, float om, float om2, int oj) {
+    if (om < m) {
+        m2 = fminf(m, om2);
+        m = om;
+        j = oj;
+    } else {
+        if (om == m && oj < j) j = oj;
+        m2 = fminf(m2, om); // om == m counts as a tie: m2 == m sends the query to the exact phase
+    }
+}
+
+// single-thread driver (rewards kernel)
+LCS_D int lcs_nearest_edge(const LcsParams& p, int s, double qx, double qy, bool* offroad) {
+    *offroad = false;
+    if (p.n_edge[s] == 0) return -1;
+    LcsEdgeQ q;
+    lcs_edge_begin(p, s, qx, qy, q);
+    float m, m2, thr = 0.f;
+    int j;
+    for (;;) {
+        lcs_edge_lane_scan(q, 0, 1, m, m2, j);
+        const int st = lcs_edge_step(q, m, j, thr);
+        if (st < 0) return -1;
+        if (st > 0) break;
+    }
+    int best = p.ge_idx[(size_t)s * p.E + j];
     if (m2 <= thr) {
-        // near-tie: float64 evaluation of every candidate in the window; (distance, index) lexicographic
-        const int wx0 = x0 < 0 ? 0 : x0, wx1 = x1 > W - 1 ? W - 1 : x1;
-        const int wy0 = y0 < 0 ? 0 : y0, wy1 = y1 > H - 1 ? H - 1 : y1;
+        double bd;
+        lcs_edge_lane_exact(p, s, q, qx, qy, thr, 0, 1, bd, best);
+    }
+    *offroad = lcs_edge_side(p, s, qx, qy, best);
+    return best;
+}
+
+// Nearest edge point with a HINT: `hint` is the original index of some edge point (the agent's nearest point of
+// the previous tick, or of its home pose).  Its distance bounds the answer, so only the grid rows / chords that
+// intersect the disk of that radius are scanned, in 32-byte blocks (4 points per load), in a single pass.
+LCS_D int lcs_nearest_edge_hint(const LcsParams& p, int s, double qx, double qy, int hint, bool* offroad) {
+    if (hint < 0) return lcs_nearest_edge(p, s, qx, qy, offroad);
+    *offroad = false;
+    LcsEdgeQ q;
+    lcs_edge_begin(p, s, qx, qy, q);
+    const double* e64 = p.edge_xy + (size_t)s * p.E * 2;
+    const float fqx = q.fqx, fqy = q.fqy;
+    // upper bound of the hint's filter value, then of the candidate radius D0 (monotone in the filter minimum)
+    const float hx = (float)(e64[2 * hint] - qx), hy = (float)(e64[2 * hint + 1] - qy);
+    const float eta = lcs_filter_eta(q.eta0, fqx, fqy, hx * hx + hy * hy);
+    const float b0 = sqrtf(hx * hx + hy * hy) * 1.000001f + 2.1f * eta + 1e-6f;
+    const float thr0 = lcs_filter_thr(b0 * b0 * 1.000001f, eta);
+    const float slack = 1e-3f + 4e-7f * (fabsf(fqx) + fabsf(fqy) + fabsf(q.gx0) + fabsf(q.gy0));
+    const float D0 = sqrtf(thr0) * 1.000001f + slack;
+    const float cell = p.grid_geom[4 * s + 3];
+    int y0 = (int)fmaxf(floorf((fqy - D0 - q.gy0) * q.inv), 0.0f);
+    int y1 = (int)fminf(floorf((fqy + D0 - q.gy0) * q.inv), (float)(q.H - 1));
+    float m = lcs_inf_f(), m2 = lcs_inf_f();
+    int j = -1;
+    for (int y = y0; y <= y1; y++) {
+        // distance from the query to this row's band, shrunk by the rounding slack -> half chord of the disk
+        const float lo = q.gy0 + (float)y * cell, hi = lo + cell;
+        const float dy = fmaxf(fmaxf(lo - fqy, fqy - hi) - slack, 0.0f);
+        const float h2 = D0 * D0 - dy * dy;
+        if (h2 < 0.0f) continue;
+        const float hc = sqrtf(h2) * 1.000001f + slack;
+        const int x0 = (int)fmaxf(floorf((fqx - hc - q.gx0) * q.inv), 0.0f);
+        const int x1 = (int)fminf(floorf((fqx + hc - q.gx0) * q.inv), (float)(q.W - 1));
+        if (x0 > x1) continue;
+        const int b = q.cs[y * q.W + x0] & ~3, e = q.cs[y * q.W + x1 + 1];
+        const lcs_f8* blk = (const lcs_f8*)(q.gp + b);
+        for (int k = b; k < e; k += 4, blk++) { // whole 32-byte blocks: the extra points are real points too
+            const lcs_f8 v = lcs_ld32(blk);
+            LCS_SCAN_POINT(v.v[0], v.v[1], k)
+            LCS_SCAN_POINT(v.v[2], v.v[3], k + 1)
+            LCS_SCAN_POINT(v.v[4], v.v[5], k + 2)
+            LCS_SCAN_POINT(v.v[6], v.v[7], k + 3)
+        }
+    }
+    if (j < 0) return lcs_nearest_edge(p, s, qx, qy, offroad); // cannot happen: the hint itself lies in the disk
+    const float thr = lcs_filter_thr(m, lcs_filter_eta(q.eta0, fqx, fqy, m));
+    if (thr > thr0) return lcs_nearest_edge(p, s, qx, qy, offroad); // idem (monotonicity); kept as a guard
+    int best = p.ge_idx[(size_t)s * p.E + j];
+    if (m2 <= thr) {
+        const int32_t* gi = p.ge_idx + (size_t)s * p.E;
         double bd = lcs_inf_d();
         best = 0x7fffffff;
-        for (int y = wy0; y <= wy1; y++) {
-            const int b = cs[y * W + wx0], e = cs[y * W + wx1 + 1];
+        for (int y = y0; y <= y1; y++) {
+            const float lo = q.gy0 + (float)y * cell, hi = lo + cell;
+            const float dy = fmaxf(fmaxf(lo - fqy, fqy - hi) - slack, 0.0f);
+            const float h2 = D0 * D0 - dy * dy;
+            if (h2 < 0.0f) continue;
+            const float hc = sqrtf(h2) * 1.000001f + slack;
+            const int x0 = (int)fmaxf(floorf((fqx - hc - q.gx0) * q.inv), 0.0f);
+            const int x1 = (int)fminf(floorf((fqx + hc - q.gx0) * q.inv), (float)(q.W - 1));
+            if (x0 > x1) continue;
+            const int b = q.cs[y * q.W + x0] & ~3, e = q.cs[y * q.W + x1 + 1];
             for (int k = b; k < e; k++) {
-                lcs_f2 pt = gp[k];
-                float dx = pt.x - fqx, dy = pt.y - fqy;
-                float d = dx * dx + dy * dy;
-                if (d <= thr) {
+                const lcs_f2 pt = q.gp[k];
+                const float dx = pt.x - fqx, dyy = pt.y - fqy;
+                if (dx * dx + dyy * dyy <= thr) {
                     const int idx = gi[k];
-                    double ee = lcs_norm2_axis(lcs_dsub(e64[2 * idx], qx), lcs_dsub(e64[2 * idx + 1], qy));
+                    const double ee = lcs_norm2_axis(lcs_dsub(e64[2 * idx], qx), lcs_dsub(e64[2 * idx + 1], qy));
                     if (ee < bd || (ee == bd && idx < best)) { bd = ee; best = idx; }
                 }
             }
         }
     }
-    const double* d64 = p.edge_dir + (size_t)s * p.E * 2;
-    const double ax = lcs_dsub(e64[2 * best], qx), ay = lcs_dsub(e64[2 * best + 1], qy);
-    const double cross = lcs_dsub(lcs_dmul(ax, d64[2 * best + 1]), lcs_dmul(ay, d64[2 * best])); // np.cross, 2-vectors
-    *offroad = cross < 0;
+    *offroad = lcs_edge_side(p, s, qx, qy, best);
     return best;
 }
 
@@ -595,6 +732,7 @@ LCS_D void lcs_reset_agent(const LcsParams& p, int s, int a) {
     p.stale_valid[ia] = 0;
     p.coll_count[ia] = 0;
     p.nearest_edge[ia] = -1;
+    p.edge_hint[ia] = p.home_edge[ia];
     p.offroad[ia] = 0;
     for (int k = 0; k < LCS_H * 5; k++) p.ring[ia * LCS_H * 5 + k] = 0.0;
     if (a >= p.n_agents[s]) { // padding agents: inert but defined
@@ -610,6 +748,8 @@ LCS_D void lcs_reset_agent(const LcsParams& p, int s, int a) {
             p.traj_vel[2 * t] = p.traj_vel0[2 * t];
             p.traj_vel[2 * t + 1] = p.traj_vel0[2 * t + 1];
             p.traj_h[t] = p.traj_h0[t];
+        }
+        for (int k = 0; k < p.Tp; k++) {
             const size_t f = lcs_tf_index(p, s, k, a);
             p.tf_xy[f] = p.tf_xy0[f];
         }
@@ -776,12 +916,6 @@ LCS_D int lcs_phase_init(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThr
 LCS_D void lcs_phase_update(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
     const int a = lcs_phase_init(p, sm, s, tid, t);
     if (a < 0) return;
-#ifndef LCSIM_HOSTEMU
-    if (p.prefetch) { // pull this agent's filter column towards L2 while the dependent state loads run
-        const lcs_f4* tf = (const lcs_f4*)p.tf_xy + (size_t)s * p.T2 * p.Ap + a;
-        for (int k2 = 0; k2 < p.T2; k2++) asm volatile("prefetch.global.L2 [%0];" ::"l"(tf + (size_t)k2 * p.Ap));
-    }
-#endif
     LcsUpd u;
     LcsScan sc;
     lcs_update_pre(p, s, a, u);
@@ -878,6 +1012,12 @@ LCS_D void lcs_phase_publish(const LcsParams& p, LcsSmem& sm, int s, int tid) {
     r.w = 5e-5f + 1.2e-7f * (fabsf(r.x) + fabsf(r.y)); // float32 coordinate error
     r.z = 0.5f * sqrtf(L * L + W * W) * 1.00001f + r.w; // half diagonal, rounded up
     sm.crec[tid] = r;
+    lcs_f4 r2;
+    r2.x = (float)ex[3];
+    r2.y = (float)ex[4];
+    r2.z = 0.5f * L;
+    r2.w = 0.5f * W;
+    sm.crec2[tid] = r2;
 }
 
 LCS_D void lcs_push_pair(LcsSmem& sm, int cap, int i, int j, bool* overflow) {
@@ -938,22 +1078,35 @@ LCS_D void lcs_phase_lead_out(const LcsParams& p, LcsSmem& sm, int s, int tid) {
     p.lead_v[ia] = valid ? vl : 0.0;
 }
 
+// float64 narrowphase of one queued pair (the float32 test could not decide it)
 LCS_D void lcs_collide_eval(LcsSmem& sm, int i, int j) {
-    const double *ea = sm.ex + 8 * sm.act2[i], *eb = sm.ex + 8 * sm.act2[j];
-    int r = lcs_sat_f32(ea, eb);
-    if (r < 0) r = lcs_collide(ea, eb) ? 1 : 0;
-    if (r) {
+    if (lcs_collide(sm.ex + 8 * sm.act2[i], sm.ex + 8 * sm.act2[j])) {
         lcs_atomic_add(&sm.cnt[i], 1);
         lcs_atomic_add(&sm.cnt[j], 1);
     }
 }
+// float32 SAT on the slot records; dx, dy carry the coordinate slack of both boxes -> wider margin
+LCS_D int lcs_sat_rec(const lcs_f4 a, const lcs_f4 a2, const lcs_f4 b, const lcs_f4 b2) {
+    const float dx = b.x - a.x, dy = b.y - a.y;
+    const float ca = a2.x, sa = a2.y, cb = b2.x, sb = b2.y;
+    const float ac = fabsf(ca * cb + sa * sb), as = fabsf(sb * ca - cb * sa);
+    const float t1 = fabsf(dx * ca + dy * sa) - (a2.z + b2.z * ac + b2.w * as);
+    const float t2 = fabsf(dy * ca - dx * sa) - (a2.w + b2.z * as + b2.w * ac);
+    const float t3 = fabsf(dx * cb + dy * sb) - (b2.z + a2.z * ac + a2.w * as);
+    const float t4 = fabsf(dy * cb - dx * sb) - (b2.w + a2.z * as + a2.w * ac);
+    const float tmax = fmaxf(fmaxf(t1, t2), fmaxf(t3, t4));
+    const float mrg = LCS_SAT_MARGIN + 1.5f * (a.w + b.w);
+    if (tmax > mrg) return 0;
+    if (tmax < -mrg) return 1;
+    return -1;
+}
 
-// Phase E1: check_collision_all (manager.py:313-327 -> polygon.py:195-235), bounding-circle broadphase.
-// Every unordered pair of slots is visited once: slot i tests i+1 .. i+n/2 (mod n).
+// Phase E1: check_collision_all (manager.py:313-327 -> polygon.py:195-235): bounding-circle broadphase, then
+// a float32 SAT on the survivors.  Every unordered pair of slots is visited once: slot i tests i+1 .. i+n/2 (mod n).
 LCS_D void lcs_phase_collision_filter(const LcsParams& p, LcsSmem& sm, int s, int tid) {
     const int n = sm.misc[1], cap = LCS_QPER * p.Ap;
     if (tid >= n) return;
-    const lcs_f4 me = sm.crec[tid];
+    const lcs_f4 me = sm.crec[tid], me2 = sm.crec2[tid];
     const int half = n >> 1;
     for (int d = 1; d <= half; d++) {
         int j = tid + d;
@@ -962,13 +1115,19 @@ LCS_D void lcs_phase_collision_filter(const LcsParams& p, LcsSmem& sm, int s, in
         const float dx = ot.x - me.x, dy = ot.y - me.y;
         const float rr = ot.z + me.z; // both radii already include their coordinate slack
         if (dx * dx + dy * dy <= rr * rr * 1.00001f && !(2 * d == n && tid >= half)) {
-            bool overflow;
-            lcs_push_pair(sm, cap, tid, j, &overflow);
-            if (overflow) lcs_collide_eval(sm, tid, j);
+            const int r = lcs_sat_rec(me, me2, ot, sm.crec2[j]);
+            if (r > 0) {
+                lcs_atomic_add(&sm.cnt[tid], 1);
+                lcs_atomic_add(&sm.cnt[j], 1);
+            } else if (r < 0) { // within the float32 error of touching: float64 decides (rare)
+                bool overflow;
+                lcs_push_pair(sm, cap, tid, j, &overflow);
+                if (overflow) lcs_collide_eval(sm, tid, j);
+            }
         }
     }
 }
-// Phase E2: narrowphase over the queued pairs (float32 SAT, float64 SAT when within the margin)
+// Phase E2: float64 narrowphase over the queued (undecided) pairs
 LCS_D void lcs_phase_collision_drain(const LcsParams& p, LcsSmem& sm, int s, int tid) {
     const int cap = LCS_QPER * p.Ap;
     const int n = sm.misc[6] < cap ? sm.misc[6] : cap;
@@ -985,8 +1144,9 @@ LCS_D void lcs_phase_offroad(const LcsParams& p, LcsSmem& sm, int s, int tid, Lc
     const int a = sm.act2[tid];
     const size_t ia = (size_t)s * p.Ap + a;
     bool off;
-    const int k = lcs_nearest_edge(p, s, sm.ex[8 * a], sm.ex[8 * a + 1], &off);
+    const int k = lcs_nearest_edge_hint(p, s, sm.ex[8 * a], sm.ex[8 * a + 1], p.edge_hint[ia], &off);
     p.nearest_edge[ia] = k;
+    p.edge_hint[ia] = k;
     p.offroad[ia] = off ? 1 : 0;
     t.off = off ? 1 : 0;
 }
