@@ -40,6 +40,10 @@ static cudaError_t cudaGetLastError() { return 0; }
 
 #include "lcsim_core.cuh"
 
+#ifndef LCS_MIN_CTAS
+#define LCS_MIN_CTAS 7 // resident CTAs per SM the 128-thread tick kernel is compiled for (register cap)
+#endif
+
 // ------------------------------------------------------------------------------------ kernels
 
 // One CTA per scenario, one thread per active-list slot; the whole tick in one launch (reference:
@@ -74,9 +78,9 @@ static cudaError_t cudaGetLastError() { return 0; }
 
 #ifndef LCSIM_HOSTEMU
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? 8 : 1)) lcs_tick_kernel_ldg(const LcsParams p) {
+__global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_tick_kernel_ldg(const LcsParams p) {
     extern __shared__ __align__(128) unsigned char lcs_smem_raw[];
-    const int s = blockIdx.x, tid = threadIdx.x;
+    const int s = blockIdx.x + p.s0, tid = threadIdx.x;
     if (p.mode == 1 && p.reset_mask && !p.reset_mask[s]) return;
     LcsSmem sm;
     lcs_smem_carve(sm, lcs_smem_raw, p.Ap);
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? 8 : 1)) lcs_tick_kernel_l
 // boundary into p.dbg[s][*]; used only by profiles/phase_clocks.py.
 __global__ void __launch_bounds__(128) lcs_tick_kernel_clk(const LcsParams p) {
     extern __shared__ __align__(128) unsigned char lcs_smem_raw[];
-    const int s = blockIdx.x, tid = threadIdx.x;
+    const int s = blockIdx.x + p.s0, tid = threadIdx.x;
     if (p.mode == 1) return;
     LcsSmem sm;
     lcs_smem_carve(sm, lcs_smem_raw, p.Ap);
@@ -155,21 +159,24 @@ __global__ void __launch_bounds__(128) lcs_tick_kernel_clk(const LcsParams p) {
 
 static cudaError_t lcs_configure_kernels() { return cudaSuccess; }
 
-static void lcs_launch_tick(const LcsParams& p, cudaStream_t stream) {
+static void lcs_launch_tick(const LcsParams& pfull, cudaStream_t stream, int s0 = 0, int ns = -1) {
+    LcsParams p = pfull;
 #ifndef LCSIM_HOSTEMU
+    p.s0 = s0;
+    const int nblk = ns < 0 ? p.S : ns;
     if (p.dbg && p.Ap == 128 && p.mode == 0) {
-        lcs_tick_kernel_clk<<<p.S, p.Ap, lcs_smem_bytes(p.Ap), stream>>>(p);
+        lcs_tick_kernel_clk<<<nblk, p.Ap, lcs_smem_bytes(p.Ap), stream>>>(p);
         return;
     }
     const size_t smem = lcs_smem_bytes(p.Ap);
     if (p.Ap <= 128)
-        lcs_tick_kernel_ldg<128><<<p.S, p.Ap, smem, stream>>>(p);
+        lcs_tick_kernel_ldg<128><<<nblk, p.Ap, smem, stream>>>(p);
     else if (p.Ap <= 256)
-        lcs_tick_kernel_ldg<256><<<p.S, p.Ap, smem, stream>>>(p);
+        lcs_tick_kernel_ldg<256><<<nblk, p.Ap, smem, stream>>>(p);
     else if (p.Ap <= 512)
-        lcs_tick_kernel_ldg<512><<<p.S, p.Ap, smem, stream>>>(p);
+        lcs_tick_kernel_ldg<512><<<nblk, p.Ap, smem, stream>>>(p);
     else
-        lcs_tick_kernel_ldg<1024><<<p.S, p.Ap, smem, stream>>>(p);
+        lcs_tick_kernel_ldg<1024><<<nblk, p.Ap, smem, stream>>>(p);
 #else
     const int Ap = p.Ap;
     std::vector<unsigned char> raw(lcs_smem_bytes(Ap) + 16);
@@ -423,6 +430,11 @@ struct lcsim_b200_engine {
     double* s_tab0 = nullptr;
     bool uploaded = false;
     int64_t launches = 0;
+    int n_groups = 1; // rollout() splits the batch into this many scenario groups, one stream each
+#ifndef LCSIM_HOSTEMU
+    cudaStream_t gstream[8] = {};
+    cudaEvent_t gevent[9] = {};
+#endif
     std::string err;
 };
 
@@ -467,6 +479,12 @@ extern "C" int64_t lcsim_b200_launch_count(const lcsim_b200_engine* e) { return 
 extern "C" void lcsim_b200_destroy(lcsim_b200_engine* e) {
     if (!e) return;
     for (void* q : e->allocs) cudaFree(q);
+#ifndef LCSIM_HOSTEMU
+    for (int g = 0; g < 8; g++)
+        if (e->gstream[g]) cudaStreamDestroy(e->gstream[g]);
+    for (int g = 0; g < 9; g++)
+        if (e->gevent[g]) cudaEventDestroy(e->gevent[g]);
+#endif
     delete e;
 }
 
@@ -479,6 +497,11 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || d->device < 0 || d->device >= ndev) return LCSIM_B200_ERR_CUDA;
     if (cudaSetDevice(d->device) != cudaSuccess) return LCSIM_B200_ERR_CUDA;
     if (lcs_configure_kernels() != cudaSuccess) return LCSIM_B200_ERR_CUDA;
+    int n_groups = 1;
+    {
+        const char* env = getenv("LCSIM_B200_GROUPS");
+        if (env) n_groups = std::min(8, std::max(1, atoi(env)));
+    }
 
     lcsim_b200_engine* e = new lcsim_b200_engine();
     e->desc = *d;
@@ -496,7 +519,18 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     p.no_static = d->no_static;
     p.allow_new_obj = d->allow_new_obj;
     p.with_metrics = d->with_metrics;
+    {
+        const char* env = getenv("LCSIM_B200_PREFETCH");
+        p.prefetch = env && env[0] == '1'; // measured neutral-to-negative on B200 (profiles/NOTES_r1.md): off by default
+    }
     *out = e; // returned even on failure below so the caller can read last_error and destroy
+    e->n_groups = n_groups;
+#ifndef LCSIM_HOSTEMU
+    if (n_groups > 1) {
+        for (int g = 0; g < n_groups; g++) LCS_CUDA(e, cudaStreamCreateWithFlags(&e->gstream[g], cudaStreamNonBlocking));
+        for (int g = 0; g <= n_groups; g++) LCS_CUDA(e, cudaEventCreateWithFlags(&e->gevent[g], cudaEventDisableTiming));
+    }
+#endif
     const size_t S = p.S, SA = S * p.Ap, SAT = SA * p.T, SE = S * p.E;
     LCS_ALLOC(e, p.n_agents, S);
     LCS_ALLOC(e, p.ads_index, S);
@@ -852,6 +886,30 @@ extern "C" int lcsim_b200_step(lcsim_b200_engine* e, const int32_t* act_agent, c
 
 extern "C" int lcsim_b200_rollout(lcsim_b200_engine* e, int n_ticks, void* stream) {
     if (!e || n_ticks < 0) return LCSIM_B200_ERR_ARG;
+#ifndef LCSIM_HOSTEMU
+    if (e->n_groups > 1 && e->uploaded && n_ticks > 0) {
+        // Scenarios are independent, so the batch is stepped as n_groups sub-batches on their own streams:
+        // their ticks drift apart in time and the memory-bound and compute-bound phases of different groups
+        // overlap instead of every CTA of the chip hitting the same phase at once.
+        const int G = e->n_groups;
+        cudaStream_t us = (cudaStream_t)stream;
+        LCS_CUDA(e, cudaEventRecord(e->gevent[G], us));
+        LcsParams q = e->p;
+        q.mode = 0;
+        q.K = 0;
+        for (int g = 0; g < G; g++) {
+            const int s0 = (int)((long long)q.S * g / G), s1 = (int)((long long)q.S * (g + 1) / G);
+            LCS_CUDA(e, cudaStreamWaitEvent(e->gstream[g], e->gevent[G], 0));
+            if (s1 > s0)
+                for (int k = 0; k < n_ticks; k++) lcs_launch_tick(q, e->gstream[g], s0, s1 - s0);
+            LCS_CUDA(e, cudaEventRecord(e->gevent[g], e->gstream[g]));
+            LCS_CUDA(e, cudaStreamWaitEvent(us, e->gevent[g], 0));
+        }
+        e->launches += (int64_t)n_ticks * G;
+        LCS_CUDA(e, cudaGetLastError());
+        return 0;
+    }
+#endif
     for (int k = 0; k < n_ticks; k++) {
         int rc = lcsim_b200_step(e, nullptr, nullptr, nullptr, 0, stream);
         if (rc) return rc;

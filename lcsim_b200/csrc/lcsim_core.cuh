@@ -135,11 +135,14 @@ struct LcsParams {
     int32_t K;
     // ---- launch mode
     long long* dbg; // [S][16] phase clocks (debug builds of the launch only)
+    int32_t prefetch; // LCSIM_B200_PREFETCH=1 (default off): early L2 prefetch of the per-agent lines
+    int32_t s0; // first scenario of this launch (sub-batch launches)
     int32_t mode; // 0 = step, 1 = reset
     const uint8_t* reset_mask; // [S] or null
 };
 
 // Shared memory of one CTA (Ap threads).  Carved from one dynamic allocation.
+#define LCS_CAND 8 // private broadphase list per thread
 #define LCS_QPER 8 // pair-queue capacity per thread (queue = LCS_QPER * Ap candidate pairs)
 struct LcsSmem {
     double* ex; // [Ap][8]  x, y, v, cos h, sin h, L, W, h          (agent index)
@@ -151,6 +154,7 @@ struct LcsSmem {
     int32_t* dlist; // [Ap] agents activated this tick, in waiting-list order
     int32_t* cnt; // [Ap] collision counts (slot index)
     uint32_t* queue; // [LCS_QPER * Ap] candidate pairs (slot_i << 16 | slot_j)
+    uint16_t* cand; // [LCS_CAND][Ap] per-thread broadphase survivors
     uint32_t* mask; // [3][32] ballot words: finished, popped, activated
     int32_t* misc; // [8] n_old, n_new, collision sum, off-road sum, tick, wait_ptr, queue length
 };
@@ -161,7 +165,7 @@ static inline
 __host__ __device__ inline
 #endif
 size_t lcs_smem_bytes(int Ap) {
-    return (size_t)Ap * (64 + 8 + 32 + 4 * 4 + 4 * LCS_QPER) + 3 * 32 * 4 + 8 * 4 + 64;
+    return (size_t)Ap * (64 + 8 + 32 + 4 * 4 + 4 * LCS_QPER + 2 * LCS_CAND) + 3 * 32 * 4 + 8 * 4 + 64;
 }
 
 LCS_D void lcs_smem_carve(LcsSmem& sm, unsigned char* base, int Ap) {
@@ -176,7 +180,8 @@ LCS_D void lcs_smem_carve(LcsSmem& sm, unsigned char* base, int Ap) {
     sm.cnt = (int32_t*)p; p += (size_t)Ap * 4;
     sm.queue = (uint32_t*)p; p += (size_t)Ap * 4 * LCS_QPER;
     sm.mask = (uint32_t*)p; p += 3 * 32 * 4;
-    sm.misc = (int32_t*)p;
+    sm.misc = (int32_t*)p; p += 8 * 4;
+    sm.cand = (uint16_t*)p;
 }
 
 // ------------------------------------------------------------------ small float64 helpers
@@ -260,7 +265,8 @@ LCS_D lcs_f8 lcs_ld32(const lcs_f8* q) {
     return *q;
 #else
     lcs_f8 r;
-    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    // not volatile: the scheduler must be free to issue several of these before the first use
+    asm("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
                  : "l"(q));
     return r;
@@ -303,8 +309,15 @@ LCS_D void lcs_scan_quad(LcsScan& sc, const lcs_f8 v, int k) {
 LCS_D void lcs_scan_global(const LcsParams& p, int s, int a, int len, LcsScan& sc) {
     const lcs_f8* tf = (const lcs_f8*)(p.tf_xy + lcs_tf_index(p, s, 0, a));
     const int n4 = (len + 3) >> 2;
-#pragma unroll 4
-    for (int k4 = 0; k4 < n4; k4++) lcs_scan_quad(sc, lcs_ld32(tf + k4), 4 * k4);
+    for (int k4 = 0; k4 < n4; k4 += 4) { // four 32-byte loads in flight, then their 16 points
+        lcs_f8 v[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (k4 + r < n4) v[r] = lcs_ld32(tf + k4 + r);
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (k4 + r < n4) lcs_scan_quad(sc, v[r], 4 * (k4 + r));
+    }
 }
 // the cursor from a finished scan: unique candidate -> done; near-tie -> float64 on every candidate,
 // first minimum wins (np.argmin)
@@ -491,24 +504,52 @@ LCS_D int lcs_nearest_edge_hint(const LcsParams& p, int s, double qx, double qy,
     int y1 = (int)fminf(floorf((fqy + D0 - q.gy0) * q.inv), (float)(q.H - 1));
     float m = lcs_inf_f(), m2 = lcs_inf_f();
     int j = -1;
-    for (int y = y0; y <= y1; y++) {
-        // distance from the query to this row's band, shrunk by the rounding slack -> half chord of the disk
-        const float lo = q.gy0 + (float)y * cell, hi = lo + cell;
-        const float dy = fmaxf(fmaxf(lo - fqy, fqy - hi) - slack, 0.0f);
-        const float h2 = D0 * D0 - dy * dy;
-        if (h2 < 0.0f) continue;
-        const float hc = sqrtf(h2) * 1.000001f + slack;
-        const int x0 = (int)fmaxf(floorf((fqx - hc - q.gx0) * q.inv), 0.0f);
-        const int x1 = (int)fminf(floorf((fqx + hc - q.gx0) * q.inv), (float)(q.W - 1));
-        if (x0 > x1) continue;
-        const int b = q.cs[y * q.W + x0] & ~3, e = q.cs[y * q.W + x1 + 1];
-        const lcs_f8* blk = (const lcs_f8*)(q.gp + b);
-        for (int k = b; k < e; k += 4, blk++) { // whole 32-byte blocks: the extra points are real points too
-            const lcs_f8 v = lcs_ld32(blk);
-            LCS_SCAN_POINT(v.v[0], v.v[1], k)
-            LCS_SCAN_POINT(v.v[2], v.v[3], k + 1)
-            LCS_SCAN_POINT(v.v[4], v.v[5], k + 2)
-            LCS_SCAN_POINT(v.v[6], v.v[7], k + 3)
+    // rows are handled four at a time: first every row's span lookup (8 independent loads), then block i of
+    // every row together (4 independent 32-byte loads) -> few dependent round trips instead of one per block
+    for (int yb = y0; yb <= y1; yb += 4) {
+        int bs[4], nb[4], nbmax = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int y = yb + r;
+            bs[r] = 0;
+            nb[r] = 0;
+            if (y <= y1) {
+                // distance from the query to this row's band, shrunk by the rounding slack -> half chord
+                const float lo = q.gy0 + (float)y * cell, hi = lo + cell;
+                const float dy = fmaxf(fmaxf(lo - fqy, fqy - hi) - slack, 0.0f);
+                const float h2 = D0 * D0 - dy * dy;
+                if (h2 >= 0.0f) {
+                    const float hc = sqrtf(h2) * 1.000001f + slack;
+                    const int x0 = (int)fmaxf(floorf((fqx - hc - q.gx0) * q.inv), 0.0f);
+                    const int x1 = (int)fminf(floorf((fqx + hc - q.gx0) * q.inv), (float)(q.W - 1));
+                    if (x0 <= x1) {
+                        bs[r] = q.cs[y * q.W + x0];
+                        nb[r] = q.cs[y * q.W + x1 + 1];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int b = bs[r] & ~3; // whole 32-byte blocks: the extra points are real points too
+            nb[r] = nb[r] > b ? (nb[r] - b + 3) >> 2 : 0;
+            bs[r] = b;
+            nbmax = nb[r] > nbmax ? nb[r] : nbmax;
+        }
+        for (int i = 0; i < nbmax; i++) {
+            lcs_f8 v[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                if (i < nb[r]) v[r] = lcs_ld32((const lcs_f8*)(q.gp + bs[r]) + i);
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                if (i < nb[r]) {
+                    const int k = bs[r] + 4 * i;
+                    LCS_SCAN_POINT(v[r].v[0], v[r].v[1], k)
+                    LCS_SCAN_POINT(v[r].v[2], v[r].v[3], k + 1)
+                    LCS_SCAN_POINT(v[r].v[4], v[r].v[5], k + 2)
+                    LCS_SCAN_POINT(v[r].v[6], v[r].v[7], k + 3)
+                }
         }
     }
     if (j < 0) return lcs_nearest_edge(p, s, qx, qy, offroad); // cannot happen: the hint itself lies in the disk
@@ -889,7 +930,45 @@ LCS_D bool lcs_update_post(const LcsParams& p, LcsSmem& sm, int s, int a, const 
 
 // Phase A: shared-memory init + update (step mode: thread = old list slot) or reset (thread = agent).
 // lcs_phase_init returns the agent this thread updates (-1: none).
+#ifndef LCSIM_HOSTEMU
+LCS_D void lcs_pf(const void* q) { asm volatile("prefetch.global.L2 [%0];" ::"l"(q)); }
+// Thread = agent index: start every cache line this tick will need for the agent on its way to L2 now, so the
+// dependent loads of the slot-mapped phases (state -> waypoint -> filter row -> ring -> edge hint) hit L2
+// instead of paying a DRAM round trip each.
+LCS_D void lcs_prefetch_agent(const LcsParams& p, int s, int a) {
+    const size_t ia = (size_t)s * p.Ap + a;
+    if (a >= p.A || p.status[ia] != LCS_ACTIVE) return;
+    const int cur = p.cursor[ia], hint = p.edge_hint[ia], head = p.ring_head[ia];
+    lcs_pf(p.pose64 + 4 * ia);
+    lcs_pf(p.traj_len + ia);
+    lcs_pf(p.ring_count + ia);
+    lcs_pf(p.traj_f32 + ia);
+    lcs_pf(p.stale_valid + ia);
+    lcs_pf(p.length + ia);
+    lcs_pf(p.width + ia);
+    if (p.reactive) {
+        lcs_pf(p.lead_valid + ia);
+        lcs_pf(p.lead_dis + ia);
+        lcs_pf(p.lead_v + ia);
+    }
+    const char* row = (const char*)(p.tf_xy + lcs_tf_index(p, s, 0, a));
+    for (int b = 0; b < p.Tp * 8; b += 128) lcs_pf(row + b);
+    const size_t t = ia * p.T + (cur + 1 < p.T ? cur + 1 : cur);
+    lcs_pf(p.traj_xy + 2 * t);
+    lcs_pf(p.traj_vel + 2 * t);
+    lcs_pf(p.traj_h + t);
+    lcs_pf(p.ring + (ia * LCS_H + head) * 5);
+    if (p.with_metrics && hint >= 0) {
+        lcs_pf(p.edge_xy + ((size_t)s * p.E + hint) * 2);
+        lcs_pf(p.edge_dir + ((size_t)s * p.E + hint) * 2);
+    }
+}
+#endif
+
 LCS_D int lcs_phase_init(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
+#ifndef LCSIM_HOSTEMU
+    if (p.mode == 0 && p.prefetch) lcs_prefetch_agent(p, s, tid);
+#endif
     for (int k = tid; k < 96; k += p.Ap) sm.mask[k] = 0;
     const int n_old = p.mode == 1 ? 0 : p.n_active[s];
     if (tid == 0) {
@@ -1103,11 +1182,25 @@ LCS_D int lcs_sat_rec(const lcs_f4 a, const lcs_f4 a2, const lcs_f4 b, const lcs
 
 // Phase E1: check_collision_all (manager.py:313-327 -> polygon.py:195-235): bounding-circle broadphase, then
 // a float32 SAT on the survivors.  Every unordered pair of slots is visited once: slot i tests i+1 .. i+n/2 (mod n).
+LCS_D void lcs_collision_narrow(LcsSmem& sm, int cap, int i, int j, const lcs_f4 me, const lcs_f4 me2) {
+    const int r = lcs_sat_rec(me, me2, sm.crec[j], sm.crec2[j]);
+    if (r > 0) {
+        lcs_atomic_add(&sm.cnt[i], 1);
+        lcs_atomic_add(&sm.cnt[j], 1);
+    } else if (r < 0) { // within the float32 error of touching: float64 decides (rare)
+        bool overflow;
+        lcs_push_pair(sm, cap, i, j, &overflow);
+        if (overflow) lcs_collide_eval(sm, i, j);
+    }
+}
 LCS_D void lcs_phase_collision_filter(const LcsParams& p, LcsSmem& sm, int s, int tid) {
     const int n = sm.misc[1], cap = LCS_QPER * p.Ap;
     if (tid >= n) return;
     const lcs_f4 me = sm.crec[tid], me2 = sm.crec2[tid];
     const int half = n >> 1;
+    int nc = 0;
+    // the circle test runs over all partners first; the survivors (a handful per thread) are kept in a private
+    // list so that the warp does not serialise a SAT evaluation into almost every iteration of this loop
     for (int d = 1; d <= half; d++) {
         int j = tid + d;
         if (j >= n) j -= n;
@@ -1115,17 +1208,13 @@ LCS_D void lcs_phase_collision_filter(const LcsParams& p, LcsSmem& sm, int s, in
         const float dx = ot.x - me.x, dy = ot.y - me.y;
         const float rr = ot.z + me.z; // both radii already include their coordinate slack
         if (dx * dx + dy * dy <= rr * rr * 1.00001f && !(2 * d == n && tid >= half)) {
-            const int r = lcs_sat_rec(me, me2, ot, sm.crec2[j]);
-            if (r > 0) {
-                lcs_atomic_add(&sm.cnt[tid], 1);
-                lcs_atomic_add(&sm.cnt[j], 1);
-            } else if (r < 0) { // within the float32 error of touching: float64 decides (rare)
-                bool overflow;
-                lcs_push_pair(sm, cap, tid, j, &overflow);
-                if (overflow) lcs_collide_eval(sm, tid, j);
-            }
+            if (nc < LCS_CAND)
+                sm.cand[nc++ * p.Ap + tid] = (uint16_t)j;
+            else
+                lcs_collision_narrow(sm, cap, tid, j, me, me2);
         }
     }
+    for (int k = 0; k < nc; k++) lcs_collision_narrow(sm, cap, tid, sm.cand[k * p.Ap + tid], me, me2);
 }
 // Phase E2: float64 narrowphase over the queued (undecided) pairs
 LCS_D void lcs_phase_collision_drain(const LcsParams& p, LcsSmem& sm, int s, int tid) {

@@ -143,6 +143,10 @@ def load() -> C.CDLL:
     """The CUDA library.  Built on first use when nvcc is present; otherwise it must already be in-tree."""
     global _LIB
     if _LIB is None:
+        alt = os.environ.get("LCSIM_B200_LIB")  # experiments: another build of the same CUDA source
+        if alt:
+            _LIB = bind(alt)
+            return _LIB
         if _nvcc() is not None:
             build()
         if not os.path.exists(LIB_PATH):
