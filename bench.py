@@ -198,46 +198,37 @@ def run_b200(args):
     e2e_val, h2d, d2h = None, 0, 0
     if not args.kernel_only:
         # ------------------------------------------------------------- end-to-end arm ("e2e"): host buffers
-        # per tick: H2D of the ADS action of every scenario from pinned memory, step, rewards kernel, D2H of the
-        # reward terms / terminated / truncated; per rollout: D2H of the final state a host caller reads.
-        act_agent = torch.from_numpy(np.ascontiguousarray(sb.ads_index.reshape(S, 1))).pin_memory()
-        act_type = torch.full((S, 1), native.ACT_BICYCLE, dtype=torch.int32).pin_memory()
+        # The reference-facing call: lcsim_b200_env_step == BicycleSingleEnv.step for all S scenarios.  Every tick the
+        # normalised ADS action of every scenario goes host -> device from pinned memory and reward / terms / route /
+        # terminated / truncated come back device -> host; the host reads them (stream sync) before the next tick,
+        # like an RL loop does.  Every rollout ends with the D2H of the state a host caller reads.
         rng = np.random.default_rng(1)
-        act_data = torch.zeros(N_TICKS, S, 1, 5, dtype=torch.float64)
-        act_data[..., 0] = torch.from_numpy(rng.uniform(-2, 2, (N_TICKS, S, 1)))
-        act_data[..., 1] = torch.from_numpy(rng.uniform(-0.05, 0.05, (N_TICKS, S, 1)))
-        act_data = act_data.pin_memory()
-        d_agent = torch.empty(S, 1, dtype=torch.int32, device=dev)
-        d_type = torch.empty(S, 1, dtype=torch.int32, device=dev)
-        d_data = torch.empty(S, 1, 5, dtype=torch.float64, device=dev)
-        h_terms = torch.empty(S, native.N_REWARD_TERMS, dtype=torch.float64).pin_memory()
-        h_flags = torch.empty(2, S, dtype=torch.uint8).pin_memory()
+        acts = torch.from_numpy(np.stack([rng.uniform(-0.3, 0.3, (N_TICKS, S)), rng.uniform(-0.2, 0.2, (N_TICKS, S))],
+                                         axis=-1)).contiguous().pin_memory()
+        h_out = torch.empty(S * native.ENV_OUT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        out_np = h_out.numpy().view(native.ENV_OUT_DTYPE)
+        coef = {"forward": 2, "collision": 5, "smooth": 1, "destination": 1}
         h_pose = torch.empty(S, be.A, 4, dtype=torch.float32).pin_memory()
         h_int = torch.empty(3, S, be.A, dtype=torch.int32).pin_memory()
         h_stats = torch.empty(native.N_STATS, dtype=torch.int64).pin_memory()
         h2d = d2h = 0
+        ret = 0.0
 
         def e2e_rollout(count=False):
-            nonlocal h2d, d2h
+            nonlocal h2d, d2h, ret
             be.reset()
             for k in range(N_TICKS):
-                d_agent.copy_(act_agent, non_blocking=True)
-                d_type.copy_(act_type, non_blocking=True)
-                d_data.copy_(act_data[k], non_blocking=True)
-                be.step(d_agent, d_type, d_data)
-                r = be.rewards()
-                h_terms.copy_(r["terms"], non_blocking=True)
-                h_flags[0].copy_(r["terminated"], non_blocking=True)
-                h_flags[1].copy_(r["truncated"], non_blocking=True)
+                be.env_step(acts[k], h_out, coef=coef, sync=True)
+                ret += float(out_np["reward"][0])  # the host consumes the result
                 if count:
-                    h2d += act_agent.numel() * 4 + act_type.numel() * 4 + act_data[k].numel() * 8
-                    d2h += h_terms.numel() * 8 + 2 * S
+                    h2d += acts[k].numel() * 8
+                    d2h += h_out.numel()
             h_pose.copy_(be.pose32, non_blocking=True)
             h_int[0].copy_(be.status, non_blocking=True)
             h_int[1].copy_(be.coll_count, non_blocking=True)
             h_int[2].copy_(be.nearest_edge, non_blocking=True)
             h_stats.copy_(be.episode_stats(), non_blocking=True)
-            torch.cuda.current_stream(dev).synchronize()  # the host reads the result of the step
+            torch.cuda.current_stream(dev).synchronize()
             if count:
                 d2h += h_pose.numel() * 4 + h_int.numel() * 4 + h_stats.numel() * 8
             return int(h_stats[0])
@@ -285,9 +276,9 @@ def run_b200(args):
             "config": _config(args, "inputs 1.3 GB/GPU > 126 MB L2; L2 flushed between timed rollouts"),
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "per tick: pinned H2D of one BICYCLE action per scenario, step, rewards kernel, D2H of "
-                            "reward terms + terminated/truncated; per rollout: D2H of pose32/status/collision "
-                            "counts/nearest-edge + episode stats, then a stream sync"},
+                    "what": "lcsim_b200_env_step per tick (pinned H2D of the ADS action of every scenario, tick, reward kernel, "
+                            "D2H of reward/terms/route/flags, stream sync); per rollout: D2H of pose32/status/collision "
+                            "counts/nearest-edge + episode stats"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": which, "kernel": "lcs_tick_kernel",

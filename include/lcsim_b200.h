@@ -201,6 +201,22 @@ typedef struct {
 int lcsim_b200_upload_polylines(lcsim_b200_engine* e, const int32_t* n_poly, const double* poly_xyh, int P);
 int lcsim_b200_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_desc* obs, void* stream);
 
+/* One environment step for ALL S scenarios with HOST buffers: the batched form of
+ * BicycleSingleEnv.step (lcsim/envs/gym_warpper.py:78-87).  actions_host [S][2] are the normalised
+ * (acc, steer) in [-1, 1] of every scenario's ADS -> BicycleAction.init_with_normalized (x6.0, x0.3;
+ * policy/type.py:100-102) -> Engine.step({ads: action}) -> Engine.get_step_return's reward, terminated,
+ * truncated, reward terms and route (engine.py:160-201).  NULL actions let the ADS follow its own policy.
+ * The call enqueues H2D copy, tick, reward kernel and D2H copy on `stream`; with sync != 0 it also waits for
+ * the stream, so out_host is readable on return.  Use pinned host memory for truly asynchronous copies. */
+typedef struct {
+    double reward; /* sum coef6[k] * terms[k] (0 when coef6 is NULL) */
+    double terms[LCSIM_B200_N_REWARD_TERMS];
+    double route[LCSIM_B200_ROUTE_LEN][2];
+    uint8_t terminated, truncated, finished, pad[5]; /* finished: the ADS is IDLE/FINISHED (obs are zeros then) */
+} lcsim_b200_env_out;
+int lcsim_b200_env_step(lcsim_b200_engine* e, const double* actions_host, const double* coef6,
+                        lcsim_b200_env_out* out_host, int sync, void* stream);
+
 int lcsim_b200_views(lcsim_b200_engine* e, lcsim_b200_state_views* out);
 
 /* Sums the per-scenario statistics into stats_device[LCSIM_B200_N_STATS] (int64, device). */

@@ -156,6 +156,24 @@ class BatchEngine:
         self._keep = ag
         return out
 
+    # ------------------------------------------------------------------ batched env step with host buffers
+    def env_step(self, actions, out, coef: Optional[dict] = None, sync: bool = True):
+        """BicycleSingleEnv.step for every scenario at once (lcsim/envs/gym_warpper.py:78-87).
+
+        actions: (S,2) float64 HOST array/tensor of normalised (acc, steer) for each scenario's ADS (None: own policy);
+        out: HOST buffer of S records of native.ENV_OUT_DTYPE (numpy structured array, or a pinned uint8 tensor of
+        S*224 bytes).  H2D copy, tick, reward kernel and D2H copy are enqueued on the current stream."""
+        def host_ptr(x):
+            return x.ctypes.data if isinstance(x, np.ndarray) else int(x.data_ptr())
+
+        cf = None
+        if coef is not None:
+            cf = np.asarray([float(coef.get(k, 0.0)) for k in native.REWARD_KEYS], np.float64)
+        self._check(self.lib.lcsim_b200_env_step(self._h, None if actions is None else host_ptr(actions),
+                                                 None if cf is None else cf.ctypes.data, host_ptr(out), int(sync),
+                                                 self.backend.stream()), "env_step")
+        self._keep = (actions, out)
+
     # ------------------------------------------------------------------ aggregates
     def episode_stats(self):
         """(8,) int64 device tensor: this rank's sums (see native.STAT_KEYS)."""

@@ -24,7 +24,7 @@ typedef void* cudaStream_t;
 static const char* cudaGetErrorString(cudaError_t) { return "hostemu"; }
 static cudaError_t cudaMalloc(void** p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 2; }
 static cudaError_t cudaFree(void* p) { free(p); return 0; }
-enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 static cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { memcpy(d, s, n); return 0; }
 static cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return 0; }
 static cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return 0; }
@@ -257,6 +257,7 @@ struct LcsRewardArgs {
     int has_coef;
     double *reward, *terms, *route;
     uint8_t *terminated, *truncated;
+    lcsim_b200_env_out* env; // [S] packed output of env_step, or null
     const double* s_tab0; // [S][Ap][T] np.sum(seg[:k]) of the pristine trajectories
 };
 
@@ -320,7 +321,13 @@ LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s) {
         const double* p1 = p.ring + (ia * LCS_H + (head + LCS_H - 1) % LCS_H) * 5;
         const double* p0 = p.ring + (ia * LCS_H + (head + LCS_H - 2) % LCS_H) * 5;
         const double cur_v = lcs_norm2_vec(p1[2], p1[3]);
-        const int i0 = lcs_argmin_exact(xy, n, p0[0], p0[1]), i1 = lcs_argmin_exact(xy, n, p1[0], p1[1]);
+        // frenet_projection index = the same first-index argmin the tick uses for the cursor (filter + exact ties)
+        LcsScan sc0, sc1;
+        lcs_scan_begin(p, s, p0[0], p0[1], sc0);
+        lcs_scan_global(p, s, a, n, sc0);
+        lcs_scan_begin(p, s, p1[0], p1[1], sc1);
+        lcs_scan_global(p, s, a, n, sc1);
+        const int i0 = lcs_scan_finish(p, s, a, n, p0[0], p0[1], sc0), i1 = lcs_scan_finish(p, s, a, n, p1[0], p1[1], sc1);
         const double d0 = lcs_norm2_vec(lcs_dsub(p0[0], xy[2 * i0]), lcs_dsub(p0[1], xy[2 * i0 + 1]));
         const double d1 = lcs_norm2_vec(lcs_dsub(p1[0], xy[2 * i1]), lcs_dsub(p1[1], xy[2 * i1 + 1]));
         if (f32) {
@@ -340,7 +347,10 @@ LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s) {
     }
     // collision of this agent against every other active agent
     bool collision = false;
-    if (status == LCS_ACTIVE) {
+    const bool have_metrics = p.with_metrics && status == LCS_ACTIVE; // the tick already evaluated this agent
+    if (have_metrics) {
+        collision = p.coll_count[ia] > 0;
+    } else if (status == LCS_ACTIVE) {
         double ea[8], eo[8];
         ea[0] = x; ea[1] = y; ea[2] = ps[3];
         lcs_sincos(h, &ea[4], &ea[3]);
@@ -365,26 +375,23 @@ LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s) {
     }
     terms[3] = collision ? -1.0 : 0.0;
     bool off;
-    lcs_nearest_edge(p, s, x, y, &off);
+    if (have_metrics)
+        off = p.offroad[ia] != 0;
+    else
+        lcs_nearest_edge_hint(p, s, x, y, p.edge_hint[ia], &off);
     terms[4] = off ? -1.0 : 0.0;
     if (status == LCS_IDLE || status == LCS_FINISHED) {
         const double dis = lcs_norm2_vec(lcs_dsub(xy[2 * (n - 1)], x), lcs_dsub(xy[2 * (n - 1) + 1], y));
         terms[5] = dis < 2.5 ? 10.0 : -5.0;
     }
-    if (r.terms)
-        for (int k = 0; k < 6; k++) r.terms[6 * (size_t)s + k] = terms[k];
-    if (r.terminated) r.terminated[s] = (collision || off) ? 1 : 0;
-    // engine.py:197-200: current_step >= total_steps or the agent finished (clock already advanced)
-    if (r.truncated) r.truncated[s] = (p.tick[s] >= p.total_steps || status == LCS_IDLE || status == LCS_FINISHED) ? 1 : 0;
-    if (r.reward) {
-        double acc = 0.0;
-        if (r.has_coef)
-            for (int k = 0; k < 6; k++)
-                if (r.coef[k] != 0.0) acc = lcs_dadd(acc, lcs_dmul(terms[k], r.coef[k]));
-        r.reward[s] = acc;
-    }
-    if (r.route) {
-        double* out = r.route + (size_t)s * LCS_ROUTE * 2;
+    const bool finished = status == LCS_IDLE || status == LCS_FINISHED;
+    const bool truncated = p.tick[s] >= p.total_steps || finished; // engine.py:197-200 (clock already advanced)
+    double rew = 0.0;
+    if (r.has_coef)
+        for (int k = 0; k < 6; k++)
+            if (r.coef[k] != 0.0) rew = lcs_dadd(rew, lcs_dmul(terms[k], r.coef[k]));
+    double route[LCS_ROUTE * 2];
+    {
         double sn, c;
         lcs_sincos(h, &sn, &c);
         const int cur = p.cursor[ia];
@@ -392,14 +399,30 @@ LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s) {
             const int k = cur + 1 + q;
             if (k < n) {
                 const double dx = lcs_dsub(xy[2 * k], x), dy = lcs_dsub(xy[2 * k + 1], y);
-                out[2 * q] = lcs_dot2(dx, c, dy, sn);
-                out[2 * q + 1] = lcs_dot2(dx, -sn, dy, c);
+                route[2 * q] = lcs_dot2(dx, c, dy, sn);
+                route[2 * q + 1] = lcs_dot2(dx, -sn, dy, c);
             } else {
-                out[2 * q] = 0.0;
-                out[2 * q + 1] = 0.0;
+                route[2 * q] = 0.0;
+                route[2 * q + 1] = 0.0;
             }
         }
     }
+    if (r.env) {
+        lcsim_b200_env_out* o = r.env + s;
+        o->reward = rew;
+        for (int k = 0; k < 6; k++) o->terms[k] = terms[k];
+        for (int k = 0; k < LCS_ROUTE * 2; k++) o->route[k / 2][k % 2] = finished ? 0.0 : route[k]; // engine.py:189-192
+        o->terminated = (collision || off) ? 1 : 0;
+        o->truncated = truncated ? 1 : 0;
+        o->finished = finished ? 1 : 0;
+    }
+    if (r.terms)
+        for (int k = 0; k < 6; k++) r.terms[6 * (size_t)s + k] = terms[k];
+    if (r.terminated) r.terminated[s] = (collision || off) ? 1 : 0;
+    if (r.truncated) r.truncated[s] = truncated ? 1 : 0;
+    if (r.reward) r.reward[s] = rew;
+    if (r.route)
+        for (int k = 0; k < LCS_ROUTE * 2; k++) r.route[(size_t)s * LCS_ROUTE * 2 + k] = route[k];
 }
 #ifndef LCSIM_HOSTEMU
 __global__ void lcs_rewards_kernel(const LcsParams p, const LcsRewardArgs r) {
@@ -430,6 +453,8 @@ struct lcsim_b200_engine {
     double* s_tab0 = nullptr;
     bool uploaded = false;
     int64_t launches = 0;
+    double* env_act = nullptr; // [S][2] staging of env_step actions
+    lcsim_b200_env_out* env_out = nullptr; // [S] staging of env_step outputs
     int n_groups = 1; // rollout() splits the batch into this many scenario groups, one stream each
 #ifndef LCSIM_HOSTEMU
     cudaStream_t gstream[8] = {};
@@ -584,6 +609,8 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     LCS_ALLOC(e, p.home_edge, SA);
     LCS_ALLOC(e, p.offroad, SA);
     LCS_ALLOC(e, e->s_tab0, SAT);
+    LCS_ALLOC(e, e->env_act, S * 2);
+    LCS_ALLOC(e, e->env_out, S);
     {
         const char* env = getenv("LCSIM_B200_CLOCKS");
         if (env && env[0] == '1') LCS_ALLOC(e, p.dbg, S * 16);
@@ -958,6 +985,38 @@ extern "C" int lcsim_b200_rewards(lcsim_b200_engine* e, const int32_t* agent, co
     LCS_CUDA(e, cudaGetLastError());
 #else
     for (int s = 0; s < e->p.S; s++) lcs_rewards_one(e->p, r, s);
+#endif
+    return 0;
+}
+
+extern "C" int lcsim_b200_env_step(lcsim_b200_engine* e, const double* actions_host, const double* coef6,
+                                   lcsim_b200_env_out* out_host, int sync, void* stream) {
+    if (!e || !out_host) return LCSIM_B200_ERR_ARG;
+    if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "env_step before upload_static");
+    cudaStream_t st = (cudaStream_t)stream;
+    LcsParams q = e->p;
+    q.mode = 0;
+    q.K = 0;
+    if (actions_host) {
+        LCS_CUDA(e, cudaMemcpyAsync(e->env_act, actions_host, sizeof(double) * 2 * q.S, cudaMemcpyHostToDevice, st));
+        q.ads_action = e->env_act;
+    }
+    lcs_launch_tick(q, st);
+    e->launches++;
+    LcsRewardArgs r;
+    memset(&r, 0, sizeof r);
+    r.has_coef = coef6 != nullptr;
+    if (coef6) memcpy(r.coef, coef6, sizeof r.coef);
+    r.env = e->env_out;
+    r.s_tab0 = e->s_tab0;
+#ifndef LCSIM_HOSTEMU
+    lcs_rewards_kernel<<<(q.S + 63) / 64, 64, 0, st>>>(e->p, r);
+    LCS_CUDA(e, cudaGetLastError());
+    LCS_CUDA(e, cudaMemcpyAsync(out_host, e->env_out, sizeof(lcsim_b200_env_out) * q.S, cudaMemcpyDeviceToHost, st));
+    if (sync) LCS_CUDA(e, cudaStreamSynchronize(st));
+#else
+    for (int s = 0; s < q.S; s++) lcs_rewards_one(e->p, r, s);
+    memcpy(out_host, e->env_out, sizeof(lcsim_b200_env_out) * q.S);
 #endif
     return 0;
 }

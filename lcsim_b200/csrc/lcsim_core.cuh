@@ -133,6 +133,7 @@ struct LcsParams {
     const int32_t *act_agent, *act_type; // [S][K]
     const double* act_data; // [S][K][5]
     int32_t K;
+    const double* ads_action; // [S][2] normalised (acc, steer) of every scenario's ADS, or null (env_step)
     // ---- launch mode
     long long* dbg; // [S][16] phase clocks (debug builds of the launch only)
     int32_t prefetch; // LCSIM_B200_PREFETCH=1 (default off): early L2 prefetch of the per-agent lines
@@ -836,6 +837,12 @@ LCS_D void lcs_update_pre(const LcsParams& p, int s, int a, LcsUpd& u) {
             d3 = p.act_data[5 * q + 3];
             d4 = p.act_data[5 * q + 4];
         }
+    }
+    if (p.ads_action && a == p.ads_index[s]) {
+        // BicycleAction.init_with_normalized (type.py:100-102) as BicycleSingleEnv.step applies it
+        type = LCS_ACT_BICYCLE;
+        d0 = lcs_dmul(p.ads_action[2 * s], 6.0);
+        d1 = lcs_dmul(p.ads_action[2 * s + 1], 0.3);
     }
     if (type == LCS_ACT_NONE) {
         double wp[5];

@@ -89,6 +89,11 @@ class StateViews(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("S", "A", "A_stride", "T", "E", "H")] + [(n, C.c_void_p) for n, _ in VIEW_FIELDS]
 
 
+ENV_OUT_DTYPE = np.dtype([("reward", "<f8"), ("terms", "<f8", (N_REWARD_TERMS,)), ("route", "<f8", (ROUTE_LEN, 2)),
+                          ("terminated", "u1"), ("truncated", "u1"), ("finished", "u1"), ("pad", "u1", (5,))])
+assert ENV_OUT_DTYPE.itemsize == 224
+
+
 class ObsDesc(C.Structure):
     _fields_ = [("ego", C.c_void_p), ("radius", C.c_double), ("k_agents", C.c_int32), ("k_polys", C.c_int32),
                 ("sort_by_distance", C.c_int32), ("nbr_agent", C.c_void_p), ("nbr_agent_feat", C.c_void_p),
@@ -98,7 +103,7 @@ class ObsDesc(C.Structure):
 
 EXPORTS = ("lcsim_b200_abi_version", "lcsim_b200_create", "lcsim_b200_upload_static", "lcsim_b200_reset",
            "lcsim_b200_step", "lcsim_b200_rollout", "lcsim_b200_set_ref_trajectory", "lcsim_b200_rewards",
-           "lcsim_b200_upload_polylines", "lcsim_b200_build_obs", "lcsim_b200_views", "lcsim_b200_episode_stats",
+           "lcsim_b200_env_step", "lcsim_b200_upload_polylines", "lcsim_b200_build_obs", "lcsim_b200_views", "lcsim_b200_episode_stats",
            "lcsim_b200_launch_count", "lcsim_b200_last_error", "lcsim_b200_destroy")
 
 
@@ -117,6 +122,7 @@ def bind(path: str) -> C.CDLL:
     lib.lcsim_b200_rollout.argtypes = [vp, i32, vp]
     lib.lcsim_b200_set_ref_trajectory.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
     lib.lcsim_b200_rewards.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.lcsim_b200_env_step.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.lcsim_b200_upload_polylines.argtypes = [vp, vp, vp, i32]
     lib.lcsim_b200_build_obs.argtypes = [vp, C.POINTER(ObsDesc), vp]
     lib.lcsim_b200_views.argtypes = [vp, C.POINTER(StateViews)]

@@ -162,3 +162,30 @@ def test_abi_rejects_bad_calls(backend, synth8):
     bad.traj_len[0, 0] = bad.T + 5
     with pytest.raises(native.NativeLibraryError, match="traj_len"):
         BatchEngine(bad, backend=backend)
+
+
+@pytest.mark.parametrize("name", ["synth1_ads_bicycle_replay", "synth1_ads_bicycle_reactive"])
+def test_env_step_matches_reference_golden(name, backend):
+    """lcsim_b200_env_step == BicycleSingleEnv.step (gym_warpper.py:78-87): normalised ADS action in from host memory,
+    reward terms / terminated / truncated / route out to host memory, per tick, against the reference's own values."""
+    c = Case(name)
+    be = BatchEngine(c.static, reactive=c.reactive, with_metrics=True, backend=backend)
+    coef = {"forward": 2, "collision": 5, "smooth": 1, "destination": 1}  # lcsim/config/example.yml:22-26
+    out = np.zeros(1, native.ENV_OUT_DTYPE)
+    tn = be.backend.to_numpy
+    for k in range(c.n_steps):
+        act = np.ascontiguousarray(c.ads_actions[k].reshape(1, 2), np.float64)
+        be.env_step(act, out, coef=coef, sync=True)
+        ref = c.ref
+        np.testing.assert_array_equal(ref["cursor"][k + 1], tn(be.cursor)[0], err_msg=f"tick {k + 1}: cursor")
+        np.testing.assert_allclose(tn(be.pose64)[0][:, 0], ref["x"][k + 1], rtol=0, atol=POSE_TOL)
+        np.testing.assert_allclose(out["terms"][0], ref["rewards"][k + 1], rtol=0, atol=1e-9, equal_nan=True)
+        assert bool(out["terminated"][0]) == bool(ref["terminated"][k + 1])
+        fin = ref["status"][k + 1][c.ads] in (native.IDLE, native.FINISHED)
+        assert bool(out["finished"][0]) == fin
+        assert bool(out["truncated"][0]) == (k + 1 >= c.static.total_steps or fin)
+        if not fin:
+            np.testing.assert_allclose(out["route"][0], ref["route"][k + 1], rtol=0, atol=POSE_TOL)
+        want = sum(coef[key] * ref["rewards"][k + 1][i] for i, key in enumerate(native.REWARD_KEYS) if key in coef)
+        np.testing.assert_allclose(out["reward"][0], want, rtol=0, atol=1e-9)
+    be.close()
