@@ -176,28 +176,37 @@ int lcsim_b200_set_ref_trajectory(lcsim_b200_engine* e, const int32_t* scenario,
 int lcsim_b200_rewards(lcsim_b200_engine* e, const int32_t* agent, const double* coef6, double* reward, double* terms,
                        uint8_t* terminated, uint8_t* truncated, double* route, void* stream);
 
-/* Ego-centric neighbour gather feeding lcsim.envs observations: the radius sets of
- * motion_diff/modules/agent_encoder.py:208-215,235-241 (torch_cluster.radius / radius_graph call-site
- * contract: strict d^2 < r^2, ascending source index, at most max_nbr per query) for one ego per
- * scenario, optionally as a distance-sorted top-k, plus the (N,11,.) history gather of
- * junction/junction.py:280-336.  See lcsim_b200_obs_desc. */
+/* Ego-centric neighbour gather feeding lcsim.envs observations.  For one ego per scenario:
+ *  - a2a: the other ACTIVE agents whose last history position lies within `radius` of the ego's
+ *    (motion_diff/modules/agent_encoder.py:235-242 torch_cluster.radius_graph call-site contract: float32
+ *    positions, strict d^2 < r^2, no self loop, ascending source order = active-list order here, at most
+ *    k_agents kept), each with the reference's relation feature r_a2a = (|d|, angle_between(head_ego, d),
+ *    wrap(h_nbr - h_ego)) (:243-255), d = pos_nbr - pos_ego;
+ *  - pl2a: the polyline centres within `radius` of the ego (:208-216 torch_cluster.radius), same feature
+ *    with the polyline heading atan2(dir_y, dir_x) (:217-231);
+ *  - sort_by_distance = 1 returns the k NEAREST instead of the first k in index order (top-k select);
+ *  - history: the (N,11,.) float32 stack of junction/junction.py:301-334 for the active list, row i = list slot i.
+ * The neighbour arithmetic of the reference lives in torch_cluster (not vendored): parity at that boundary is
+ * pinned only against tests/obs_oracle.py, a numpy restatement of the call-site contract. */
 typedef struct {
-    const int32_t* ego; /* [S] device, NULL = the ADS */
+    const int32_t* ego; /* [S] device agent index, NULL = the ADS */
     double radius; /* 50.0 in the reference */
-    int32_t k_agents; /* capacity of the agent-neighbour list per ego */
-    int32_t k_polys; /* capacity of the polyline-neighbour list per ego */
+    int32_t k_agents; /* capacity of the agent-neighbour list per ego (<= 1024) */
+    int32_t k_polys; /* capacity of the polyline-neighbour list per ego (<= 1024) */
     int32_t sort_by_distance; /* 0: ascending index (torch_cluster order); 1: nearest first */
-    /* outputs, device, caller-owned */
-    int32_t* nbr_agent; /* [S][k_agents] agent index or -1 */
-    float* nbr_agent_feat; /* [S][k_agents][4] ego-frame dx, dy, wrap(dheading), v */
-    int32_t* n_nbr_agent; /* [S] */
-    int32_t* nbr_poly; /* [S][k_polys] polyline-centre index or -1 */
-    float* nbr_poly_feat; /* [S][k_polys][3] ego-frame dx, dy, wrap(dheading) */
+    /* outputs, device, caller-owned; any may be NULL */
+    int32_t* nbr_agent; /* [S][k_agents] agent index, -1 padded */
+    float* nbr_agent_feat; /* [S][k_agents][3] */
+    int32_t* n_nbr_agent; /* [S] neighbours found (before the cap) */
+    int32_t* nbr_poly; /* [S][k_polys] polyline-centre index, -1 padded */
+    float* nbr_poly_feat; /* [S][k_polys][3] */
     int32_t* n_nbr_poly; /* [S] */
-    float* history; /* [S][A_stride][H][6] x, y, vx, vy, heading, valid in shift-register order */
+    float* history; /* [S][A_stride][H][6] x, y, vx, vy, heading, valid; shift-register order, rows = list slots */
+    int32_t* history_agent; /* [S][A_stride] agent index of every history row, -1 beyond n_active */
 } lcsim_b200_obs_desc;
 
-/* polyline centres (junction/junction.py:117-184, polygon.py:11-75): host [S][P][3] x, y, heading */
+/* polyline centres of the roadgraph (lane/lane.py:108-124, junction/junction.py:117-184 ->
+ * polygon.py:11-75): host [S][P][3] = x, y, heading; packer.polyline_centres() computes them */
 int lcsim_b200_upload_polylines(lcsim_b200_engine* e, const int32_t* n_poly, const double* poly_xyh, int P);
 int lcsim_b200_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_desc* obs, void* stream);
 

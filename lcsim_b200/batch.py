@@ -174,6 +174,42 @@ class BatchEngine:
                                                  self.backend.stream()), "env_step")
         self._keep = (actions, out)
 
+    # ------------------------------------------------------------------ observation builder
+    def upload_polylines(self, centres):
+        """centres: list of (P_s,3) arrays (x, y, heading) per scenario — packer.polyline_centres()."""
+        assert len(centres) == self.S
+        P = max(1, max(len(c) for c in centres))
+        arr = np.zeros((self.S, P, 3))
+        n = np.zeros(self.S, np.int32)
+        for i, c in enumerate(centres):
+            n[i] = len(c)
+            arr[i, : len(c)] = c
+        self._check(self.lib.lcsim_b200_upload_polylines(self._h, n.ctypes.data, arr.ctypes.data, P), "upload_polylines")
+        self.P = P
+
+    def build_obs(self, k_agents: int = 32, k_polys: int = 64, radius: float = 50.0, sort_by_distance: bool = False,
+                  ego=None, with_polys: bool = True, with_history: bool = True):
+        """Ego-centric neighbour gather + history stack (include/lcsim_b200.h lcsim_b200_obs_desc).  Returns a dict of
+        device tensors written in place by one launch."""
+        b = self.backend
+        out = dict(nbr_agent=b.empty((self.S, k_agents), np.int32), nbr_agent_feat=b.empty((self.S, k_agents, 3), np.float32),
+                   n_nbr_agent=b.empty((self.S,), np.int32))
+        if with_polys:
+            out.update(nbr_poly=b.empty((self.S, k_polys), np.int32), nbr_poly_feat=b.empty((self.S, k_polys, 3), np.float32),
+                       n_nbr_poly=b.empty((self.S,), np.int32))
+        if with_history:
+            out.update(history=b.empty((self.S, self.A_stride, native.H_STEPS, 6), np.float32),
+                       history_agent=b.empty((self.S, self.A_stride), np.int32))
+        d = native.ObsDesc()
+        eg = None if ego is None else b.to_device(ego, np.int32)
+        d.ego = None if eg is None else b.ptr(eg)
+        d.radius, d.k_agents, d.k_polys, d.sort_by_distance = float(radius), int(k_agents), int(k_polys), int(sort_by_distance)
+        for k, v in out.items():
+            setattr(d, k, b.ptr(v))
+        self._check(self.lib.lcsim_b200_build_obs(self._h, C.byref(d), b.stream()), "build_obs")
+        self._keep = eg
+        return out
+
     # ------------------------------------------------------------------ aggregates
     def episode_stats(self):
         """(8,) int64 device tensor: this rank's sums (see native.STAT_KEYS)."""

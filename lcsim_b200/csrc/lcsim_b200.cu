@@ -453,6 +453,9 @@ struct lcsim_b200_engine {
     double* s_tab0 = nullptr;
     bool uploaded = false;
     int64_t launches = 0;
+    float* poly = nullptr; // [S][P][3] polyline centres (upload_polylines)
+    int32_t* n_poly = nullptr;
+    int P = 0;
     double* env_act = nullptr; // [S][2] staging of env_step actions
     lcsim_b200_env_out* env_out = nullptr; // [S] staging of env_step outputs
     int n_groups = 1; // rollout() splits the batch into this many scenario groups, one stream each
@@ -1021,11 +1024,228 @@ extern "C" int lcsim_b200_env_step(lcsim_b200_engine* e, const double* actions_h
     return 0;
 }
 
-extern "C" int lcsim_b200_upload_polylines(lcsim_b200_engine* e, const int32_t*, const double*, int) {
-    return lcs_fail(e, LCSIM_B200_ERR_STATE, "upload_polylines: not built yet");
+// ---- observation builder -------------------------------------------------------------------
+struct LcsObsArgs {
+    lcsim_b200_obs_desc d;
+    float r2;
+    const float* poly; // [S][P][3] x, y, heading (float32, world frame like the reference's tensors)
+    const int32_t* n_poly;
+    int P;
+};
+#define LCS_OBS_CAP 1024 // candidates kept per list before the top-k / first-k cut
+
+// motion_diff/modules/utils.py:116-119 wrap_angle on float32 tensors (Python-style modulo)
+LCS_D float lcs_wrap_f32(float a) {
+    const float pi = 3.14159265358979323846f, two_pi = 6.28318530717958647692f;
+    float r = fmodf(a + pi, two_pi);
+    if (r != 0.0f && r < 0.0f) r += two_pi;
+    return -pi + r;
 }
-extern "C" int lcsim_b200_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_desc*, void*) {
-    return lcs_fail(e, LCSIM_B200_ERR_STATE, "build_obs: not built yet");
+// relation feature of the encoder (agent_encoder.py:217-231,243-255): |d|, angle_between(head_ego, d), wrap(dh)
+LCS_D void lcs_rel_feature(float ex, float ey, float eh, float nx, float ny, float nh, float* f) {
+    const float rx = nx - ex, ry = ny - ey;
+    f[0] = sqrtf(rx * rx + ry * ry);
+    const float hx = cosf(eh), hy = sinf(eh);
+    f[1] = atan2f(hx * ry - hy * rx, hx * rx + hy * ry);
+    f[2] = lcs_wrap_f32(nh - eh);
+}
+// newest history entry of agent a as the float32 tensors the reference builds (junction.py:319-325)
+LCS_D void lcs_last_pose_f32(const LcsParams& p, size_t ia, float* x, float* y, float* h) {
+    const int head = p.ring_head[ia];
+    const double* r = p.ring + (ia * LCS_H + (head + LCS_H - 1) % LCS_H) * 5;
+    *x = (float)r[0];
+    *y = (float)r[1];
+    *h = (float)r[4];
+}
+// one row of the (N,11,6) history stack: list slot `slot`, shift-register position k
+LCS_D void lcs_history_cell(const LcsParams& p, const LcsObsArgs& o, int s, int slot, int k) {
+    float* out = o.d.history + (((size_t)s * p.Ap + slot) * LCS_H + k) * 6;
+    const int a = slot < p.n_active[s] ? p.active[(size_t)s * p.Ap + slot] : -1;
+    if (k == 0 && o.d.history_agent) o.d.history_agent[(size_t)s * p.Ap + slot] = a;
+    if (a < 0) {
+        for (int c = 0; c < 6; c++) out[c] = 0.f;
+        return;
+    }
+    const size_t ia = (size_t)s * p.Ap + a;
+    const int head = p.ring_head[ia], cnt = p.ring_count[ia];
+    const double* r = p.ring + (ia * LCS_H + (head + k) % LCS_H) * 5;
+    for (int c = 0; c < 5; c++) out[c] = (float)r[c];
+    out[5] = k >= LCS_H - cnt ? 1.f : 0.f;
+}
+
+#ifdef LCSIM_HOSTEMU
+// Serial statement of one scenario's gather (host emulation only).
+static void lcs_obs_scenario_serial(const LcsParams& p, const LcsObsArgs& o, int s) {
+    const int e = o.d.ego ? o.d.ego[s] : p.ads_index[s];
+    const size_t ie = (size_t)s * p.Ap + e;
+    for (int which = 0; which < 2; which++) {
+        const int cap = which == 0 ? o.d.k_agents : o.d.k_polys;
+        int32_t* idx_out = which == 0 ? o.d.nbr_agent : o.d.nbr_poly;
+        float* feat_out = which == 0 ? o.d.nbr_agent_feat : o.d.nbr_poly_feat;
+        int32_t* n_out = which == 0 ? o.d.n_nbr_agent : o.d.n_nbr_poly;
+        std::vector<std::pair<float, int>> cand;
+        std::vector<float> nx, ny, nh;
+        float ex = 0, ey = 0, eh = 0;
+        if (p.status[ie] == LCS_ACTIVE) {
+            lcs_last_pose_f32(p, ie, &ex, &ey, &eh);
+            const int n = which == 0 ? p.n_active[s] : (o.poly ? o.n_poly[s] : 0);
+            for (int j = 0; j < n; j++) {
+                float x, y, h;
+                int id;
+                if (which == 0) {
+                    id = p.active[(size_t)s * p.Ap + j];
+                    if (id == e) continue;
+                    lcs_last_pose_f32(p, (size_t)s * p.Ap + id, &x, &y, &h);
+                } else {
+                    id = j;
+                    const float* q = o.poly + ((size_t)s * o.P + j) * 3;
+                    x = q[0]; y = q[1]; h = q[2];
+                }
+                const float dx = x - ex, dy = y - ey, d2 = lcs_fadd(lcs_fmul(dx, dx), lcs_fmul(dy, dy)); // unfused, like torch
+                if (d2 < o.r2) {
+                    cand.push_back({d2, id});
+                    nx.push_back(x); ny.push_back(y); nh.push_back(h);
+                }
+            }
+        }
+        std::vector<int> order(cand.size());
+        for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+        if (o.d.sort_by_distance)
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cand[a] < cand[b]; });
+        if (n_out) n_out[s] = (int)cand.size();
+        for (int k = 0; k < cap; k++) {
+            const bool have = k < (int)order.size();
+            if (idx_out) idx_out[(size_t)s * cap + k] = have ? cand[order[k]].second : -1;
+            if (feat_out) {
+                float f[3] = {0.f, 0.f, 0.f};
+                if (have) lcs_rel_feature(ex, ey, eh, nx[order[k]], ny[order[k]], nh[order[k]], f);
+                for (int c = 0; c < 3; c++) feat_out[((size_t)s * cap + k) * 3 + c] = f[c];
+            }
+        }
+    }
+    if (o.d.history)
+        for (int slot = 0; slot < p.Ap; slot++)
+            for (int k = 0; k < LCS_H; k++) lcs_history_cell(p, o, s, slot, k);
+}
+#endif
+
+#ifndef LCSIM_HOSTEMU
+// One CTA per scenario.  Candidates are compacted in index order with ballot-word prefix sums; the top-k by
+// distance is a rank select over the (<= LCS_OBS_CAP) candidates held in shared memory.
+__global__ void __launch_bounds__(128) lcs_obs_kernel(const LcsParams p, const LcsObsArgs o) {
+    __shared__ float c_d[LCS_OBS_CAP], c_x[LCS_OBS_CAP], c_y[LCS_OBS_CAP], c_h[LCS_OBS_CAP];
+    __shared__ int c_id[LCS_OBS_CAP];
+    __shared__ uint32_t words[4];
+    __shared__ int s_count;
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int e = o.d.ego ? o.d.ego[s] : p.ads_index[s];
+    const size_t ie = (size_t)s * p.Ap + e;
+    const bool ego_active = p.status[ie] == LCS_ACTIVE;
+    float ex = 0, ey = 0, eh = 0;
+    if (ego_active) lcs_last_pose_f32(p, ie, &ex, &ey, &eh);
+    for (int which = 0; which < 2; which++) {
+        const int cap = which == 0 ? o.d.k_agents : o.d.k_polys;
+        int32_t* idx_out = which == 0 ? o.d.nbr_agent : o.d.nbr_poly;
+        float* feat_out = which == 0 ? o.d.nbr_agent_feat : o.d.nbr_poly_feat;
+        int32_t* n_out = which == 0 ? o.d.n_nbr_agent : o.d.n_nbr_poly;
+        const int n = !ego_active ? 0 : (which == 0 ? p.n_active[s] : (o.poly ? o.n_poly[s] : 0));
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        for (int j0 = 0; j0 < n; j0 += 128) {
+            const int j = j0 + tid;
+            bool hit = false;
+            float x = 0, y = 0, h = 0, d2 = 0;
+            int id = -1;
+            if (j < n) {
+                if (which == 0) {
+                    id = p.active[(size_t)s * p.Ap + j];
+                    if (id != e) lcs_last_pose_f32(p, (size_t)s * p.Ap + id, &x, &y, &h);
+                } else {
+                    id = j;
+                    const float* q = o.poly + ((size_t)s * o.P + j) * 3;
+                    x = q[0]; y = q[1]; h = q[2];
+                }
+                const float dx = x - ex, dy = y - ey;
+                d2 = lcs_fadd(lcs_fmul(dx, dx), lcs_fmul(dy, dy)); // unfused, like torch
+                hit = !(which == 0 && id == e) && d2 < o.r2;
+            }
+            lcs_set_flag(words, tid, hit);
+            __syncthreads();
+            const int base = s_count, pos = base + lcs_prefix(words, tid);
+            if (hit && pos < LCS_OBS_CAP) {
+                c_d[pos] = d2; c_x[pos] = x; c_y[pos] = y; c_h[pos] = h; c_id[pos] = id;
+            }
+            __syncthreads();
+            if (tid == 0) s_count = base + lcs_total(words, 4);
+            __syncthreads();
+        }
+        const int found = s_count, m = found < LCS_OBS_CAP ? found : LCS_OBS_CAP;
+        if (tid == 0 && n_out) n_out[s] = found;
+        // output position of candidate c: its index (ascending order) or its rank by (distance, index)
+        for (int c = tid; c < m; c += 128) {
+            int pos = c;
+            if (o.d.sort_by_distance) {
+                pos = 0;
+                const float dc = c_d[c];
+                for (int q = 0; q < m; q++) pos += (c_d[q] < dc || (c_d[q] == dc && q < c)) ? 1 : 0;
+            }
+            if (pos < cap) {
+                if (idx_out) idx_out[(size_t)s * cap + pos] = c_id[c];
+                if (feat_out) {
+                    float f[3];
+                    lcs_rel_feature(ex, ey, eh, c_x[c], c_y[c], c_h[c], f);
+                    for (int k = 0; k < 3; k++) feat_out[((size_t)s * cap + pos) * 3 + k] = f[k];
+                }
+            }
+        }
+        for (int k = m + tid; k < cap; k += 128) {
+            if (idx_out) idx_out[(size_t)s * cap + k] = -1;
+            if (feat_out)
+                for (int c = 0; c < 3; c++) feat_out[((size_t)s * cap + k) * 3 + c] = 0.f;
+        }
+        __syncthreads();
+    }
+    if (o.d.history)
+        for (int c = tid; c < p.Ap * LCS_H; c += 128) lcs_history_cell(p, o, s, c / LCS_H, c % LCS_H);
+}
+#endif
+
+extern "C" int lcsim_b200_upload_polylines(lcsim_b200_engine* e, const int32_t* n_poly, const double* poly_xyh, int P) {
+    if (!e || !n_poly || !poly_xyh || P < 1) return LCSIM_B200_ERR_ARG;
+    const int S = e->p.S;
+    std::vector<float> f((size_t)S * P * 3, 0.f);
+    for (int s = 0; s < S; s++) {
+        if (n_poly[s] < 0 || n_poly[s] > P) return lcs_fail(e, LCSIM_B200_ERR_ARG, "scenario %d: n_poly %d out of [0,%d]", s, n_poly[s], P);
+        for (size_t k = 0; k < (size_t)n_poly[s] * 3; k++) f[(size_t)s * P * 3 + k] = (float)poly_xyh[(size_t)s * P * 3 + k];
+    }
+    LCS_ALLOC(e, e->poly, (size_t)S * P * 3);
+    LCS_ALLOC(e, e->n_poly, S);
+    LCS_CUDA(e, cudaMemcpy(e->poly, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
+    LCS_CUDA(e, cudaMemcpy(e->n_poly, n_poly, sizeof(int32_t) * S, cudaMemcpyHostToDevice));
+    e->P = P;
+    return 0;
+}
+
+extern "C" int lcsim_b200_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_desc* obs, void* stream) {
+    if (!e || !obs) return LCSIM_B200_ERR_ARG;
+    if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "build_obs before upload_static");
+    if (obs->k_agents < 0 || obs->k_polys < 0 || obs->k_agents > LCS_OBS_CAP || obs->k_polys > LCS_OBS_CAP || !(obs->radius > 0))
+        return lcs_fail(e, LCSIM_B200_ERR_ARG, "build_obs: k_agents/k_polys must be in [0,%d], radius > 0", LCS_OBS_CAP);
+    if ((obs->nbr_poly || obs->nbr_poly_feat) && !e->poly)
+        return lcs_fail(e, LCSIM_B200_ERR_STATE, "build_obs: polyline outputs requested before upload_polylines");
+    LcsObsArgs o;
+    o.d = *obs;
+    o.r2 = (float)obs->radius * (float)obs->radius;
+    o.poly = e->poly;
+    o.n_poly = e->n_poly;
+    o.P = e->P;
+#ifndef LCSIM_HOSTEMU
+    lcs_obs_kernel<<<e->p.S, 128, 0, (cudaStream_t)stream>>>(e->p, o);
+    LCS_CUDA(e, cudaGetLastError());
+#else
+    for (int s = 0; s < e->p.S; s++) lcs_obs_scenario_serial(e->p, o, s);
+#endif
+    return 0;
 }
 
 extern "C" int lcsim_b200_views(lcsim_b200_engine* e, lcsim_b200_state_views* v) {

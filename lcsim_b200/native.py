@@ -98,7 +98,7 @@ class ObsDesc(C.Structure):
     _fields_ = [("ego", C.c_void_p), ("radius", C.c_double), ("k_agents", C.c_int32), ("k_polys", C.c_int32),
                 ("sort_by_distance", C.c_int32), ("nbr_agent", C.c_void_p), ("nbr_agent_feat", C.c_void_p),
                 ("n_nbr_agent", C.c_void_p), ("nbr_poly", C.c_void_p), ("nbr_poly_feat", C.c_void_p),
-                ("n_nbr_poly", C.c_void_p), ("history", C.c_void_p)]
+                ("n_nbr_poly", C.c_void_p), ("history", C.c_void_p), ("history_agent", C.c_void_p)]
 
 
 EXPORTS = ("lcsim_b200_abi_version", "lcsim_b200_create", "lcsim_b200_upload_static", "lcsim_b200_reset",

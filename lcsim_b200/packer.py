@@ -179,6 +179,32 @@ def scenario_from_raw(raw: dict) -> ScenarioArrays:
     )
 
 
+def _chunk_centres(pts: np.ndarray, chunk: int) -> np.ndarray:
+    """(x, y, heading) of every `chunk`-point piece of one resampled polyline: the float32 mean of
+    [x, y, z, dir_x, dir_y, dir_z] (reference: polygon.py:41-50) and atan2(dir_y, dir_x) in float32
+    (motion_diff/modules/agent_encoder.py:125-134)."""
+    if len(pts) == 0:
+        return np.zeros((0, 3))
+    with_z = np.concatenate([pts, np.zeros((len(pts), 1))], axis=1)
+    rows = np.concatenate([with_z, polyline_dir(with_z)], axis=1)
+    out = []
+    for i in range(0, len(rows), chunk):
+        c = rows[i:i + chunk].mean(axis=0).astype(np.float32)
+        out.append([float(c[0]), float(c[1]), float(np.arctan2(c[4], c[3]))])
+    return np.asarray(out)
+
+
+def polyline_centres(lanes) -> np.ndarray:
+    """(P,3) polyline centres (x, y, heading) of a WOMD-shaped scenario, in the order
+    Junction.init_roadgraph_data concatenates them (junction/junction.py:194-205,231-236): only the
+    junction's LANES contribute (0.5 m-resampled centrelines cut into 10-point pieces, lane/lane.py:59-63,
+    108-124); the junction's road lines / edges go to `roadgraph_points`, not to the polyline set.
+    `lanes` = ScenarioArrays.lanes = [(centre-line nodes (n,2), lane id)] in pb order."""
+    parts = [_chunk_centres(resample_polyline(np.asarray(p, np.float64)), 10) for p, _ in lanes]
+    parts = [p for p in parts if len(p)]
+    return np.concatenate(parts) if parts else np.zeros((0, 3))
+
+
 @dataclass
 class StaticBatch:
     """Padded SoA for S scenarios; layout documented in DESIGN.md §3 and include/lcsim_b200.h."""

@@ -1,0 +1,94 @@
+"""Observation builder: polyline centres pinned to the reference, neighbour gather and history stack
+against the numpy restatement of the call-site contract (tests/obs_oracle.py, parity unpinned at the torch_cluster
+boundary), on both backends."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import obs_oracle
+from lcsim_b200 import native, packer, synth, workload
+from lcsim_b200.batch import BatchEngine
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module", params=["hostemu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def backend(request):
+    if request.param == "cuda":
+        return native.TorchCudaBackend(0)
+    from hostemu import NumpyEmuBackend
+
+    return NumpyEmuBackend()
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden_poly", "*.npz"))))
+def test_polyline_centres_match_reference(path):
+    """packer.polyline_centres == Junction.roadgraph_data['poly_center_points'] of the real reference (oracle/gen_golden_poly.py)."""
+    z = np.load(path)
+    off = np.concatenate([[0], np.cumsum(z["lane_len"])])
+    lanes = [(z["lanes"][off[i]:off[i + 1]], i) for i in range(len(z["lane_len"]))]
+    c = packer.polyline_centres(lanes)
+    ref = z["centre"]
+    assert c.shape[0] == ref.shape[0]
+    np.testing.assert_array_equal(c[:, :2].astype(np.float32), ref[:, :2])
+    np.testing.assert_array_equal(c[:, 2].astype(np.float32), np.arctan2(ref[:, 4], ref[:, 3]))
+
+
+@pytest.mark.parametrize("sort", [False, True])
+def test_neighbour_gather_and_history(backend, sort):
+    raws = [synth.make_raw_scenario(200 + i, 128) for i in range(3)]
+    scs = [packer.scenario_from_raw(r) for r in raws]
+    sb = packer.pack(scs)
+    centres = [packer.polyline_centres(sc.lanes) for sc in scs]
+    be = BatchEngine(sb, reactive=True, with_metrics=True, backend=backend)
+    be.upload_polylines(centres)
+    o = orc.Oracle(sb, reactive=True)
+    tn = be.backend.to_numpy
+    KA, KP = 16, 48  # small caps so that both the cap and the top-k cut are exercised
+    for tick in range(60):
+        be.step()
+        o.step()
+        if tick % 6:
+            continue
+        ego = sb.ads_index.copy() if tick % 12 == 0 else np.asarray([o.active[s, tick % max(1, o.n_active[s])] for s in range(sb.S)], np.int32)
+        out = {k: tn(v) for k, v in be.build_obs(k_agents=KA, k_polys=KP, radius=50.0, sort_by_distance=sort, ego=ego).items()}
+        ring_last = o.ring[:, :, -1, :]  # newest history entry of every agent (x, y, vx, vy, h)
+        for s in range(sb.S):
+            e = int(ego[s])
+            n = int(o.n_active[s])
+            act = o.active[s, :n]
+            np.testing.assert_array_equal(out["history_agent"][s, :n], act)
+            assert (out["history_agent"][s, n:] == -1).all()
+            np.testing.assert_array_equal(out["history"][s, :n, :, :5], o.ring[s, act].astype(np.float32))
+            valid = (np.arange(11)[None, :] >= 11 - o.ring_valid[s, act][:, None]).astype(np.float32)
+            np.testing.assert_array_equal(out["history"][s, :n, :, 5], valid)
+            if o.status[s, e] != orc.ACTIVE:
+                assert out["n_nbr_agent"][s] == 0 and out["n_nbr_poly"][s] == 0
+                assert (out["nbr_agent"][s] == -1).all() and (out["nbr_poly"][s] == -1).all()
+                continue
+            exyh = ring_last[s, e][[0, 1, 4]].astype(np.float32)
+            others = act[act != e]
+            idx, feat, cnt = obs_oracle.gather(exyh, others, ring_last[s, others][:, [0, 1, 4]].astype(np.float32), 50.0, KA, sort)
+            assert cnt == out["n_nbr_agent"][s]
+            np.testing.assert_array_equal(out["nbr_agent"][s], idx)
+            np.testing.assert_allclose(out["nbr_agent_feat"][s], feat, rtol=0, atol=2e-6)  # float32 libm ulps (sqrt/atan2/cos/sin)
+            c = centres[s].astype(np.float32)
+            idx, feat, cnt = obs_oracle.gather(exyh, np.arange(len(c), dtype=np.int32), c, 50.0, KP, sort)
+            assert cnt == out["n_nbr_poly"][s]
+            np.testing.assert_array_equal(out["nbr_poly"][s], idx)
+            np.testing.assert_allclose(out["nbr_poly_feat"][s], feat, rtol=0, atol=2e-6)
+    be.close()
+
+
+def test_build_obs_argument_errors(backend):
+    sb = workload.synthetic_batch(300, 1, 16, workers=1)
+    be = BatchEngine(sb, backend=backend)
+    with pytest.raises(native.NativeLibraryError, match="upload_polylines"):
+        be.build_obs()
+    be.build_obs(with_polys=False)
+    with pytest.raises(native.NativeLibraryError, match="k_agents"):
+        be.build_obs(k_agents=5000, with_polys=False)
+    be.close()
