@@ -74,12 +74,12 @@ def test_neighbour_gather_and_history(backend, sort):
             idx, feat, cnt = obs_oracle.gather(exyh, others, ring_last[s, others][:, [0, 1, 4]].astype(np.float32), 50.0, KA, sort)
             assert cnt == out["n_nbr_agent"][s]
             np.testing.assert_array_equal(out["nbr_agent"][s], idx)
-            np.testing.assert_allclose(out["nbr_agent_feat"][s], feat, rtol=0, atol=2e-6)  # float32 libm ulps (sqrt/atan2/cos/sin)
+            np.testing.assert_allclose(out["nbr_agent_feat"][s], feat, rtol=3e-7, atol=2e-6)  # float32 ulps (contraction, sqrt/atan2/cos/sin)
             c = centres[s].astype(np.float32)
             idx, feat, cnt = obs_oracle.gather(exyh, np.arange(len(c), dtype=np.int32), c, 50.0, KP, sort)
             assert cnt == out["n_nbr_poly"][s]
             np.testing.assert_array_equal(out["nbr_poly"][s], idx)
-            np.testing.assert_allclose(out["nbr_poly_feat"][s], feat, rtol=0, atol=2e-6)
+            np.testing.assert_allclose(out["nbr_poly_feat"][s], feat, rtol=3e-7, atol=2e-6)
     be.close()
 
 
