@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — agent-steps/s of the per-tick agent-stepping path on synthetic WOMD-shaped scenarios.
 
-A "step" is one 91-tick rollout (reset + 91 ticks, one CUDA launch per tick) of this rank's batch of
+A "step" is one 91-tick rollout (reset launch + one fused launch that runs the 91 ticks) of this rank's batch of
 independent scenarios (BASELINE.json configs[1]: 1024 scenarios x 128 agents on one B200; log-replay
 control with the collision / off-road metrics fused into every tick).  agent-steps = sum over ticks of the
 ACTIVE agents updated.
@@ -150,7 +150,8 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     S = args.scenarios
     sb = workload.synthetic_batch(rank * S, S, args.agents, workers=max(1, min(32, (os.cpu_count() or 1) // world)))
-    be = BatchEngine(sb, reactive=(args.mode == "reactive"), with_metrics=not args.no_metrics, device=local)
+    be = BatchEngine(sb, reactive=(args.mode == "reactive"), with_metrics=not args.no_metrics, device=local,
+                     grid_cell=args.grid_cell)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -160,9 +161,17 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
 
     # ------------------------------------------------------------- device-resident arm ("value")
-    def rollout():
+    kev = []  # CUDA events around the rollout kernel alone (the roofline's launch duration)
+
+    def rollout(timed=False):
         be.reset()
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
         be.rollout(N_TICKS)
+        if timed:
+            b.record()
+            kev.append((a, b))
 
     for _ in range(args.warmup):
         rollout()
@@ -178,7 +187,7 @@ def run_b200(args):
     for k in range(args.steps):
         flush.fill_(k)  # L2 flushed between timed rollouts (not timed)
         ev[k][0].record()
-        rollout()
+        rollout(timed=True)
         ev[k][1].record()
         stats_acc += be.episode_stats()
     barrier()
@@ -255,10 +264,11 @@ def run_b200(args):
 
     if rank == 0:
         peak, which = _peaks()
-        per_launch_steps = agent_steps_rank / max(launches, 1)
-        # launches include the reset launch of every rollout; duration = timed region / launches (upper bound on the
-        # kernel's own duration: launch gaps are inside it)
-        launch_ms = ms / max(launches, 1)
+        # dominant kernel: the stepping launches of a rollout (one fused lcs_rollout_kernel launch of 91 ticks, or 91
+        # lcs_tick_kernel launches with LCSIM_B200_FUSED=0), timed by their own CUDA events inside the timed region
+        n_step_launches = max(launches - args.steps, 1)  # every rollout also has one reset launch
+        per_launch_steps = agent_steps_rank / n_step_launches
+        launch_ms = sum(a.elapsed_time(b) for a, b in kev) / n_step_launches
         achieved = per_launch_steps * B_ALG / (launch_ms * 1e-3) / 1e9
         traffic = None
         try:
@@ -281,7 +291,8 @@ def run_b200(args):
                             "counts/nearest-edge + episode stats"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": which, "kernel": "lcs_tick_kernel",
+                         "traffic": traffic, "peak_source": which,
+                         "kernel": "lcs_rollout_kernel" if n_step_launches == args.steps else "lcs_tick_kernel",
                          "bytes_per_agent_step": B_ALG, "agent_steps_per_launch": per_launch_steps,
                          "launch_ms": launch_ms},
             "cpu_baseline": {"value": cpu_steps / cpu_secs, "unit": "agent-steps/s", "cores": cores, "kind": "port",
@@ -305,6 +316,7 @@ def main():
     ap.add_argument("--scenarios", type=int, default=1024, help="scenarios per GPU")
     ap.add_argument("--agents", type=int, default=128)
     ap.add_argument("--mode", default="replay", choices=["replay", "reactive"], help="control mode of the timed rollout")
+    ap.add_argument("--grid-cell", type=float, default=0.0, help="experiment: road-edge grid cell (m); 0 = library default")
     ap.add_argument("--no-metrics", action="store_true", help="experiment: skip the fused collision/off-road phases")
     ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and CPU legs (profiling runs)")
     ap.add_argument("--cpu-scenarios", type=int, default=0, help="bounded CPU sample (scenarios per rollout); "

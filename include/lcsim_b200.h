@@ -159,8 +159,16 @@ int lcsim_b200_reset(lcsim_b200_engine* e, const uint8_t* reset_mask, void* stre
 int lcsim_b200_step(lcsim_b200_engine* e, const int32_t* act_agent, const int32_t* act_type, const double* act_data,
                     int K, void* stream);
 
-/* n_ticks consecutive steps without external actions (one kernel launch per tick). */
+/* n_ticks consecutive Engine.step() calls without external actions (engine.py:145-158), i.e. the reference's
+ * `for _ in range(n): engine.step()` loop for every scenario of the batch.  One launch: the CTA of a scenario runs
+ * all n_ticks ticks back to back (scenarios are independent), state and outputs afterwards are those of the last
+ * tick.  LCSIM_B200_FUSED=0 in the environment of create() selects one launch per tick instead. */
 int lcsim_b200_rollout(lcsim_b200_engine* e, int n_ticks, void* stream);
+
+/* Same, and additionally records per tick and scenario what the reference's caller could have read between the
+ * steps: tick_log (device, int32 [n_ticks][S][4]) = agents updated by the tick, len(active_agents) after it,
+ * sum(check_collision_all()) and the number of off-road agents (manager.py:313-345); needs desc.with_metrics. */
+int lcsim_b200_rollout_log(lcsim_b200_engine* e, int n_ticks, int32_t* tick_log, void* stream);
 
 /* Agent.set_ref_trajectory (agent.py:462-466) as called from Engine._plan_trajectory
  * (engine.py:286-297): n (scenario, agent) pairs receive float32 (T,2) xy, (T,2) vel, (T,) heading

@@ -119,8 +119,16 @@ class BatchEngine:
                                              K, self.backend.stream()), "step")
         self._keep = (aa, at, ad)  # the launch is asynchronous: keep the buffers alive until the next call
 
-    def rollout(self, n_ticks: int):
-        self._check(self.lib.lcsim_b200_rollout(self._h, int(n_ticks), self.backend.stream()), "rollout")
+    def rollout(self, n_ticks: int, log: bool = False):
+        """``for _ in range(n_ticks): engine.step()`` for the whole batch in one launch.  With ``log`` returns the
+        (n_ticks, S, 4) int32 device tensor of per-tick [agents updated, active after, collision sum, off-road count]."""
+        if not log:
+            self._check(self.lib.lcsim_b200_rollout(self._h, int(n_ticks), self.backend.stream()), "rollout")
+            return None
+        out = self.backend.empty((int(n_ticks), self.S, 4), np.int32)
+        self._check(self.lib.lcsim_b200_rollout_log(self._h, int(n_ticks), self.backend.ptr(out), self.backend.stream()),
+                    "rollout_log")
+        return out
 
     # ------------------------------------------------------------------ diffusion-action ingest
     def set_ref_trajectory(self, scenario, agent, xy, vel, heading):

@@ -73,7 +73,7 @@ static cudaError_t cudaGetLastError() { return 0; }
         SYNC;                                                                       \
         FOR_T lcs_phase_metrics_out(p, sm, s, tid, TH);                             \
         SYNC;                                                                       \
-        FOR_T lcs_phase_stats_out(p, sm, s, tid);                                   \
+        FOR_T lcs_phase_stats_out(p, sm, s, tid, TH);                               \
     }
 
 #ifndef LCSIM_HOSTEMU
@@ -85,11 +85,38 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_ti
     LcsSmem sm;
     lcs_smem_carve(sm, lcs_smem_raw, p.Ap);
     LcsThread th;
+    th.k = 0;
     lcs_phase_update(p, sm, s, tid, th);
     __syncthreads();
 #define TH th
     LCS_TICK_REST(__syncthreads(), )
 #undef TH
+}
+
+// Fused rollout: the CTA of a scenario runs p.n_ticks consecutive ticks in ONE launch.  Scenarios never exchange
+// anything, so nothing forces them to advance in lock step: without a launch boundary per tick there is no wave
+// tail (the slowest scenario of every tick), the CTAs drift apart so that memory-bound and shared-memory-bound
+// phases of different scenarios overlap, and a scenario's working set (state lines, replay records, the edge-grid
+// cells around its agents) is still in L1/L2 when the next tick asks for it.  State written by one thread and read
+// by another one tick later is ordered by the __syncthreads() between the phases (same CTA, same SM).
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_rollout_kernel(const LcsParams p) {
+    extern __shared__ __align__(128) unsigned char lcs_smem_raw[];
+    const int s0 = blockIdx.x + p.s0, tid0 = threadIdx.x;
+#pragma unroll 1
+    for (int k = 0; k < p.n_ticks; k++) {
+        const int s = s0, tid = tid0;
+        LcsSmem sm;
+        lcs_smem_carve(sm, lcs_smem_raw, p.Ap);
+        LcsThread th;
+        th.k = k;
+        lcs_phase_update(p, sm, s, tid, th);
+        __syncthreads();
+#define TH th
+        LCS_TICK_REST(__syncthreads(), )
+#undef TH
+        __syncthreads();
+    }
 }
 
 // Instrumented copy of the plain kernel (LCSIM_B200_CLOCKS=1): thread 0 stamps clock64() at every phase
@@ -101,6 +128,7 @@ __global__ void __launch_bounds__(128) lcs_tick_kernel_clk(const LcsParams p) {
     LcsSmem sm;
     lcs_smem_carve(sm, lcs_smem_raw, p.Ap);
     LcsThread th;
+    th.k = 0;
     long long* dbg = p.dbg + (size_t)s * 16;
     int k = 0;
 #define STAMP() do { if (tid == 0) dbg[k] = clock64(); k++; } while (0)
@@ -150,7 +178,7 @@ __global__ void __launch_bounds__(128) lcs_tick_kernel_clk(const LcsParams p) {
         STAMP(); // 8: collision drain
         lcs_phase_metrics_out(p, sm, s, tid, th);
         __syncthreads();
-        lcs_phase_stats_out(p, sm, s, tid);
+        lcs_phase_stats_out(p, sm, s, tid, th);
     }
     STAMP(); // 9: end
 #undef STAMP
@@ -169,6 +197,17 @@ static void lcs_launch_tick(const LcsParams& pfull, cudaStream_t stream, int s0 
         return;
     }
     const size_t smem = lcs_smem_bytes(p.Ap);
+    if (p.n_ticks > 1 && p.mode == 0) {
+        if (p.Ap <= 128)
+            lcs_rollout_kernel<128><<<nblk, p.Ap, smem, stream>>>(p);
+        else if (p.Ap <= 256)
+            lcs_rollout_kernel<256><<<nblk, p.Ap, smem, stream>>>(p);
+        else if (p.Ap <= 512)
+            lcs_rollout_kernel<512><<<nblk, p.Ap, smem, stream>>>(p);
+        else
+            lcs_rollout_kernel<1024><<<nblk, p.Ap, smem, stream>>>(p);
+        return;
+    }
     if (p.Ap <= 128)
         lcs_tick_kernel_ldg<128><<<nblk, p.Ap, smem, stream>>>(p);
     else if (p.Ap <= 256)
@@ -181,14 +220,18 @@ static void lcs_launch_tick(const LcsParams& pfull, cudaStream_t stream, int s0 
     const int Ap = p.Ap;
     std::vector<unsigned char> raw(lcs_smem_bytes(Ap) + 16);
     std::vector<LcsThread> ths(Ap);
+    const int n_ticks = p.mode == 0 && p.n_ticks > 1 ? p.n_ticks : 1;
     for (int s = 0; s < p.S; s++) {
         if (p.mode == 1 && p.reset_mask && !p.reset_mask[s]) continue;
         LcsSmem sm;
         lcs_smem_carve(sm, (unsigned char*)(((uintptr_t)raw.data() + 15) & ~(uintptr_t)15), Ap);
 #define TH ths[tid]
 #define LCS_FOR_T for (int tid = 0; tid < Ap; tid++)
-        LCS_FOR_T lcs_phase_update(p, sm, s, tid, TH);
-        LCS_TICK_REST((void)0, LCS_FOR_T)
+        for (int k = 0; k < n_ticks; k++) {
+            LCS_FOR_T ths[tid].k = k;
+            LCS_FOR_T lcs_phase_update(p, sm, s, tid, TH);
+            LCS_TICK_REST((void)0, LCS_FOR_T)
+        }
 #undef LCS_FOR_T
 #undef TH
     }
@@ -458,6 +501,8 @@ struct lcsim_b200_engine {
     int P = 0;
     double* env_act = nullptr; // [S][2] staging of env_step actions
     lcsim_b200_env_out* env_out = nullptr; // [S] staging of env_step outputs
+    LcsWpRec* wp_rec = nullptr;
+    int fused = 1; // rollout(): one launch for all ticks (LCSIM_B200_FUSED=0: one launch per tick)
     int n_groups = 1; // rollout() splits the batch into this many scenario groups, one stream each
 #ifndef LCSIM_HOSTEMU
     cudaStream_t gstream[8] = {};
@@ -575,6 +620,16 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     LCS_ALLOC(e, p.traj_vel0, SAT * 2);
     LCS_ALLOC(e, p.traj_h0, SAT);
     LCS_ALLOC(e, p.tf_xy0, SA * p.Tp);
+    {
+        const char* env = getenv("LCSIM_B200_RECORDS"); // =0: experiments without the replay records
+        if (!(env && env[0] == '0')) {
+            LCS_ALLOC(e, e->wp_rec, SAT);
+            p.wp_rec = e->wp_rec;
+        }
+        env = getenv("LCSIM_B200_FUSED");
+        e->fused = !(env && env[0] == '0');
+    }
+    p.n_ticks = 1;
     LCS_ALLOC(e, p.traj_len, SA);
     LCS_ALLOC(e, p.traj_xy, SAT * 2);
     LCS_ALLOC(e, p.traj_vel, SAT * 2);
@@ -630,6 +685,7 @@ struct Staging {
     std::vector<uint8_t> dynamic;
     std::vector<double> length, width, home_xy, traj_xy, traj_vel, traj_h, s_tab, edge_xy, edge_dir;
     std::vector<lcs_f2> tf_xy, ge_xy;
+    std::vector<LcsWpRec> wp_rec;
     std::vector<float> grid_geom, eta;
 };
 
@@ -704,6 +760,11 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     g.traj_vel.assign(SAT * 2, 0.0);
     g.traj_h.assign(SAT, 0.0);
     g.s_tab.assign(SAT, 0.0);
+    if (e->wp_rec) {
+        LcsWpRec z;
+        memset(&z, 0, sizeof z);
+        g.wp_rec.assign(SAT, z);
+    }
     lcs_f2 far;
     far.x = LCS_FAR;
     far.y = LCS_FAR;
@@ -764,6 +825,29 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
                     seg[k] = std::sqrt(dx * dx + dy * dy);
                 }
                 for (int k = 0; k < n; k++) g.s_tab[dst * T + k] = np_sum_rec(seg.data(), k);
+                if (e->wp_rec) {
+                    const double* vel = st->traj_vel + src * T * 2;
+                    const double* hd = st->traj_h + src * T;
+                    for (int k = 0; k < n; k++) {
+                        LcsWpRec& r = g.wp_rec[dst * T + k];
+                        r.x = xy[2 * k];
+                        r.y = xy[2 * k + 1];
+                        r.h = hd[k];
+                        const double vx = vel[2 * k], vy = vel[2 * k + 1];
+                        const double vx2 = vx * vx, vy2 = vy * vy; // rounded products: no contraction possible below
+                        r.v = std::sqrt(vx2 + vy2);
+                        r.vn = std::sqrt(std::fma(vy, vy, vx2));
+                        r.ch = std::cos(r.h);
+                        r.sh = std::sin(r.h);
+                        int canon = k;
+                        for (int j = 0; j < k; j++) {
+                            const double dx = xy[2 * j] - xy[2 * k], dy = xy[2 * j + 1] - xy[2 * k + 1];
+                            const double dx2 = dx * dx, dy2 = dy * dy;
+                            if (std::sqrt(dx2 + dy2) == 0.0) { canon = j; break; }
+                        }
+                        r.canon = canon;
+                    }
+                }
             }
             for (int i = 0; i < A; i++) g.wait_order[(size_t)s * Ap + i] = st->wait_order[(size_t)s * A + i];
             // ---- road edges: exact arrays + hash grid over the de-duplicated float32 points
@@ -866,6 +950,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     LCS_UP(p.traj_h, g.traj_h);
     LCS_UP(p.tf_xy, g.tf_xy);
     LCS_UP(e->s_tab0, g.s_tab);
+    if (e->wp_rec) LCS_UP(e->wp_rec, g.wp_rec);
     LCS_UP(p.edge_xy, g.edge_xy);
     LCS_UP(p.edge_dir, g.edge_dir);
     LCS_UP(p.grid_geom, g.grid_geom);
@@ -914,6 +999,32 @@ extern "C" int lcsim_b200_step(lcsim_b200_engine* e, const int32_t* act_agent, c
     return 0;
 }
 
+// n_ticks steps without external actions; tick_log (device, [n_ticks][S][4], may be null) receives per tick and
+// scenario: agents updated, active agents after the tick, collision-count sum, off-road count (with_metrics only)
+static int lcs_rollout(lcsim_b200_engine* e, int n_ticks, int32_t* tick_log, void* stream) {
+    if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "rollout before upload_static");
+    if (n_ticks == 0) return 0;
+    LcsParams q = e->p;
+    q.mode = 0;
+    q.K = 0;
+    q.tick_log = tick_log;
+    if (e->fused && !q.dbg) {
+        q.n_ticks = n_ticks;
+        lcs_launch_tick(q, (cudaStream_t)stream);
+        e->launches++;
+        LCS_CUDA(e, cudaGetLastError());
+        return 0;
+    }
+    for (int k = 0; k < n_ticks; k++) {
+        q.n_ticks = 1;
+        if (tick_log) q.tick_log = tick_log + (size_t)k * q.S * 4;
+        lcs_launch_tick(q, (cudaStream_t)stream);
+        e->launches++;
+    }
+    LCS_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
 extern "C" int lcsim_b200_rollout(lcsim_b200_engine* e, int n_ticks, void* stream) {
     if (!e || n_ticks < 0) return LCSIM_B200_ERR_ARG;
 #ifndef LCSIM_HOSTEMU
@@ -940,11 +1051,12 @@ extern "C" int lcsim_b200_rollout(lcsim_b200_engine* e, int n_ticks, void* strea
         return 0;
     }
 #endif
-    for (int k = 0; k < n_ticks; k++) {
-        int rc = lcsim_b200_step(e, nullptr, nullptr, nullptr, 0, stream);
-        if (rc) return rc;
-    }
-    return 0;
+    return lcs_rollout(e, n_ticks, nullptr, stream);
+}
+
+extern "C" int lcsim_b200_rollout_log(lcsim_b200_engine* e, int n_ticks, int32_t* tick_log, void* stream) {
+    if (!e || n_ticks < 0) return LCSIM_B200_ERR_ARG;
+    return lcs_rollout(e, n_ticks, tick_log, stream);
 }
 
 extern "C" int lcsim_b200_set_ref_trajectory(lcsim_b200_engine* e, const int32_t* scenario, const int32_t* agent,

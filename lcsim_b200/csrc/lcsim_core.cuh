@@ -78,6 +78,19 @@ LCS_D double lcs_inf_d() {
 #endif
 }
 
+// Replay record of waypoint k of a pristine (float64) reference trajectory: everything the policy's own STATE
+// action (StateExpert, expert_policy.py:18-33 -> agent.py:377-388) produces when it lands on that waypoint, so the
+// log-replay update is one 64-byte load.  canon = first index j with sqrt((x_j-x_k)^2 + (y_j-y_k)^2) == 0, i.e. the
+// value Trajectory.next (type.py:42-48) returns for a query that IS waypoint k: the distance to k is exactly 0, the
+// global minimum, and np.argmin takes the first index that attains it.
+struct alignas(64) LcsWpRec {
+    double x, y, h;
+    double v; // np.sqrt(vx**2 + vy**2)                (agent.py:383, unfused)
+    double ch, sh; // cos / sin of h
+    double vn; // np.linalg.norm(vel) = sqrt(ddot)      (idm_policy.py:200, BLAS order: vx*vx then fma)
+    int32_t canon, pad;
+};
+
 // Everything a tick needs, as raw device pointers.  Layouts: DESIGN.md §3.
 struct LcsParams {
     int32_t S, A, Ap, T, Tp, E; // Tp = T rounded up to 4 points (32-byte filter entries)
@@ -95,6 +108,7 @@ struct LcsParams {
     // pristine trajectories (reset restores re-planned ones from here)
     const int32_t* traj_len0;
     const double *traj_xy0, *traj_vel0, *traj_h0; // [S][Ap][T][2], [S][Ap][T][2], [S][Ap][T]
+    const LcsWpRec* wp_rec; // [S][Ap][T] replay records of the pristine trajectories (null: not built)
     const lcs_f2* tf_xy0; // [S][Ap][Tp] float32 filter copy, contiguous per agent, relative to the origin;
                           // exact duplicates and the padding past traj_len -> LCS_FAR
     // ---- current trajectories (set_ref_trajectory overwrites)
@@ -139,6 +153,8 @@ struct LcsParams {
     int32_t prefetch; // LCSIM_B200_PREFETCH=1 (default off): early L2 prefetch of the per-agent lines
     int32_t s0; // first scenario of this launch (sub-batch launches)
     int32_t mode; // 0 = step, 1 = reset
+    int32_t n_ticks; // ticks per launch of the fused rollout kernel (1 for the per-tick kernel)
+    int32_t* tick_log; // [n_ticks][S][4] agents updated, active after, collision sum, off-road sum (or null)
     const uint8_t* reset_mask; // [S] or null
 };
 
@@ -158,6 +174,7 @@ struct LcsSmem {
     uint16_t* cand; // [LCS_CAND][Ap] per-thread broadphase survivors
     uint32_t* mask; // [3][32] ballot words: finished, popped, activated
     int32_t* misc; // [8] n_old, n_new, collision sum, off-road sum, tick, wait_ptr, queue length
+    uint8_t* moved; // [Ap] 0: the agent's position is bit-identical to the one its edge outputs were computed for (agent index)
 };
 
 #ifdef LCSIM_HOSTEMU
@@ -166,7 +183,7 @@ static inline
 __host__ __device__ inline
 #endif
 size_t lcs_smem_bytes(int Ap) {
-    return (size_t)Ap * (64 + 8 + 32 + 4 * 4 + 4 * LCS_QPER + 2 * LCS_CAND) + 3 * 32 * 4 + 8 * 4 + 64;
+    return (size_t)Ap * (64 + 8 + 32 + 4 * 4 + 4 * LCS_QPER + 2 * LCS_CAND + 1) + 3 * 32 * 4 + 8 * 4 + 64;
 }
 
 LCS_D void lcs_smem_carve(LcsSmem& sm, unsigned char* base, int Ap) {
@@ -182,7 +199,8 @@ LCS_D void lcs_smem_carve(LcsSmem& sm, unsigned char* base, int Ap) {
     sm.queue = (uint32_t*)p; p += (size_t)Ap * 4 * LCS_QPER;
     sm.mask = (uint32_t*)p; p += 3 * 32 * 4;
     sm.misc = (int32_t*)p; p += 8 * 4;
-    sm.cand = (uint16_t*)p;
+    sm.cand = (uint16_t*)p; p += (size_t)Ap * 2 * LCS_CAND;
+    sm.moved = (uint8_t*)p;
 }
 
 // ------------------------------------------------------------------ small float64 helpers
@@ -744,6 +762,7 @@ LCS_D int lcs_sat_f32(const double* ea, const double* eb) {
 struct LcsThread { // per-thread values that live across phases (registers on the device)
     bool fin, pop, act;
     int aw, off;
+    int k; // tick index inside the launch (fused rollout kernel)
 };
 
 LCS_D void lcs_store_ex(LcsSmem& sm, int a, double x, double y, double v, double ch, double sh, double L, double W, double h) {
@@ -815,7 +834,9 @@ LCS_D void lcs_reset_agent(const LcsParams& p, int s, int a) {
 struct LcsUpd {
     double x, y, h, v, ch, sh, qx, qy;
     int len;
+    int direct; // >= 0: the cursor is known without a scan (replay record)
     bool ring_f32;
+    bool moved; // new position differs from the old one
 };
 LCS_D void lcs_update_pre(const LcsParams& p, int s, int a, LcsUpd& u) {
     const size_t ia = (size_t)s * p.Ap + a;
@@ -844,17 +865,38 @@ LCS_D void lcs_update_pre(const LcsParams& p, int s, int a, LcsUpd& u) {
         d0 = lcs_dmul(p.ads_action[2 * s], 6.0);
         d1 = lcs_dmul(p.ads_action[2 * s + 1], 0.3);
     }
+    u.direct = -1;
+    const double x_old = x, y_old = y;
     if (type == LCS_ACT_NONE) {
         double wp[5];
-        const bool wp_f32 = lcs_policy_waypoint(p, ia, cursor, len, wp);
-        if (p.reactive) {
-            // ---- TrajIDM.get_action (idm_policy.py:196-224), dt = 0.1 default argument
-            const double pdt = 0.1;
-            double vn = lcs_norm2_vec(wp[2], wp[3]);
+        bool wp_f32 = false;
+        double vn;
+        // pristine float64 trajectory and a fresh observation: the waypoint comes as one replay record
+        const bool use_rec = p.wp_rec && !p.stale_valid[ia] && !p.traj_f32[ia];
+        if (use_rec) {
+            const LcsWpRec r = p.wp_rec[ia * p.T + (len == 1 ? cursor : cursor + 1)];
+            if (!p.reactive) {
+                // StateExpert -> STATE action -> Trajectory.next(new xy): all of it is in the record
+                u.x = r.x; u.y = r.y; u.h = r.h; u.v = r.v; u.ch = r.ch; u.sh = r.sh; u.qx = r.x; u.qy = r.y;
+                u.len = len;
+                u.direct = r.canon;
+                u.ring_f32 = false;
+                u.moved = !(r.x == x_old && r.y == y_old);
+                return;
+            }
+            wp[4] = r.h;
+            vn = r.vn;
+        } else {
+            wp_f32 = lcs_policy_waypoint(p, ia, cursor, len, wp);
+            vn = lcs_norm2_vec(wp[2], wp[3]);
             if (wp_f32) {
                 const float fvx = (float)wp[2], fvy = (float)wp[3];
                 vn = (double)sqrtf(fmaf(fvy, fvy, lcs_fmul(fvx, fvx))); // float32 BLAS-style dot
             }
+        }
+        if (p.reactive) {
+            // ---- TrajIDM.get_action (idm_policy.py:196-224), dt = 0.1 default argument
+            const double pdt = 0.1;
             double acc = lcs_npclip(lcs_dsub(vn, v) / pdt, -3.0, 3.0);
             const double dh = lcs_wrap_angle(lcs_dsub(wp[4], h));
             double steer;
@@ -913,11 +955,13 @@ LCS_D void lcs_update_pre(const LcsParams& p, int s, int a, LcsUpd& u) {
     u.x = x; u.y = y; u.h = h; u.v = v; u.ch = ch; u.sh = sh; u.qx = qx; u.qy = qy;
     u.len = len;
     u.ring_f32 = ring_f32;
+    u.moved = !(x == x_old && y == y_old);
 }
 LCS_D bool lcs_update_post(const LcsParams& p, LcsSmem& sm, int s, int a, const LcsUpd& u, const LcsScan& sc) {
     const size_t ia = (size_t)s * p.Ap + a;
-    const int cursor = lcs_scan_finish(p, s, a, u.len, u.qx, u.qy, sc);
+    const int cursor = u.direct >= 0 ? u.direct : lcs_scan_finish(p, s, a, u.len, u.qx, u.qy, sc);
     p.cursor[ia] = cursor;
+    sm.moved[a] = u.moved ? 1 : 0;
     lcs_ring_push(p, ia, u.x, u.y, u.h, u.v, u.ch, u.sh, u.ring_f32);
     lcs_store_pose(p, s, ia, u.x, u.y, u.h, u.v);
     lcs_store_ex(sm, a, u.x, u.y, u.v, u.ch, u.sh, p.length[ia], p.width[ia], u.h);
@@ -988,6 +1032,7 @@ LCS_D int lcs_phase_init(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThr
         sm.misc[6] = 0; // pair-queue length
     }
     sm.cnt[tid] = 0;
+    sm.moved[tid] = 1; // agents that enter the list this tick have no edge outputs yet
     sm.lead_key[tid] = ~0ull;
     t.fin = false;
     t.off = 0;
@@ -1005,8 +1050,10 @@ LCS_D void lcs_phase_update(const LcsParams& p, LcsSmem& sm, int s, int tid, Lcs
     LcsUpd u;
     LcsScan sc;
     lcs_update_pre(p, s, a, u);
-    lcs_scan_begin(p, s, u.qx, u.qy, sc);
-    lcs_scan_global(p, s, a, u.len, sc);
+    if (u.direct < 0) {
+        lcs_scan_begin(p, s, u.qx, u.qy, sc);
+        lcs_scan_global(p, s, a, u.len, sc);
+    }
     t.fin = lcs_update_post(p, sm, s, a, u, sc);
 }
 
@@ -1239,6 +1286,12 @@ LCS_D void lcs_phase_offroad(const LcsParams& p, LcsSmem& sm, int s, int tid, Lc
     if (tid >= sm.misc[1]) return;
     const int a = sm.act2[tid];
     const size_t ia = (size_t)s * p.Ap + a;
+    if (!sm.moved[a]) {
+        // same query as the tick before (parked / waiting agents, exact-duplicate waypoints): the stored nearest
+        // point and side flag were computed for exactly this position and stay as they are
+        t.off = p.offroad[ia];
+        return;
+    }
     bool off;
     const int k = lcs_nearest_edge_hint(p, s, sm.ex[8 * a], sm.ex[8 * a + 1], p.edge_hint[ia], &off);
     p.nearest_edge[ia] = k;
@@ -1255,10 +1308,17 @@ LCS_D void lcs_phase_metrics_out(const LcsParams& p, LcsSmem& sm, int s, int tid
     if (c) lcs_atomic_add(&sm.misc[2], c);
     if (t.off) lcs_atomic_add(&sm.misc[3], 1);
 }
-LCS_D void lcs_phase_stats_out(const LcsParams& p, LcsSmem& sm, int s, int tid) {
+LCS_D void lcs_phase_stats_out(const LcsParams& p, LcsSmem& sm, int s, int tid, const LcsThread& t) {
     if (tid == 0 && p.mode == 0) {
         int64_t* st = p.stats + (size_t)s * LCS_NSTAT;
         st[2] += sm.misc[2];
         st[3] += sm.misc[3];
+        if (p.tick_log) {
+            int32_t* lg = p.tick_log + ((size_t)t.k * p.S + s) * 4;
+            lg[0] = sm.misc[0];
+            lg[1] = sm.misc[1];
+            lg[2] = sm.misc[2];
+            lg[3] = sm.misc[3];
+        }
     }
 }

@@ -68,6 +68,39 @@ def test_synthetic_batch_matches_oracle_every_tick(backend, synth8, reactive):
     be.close()
 
 
+@pytest.mark.parametrize("reactive", [False, True])
+def test_fused_rollout_matches_oracle(backend, synth8, reactive):
+    """lcsim_b200_rollout_log: all ticks of a scenario in one launch.  The end state equals the oracle's after the
+    same number of steps, the per-tick log equals the oracle's per-tick sums, and a rollout split into uneven
+    chunks (1 + 17 + 73 ticks: per-tick kernel, then two fused launches) lands on bit-identical state."""
+    sb = synth8
+    o = orc.Oracle(sb, reactive=reactive)
+    want = np.zeros((91, sb.S, 4), np.int64)
+    for k in range(91):
+        want[k, :, 0] = o.n_active
+        o.step()
+        o.metrics()
+        want[k, :, 1] = o.n_active
+        want[k, :, 2] = o.coll_count.sum(axis=1)
+        want[k, :, 3] = o.offroad.sum(axis=1)
+    be = BatchEngine(sb, reactive=reactive, with_metrics=True, backend=backend)
+    tn = be.backend.to_numpy
+    log = tn(be.rollout(91, log=True))
+    np.testing.assert_array_equal(log, want)
+    compare_engine_with_oracle(be, o, POSE_TOL)
+    np.testing.assert_allclose(tn(be.ring_ordered()), o.ring, rtol=0, atol=POSE_TOL)
+    np.testing.assert_array_equal(tn(be.stats)[:, 0], o.agent_steps)
+    keys = ("pose64", "pose32", "status", "cursor", "active", "coll_count", "nearest_edge", "offroad", "ring", "ring_head",
+            "stats", "lead_valid", "lead_dis", "lead_v")
+    snap = {k: tn(getattr(be, k)).copy() for k in keys}
+    be.reset()
+    parts = [tn(be.rollout(n, log=True)) for n in (1, 17, 73)]
+    np.testing.assert_array_equal(np.concatenate(parts), want)
+    for k, v in snap.items():
+        np.testing.assert_array_equal(tn(getattr(be, k)), v, err_msg=k)
+    be.close()
+
+
 def test_external_actions_all_types(backend, synth8):
     """BICYCLE / DELTA / STATE actions for several agents per scenario (policy-action mode, agent.py:377-416)."""
     sb = synth8.scenario_slice(0, 4)
