@@ -502,7 +502,7 @@ struct lcsim_b200_engine {
     double* env_act = nullptr; // [S][2] staging of env_step actions
     lcsim_b200_env_out* env_out = nullptr; // [S] staging of env_step outputs
     LcsWpRec* wp_rec = nullptr;
-    int fused = 1; // rollout(): one launch for all ticks (LCSIM_B200_FUSED=0: one launch per tick)
+    int fused = -1; // rollout(): 1 = one launch for all ticks, 0 = one launch per tick, -1 = by batch size
     int n_groups = 1; // rollout() splits the batch into this many scenario groups, one stream each
 #ifndef LCSIM_HOSTEMU
     cudaStream_t gstream[8] = {};
@@ -626,8 +626,11 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
             LCS_ALLOC(e, e->wp_rec, SAT);
             p.wp_rec = e->wp_rec;
         }
+        // rollout(): -1 = pick per batch (fused when the batch needs more than one wave of CTAs: no tail per tick;
+        // per-tick launches when all scenarios are co-resident: lock-step phases share the instruction cache and
+        // measured 7 % faster at S = 1024), 0 / 1 = force
         env = getenv("LCSIM_B200_FUSED");
-        e->fused = !(env && env[0] == '0');
+        e->fused = env ? (env[0] == '0' ? 0 : 1) : -1;
     }
     p.n_ticks = 1;
     LCS_ALLOC(e, p.traj_len, SA);
@@ -1008,7 +1011,8 @@ static int lcs_rollout(lcsim_b200_engine* e, int n_ticks, int32_t* tick_log, voi
     q.mode = 0;
     q.K = 0;
     q.tick_log = tick_log;
-    if (e->fused && !q.dbg) {
+    const int fused = e->fused >= 0 ? e->fused : (q.S > 148 * LCS_MIN_CTAS || q.Ap > 128);
+    if (fused && !q.dbg) {
         q.n_ticks = n_ticks;
         lcs_launch_tick(q, (cudaStream_t)stream);
         e->launches++;

@@ -68,11 +68,13 @@ def test_synthetic_batch_matches_oracle_every_tick(backend, synth8, reactive):
     be.close()
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
 @pytest.mark.parametrize("reactive", [False, True])
-def test_fused_rollout_matches_oracle(backend, synth8, reactive):
+def test_fused_rollout_matches_oracle(backend, synth8, reactive, fused, monkeypatch):
     """lcsim_b200_rollout_log: all ticks of a scenario in one launch.  The end state equals the oracle's after the
     same number of steps, the per-tick log equals the oracle's per-tick sums, and a rollout split into uneven
     chunks (1 + 17 + 73 ticks: per-tick kernel, then two fused launches) lands on bit-identical state."""
+    monkeypatch.setenv("LCSIM_B200_FUSED", fused)  # read by lcsim_b200_create: force the fused / per-tick form
     sb = synth8
     o = orc.Oracle(sb, reactive=reactive)
     want = np.zeros((91, sb.S, 4), np.int64)
