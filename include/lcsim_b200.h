@@ -235,6 +235,34 @@ typedef struct {
 int lcsim_b200_env_step(lcsim_b200_engine* e, const double* actions_host, const double* coef6,
                         lcsim_b200_env_out* out_host, int sync, void* stream);
 
+/* Lane-centreline projection.  The centreline points are Junction.roadgraph_points restricted to
+ * the centreline types 1|2 (junction/junction.py:186-253 <- lane/lane.py:108-124: the 0.5 m-resampled lane
+ * centrelines, float32, lane order); upload them once: xy_theta [S][N][3] = x, y, atan2(dir_y, dir_x) (float32,
+ * world frame like the reference's tensors), ids [S][N] = polyline (lane) id of every point.
+ * packer.centreline_points() builds both from a scenario. */
+int lcsim_b200_upload_centrelines(lcsim_b200_engine* e, const int32_t* n_pts, const float* xy_theta, const int32_t* ids,
+                                  int N);
+
+/* For every ACTIVE agent (query = float32 world position and heading of its pose), outputs [S][A_stride], device,
+ * caller-owned, any may be NULL; inactive agents get -1 / +inf / -1:
+ *   lane_pt      first-index argmin over the centreline points of the float32 squared distance
+ *   lane_id      ids[lane_pt]: the lane the agent is on (the integer lane id a WOMD agent lacks in the reference)
+ *   lane_dist    sqrt of that minimum
+ *   onlane_dist  OnLane.loss's per-query term (motion_diff/modules/guidance.py:100-133): min distance over the
+ *                points with |wrap(heading - theta)| < 0.2 and distance < 5.0, +inf if none
+ *   heading_diff compute_lane_heading_diff's per-query term (motion_diff/metrics/roadgraph.py:146-155): min
+ *                |wrap(heading - theta)| over the top_k (64 in the reference, <= 64) nearest points by squared
+ *                distance; -1 when the scenario has fewer than top_k centreline points (the reference skips it). */
+typedef struct {
+    int32_t top_k;
+    int32_t* lane_pt;
+    int32_t* lane_id;
+    float* lane_dist;
+    float* onlane_dist;
+    float* heading_diff;
+} lcsim_b200_lane_desc;
+int lcsim_b200_project_lanes(lcsim_b200_engine* e, const lcsim_b200_lane_desc* d, void* stream);
+
 int lcsim_b200_views(lcsim_b200_engine* e, lcsim_b200_state_views* out);
 
 /* Sums the per-scenario statistics into stats_device[LCSIM_B200_N_STATS] (int64, device). */

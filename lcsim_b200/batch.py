@@ -218,6 +218,36 @@ class BatchEngine:
         self._keep = eg
         return out
 
+    # ------------------------------------------------------------------ lane-centreline projection
+    def upload_centrelines(self, points):
+        """points: per scenario a tuple (xy_theta (N_s,3) float32, ids (N_s,) int32) — packer.centreline_points()."""
+        assert len(points) == self.S
+        N = max(1, max(len(p[0]) for p in points))
+        arr = np.zeros((self.S, N, 3), np.float32)
+        ids = np.zeros((self.S, N), np.int32)
+        n = np.zeros(self.S, np.int32)
+        for i, (xyt, pid) in enumerate(points):
+            n[i] = len(xyt)
+            arr[i, : len(xyt)] = xyt
+            ids[i, : len(xyt)] = pid
+        self._check(self.lib.lcsim_b200_upload_centrelines(self._h, n.ctypes.data, arr.ctypes.data, ids.ctypes.data, N),
+                    "upload_centrelines")
+
+    def project_lanes(self, top_k: int = 64):
+        """Nearest lane-centreline point / lane id / OnLane distance / top-k heading difference of every active agent
+        (include/lcsim_b200.h lcsim_b200_lane_desc).  Returns a dict of (S, A) device tensors."""
+        b = self.backend
+        out = dict(lane_pt=b.empty((self.S, self.A_stride), np.int32), lane_id=b.empty((self.S, self.A_stride), np.int32),
+                   lane_dist=b.empty((self.S, self.A_stride), np.float32),
+                   onlane_dist=b.empty((self.S, self.A_stride), np.float32),
+                   heading_diff=b.empty((self.S, self.A_stride), np.float32))
+        d = native.LaneDesc()
+        d.top_k = int(top_k)
+        for k, v in out.items():
+            setattr(d, k, b.ptr(v))
+        self._check(self.lib.lcsim_b200_project_lanes(self._h, C.byref(d), b.stream()), "project_lanes")
+        return {k: v[:, : self.A] for k, v in out.items()}
+
     # ------------------------------------------------------------------ aggregates
     def episode_stats(self):
         """(8,) int64 device tensor: this rank's sums (see native.STAT_KEYS)."""

@@ -34,6 +34,7 @@ static cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
 static cudaError_t cudaDeviceSynchronize() { return 0; }
 static cudaError_t cudaGetLastError() { return 0; }
 #define __global__
+struct alignas(16) float4 { float x, y, z, w; };
 #else
 #include <cuda_runtime.h>
 #endif
@@ -502,6 +503,9 @@ struct lcsim_b200_engine {
     double* env_act = nullptr; // [S][2] staging of env_step actions
     lcsim_b200_env_out* env_out = nullptr; // [S] staging of env_step outputs
     LcsWpRec* wp_rec = nullptr;
+    float* lane_pts = nullptr; // [S][N][4] centreline points x, y, theta, 0 (upload_centrelines)
+    int32_t *lane_ids = nullptr, *lane_n = nullptr;
+    int lane_N = 0;
     int fused = -1; // rollout(): 1 = one launch for all ticks, 0 = one launch per tick, -1 = by batch size
     int n_groups = 1; // rollout() splits the batch into this many scenario groups, one stream each
 #ifndef LCSIM_HOSTEMU
@@ -1360,6 +1364,209 @@ extern "C" int lcsim_b200_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_d
     LCS_CUDA(e, cudaGetLastError());
 #else
     for (int s = 0; s < e->p.S; s++) lcs_obs_scenario_serial(e->p, o, s);
+#endif
+    return 0;
+}
+
+// ---- lane-centreline projection -----------------------------------------------------------
+// The reference never projects a WOMD agent onto a lane inside the engine (agents carry lane=None, agent.py:133-139);
+// the lane-centreline projections live in motion_diff: OnLane.loss (modules/guidance.py:100-133: nearest centreline
+// point with |wrap(dheading)| < 0.2 rad and distance < 5 m) and compute_lane_heading_diff (metrics/roadgraph.py:
+// 91-157: among the 64 nearest centreline points by squared distance, the smallest |wrap(dheading)|).  Both work on
+// the float32 tensors Junction.roadgraph_points (junction.py:186-253) restricted to centreline types 1|2, i.e. the
+// 0.5 m-resampled lane centrelines in lane order.  One kernel produces, for every ACTIVE agent (query = its float32
+// world position and heading, like data["agent"]["xyz"/"heading"]): the first-index argmin point, that point's
+// polyline id (= the agent's lane), the distance, the OnLane gated distance and the top-K heading difference.
+struct LcsLaneArgs {
+    lcsim_b200_lane_desc d;
+    const float4* pts; // [S][N] x, y, theta = atan2(dir_y, dir_x) (float32, computed at upload), unused
+    const int32_t* ids; // [S][N]
+    const int32_t* n_pts; // [S]
+    int N, K;
+};
+#define LCS_LANE_TILE 1024
+#define LCS_LANE_KMAX 64
+
+LCS_D float lcs_lane_d2(float qx, float qy, float px, float py) {
+    const float dx = qx - px, dy = qy - py;
+    return lcs_fadd(lcs_fmul(dx, dx), lcs_fmul(dy, dy)); // torch: sum((q - c) ** 2, -1), unfused
+}
+// serial statement of one query (host emulation, and the definition the kernel is tested against)
+LCS_D void lcs_lane_query_serial(const LcsLaneArgs& o, int s, float qx, float qy, float qh, int* best_i, float* best_d2,
+                                 float* on_d2, float* hdiff, float* heap_d, int* heap_i) {
+    const float4* P = o.pts + (size_t)s * o.N;
+    const int n = o.n_pts[s], K = o.K;
+    *best_i = -1;
+    *best_d2 = lcs_inf_f();
+    *on_d2 = lcs_inf_f();
+    int hn = 0;
+    for (int k = 0; k < n; k++) {
+        const float d2 = lcs_lane_d2(qx, qy, P[k].x, P[k].y);
+        if (d2 < *best_d2) { *best_d2 = d2; *best_i = k; }
+        if (d2 < *on_d2 && sqrtf(d2) < 5.0f && fabsf(lcs_wrap_f32(qh - P[k].z)) < 0.2f) *on_d2 = d2;
+        if (K > 0) { // bounded set of the K smallest (d2, index): replace the current maximum
+            if (hn < K) {
+                heap_d[hn] = d2; heap_i[hn] = k; hn++;
+            } else {
+                int m = 0;
+                for (int q = 1; q < K; q++)
+                    if (heap_d[q] > heap_d[m] || (heap_d[q] == heap_d[m] && heap_i[q] > heap_i[m])) m = q;
+                if (d2 < heap_d[m]) { heap_d[m] = d2; heap_i[m] = k; }
+            }
+        }
+    }
+    *hdiff = -1.0f; // fewer than K centreline points: the reference skips the batch (roadgraph.py:144-145)
+    if (K > 0 && hn == K) {
+        float best = lcs_inf_f();
+        for (int q = 0; q < K; q++) best = fminf(best, fabsf(lcs_wrap_f32(qh - P[heap_i[q]].z)));
+        *hdiff = best;
+    }
+}
+LCS_D void lcs_lane_store(const LcsParams& p, const LcsLaneArgs& o, int s, int a, int bi, float bd2, float on_d2, float hd) {
+    const size_t ia = (size_t)s * p.Ap + a;
+    if (o.d.lane_pt) o.d.lane_pt[ia] = bi;
+    if (o.d.lane_id) o.d.lane_id[ia] = bi >= 0 ? o.ids[(size_t)s * o.N + bi] : -1;
+    if (o.d.lane_dist) o.d.lane_dist[ia] = bi >= 0 ? sqrtf(bd2) : lcs_inf_f();
+    if (o.d.onlane_dist) o.d.onlane_dist[ia] = sqrtf(on_d2);
+    if (o.d.heading_diff) o.d.heading_diff[ia] = hd;
+}
+LCS_D void lcs_lane_store_inactive(const LcsParams& p, const LcsLaneArgs& o, int s, int a) {
+    const size_t ia = (size_t)s * p.Ap + a;
+    if (o.d.lane_pt) o.d.lane_pt[ia] = -1;
+    if (o.d.lane_id) o.d.lane_id[ia] = -1;
+    if (o.d.lane_dist) o.d.lane_dist[ia] = lcs_inf_f();
+    if (o.d.onlane_dist) o.d.onlane_dist[ia] = lcs_inf_f();
+    if (o.d.heading_diff) o.d.heading_diff[ia] = -1.0f;
+}
+
+#ifndef LCSIM_HOSTEMU
+// One CTA per scenario, thread = active-list slot; the centreline points stream through shared memory in tiles of
+// LCS_LANE_TILE (coalesced float4 loads), every thread tests its query against the tile.  The K smallest distances
+// of a query live in a shared-memory column [K][threads] (conflict-free); a point enters only when it beats the
+// column's maximum, which is tracked in registers, so the O(K) maximum search runs ~K ln(N/K) times per query.
+__global__ void __launch_bounds__(128) lcs_lane_kernel(const LcsParams p, const LcsLaneArgs o) {
+    extern __shared__ __align__(16) unsigned char lane_smem[];
+    float4* tile = (float4*)lane_smem;
+    float* hd = (float*)(tile + LCS_LANE_TILE); // [K][128]
+    int* hi = (int*)(hd + (size_t)o.K * 128);
+    const int s = blockIdx.x, tid = threadIdx.x, K = o.K;
+    const int n = o.n_pts[s], na = p.n_active[s];
+    const float4* P = o.pts + (size_t)s * o.N;
+    for (int a = tid; a < p.Ap; a += 128)
+        if (a < p.A && p.status[(size_t)s * p.Ap + a] != LCS_ACTIVE) lcs_lane_store_inactive(p, o, s, a);
+    for (int base = 0; base < na; base += 128) {
+        const int slot = base + tid;
+        const int a = slot < na ? p.active[(size_t)s * p.Ap + slot] : -1;
+        float qx = 0, qy = 0, qh = 0;
+        if (a >= 0) {
+            const double* ps = p.pose64 + 4 * ((size_t)s * p.Ap + a);
+            qx = (float)ps[0]; qy = (float)ps[1]; qh = (float)ps[2];
+        }
+        int bi = -1, hn = 0, hmax_q = 0;
+        float bd2 = lcs_inf_f(), on_d2 = lcs_inf_f(), hmax = lcs_inf_f();
+        int hmax_i = 0x7fffffff;
+        for (int t0 = 0; t0 < n; t0 += LCS_LANE_TILE) {
+            __syncthreads();
+            for (int k = tid; k < LCS_LANE_TILE && t0 + k < n; k += 128) tile[k] = P[t0 + k];
+            __syncthreads();
+            if (a < 0) continue;
+            const int m = min(LCS_LANE_TILE, n - t0);
+            for (int k = 0; k < m; k++) {
+                const float4 c = tile[k];
+                const float d2 = lcs_lane_d2(qx, qy, c.x, c.y);
+                if (d2 < bd2) { bd2 = d2; bi = t0 + k; }
+                if (d2 < on_d2 && d2 < 25.001f) // cheap pre-test, then the reference's exact gates
+                    if (sqrtf(d2) < 5.0f && fabsf(lcs_wrap_f32(qh - c.z)) < 0.2f) on_d2 = d2;
+                if (K > 0) {
+                    if (hn < K) {
+                        hd[hn * 128 + tid] = d2; hi[hn * 128 + tid] = t0 + k; hn++;
+                        if (hn == K) { // first full column: find its maximum
+                            hmax_q = 0;
+                            for (int q = 1; q < K; q++) {
+                                const float dq = hd[q * 128 + tid], dm = hd[hmax_q * 128 + tid];
+                                if (dq > dm || (dq == dm && hi[q * 128 + tid] > hi[hmax_q * 128 + tid])) hmax_q = q;
+                            }
+                            hmax = hd[hmax_q * 128 + tid]; hmax_i = hi[hmax_q * 128 + tid];
+                        }
+                    } else if (d2 < hmax) {
+                        hd[hmax_q * 128 + tid] = d2; hi[hmax_q * 128 + tid] = t0 + k;
+                        hmax_q = 0;
+                        for (int q = 1; q < K; q++) {
+                            const float dq = hd[q * 128 + tid], dm = hd[hmax_q * 128 + tid];
+                            if (dq > dm || (dq == dm && hi[q * 128 + tid] > hi[hmax_q * 128 + tid])) hmax_q = q;
+                        }
+                        hmax = hd[hmax_q * 128 + tid]; hmax_i = hi[hmax_q * 128 + tid];
+                    }
+                }
+            }
+        }
+        (void)hmax_i;
+        if (a >= 0) {
+            float hdiff = -1.0f;
+            if (K > 0 && hn == K) {
+                hdiff = lcs_inf_f();
+                for (int q = 0; q < K; q++) hdiff = fminf(hdiff, fabsf(lcs_wrap_f32(qh - P[hi[q * 128 + tid]].z)));
+            }
+            lcs_lane_store(p, o, s, a, bi, bd2, on_d2, hdiff);
+        }
+    }
+}
+#endif
+
+extern "C" int lcsim_b200_upload_centrelines(lcsim_b200_engine* e, const int32_t* n_pts, const float* xy_theta,
+                                             const int32_t* ids, int N) {
+    if (!e || !n_pts || !xy_theta || !ids || N < 1) return LCSIM_B200_ERR_ARG;
+    const int S = e->p.S;
+    std::vector<float> f((size_t)S * N * 4, 0.f);
+    for (int s = 0; s < S; s++) {
+        if (n_pts[s] < 0 || n_pts[s] > N) return lcs_fail(e, LCSIM_B200_ERR_ARG, "scenario %d: n_pts %d out of [0,%d]", s, n_pts[s], N);
+        for (int k = 0; k < n_pts[s]; k++)
+            for (int c = 0; c < 3; c++) f[((size_t)s * N + k) * 4 + c] = xy_theta[((size_t)s * N + k) * 3 + c];
+    }
+    LCS_ALLOC(e, e->lane_pts, (size_t)S * N * 4);
+    LCS_ALLOC(e, e->lane_ids, (size_t)S * N);
+    LCS_ALLOC(e, e->lane_n, S);
+    LCS_CUDA(e, cudaMemcpy(e->lane_pts, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
+    LCS_CUDA(e, cudaMemcpy(e->lane_ids, ids, sizeof(int32_t) * (size_t)S * N, cudaMemcpyHostToDevice));
+    LCS_CUDA(e, cudaMemcpy(e->lane_n, n_pts, sizeof(int32_t) * S, cudaMemcpyHostToDevice));
+    e->lane_N = N;
+    return 0;
+}
+
+extern "C" int lcsim_b200_project_lanes(lcsim_b200_engine* e, const lcsim_b200_lane_desc* d, void* stream) {
+    if (!e || !d) return LCSIM_B200_ERR_ARG;
+    if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "project_lanes before upload_static");
+    if (!e->lane_pts) return lcs_fail(e, LCSIM_B200_ERR_STATE, "project_lanes before upload_centrelines");
+    if (d->top_k < 0 || d->top_k > LCS_LANE_KMAX) return lcs_fail(e, LCSIM_B200_ERR_ARG, "top_k must be in [0,%d]", LCS_LANE_KMAX);
+    LcsLaneArgs o;
+    o.d = *d;
+    o.pts = (const float4*)e->lane_pts;
+    o.ids = e->lane_ids;
+    o.n_pts = e->lane_n;
+    o.N = e->lane_N;
+    o.K = d->heading_diff ? d->top_k : 0;
+#ifndef LCSIM_HOSTEMU
+    const size_t smem = sizeof(float4) * LCS_LANE_TILE + (size_t)o.K * 128 * 8;
+    if (smem > 48 * 1024) LCS_CUDA(e, cudaFuncSetAttribute(lcs_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lcs_lane_kernel<<<e->p.S, 128, smem, (cudaStream_t)stream>>>(e->p, o);
+    LCS_CUDA(e, cudaGetLastError());
+#else
+    const LcsParams& p = e->p;
+    std::vector<float> hd(LCS_LANE_KMAX);
+    std::vector<int> hi(LCS_LANE_KMAX);
+    for (int s = 0; s < p.S; s++)
+        for (int a = 0; a < p.A; a++) {
+            const size_t ia = (size_t)s * p.Ap + a;
+            if (p.status[ia] != LCS_ACTIVE) {
+                lcs_lane_store_inactive(p, o, s, a);
+                continue;
+            }
+            int bi;
+            float bd2, on_d2, hdiff;
+            lcs_lane_query_serial(o, s, (float)p.pose64[4 * ia], (float)p.pose64[4 * ia + 1], (float)p.pose64[4 * ia + 2], &bi, &bd2,
+                                  &on_d2, &hdiff, hd.data(), hi.data());
+            lcs_lane_store(p, o, s, a, bi, bd2, on_d2, hdiff);
+        }
 #endif
     return 0;
 }

@@ -101,9 +101,15 @@ class ObsDesc(C.Structure):
                 ("n_nbr_poly", C.c_void_p), ("history", C.c_void_p), ("history_agent", C.c_void_p)]
 
 
+class LaneDesc(C.Structure):
+    _fields_ = [("top_k", C.c_int32), ("lane_pt", C.c_void_p), ("lane_id", C.c_void_p), ("lane_dist", C.c_void_p),
+                ("onlane_dist", C.c_void_p), ("heading_diff", C.c_void_p)]
+
+
 EXPORTS = ("lcsim_b200_abi_version", "lcsim_b200_create", "lcsim_b200_upload_static", "lcsim_b200_reset",
            "lcsim_b200_step", "lcsim_b200_rollout", "lcsim_b200_rollout_log", "lcsim_b200_set_ref_trajectory", "lcsim_b200_rewards",
-           "lcsim_b200_env_step", "lcsim_b200_upload_polylines", "lcsim_b200_build_obs", "lcsim_b200_views", "lcsim_b200_episode_stats",
+           "lcsim_b200_env_step", "lcsim_b200_upload_polylines", "lcsim_b200_build_obs",
+           "lcsim_b200_upload_centrelines", "lcsim_b200_project_lanes", "lcsim_b200_views", "lcsim_b200_episode_stats",
            "lcsim_b200_launch_count", "lcsim_b200_last_error", "lcsim_b200_destroy")
 
 
@@ -126,6 +132,8 @@ def bind(path: str) -> C.CDLL:
     lib.lcsim_b200_env_step.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.lcsim_b200_upload_polylines.argtypes = [vp, vp, vp, i32]
     lib.lcsim_b200_build_obs.argtypes = [vp, C.POINTER(ObsDesc), vp]
+    lib.lcsim_b200_upload_centrelines.argtypes = [vp, vp, vp, vp, i32]
+    lib.lcsim_b200_project_lanes.argtypes = [vp, C.POINTER(LaneDesc), vp]
     lib.lcsim_b200_views.argtypes = [vp, C.POINTER(StateViews)]
     lib.lcsim_b200_episode_stats.argtypes = [vp, vp, vp]
     lib.lcsim_b200_launch_count.argtypes = [vp]

@@ -205,6 +205,34 @@ def polyline_centres(lanes) -> np.ndarray:
     return np.concatenate(parts) if parts else np.zeros((0, 3))
 
 
+def centreline_points(lanes, lines=()):
+    """The points the reference's lane projections search: Junction.roadgraph_points with type 1|2
+    (motion_diff/modules/guidance.py:110-111, metrics/roadgraph.py:139-142), in the order
+    Junction.init_roadgraph_data concatenates them (junction/junction.py:194-205,240-253): per lane the 0.5 m-resampled
+    centre-line (lane/lane.py:108-124; type CENTER_LINE_TYPE_SURFACE_STREET = 2, polyline id = lane ordinal), then —
+    a quirk of the reference's type test — every junction ROAD LINE whose raw pb type is 1 or 2 (junction.py:122-132
+    stores road-line types without a prefix), polyline id = number of lanes + line ordinal.  float32 xyz and float32
+    get_polyline_dir.  `lanes` = ScenarioArrays.lanes, `lines` = ScenarioArrays.lines.  Returns
+    (xy_theta (N,3) float32 with theta = atan2(dir_y, dir_x) in float32 like roadgraph.py:149, ids (N,) int32,
+    xy_dir (N,4) float32 for parity checks)."""
+    xs, ds, ids = [], [], []
+    polys = [(p, i) for i, (p, _) in enumerate(lanes)]
+    polys += [(p, len(lanes) + j) for j, (p, t) in enumerate(lines) if int(t) in (1, 2)]
+    for p, pid in polys:
+        c = resample_polyline(np.asarray(p, np.float64))
+        if len(c) == 0:
+            continue
+        with_z = np.concatenate([c, np.zeros((len(c), 1))], axis=1)
+        xs.append(c.astype(np.float32))
+        ds.append(polyline_dir(with_z)[:, :2].astype(np.float32))
+        ids.append(np.full(len(c), pid, np.int32))
+    if not xs:
+        return np.zeros((0, 3), np.float32), np.zeros(0, np.int32), np.zeros((0, 4), np.float32)
+    xy, d = np.concatenate(xs), np.concatenate(ds)
+    theta = np.arctan2(d[:, 1], d[:, 0]).astype(np.float32)
+    return np.concatenate([xy, theta[:, None]], axis=1).astype(np.float32), np.concatenate(ids), np.concatenate([xy, d], axis=1)
+
+
 @dataclass
 class StaticBatch:
     """Padded SoA for S scenarios; layout documented in DESIGN.md §3 and include/lcsim_b200.h."""
