@@ -274,6 +274,80 @@ int64_t lcsim_b200_launch_count(const lcsim_b200_engine* e);
 const char* lcsim_b200_last_error(const lcsim_b200_engine* e);
 void lcsim_b200_destroy(lcsim_b200_engine* e);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * City engine: ONE scenario with lane-position agents driven by LaneIDM on the lane graph (SURVEY.md A13,
+ * BASELINE configs[3]: a MOSS-shaped city with up to 200k vehicles).  Replaces, for such a scenario, Engine.reset /
+ * Engine.step (engine.py:132-158,203-225) with AgentManager.update / check_departure_and_arrival / prepare_obs
+ * (manager.py:50-115), the LaneIDM branch of Agent.prepare_obs (agent.py:198-243), LaneIDM.get_action
+ * (policy/idm_policy.py:53-116), the LANE branch of update_runtime_by_action (agent.py:314-376), Lane.* (lane/lane.py:
+ * 171-300), Route.* (agent/route.py:102-203), check_collision_all (manager.py:313-327, via a spatial hash) and
+ * Agent.is_offroad (agent.py:482-494).  NOT built: the forced-lane-change branch (idm_policy.py:118-167,
+ * agent.py:331-368): scalars[6] becomes 1 when the reference would start a lane change.
+ * Static arrays: lcsim_b200.city.CityStatic / pack_city (dense indices in pb order), host pointers. */
+typedef struct {
+    double start, interval;
+    int32_t n_lanes, n_agents, n_esets, n_groups;
+    const double* lane_length; /* [NL] Lane.length */
+    const double* lane_max_speed;
+    const int32_t* lane_road; /* [NL] parent road index or -1 */
+    const int32_t* lane_junction; /* [NL] parent junction index or -1 */
+    const int32_t* lane_offset; /* [NL] offset_in_road */
+    const int32_t* lane_succ0; /* [NL] first successor (unique_successor of junction lanes) or -1 */
+    const int32_t* lane_node_start; /* [NL+1] */
+    const double* node_xy; /* [NN][2] raw centre-line nodes */
+    const double* node_cum; /* [NN] Lane.line_lengths */
+    const double* node_dir; /* [NN] Lane.line_directions of the segment ending at the node */
+    const int32_t* lane_eset; /* [NL] edge set Agent.is_offroad checks on this lane */
+    const int32_t* eset_start; /* [n_esets+1] */
+    const double* edge_xy; /* [NE][2] */
+    const double* edge_dir; /* [NE][2] */
+    const int32_t* grp_start; /* [n_groups+1] junction lane groups (junction.py:90-103) */
+    const int32_t* grp_lane; /* junction lane index */
+    const int32_t* grp_pre_offset; /* offset_in_road of the lane's first predecessor (route.py:93-99) */
+    const double* length; /* [N] */
+    const double* width;
+    const double* idm; /* [N][5] usual_braking_a, max_braking_a, max_a, max_v, min_gap (idm_policy.py:42-51) */
+    const int32_t* home_lane;
+    const double* home_s;
+    const int32_t* end_road; /* road index of trip.end's lane */
+    const int32_t* end_offset; /* its offset_in_road */
+    const double* end_s;
+    const int32_t* depart_tick; /* first tick j with departure_time <= t_j (float64 clock) */
+    const int32_t* wait_order; /* agents sorted by departure time (stable) */
+    const int32_t* route_start; /* [N+1] into the concatenated road lists */
+    const int32_t* route_grp; /* group index of every consecutive road pair: hop h of agent a = route_grp[route_start[a] - a + h] */
+} lcsim_b200_city_static;
+
+typedef struct {
+    int32_t N, n_lanes, H;
+    int32_t* scalars; /* [16] 0: n_active, 1: waiting-list pointer, 2: current_step, 6: lane change required (unsupported) */
+    int32_t* active; /* [N] active_agents, list order */
+    int32_t* status; /* [N] */
+    int32_t* lane; /* [N] runtime.lane (dense index) */
+    double* s; /* [N] runtime.s */
+    double* v;
+    double* xy; /* [N][2] */
+    double* heading;
+    uint8_t* lead_valid; /* obs.ahead_vehicle is not None */
+    double* lead_dis;
+    double* lead_v;
+    int32_t* coll_count; /* check_collision_all() count, 0 for inactive */
+    uint8_t* offroad; /* Agent.is_offroad() */
+    double* ring; /* [N][H][5] circular history */
+    int32_t* ring_head;
+    int32_t* ring_count;
+    int64_t* stats; /* [LCSIM_B200_N_STATS] */
+} lcsim_b200_city_state_views;
+
+typedef struct lcsim_b200_city lcsim_b200_city;
+int lcsim_b200_city_create(const lcsim_b200_city_static* st, int device, int with_metrics, lcsim_b200_city** out);
+int lcsim_b200_city_reset(lcsim_b200_city* e, void* stream);
+int lcsim_b200_city_step(lcsim_b200_city* e, int n_ticks, void* stream);
+int lcsim_b200_city_views(lcsim_b200_city* e, lcsim_b200_city_state_views* out);
+int64_t lcsim_b200_city_launch_count(const lcsim_b200_city* e);
+const char* lcsim_b200_city_last_error(const lcsim_b200_city* e);
+void lcsim_b200_city_destroy(lcsim_b200_city* e);
+
 #ifdef __cplusplus
 }
 #endif

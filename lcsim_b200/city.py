@@ -74,9 +74,13 @@ def make_city(seed: int, grid: int = 3, n_agents: int = 60, n_lanes: int = 2, sp
                 lanes[lid]["right"] = lane_ids[k + 1:]
             edge = lanes[lane_ids[-1]]["pts"] + r * EDGE_OFFSET
             roads.append(dict(id=rid, lane_ids=lane_ids, frm=q, to=jid(ni, nj), u=u, edges=[(edge, proto.ROAD_EDGE_TYPE_BOUNDARY)]))
+    ins_of = [[] for _ in range(grid * grid)]
+    outs_of = [[] for _ in range(grid * grid)]
+    for r in roads:
+        ins_of[r["to"]].append(r)
+        outs_of[r["frm"]].append(r)
     for q in range(grid * grid):
-        ins = [r for r in roads if r["to"] == q]
-        outs = [r for r in roads if r["frm"] == q]
+        ins, outs = ins_of[q], outs_of[q]
         groups, jl, edges = [], [], []
         for ri in ins:
             for ro in outs:

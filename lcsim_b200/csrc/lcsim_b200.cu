@@ -1601,3 +1601,309 @@ extern "C" int lcsim_b200_episode_stats(lcsim_b200_engine* e, int64_t* stats_dev
 
 // not part of the public ABI: device pointer of the phase-clock buffer ([S][16] int64) or NULL
 extern "C" void* lcsim_b200_debug_clocks(lcsim_b200_engine* e) { return e ? (void*)e->p.dbg : nullptr; }
+
+// ====================================================================================================
+// City engine: LaneIDM on a lane graph.  Kernels: lcsim_city.cuh.
+#include "lcsim_city.cuh"
+
+// ---- exclusive prefix sum of int32 (in place), total written to *total (device).  Device: block-local scan of
+// 2048-element tiles, scan of the tile sums by one block, offset add.  n <= 2048 * 2048.
+#ifndef LCSIM_HOSTEMU
+#define LCC_SCAN_TILE 2048
+__global__ void __launch_bounds__(1024) lcc_scan_tiles(int32_t* data, int n, int32_t* tile_sum) {
+    __shared__ int32_t warp_sum[32];
+    const int tid = threadIdx.x, base = blockIdx.x * LCC_SCAN_TILE + 2 * tid;
+    const int a = base < n ? data[base] : 0, b = base + 1 < n ? data[base + 1] : 0;
+    int v = a + b;
+    const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    if (lane == 31) warp_sum[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        int s = warp_sum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += o;
+        }
+        warp_sum[lane] = s;
+    }
+    __syncthreads();
+    const int excl = v - (a + b) + (w > 0 ? warp_sum[w - 1] : 0);
+    if (base < n) data[base] = excl;
+    if (base + 1 < n) data[base + 1] = excl + a;
+    if (tid == 1023) tile_sum[blockIdx.x] = excl + a + b;
+}
+__global__ void __launch_bounds__(1024) lcc_scan_sums(int32_t* tile_sum, int n_tiles, int32_t* total) {
+    __shared__ int32_t buf[1024];
+    __shared__ int32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) { // chunks of 1024 tile sums, one after the other
+        const int i = base + threadIdx.x;
+        const int32_t own = i < n_tiles ? tile_sum[i] : 0;
+        buf[threadIdx.x] = own;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) { // inclusive Hillis-Steele
+            const int32_t o = threadIdx.x >= d ? buf[threadIdx.x - d] : 0;
+            __syncthreads();
+            buf[threadIdx.x] += o;
+            __syncthreads();
+        }
+        if (i < n_tiles) tile_sum[i] = carry + buf[threadIdx.x] - own;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += buf[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry;
+}
+__global__ void lcc_scan_add(int32_t* data, int n, const int32_t* tile_sum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) data[i] += tile_sum[i / LCC_SCAN_TILE];
+}
+#endif
+
+struct lcsim_b200_city {
+    LccP c;
+    std::vector<void*> allocs;
+    int32_t* tile_sum = nullptr;
+    int with_metrics = 1;
+    bool fresh_reset = false;
+    int64_t launches = 0;
+    std::string err;
+};
+
+static void lcc_scan(lcsim_b200_city* e, int32_t* data, int n, int32_t* total, cudaStream_t st) {
+#ifndef LCSIM_HOSTEMU
+    const int tiles = (n + LCC_SCAN_TILE - 1) / LCC_SCAN_TILE;
+    lcc_scan_tiles<<<tiles, 1024, 0, st>>>(data, n, e->tile_sum);
+    lcc_scan_sums<<<1, 1024, 0, st>>>(e->tile_sum, tiles, total);
+    lcc_scan_add<<<(n + 255) / 256, 256, 0, st>>>(data, n, e->tile_sum);
+    e->launches += 3;
+#else
+    int32_t acc = 0;
+    for (int i = 0; i < n; i++) {
+        const int32_t v = data[i];
+        data[i] = acc;
+        acc += v;
+    }
+    if (total) *total = acc;
+#endif
+}
+
+static int lcc_fail(lcsim_b200_city* e, int code, const char* msg) {
+    if (e) e->err = msg;
+    return code;
+}
+template <typename Tp>
+static int lcc_upload(lcsim_b200_city* e, const Tp** dst, const Tp* src, size_t count) {
+    void* ptr = nullptr;
+    if (cudaMalloc(&ptr, std::max<size_t>(count, 1) * sizeof(Tp)) != cudaSuccess) return lcc_fail(e, LCSIM_B200_ERR_NOMEM, "cudaMalloc failed");
+    e->allocs.push_back(ptr);
+    if (count && cudaMemcpy(ptr, src, count * sizeof(Tp), cudaMemcpyHostToDevice) != cudaSuccess) return lcc_fail(e, LCSIM_B200_ERR_CUDA, "cudaMemcpy failed");
+    *dst = (const Tp*)ptr;
+    return 0;
+}
+template <typename Tp>
+static int lcc_alloc(lcsim_b200_city* e, Tp** dst, size_t count) {
+    void* ptr = nullptr;
+    if (cudaMalloc(&ptr, std::max<size_t>(count, 1) * sizeof(Tp)) != cudaSuccess) return lcc_fail(e, LCSIM_B200_ERR_NOMEM, "cudaMalloc failed");
+    e->allocs.push_back(ptr);
+    if (cudaMemset(ptr, 0, std::max<size_t>(count, 1) * sizeof(Tp)) != cudaSuccess) return lcc_fail(e, LCSIM_B200_ERR_CUDA, "cudaMemset failed");
+    *dst = (Tp*)ptr;
+    return 0;
+}
+#define LCC_TRY(x)          \
+    do {                    \
+        int _rc = (x);      \
+        if (_rc) return _rc; \
+    } while (0)
+
+extern "C" const char* lcsim_b200_city_last_error(const lcsim_b200_city* e) { return e ? e->err.c_str() : "null city"; }
+extern "C" int64_t lcsim_b200_city_launch_count(const lcsim_b200_city* e) { return e ? e->launches : 0; }
+extern "C" void lcsim_b200_city_destroy(lcsim_b200_city* e) {
+    if (!e) return;
+    for (void* q : e->allocs) cudaFree(q);
+    delete e;
+}
+
+extern "C" int lcsim_b200_city_create(const lcsim_b200_city_static* st, int device, int with_metrics, lcsim_b200_city** out) {
+    if (!st || !out) return LCSIM_B200_ERR_ARG;
+    *out = nullptr;
+    if (st->n_agents < 1 || st->n_lanes < 1 || st->n_agents >= (1 << 24)) return LCSIM_B200_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) return LCSIM_B200_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return LCSIM_B200_ERR_CUDA;
+    lcsim_b200_city* e = new lcsim_b200_city();
+    *out = e;
+    LccP& c = e->c;
+    memset(&c, 0, sizeof c);
+    const int N = st->n_agents, NL = st->n_lanes;
+    c.N = N;
+    c.NL = NL;
+    c.dt = st->interval;
+    c.with_metrics = e->with_metrics = with_metrics;
+    const int NN = st->lane_node_start[NL];
+    // ---- validation of the graph indices the kernels follow
+    for (int l = 0; l < NL; l++) {
+        if (st->lane_node_start[l + 1] - st->lane_node_start[l] < 2) return lcc_fail(e, LCSIM_B200_ERR_ARG, "lane with fewer than 2 centre-line nodes");
+        if ((st->lane_road[l] >= 0) == (st->lane_junction[l] >= 0)) return lcc_fail(e, LCSIM_B200_ERR_ARG, "lane must belong to exactly one road or junction");
+        if (st->lane_junction[l] >= 0 && (st->lane_succ0[l] < 0 || st->lane_succ0[l] >= NL)) return lcc_fail(e, LCSIM_B200_ERR_ARG, "junction lane without successor");
+        if (st->lane_eset[l] < 0 || st->lane_eset[l] >= st->n_esets) return lcc_fail(e, LCSIM_B200_ERR_ARG, "lane_eset out of range");
+    }
+    const int n_route = st->route_start[N];
+    for (int a = 0; a < N; a++) {
+        if (st->home_lane[a] < 0 || st->home_lane[a] >= NL) return lcc_fail(e, LCSIM_B200_ERR_ARG, "home_lane out of range");
+        if (st->route_start[a + 1] - st->route_start[a] < 1) return lcc_fail(e, LCSIM_B200_ERR_ARG, "agent with an empty route (reference: Route.valid is False)");
+        if (st->wait_order[a] < 0 || st->wait_order[a] >= N) return lcc_fail(e, LCSIM_B200_ERR_ARG, "wait_order out of range");
+        if (a > 0 && st->depart_tick[st->wait_order[a]] < st->depart_tick[st->wait_order[a - 1]]) return lcc_fail(e, LCSIM_B200_ERR_ARG, "depart_tick not sorted along wait_order");
+    }
+    // ---- spatial hash geometry: bounding box of all lane nodes, cell >= largest bounding-circle diameter
+    double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300, diag = 0;
+    for (int k = 0; k < NN; k++) {
+        x0 = std::min(x0, st->node_xy[2 * k]); x1 = std::max(x1, st->node_xy[2 * k]);
+        y0 = std::min(y0, st->node_xy[2 * k + 1]); y1 = std::max(y1, st->node_xy[2 * k + 1]);
+    }
+    for (int a = 0; a < N; a++) diag = std::max(diag, std::sqrt(st->length[a] * st->length[a] + st->width[a] * st->width[a]));
+    double cell = std::max(8.0, diag * 1.01 + 1e-3);
+    for (;;) { // bound the table
+        c.cell_w = (int)std::floor((x1 - x0) / cell) + 1;
+        c.cell_h = (int)std::floor((y1 - y0) / cell) + 1;
+        if ((int64_t)c.cell_w * c.cell_h <= 4000000) break;
+        cell *= 1.5;
+    }
+    c.n_cells = c.cell_w * c.cell_h;
+    c.cell_x0 = x0; c.cell_y0 = y0; c.cell_inv = 1.0 / cell;
+    // ---- static
+    LCC_TRY(lcc_upload(e, &c.lane_length, st->lane_length, NL));
+    LCC_TRY(lcc_upload(e, &c.lane_max_speed, st->lane_max_speed, NL));
+    LCC_TRY(lcc_upload(e, &c.lane_road, st->lane_road, NL));
+    LCC_TRY(lcc_upload(e, &c.lane_junction, st->lane_junction, NL));
+    LCC_TRY(lcc_upload(e, &c.lane_offset, st->lane_offset, NL));
+    LCC_TRY(lcc_upload(e, &c.lane_succ0, st->lane_succ0, NL));
+    LCC_TRY(lcc_upload(e, &c.lane_node_start, st->lane_node_start, NL + 1));
+    LCC_TRY(lcc_upload(e, &c.lane_eset, st->lane_eset, NL));
+    LCC_TRY(lcc_upload(e, &c.node_xy, st->node_xy, (size_t)NN * 2));
+    LCC_TRY(lcc_upload(e, &c.node_cum, st->node_cum, NN));
+    LCC_TRY(lcc_upload(e, &c.node_dir, st->node_dir, NN));
+    LCC_TRY(lcc_upload(e, &c.eset_start, st->eset_start, st->n_esets + 1));
+    LCC_TRY(lcc_upload(e, &c.edge_xy, st->edge_xy, (size_t)st->eset_start[st->n_esets] * 2));
+    LCC_TRY(lcc_upload(e, &c.edge_dir, st->edge_dir, (size_t)st->eset_start[st->n_esets] * 2));
+    LCC_TRY(lcc_upload(e, &c.grp_start, st->grp_start, st->n_groups + 1));
+    LCC_TRY(lcc_upload(e, &c.grp_lane, st->grp_lane, st->grp_start[st->n_groups]));
+    LCC_TRY(lcc_upload(e, &c.grp_pre_offset, st->grp_pre_offset, st->grp_start[st->n_groups]));
+    LCC_TRY(lcc_upload(e, &c.length, st->length, N));
+    LCC_TRY(lcc_upload(e, &c.width, st->width, N));
+    LCC_TRY(lcc_upload(e, &c.idm, st->idm, (size_t)N * 5));
+    LCC_TRY(lcc_upload(e, &c.home_s, st->home_s, N));
+    LCC_TRY(lcc_upload(e, &c.end_s, st->end_s, N));
+    LCC_TRY(lcc_upload(e, &c.home_lane, st->home_lane, N));
+    LCC_TRY(lcc_upload(e, &c.end_road, st->end_road, N));
+    LCC_TRY(lcc_upload(e, &c.end_offset, st->end_offset, N));
+    LCC_TRY(lcc_upload(e, &c.depart_tick, st->depart_tick, N));
+    LCC_TRY(lcc_upload(e, &c.wait_order, st->wait_order, N));
+    LCC_TRY(lcc_upload(e, &c.route_start, st->route_start, N + 1));
+    LCC_TRY(lcc_upload(e, &c.route_grp, st->route_grp, std::max(n_route - N, 0)));
+    // ---- state
+    LCC_TRY(lcc_alloc(e, &c.status, N)); LCC_TRY(lcc_alloc(e, &c.lane, N)); LCC_TRY(lcc_alloc(e, &c.r_pop, N));
+    LCC_TRY(lcc_alloc(e, &c.g_pop, N)); LCC_TRY(lcc_alloc(e, &c.at_road, N)); LCC_TRY(lcc_alloc(e, &c.ring_head, N));
+    LCC_TRY(lcc_alloc(e, &c.ring_count, N)); LCC_TRY(lcc_alloc(e, &c.coll_count, N));
+    LCC_TRY(lcc_alloc(e, &c.s, N)); LCC_TRY(lcc_alloc(e, &c.v, N)); LCC_TRY(lcc_alloc(e, &c.xy, (size_t)N * 2));
+    LCC_TRY(lcc_alloc(e, &c.h, N)); LCC_TRY(lcc_alloc(e, &c.lead_dis, N)); LCC_TRY(lcc_alloc(e, &c.lead_v, N));
+    LCC_TRY(lcc_alloc(e, &c.ring, (size_t)N * LCS_H * 5));
+    LCC_TRY(lcc_alloc(e, &c.lead_valid, N)); LCC_TRY(lcc_alloc(e, &c.offroad, N));
+    LCC_TRY(lcc_alloc(e, &c.active, N)); LCC_TRY(lcc_alloc(e, &c.active2, N)); LCC_TRY(lcc_alloc(e, &c.fin, N));
+    LCC_TRY(lcc_alloc(e, &c.rank, N)); LCC_TRY(lcc_alloc(e, &c.scal, 16)); LCC_TRY(lcc_alloc(e, &c.stats, LCS_NSTAT));
+    LCC_TRY(lcc_alloc(e, &c.ent_lane, (size_t)2 * N)); LCC_TRY(lcc_alloc(e, &c.ent_agent, (size_t)2 * N));
+    LCC_TRY(lcc_alloc(e, &c.ent_order, (size_t)2 * N)); LCC_TRY(lcc_alloc(e, &c.ent_s, (size_t)2 * N));
+    LCC_TRY(lcc_alloc(e, &c.lane_start, NL + 1)); LCC_TRY(lcc_alloc(e, &c.lane_cur, NL + 1));
+    LCC_TRY(lcc_alloc(e, &c.bkt_agent, (size_t)2 * N)); LCC_TRY(lcc_alloc(e, &c.bkt_order, (size_t)2 * N));
+    LCC_TRY(lcc_alloc(e, &c.bkt_s, (size_t)2 * N));
+    LCC_TRY(lcc_alloc(e, &c.cell_start, c.n_cells + 1)); LCC_TRY(lcc_alloc(e, &c.cell_cur, c.n_cells + 1));
+    LCC_TRY(lcc_alloc(e, &c.cell_agent, N));
+    const int max_scan = std::max(std::max(N, NL + 1), c.n_cells + 1);
+    LCC_TRY(lcc_alloc(e, &e->tile_sum, max_scan / 2048 + 2));
+    int rc = lcsim_b200_city_reset(e, nullptr);
+    if (rc) return rc;
+    if (cudaDeviceSynchronize() != cudaSuccess) return lcc_fail(e, LCSIM_B200_ERR_CUDA, "reset failed");
+    return 0;
+}
+
+// arrivals/departures -> (lane buckets) -> observations -> metrics: the part of a tick after the update, which is
+// also everything Engine.reset does after re-initialising the agents
+static void lcc_prepare(lcsim_b200_city* e, LccP& c, bool swap_lanes, cudaStream_t st) {
+    const int N = c.N;
+    LCC_RUN(lcc_pop_count, c, N, st);
+    cudaMemcpyAsync(c.rank, c.fin, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, st);
+    lcc_scan(e, c.rank, N, c.scal + LCC_N_ARR, st);
+    LCC_RUN(lcc_place, c, N, st);
+    LCC_RUN(lcc_place_end, c, 1, st);
+    if (swap_lanes) { // Lane.prepare: agents <- new_agents (lane.py:171-175)
+        cudaMemsetAsync(c.lane_start, 0, sizeof(int32_t) * (c.NL + 1), st);
+        LCC_RUN(lcc_bucket_count, c, 2 * N, st);
+        lcc_scan(e, c.lane_start, c.NL + 1, nullptr, st);
+        cudaMemcpyAsync(c.lane_cur, c.lane_start, sizeof(int32_t) * (c.NL + 1), cudaMemcpyDeviceToDevice, st);
+        LCC_RUN(lcc_bucket_scatter, c, 2 * N, st);
+        LCC_RUN(lcc_bucket_end, c, 1, st);
+        e->launches += 3;
+    }
+    LCC_RUN(lcc_observe, c, N, st);
+    e->launches += 4;
+    if (c.with_metrics) {
+        cudaMemsetAsync(c.cell_start, 0, sizeof(int32_t) * (c.n_cells + 1), st);
+        LCC_RUN(lcc_cell_count, c, N, st);
+        lcc_scan(e, c.cell_start, c.n_cells + 1, nullptr, st);
+        cudaMemcpyAsync(c.cell_cur, c.cell_start, sizeof(int32_t) * (c.n_cells + 1), cudaMemcpyDeviceToDevice, st);
+        LCC_RUN(lcc_cell_scatter, c, N, st);
+        LCC_RUN(lcc_collide, c, N, st);
+        LCC_RUN(lcc_offroad, c, N, st);
+        e->launches += 4;
+    }
+    cudaMemcpyAsync(c.active, c.active2, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, st);
+}
+
+extern "C" int lcsim_b200_city_reset(lcsim_b200_city* e, void* stream) {
+    if (!e) return LCSIM_B200_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    LccP c = e->c;
+    c.mode = 1;
+    cudaMemsetAsync(c.scal, 0, sizeof(int32_t) * 16, st);
+    cudaMemsetAsync(c.stats, 0, sizeof(int64_t) * LCS_NSTAT, st);
+    cudaMemsetAsync(c.lane_start, 0, sizeof(int32_t) * (c.NL + 1), st); // lane_manager.reset(): every lane list empty
+    LCC_RUN(lcc_reset_agent, c, c.N, st);
+    e->launches += 1;
+    // Engine.reset (engine.py:139-143) never calls lane_manager.prepare(): the departed agents stay pending
+    lcc_prepare(e, c, false, st);
+    if (cudaGetLastError() != cudaSuccess) return lcc_fail(e, LCSIM_B200_ERR_CUDA, "city reset launch failed");
+    return 0;
+}
+
+extern "C" int lcsim_b200_city_step(lcsim_b200_city* e, int n_ticks, void* stream) {
+    if (!e || n_ticks < 0) return LCSIM_B200_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    LccP c = e->c;
+    c.mode = 0;
+    for (int k = 0; k < n_ticks; k++) {
+        LCC_RUN(lcc_update, c, c.N, st);
+        lcc_prepare(e, c, true, st);
+        LCC_RUN(lcc_tick_end, c, 1, st);
+        e->launches += 2;
+    }
+    if (cudaGetLastError() != cudaSuccess) return lcc_fail(e, LCSIM_B200_ERR_CUDA, "city step launch failed");
+    return 0;
+}
+
+extern "C" int lcsim_b200_city_views(lcsim_b200_city* e, lcsim_b200_city_state_views* v) {
+    if (!e || !v) return LCSIM_B200_ERR_ARG;
+    const LccP& c = e->c;
+    v->N = c.N; v->n_lanes = c.NL; v->H = LCS_H;
+    v->scalars = c.scal; v->active = c.active; v->status = c.status; v->lane = c.lane; v->s = c.s; v->v = c.v; v->xy = c.xy;
+    v->heading = c.h; v->lead_valid = c.lead_valid; v->lead_dis = c.lead_dis; v->lead_v = c.lead_v;
+    v->coll_count = c.coll_count; v->offroad = c.offroad; v->ring = c.ring; v->ring_head = c.ring_head;
+    v->ring_count = c.ring_count; v->stats = c.stats;
+    return 0;
+}

@@ -1,0 +1,458 @@
+// lcsim_city.cuh — LaneIDM stepping on a lane graph (BASELINE configs[3]: one MOSS-shaped city, up to
+// 200k vehicles).  Included by lcsim_b200.cu; same two builds as the rest (nvcc sm_100a / g++ -DLCSIM_HOSTEMU).
+//
+// One scenario, N agents: the parallel axis is the agent (active-list slot), not the scenario, so a tick is a short
+// sequence of flat kernels (one thread per slot / pending lane entry / grid cell) with two prefix sums in between:
+//   update -> arrivals/departures (ordered compaction of the active list) -> lane buckets (the reference's per-lane
+//   SortedDict, rebuilt per tick as a counting sort by lane) -> observations (leader search) -> metrics (uniform
+//   spatial hash + float64 SAT, per-lane edge sets) -> clock.
+// Every decision is the reference's float64 expression with pinned roundings (lcs_dmul / lcs_dadd / ...).
+// Not built: the forced-lane-change branch (idm_policy.py:118-167, agent.py:331-368); `flags[0]` is raised when the
+// reference would start one.
+#pragma once
+
+struct LccP {
+    int32_t N, NL, n_cells, cell_w, cell_h;
+    double dt, cell_x0, cell_y0, cell_inv;
+    int32_t with_metrics;
+    // ---- static: lanes
+    const double *lane_length, *lane_max_speed;
+    const int32_t *lane_road, *lane_junction, *lane_offset, *lane_succ0, *lane_node_start, *lane_eset;
+    const double *node_xy, *node_cum, *node_dir;
+    const int32_t* eset_start;
+    const double *edge_xy, *edge_dir;
+    const int32_t *grp_start, *grp_lane, *grp_pre_offset;
+    // ---- static: agents
+    const double *length, *width, *idm, *home_s, *end_s;
+    const int32_t *home_lane, *end_road, *end_offset, *depart_tick, *wait_order, *route_start, *route_grp;
+    // ---- state: agents
+    int32_t *status, *lane, *r_pop, *g_pop, *at_road, *ring_head, *ring_count, *coll_count;
+    double *s, *v, *xy, *h, *lead_dis, *lead_v, *ring;
+    uint8_t *lead_valid, *offroad;
+    // ---- state: lists
+    int32_t *active, *active2, *fin, *rank; // [N]
+    int32_t* scal; // [16] device scalars, see LCC_* below
+    int64_t* stats; // [LCS_NSTAT]
+    // pending lane entries (Lane.new_agents of all lanes) and the buckets built from them (Lane.agents)
+    int32_t *ent_lane, *ent_agent, *ent_order; // [2N]
+    double* ent_s;
+    int32_t *lane_start, *lane_cur; // [NL+1]
+    int32_t *bkt_agent, *bkt_order; // [2N]
+    double* bkt_s;
+    // spatial hash of the active agents
+    int32_t *cell_start, *cell_cur, *cell_agent; // [n_cells+1], [n_cells+1], [N]
+    int32_t mode; // 1 = reset
+};
+enum { LCC_N_ACTIVE = 0, LCC_WAIT_PTR, LCC_TICK, LCC_N_ENT, LCC_N_ARR, LCC_M_POP, LCC_LC_REQUIRED, LCC_N_BKT, LCC_N_OLD };
+
+#ifndef LCSIM_HOSTEMU
+#define LCC_KERNEL(name)                                          \
+    __global__ void name##_k(const LccP c, int n) {               \
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;      \
+        if (i < n) name(c, i);                                    \
+    }
+#define LCC_RUN(name, c, n, st)                                                                  \
+    do {                                                                                         \
+        if ((n) > 0) name##_k<<<((n) + 255) / 256, 256, 0, st>>>(c, n);                          \
+    } while (0)
+LCS_D double lcc_div(double a, double b) { return __ddiv_rn(a, b); }
+LCS_D void atomicAdd_i64(int64_t* p, int64_t v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
+#else
+#define LCC_KERNEL(name)
+#define LCC_RUN(name, c, n, st)                          \
+    do {                                                 \
+        for (int _i = 0; _i < (n); _i++) name(c, _i);    \
+    } while (0)
+LCS_D double lcc_div(double a, double b) { return a / b; }
+LCS_D void atomicAdd_i64(int64_t* p, int64_t v) { *p += v; }
+#endif
+
+// ------------------------------------------------------------------ lane geometry (lane/lane.py:269-291)
+LCS_D int lcc_segment(const LccP& c, int lane, double& s) {
+    const int a = c.lane_node_start[lane], b = c.lane_node_start[lane + 1];
+    const double L = c.lane_length[lane];
+    s = lcs_pymax(0.0, lcs_pymin(s, L)); // max(0.0, min(s, self.length))
+    int i = 1;
+    for (int k = 1; k < b - a; k++) {
+        i = k;
+        if (s <= c.node_cum[a + k]) break;
+    }
+    return a + i;
+}
+LCS_D void lcc_position(const LccP& c, int lane, double s, double* x, double* y, double* dir) {
+    const int i = lcc_segment(c, lane, s);
+    const double x1 = c.node_xy[2 * (i - 1)], y1 = c.node_xy[2 * (i - 1) + 1], x2 = c.node_xy[2 * i], y2 = c.node_xy[2 * i + 1];
+    const double ratio = lcc_div(lcs_dsub(s, c.node_cum[i - 1]), lcs_dsub(c.node_cum[i], c.node_cum[i - 1]));
+    *x = lcs_dadd(x1, lcs_dmul(ratio, lcs_dsub(x2, x1)));
+    *y = lcs_dadd(y1, lcs_dmul(ratio, lcs_dsub(y2, y1)));
+    *dir = c.node_dir[i];
+}
+
+// ------------------------------------------------------------------ Route (agent/route.py:102-203)
+LCS_D int lcc_group(const LccP& c, int a, int k) { // junc_lane_groups[k] of the remaining route, -1 = none
+    const int n_groups = c.route_start[a + 1] - c.route_start[a] - 1;
+    const int g = c.g_pop[a] + k;
+    return g < n_groups ? c.route_grp[c.route_start[a] - a + g] : -1;
+}
+LCS_D int lcc_junc_lane_by_pre_lane(const LccP& c, int a, int pre_lane, int k) { // route.py:191-203
+    const int g = lcc_group(c, a, k);
+    if (g < 0) return -1;
+    int best = 1000000, index = c.grp_start[g];
+    const int off = c.lane_offset[pre_lane];
+    for (int i = c.grp_start[g]; i < c.grp_start[g + 1]; i++) {
+        int d = off - c.grp_pre_offset[i];
+        d = d < 0 ? -d : d;
+        if (d < best) { best = d; index = i; }
+    }
+    return c.grp_lane[index];
+}
+LCS_D bool lcc_in_candidate(const LccP& c, int a, int lane) { // route.py:138-189, the in_candidate decision
+    const int off = c.lane_offset[lane];
+    const int g = lcc_group(c, a, 0);
+    if (g < 0) return c.end_offset[a] - off == 0;
+    const int lo = c.grp_pre_offset[c.grp_start[g]], hi = c.grp_pre_offset[c.grp_start[g + 1] - 1];
+    return !(lo - off > 0 || hi - off < 0);
+}
+LCS_D int lcc_route_next(const LccP& c, int a, int lane) { // route.py:102-136
+    int nxt;
+    if (c.at_road[a]) {
+        if (lcc_group(c, a, 0) < 0) return -1;
+        if (!lcc_in_candidate(c, a, lane)) c.scal[LCC_LC_REQUIRED] = 1; // reference: group.lanes[-1] / [0] by lc.side
+        nxt = lcc_junc_lane_by_pre_lane(c, a, lane, 0);
+        c.r_pop[a] += 1;
+    } else {
+        nxt = c.lane_succ0[lane];
+        c.g_pop[a] += 1;
+    }
+    c.at_road[a] = !c.at_road[a];
+    return nxt;
+}
+
+// ------------------------------------------------------------------ helpers
+LCS_D void lcc_add_to_lane(const LccP& c, int lane, double s, int a, int order) { // Lane.add_agent (lane.py:207-208)
+    const int e = lcs_atomic_add(&c.scal[LCC_N_ENT], 1);
+    c.ent_lane[e] = lane;
+    c.ent_s[e] = s;
+    c.ent_agent[e] = a;
+    c.ent_order[e] = order;
+}
+LCS_D void lcc_ring_push(const LccP& c, int a) { // agent.py:67-84,159-165,419-426 (circular instead of shifting)
+    const int head = c.ring_head[a];
+    double* r = c.ring + ((size_t)a * LCS_H + head) * 5;
+    double sh, ch;
+    lcs_sincos(c.h[a], &sh, &ch);
+    r[0] = c.xy[2 * a];
+    r[1] = c.xy[2 * a + 1];
+    r[2] = lcs_dmul(c.v[a], ch);
+    r[3] = lcs_dmul(c.v[a], sh);
+    r[4] = c.h[a];
+    c.ring_head[a] = head + 1 == LCS_H ? 0 : head + 1;
+    if (c.ring_count[a] < LCS_H) c.ring_count[a] += 1;
+}
+
+// ------------------------------------------------------------------ reset: Agent.__init__ (agent.py:106-171)
+LCS_D void lcc_reset_agent(const LccP& c, int a) {
+    c.status[a] = LCS_WAITING;
+    c.lane[a] = c.home_lane[a];
+    c.s[a] = c.home_s[a];
+    c.v[a] = 0.0;
+    double x, y, dir;
+    lcc_position(c, c.home_lane[a], c.home_s[a], &x, &y, &dir);
+    c.xy[2 * a] = x;
+    c.xy[2 * a + 1] = y;
+    c.h[a] = dir;
+    c.r_pop[a] = 0;
+    c.g_pop[a] = 0;
+    c.at_road[a] = 1;
+    c.lead_valid[a] = 0;
+    c.lead_dis[a] = lcs_inf_d();
+    c.lead_v[a] = 0.0;
+    c.coll_count[a] = 0;
+    c.offroad[a] = 0;
+    c.ring_head[a] = 0;
+    c.ring_count[a] = 0;
+    for (int k = 0; k < LCS_H * 5; k++) c.ring[(size_t)a * LCS_H * 5 + k] = 0.0;
+    lcc_ring_push(c, a);
+    c.fin[a] = 0;
+    c.active[a] = -1;
+}
+LCC_KERNEL(lcc_reset_agent)
+
+// ------------------------------------------------------------------ update: LaneIDM.get_action + LANE branch
+// idm_policy.py:92-116 _policy_car_follow
+LCS_D double lcc_car_follow(const double* idm, double self_v, double target_v, double ahead_v, double distance) {
+    const double ub = idm[0], mb = idm[1], ma = idm[2], gap = idm[4];
+    double acc;
+    if (distance < 0) {
+        acc = -lcs_inf_d();
+    } else {
+        const double den = lcs_dmul(2.0, sqrt(lcs_dmul(-ub, ma)));
+        const double t = lcs_dadd(lcs_dmul(self_v, 2.0 /* headway, idm_policy.py:35 */), lcc_div(lcs_dmul(self_v, lcs_dsub(self_v, ahead_v)), den));
+        const double s_star = lcs_dadd(gap, lcs_pymax(t, 0.0));
+        const double r1 = lcc_div(self_v, target_v), r2 = lcc_div(s_star, distance);
+        acc = lcs_dmul(ma, lcs_dsub(lcs_dsub(1.0, pow(r1, 4.0)), lcs_dmul(r2, r2)));
+    }
+    return lcs_pymax(mb, lcs_pymin(ma, acc));
+}
+// slot i of the active list: manager.py:105-115 -> idm_policy.py:53-90 -> agent.py:314-376, 419-426
+LCS_D void lcc_update(const LccP& c, int i) {
+    const int n = c.scal[LCC_N_ACTIVE];
+    if (i >= n) {
+        c.fin[i] = 0;
+        return;
+    }
+    const int a = c.active[i];
+    const int lane = c.lane[a];
+    const double* idm = c.idm + 5 * (size_t)a;
+    const bool lv = c.lead_valid[a] != 0;
+    const double distance = lv ? c.lead_dis[a] : lcs_inf_d(), ahead_v = lv ? c.lead_v[a] : 0.0;
+    const double v0 = c.v[a];
+    const double acc = lcc_car_follow(idm, v0, lcs_pymin(idm[3], c.lane_max_speed[lane]), ahead_v, distance);
+    if (c.lane_road[lane] >= 0 && !lcc_in_candidate(c, a, lane)) c.scal[LCC_LC_REQUIRED] = 1; // _policy_lane_change would act
+    // _compute_v_and_dis (agent.py:496-501)
+    const double dt = c.dt, dv = lcs_dmul(acc, dt);
+    double v, ds;
+    if (lcs_dadd(v0, dv) < 0) {
+        v = 0.0;
+        ds = lcc_div(lcs_dmul(-v0, v0), lcs_dmul(2.0, acc));
+    } else {
+        v = lcs_dadd(v0, dv);
+        ds = lcs_dmul(lcs_dadd(v0, lcs_dmul(0.5, dv)), dt);
+    }
+    c.v[a] = v;
+    double s = lcs_dadd(c.s[a], ds);
+    int cur = lane;
+    if (s > c.lane_length[lane]) {
+        while (s > c.lane_length[cur]) {
+            s = lcs_dsub(s, c.lane_length[cur]);
+            const int nxt = lcc_route_next(c, a, cur);
+            if (nxt < 0) break;
+            cur = nxt;
+        }
+    }
+    c.lane[a] = cur;
+    c.s[a] = s;
+    double x, y, dir;
+    lcc_position(c, cur, s, &x, &y, &dir);
+    c.xy[2 * a] = x;
+    c.xy[2 * a + 1] = y;
+    c.h[a] = dir;
+    // check_close_to_end (agent.py:434-441): returns before add_to_lane and the history append
+    if (c.lane_road[cur] >= 0 && c.lane_road[cur] == c.end_road[a] && lcs_dsub(c.end_s[a], s) < 5.0) {
+        c.status[a] = LCS_IDLE; // FINISHED now, IDLE after this tick's check_departure_and_arrival (single-trip schedules)
+        c.fin[i] = 1;
+        c.coll_count[a] = 0;
+        c.offroad[a] = 0;
+        return;
+    }
+    c.fin[i] = 0;
+    lcc_add_to_lane(c, cur, s, a, (1 << 24) | i);
+    lcc_ring_push(c, a);
+}
+LCC_KERNEL(lcc_update)
+
+// ------------------------------------------------------------------ arrivals / departures (manager.py:50-96)
+// waiting offset j: the popped entries are a prefix of the (sorted) waiting list; the last popped one reports m
+LCS_D void lcc_pop_count(const LccP& c, int j) {
+    const int wp = c.scal[LCC_WAIT_PTR], tick = c.scal[LCC_TICK];
+    if (j == 0) {
+        const bool any = wp < c.N && c.depart_tick[c.wait_order[wp]] <= tick;
+        if (!any) c.scal[LCC_M_POP] = 0;
+    }
+    const int p = wp + j;
+    if (p >= c.N) return;
+    if (c.depart_tick[c.wait_order[p]] <= tick && (p + 1 == c.N || c.depart_tick[c.wait_order[p + 1]] > tick)) c.scal[LCC_M_POP] = j + 1;
+}
+LCC_KERNEL(lcc_pop_count)
+// thread i: list slot i and, independently, popped waiting entry i
+LCS_D void lcc_place(const LccP& c, int i) {
+    const int n = c.scal[LCC_N_ACTIVE], n_arr = c.scal[LCC_N_ARR], m = c.scal[LCC_M_POP], wp = c.scal[LCC_WAIT_PTR];
+    if (i < n) {
+        const int r = c.rank[i]; // finished slots before i
+        if (!c.fin[i])
+            c.active2[i - (r > m ? r - m : 0)] = c.active[i];
+        else if (r < m)
+            c.active2[i] = c.wait_order[wp + r]; // departure r takes the slot of the r-th finished agent
+    }
+    if (i < m) {
+        const int a = c.wait_order[wp + i];
+        c.status[a] = LCS_ACTIVE;
+        if (i >= n_arr) c.active2[n + (i - n_arr)] = a;
+        lcc_add_to_lane(c, c.lane[a], c.s[a], a, ((c.mode == 1 ? 0 : 2) << 24) | i); // add_to_lane at the home position
+    }
+}
+LCC_KERNEL(lcc_place)
+LCS_D void lcc_place_end(const LccP& c, int i) {
+    const int n = c.scal[LCC_N_ACTIVE], n_arr = c.scal[LCC_N_ARR], m = c.scal[LCC_M_POP];
+    c.scal[LCC_N_OLD] = n;
+    c.scal[LCC_N_ACTIVE] = n - n_arr + m;
+    c.scal[LCC_WAIT_PTR] += m;
+    if (c.mode == 0) {
+        c.stats[0] += n;
+        c.stats[1] += n - n_arr + m;
+        c.stats[4] += n_arr;
+        c.stats[6] += 1;
+    }
+    c.stats[5] += m;
+}
+LCC_KERNEL(lcc_place_end)
+
+// ------------------------------------------------------------------ lane buckets = Lane.prepare (lane.py:171-175)
+LCS_D void lcc_bucket_count(const LccP& c, int e) {
+    if (e < c.scal[LCC_N_ENT]) lcs_atomic_add(&c.lane_start[c.ent_lane[e]], 1);
+}
+LCC_KERNEL(lcc_bucket_count)
+LCS_D void lcc_bucket_scatter(const LccP& c, int e) {
+    if (e >= c.scal[LCC_N_ENT]) return;
+    const int pos = lcs_atomic_add(&c.lane_cur[c.ent_lane[e]], 1);
+    c.bkt_s[pos] = c.ent_s[e];
+    c.bkt_agent[pos] = c.ent_agent[e];
+    c.bkt_order[pos] = c.ent_order[e];
+}
+LCC_KERNEL(lcc_bucket_scatter)
+LCS_D void lcc_bucket_end(const LccP& c, int i) { c.scal[LCC_N_ENT] = 0; }
+LCC_KERNEL(lcc_bucket_end)
+
+// SortedDict semantics: one entry per key; a later add_agent with the same s replaced the earlier one
+// (lane.py:207-208), so among equal keys the entry with the highest insertion order is the one that exists.
+// get_next_agent_by_s (lane.py:210-217): smallest key > s
+LCS_D bool lcc_next_agent(const LccP& c, int lane, double s, double* ks, int* agent) {
+    double best = lcs_inf_d();
+    int bo = -1, ba = -1;
+    for (int e = c.lane_start[lane]; e < c.lane_start[lane + 1]; e++) {
+        const double k = c.bkt_s[e];
+        if (k > s && (k < best || (k == best && c.bkt_order[e] > bo))) { best = k; bo = c.bkt_order[e]; ba = c.bkt_agent[e]; }
+    }
+    *ks = best;
+    *agent = ba;
+    return ba >= 0;
+}
+// get_first_agent (lane.py:228-234): smallest key
+LCS_D bool lcc_first_agent(const LccP& c, int lane, double* ks, int* agent) {
+    double best = lcs_inf_d();
+    int bo = -1, ba = -1;
+    for (int e = c.lane_start[lane]; e < c.lane_start[lane + 1]; e++) {
+        const double k = c.bkt_s[e];
+        if (ba < 0 || k < best || (k == best && c.bkt_order[e] > bo)) { best = k; bo = c.bkt_order[e]; ba = c.bkt_agent[e]; }
+    }
+    *ks = best;
+    *agent = ba;
+    return ba >= 0;
+}
+
+// ------------------------------------------------------------------ prepare_obs, LaneIDM branch (agent.py:198-243)
+LCS_D void lcc_observe(const LccP& c, int i) {
+    if (i >= c.scal[LCC_N_ACTIVE]) return;
+    const int a = c.active2[i];
+    const int lane = c.lane[a];
+    const double s = c.s[a], len_a = c.length[a];
+    double ks;
+    int other;
+    bool valid = false;
+    double dis = lcs_inf_d(), lv = 0.0;
+    if (lcc_next_agent(c, lane, s, &ks, &other)) {
+        // NB reference: ahead[0] is the leader's absolute s on the lane, not the gap (agent.py:227-230)
+        dis = lcs_dsub(ks, lcc_div(lcs_dadd(len_a, c.length[other]), 2.0));
+        lv = c.v[other];
+        valid = true;
+    } else {
+        const double view = lcs_pymax(50.0, lcs_dmul(c.v[a], 12.0));
+        double look = lcs_dsub(c.lane_length[lane], s);
+        int cur = lane, junc_index = 0;
+        while (look < view) {
+            if (c.lane_junction[cur] >= 0) {
+                cur = c.lane_succ0[cur];
+                junc_index++;
+            } else {
+                cur = lcc_junc_lane_by_pre_lane(c, a, cur, junc_index);
+            }
+            if (cur < 0) break;
+            if (lcc_first_agent(c, cur, &ks, &other)) {
+                dis = lcs_dsub(lcs_dadd(look, ks), lcc_div(lcs_dadd(len_a, c.length[other]), 2.0));
+                lv = c.v[other];
+                valid = true;
+                break;
+            }
+            look = lcs_dadd(look, c.lane_length[cur]);
+        }
+    }
+    c.lead_valid[a] = valid ? 1 : 0;
+    c.lead_dis[a] = dis;
+    c.lead_v[a] = lv;
+}
+LCC_KERNEL(lcc_observe)
+
+// ------------------------------------------------------------------ metrics
+// uniform spatial hash of the active agents; cell >= the largest bounding-circle diameter, so every overlapping
+// pair lies in neighbouring cells (check_collision_all, manager.py:313-327, is all pairs in the reference)
+LCS_D int lcc_cell_of(const LccP& c, int a) {
+    int cx = (int)floor(lcs_dmul(lcs_dsub(c.xy[2 * a], c.cell_x0), c.cell_inv));
+    int cy = (int)floor(lcs_dmul(lcs_dsub(c.xy[2 * a + 1], c.cell_y0), c.cell_inv));
+    cx = cx < 0 ? 0 : (cx >= c.cell_w ? c.cell_w - 1 : cx);
+    cy = cy < 0 ? 0 : (cy >= c.cell_h ? c.cell_h - 1 : cy);
+    return cy * c.cell_w + cx;
+}
+LCS_D void lcc_cell_count(const LccP& c, int i) {
+    if (i < c.scal[LCC_N_ACTIVE]) lcs_atomic_add(&c.cell_start[lcc_cell_of(c, c.active2[i])], 1);
+}
+LCC_KERNEL(lcc_cell_count)
+LCS_D void lcc_cell_scatter(const LccP& c, int i) {
+    if (i >= c.scal[LCC_N_ACTIVE]) return;
+    const int a = c.active2[i];
+    c.cell_agent[lcs_atomic_add(&c.cell_cur[lcc_cell_of(c, a)], 1)] = a;
+}
+LCC_KERNEL(lcc_cell_scatter)
+LCS_D void lcc_box(const LccP& c, int a, double* ex) {
+    double sh, ch;
+    lcs_sincos(c.h[a], &sh, &ch);
+    ex[0] = c.xy[2 * a]; ex[1] = c.xy[2 * a + 1]; ex[2] = c.v[a]; ex[3] = ch; ex[4] = sh; ex[5] = c.length[a]; ex[6] = c.width[a]; ex[7] = c.h[a];
+}
+LCS_D void lcc_collide(const LccP& c, int i) {
+    if (i >= c.scal[LCC_N_ACTIVE]) return;
+    const int a = c.active2[i];
+    double ea[8], eb[8];
+    lcc_box(c, a, ea);
+    const double ra = 0.5 * sqrt(ea[5] * ea[5] + ea[6] * ea[6]);
+    const int cell = lcc_cell_of(c, a), cx = cell % c.cell_w, cy = cell / c.cell_w;
+    int cnt = 0;
+    for (int y = cy - 1; y <= cy + 1; y++) {
+        if (y < 0 || y >= c.cell_h) continue;
+        for (int x = cx - 1; x <= cx + 1; x++) {
+            if (x < 0 || x >= c.cell_w) continue;
+            const int q = y * c.cell_w + x;
+            for (int e = c.cell_start[q]; e < c.cell_start[q + 1]; e++) {
+                const int b = c.cell_agent[e];
+                if (b == a) continue;
+                const double dx = c.xy[2 * b] - ea[0], dy = c.xy[2 * b + 1] - ea[1];
+                const double rb = 0.5 * sqrt(c.length[b] * c.length[b] + c.width[b] * c.width[b]);
+                const double rr = (ra + rb) * 1.000001 + 1e-6; // bounding circles apart: the SAT cannot overlap
+                if (dx * dx + dy * dy > rr * rr) continue;
+                lcc_box(c, b, eb);
+                if (lcs_collide(ea, eb)) cnt++;
+            }
+        }
+    }
+    c.coll_count[a] = cnt;
+    if (cnt) atomicAdd_i64(&c.stats[2], cnt);
+}
+LCC_KERNEL(lcc_collide)
+// Agent.is_offroad (agent.py:482-494) -> Road.check_offroad (road.py:342-362, raw nodes) /
+// Junction.check_offroad (junction.py:365-385, resampled): first-index argmin, side by the 2-D cross product
+LCS_D void lcc_offroad(const LccP& c, int i) {
+    if (i >= c.scal[LCC_N_ACTIVE]) return;
+    const int a = c.active2[i];
+    const int es = c.lane_eset[c.lane[a]];
+    const int b = c.eset_start[es], e = c.eset_start[es + 1];
+    const double px = c.xy[2 * a], py = c.xy[2 * a + 1];
+    uint8_t off = 0;
+    if (e > b) {
+        const int k = b + lcs_argmin_exact(c.edge_xy + 2 * (size_t)b, e - b, px, py);
+        const double ax = lcs_dsub(c.edge_xy[2 * k], px), ay = lcs_dsub(c.edge_xy[2 * k + 1], py);
+        off = lcs_dsub(lcs_dmul(ax, c.edge_dir[2 * k + 1]), lcs_dmul(ay, c.edge_dir[2 * k])) < 0 ? 1 : 0;
+    }
+    c.offroad[a] = off;
+    if (off) atomicAdd_i64(&c.stats[3], 1);
+}
+LCC_KERNEL(lcc_offroad)
+LCS_D void lcc_tick_end(const LccP& c, int i) { c.scal[LCC_TICK] += 1; }
+LCC_KERNEL(lcc_tick_end)

@@ -17,7 +17,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 SRC = os.path.join(_HERE, "csrc", "lcsim_b200.cu")
-HDRS = [os.path.join(_HERE, "csrc", "lcsim_core.cuh"), os.path.join(ROOT, "include", "lcsim_b200.h")]
+HDRS = [os.path.join(_HERE, "csrc", "lcsim_core.cuh"), os.path.join(_HERE, "csrc", "lcsim_city.cuh"),
+        os.path.join(ROOT, "include", "lcsim_b200.h")]
 LIB_PATH = os.path.join(_HERE, "liblcsim_b200.so")
 
 ABI_VERSION = 1
@@ -106,11 +107,39 @@ class LaneDesc(C.Structure):
                 ("onlane_dist", C.c_void_p), ("heading_diff", C.c_void_p)]
 
 
+CITY_STATIC_FIELDS = (
+    ("lane_length", np.float64), ("lane_max_speed", np.float64), ("lane_road", np.int32), ("lane_junction", np.int32),
+    ("lane_offset", np.int32), ("lane_succ0", np.int32), ("lane_node_start", np.int32), ("node_xy", np.float64),
+    ("node_cum", np.float64), ("node_dir", np.float64), ("lane_eset", np.int32), ("eset_start", np.int32),
+    ("edge_xy", np.float64), ("edge_dir", np.float64), ("grp_start", np.int32), ("grp_lane", np.int32),
+    ("grp_pre_offset", np.int32), ("length", np.float64), ("width", np.float64), ("idm", np.float64),
+    ("home_lane", np.int32), ("home_s", np.float64), ("end_road", np.int32), ("end_offset", np.int32),
+    ("end_s", np.float64), ("depart_tick", np.int32), ("wait_order", np.int32), ("route_start", np.int32),
+    ("route_grp", np.int32))
+
+
+class CityStaticC(C.Structure):
+    _fields_ = ([("start", C.c_double), ("interval", C.c_double), ("n_lanes", C.c_int32), ("n_agents", C.c_int32),
+                 ("n_esets", C.c_int32), ("n_groups", C.c_int32)] + [(n, C.c_void_p) for n, _ in CITY_STATIC_FIELDS])
+
+
+CITY_VIEW_FIELDS = (("scalars", "<i4"), ("active", "<i4"), ("status", "<i4"), ("lane", "<i4"), ("s", "<f8"), ("v", "<f8"),
+                    ("xy", "<f8"), ("heading", "<f8"), ("lead_valid", "|u1"), ("lead_dis", "<f8"), ("lead_v", "<f8"),
+                    ("coll_count", "<i4"), ("offroad", "|u1"), ("ring", "<f8"), ("ring_head", "<i4"),
+                    ("ring_count", "<i4"), ("stats", "<i8"))
+
+
+class CityViews(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("N", "n_lanes", "H")] + [(n, C.c_void_p) for n, _ in CITY_VIEW_FIELDS]
+
+
 EXPORTS = ("lcsim_b200_abi_version", "lcsim_b200_create", "lcsim_b200_upload_static", "lcsim_b200_reset",
            "lcsim_b200_step", "lcsim_b200_rollout", "lcsim_b200_rollout_log", "lcsim_b200_set_ref_trajectory", "lcsim_b200_rewards",
            "lcsim_b200_env_step", "lcsim_b200_upload_polylines", "lcsim_b200_build_obs",
            "lcsim_b200_upload_centrelines", "lcsim_b200_project_lanes", "lcsim_b200_views", "lcsim_b200_episode_stats",
-           "lcsim_b200_launch_count", "lcsim_b200_last_error", "lcsim_b200_destroy")
+           "lcsim_b200_launch_count", "lcsim_b200_last_error", "lcsim_b200_destroy",
+           "lcsim_b200_city_create", "lcsim_b200_city_reset", "lcsim_b200_city_step", "lcsim_b200_city_views",
+           "lcsim_b200_city_launch_count", "lcsim_b200_city_last_error", "lcsim_b200_city_destroy")
 
 
 def bind(path: str) -> C.CDLL:
@@ -142,6 +171,16 @@ def bind(path: str) -> C.CDLL:
     lib.lcsim_b200_last_error.restype = C.c_char_p
     lib.lcsim_b200_destroy.argtypes = [vp]
     lib.lcsim_b200_destroy.restype = None
+    lib.lcsim_b200_city_create.argtypes = [C.POINTER(CityStaticC), i32, i32, C.POINTER(vp)]
+    lib.lcsim_b200_city_reset.argtypes = [vp, vp]
+    lib.lcsim_b200_city_step.argtypes = [vp, i32, vp]
+    lib.lcsim_b200_city_views.argtypes = [vp, C.POINTER(CityViews)]
+    lib.lcsim_b200_city_launch_count.argtypes = [vp]
+    lib.lcsim_b200_city_launch_count.restype = C.c_int64
+    lib.lcsim_b200_city_last_error.argtypes = [vp]
+    lib.lcsim_b200_city_last_error.restype = C.c_char_p
+    lib.lcsim_b200_city_destroy.argtypes = [vp]
+    lib.lcsim_b200_city_destroy.restype = None
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("lcsim_b200_abi_version",):
