@@ -57,7 +57,7 @@ def run_case_against_golden(c, be, tol=1e-9, replan_tol=2e-6):
     assert int(c.ref["offroad"][1:].sum()) == int(stats[3])
 
 
-def compare_engine_with_oracle(be, o, tol, check_lead=True):
+def compare_engine_with_oracle(be, o, tol, check_lead=True, near_duplicate_edges=None):
     """Whole-batch comparison of the current state of a BatchEngine with an oracle.Oracle (after o.metrics())."""
     A = be.A
     np.testing.assert_array_equal(_np(be, be.n_active), o.n_active, err_msg="n_active")
@@ -72,7 +72,17 @@ def compare_engine_with_oracle(be, o, tol, check_lead=True):
         np.testing.assert_allclose(pose[..., i], getattr(o, nm), rtol=0, atol=tol, err_msg=nm)
     np.testing.assert_array_equal(_np(be, be.coll_count), o.coll_count, err_msg="collision counts")
     np.testing.assert_array_equal(_np(be, be.offroad), o.offroad, err_msg="offroad")
-    np.testing.assert_array_equal(_np(be, be.nearest_edge), o.nearest_edge, err_msg="nearest edge")
+    ne, want = _np(be, be.nearest_edge), o.nearest_edge
+    if near_duplicate_edges is None:
+        np.testing.assert_array_equal(ne, want, err_msg="nearest edge")
+    else:
+        # Poses that went through sin/cos agree with the oracle to an ulp, not to the bit.  Where two
+        # edge points coincide to 1e-9 m (joints of resampled polylines), that ulp may pick the other twin: accepted
+        # here only if the two indices ARE such twins; everything else stays bit-exact.
+        for s, a in np.argwhere(ne != want):
+            e = near_duplicate_edges[s]
+            assert ne[s, a] >= 0 and want[s, a] >= 0 and np.abs(e[ne[s, a]] - e[want[s, a]]).max() < 1e-9, \
+                f"nearest edge of scenario {s} agent {a}: {ne[s, a]} != {want[s, a]}"
     if check_lead and be.reactive:
         activem = o.status == native.ACTIVE
         np.testing.assert_array_equal(_np(be, be.lead_valid)[activem], o.lead_valid[activem], err_msg="lead_valid")
