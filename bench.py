@@ -205,7 +205,40 @@ def run_b200(args):
     value = agent_steps_all / (ms_max * 1e-3)
 
     e2e_val, h2d, d2h = None, 0, 0
+    roll_val, roll_h2d, roll_d2h = None, 0, 0
     if not args.kernel_only:
+        # ------------------------------------------------------------- end-to-end arm ("e2e"): host buffers, one call
+        # The reference-facing call for THIS workload (configs[1]: `engine.reset(); for _ in range(91): engine.step()`
+        # on every scenario, nothing fed in between): lcsim_b200_rollout_host.  Per step (= rollout): H2D of the reset
+        # mask from pinned memory, reset + 91 ticks, D2H of the per-tick log, float32 poses, status, collision counts,
+        # nearest edge, off-road flags and the statistics into pinned memory, stream sync.
+        Ap = be.A_stride
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()  # noqa: E731
+        r_out = dict(tick_log=pin((N_TICKS, S, 4), torch.int32), pose32=pin((S, Ap, 4), torch.float32),
+                     status=pin((S, Ap), torch.int32), coll_count=pin((S, Ap), torch.int32),
+                     nearest_edge=pin((S, Ap), torch.int32), offroad=pin((S, Ap), torch.uint8), stats=pin((8,), torch.int64))
+        r_mask = torch.ones(S, dtype=torch.uint8).pin_memory()
+        roll_h2d = r_mask.numel()
+        roll_d2h = sum(v.numel() * v.element_size() for v in r_out.values())
+        for _ in range(min(args.warmup, 3)):
+            be.rollout_host(N_TICKS, r_out, reset_mask=r_mask)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        roll_steps = 0
+        r0.record()
+        for k in range(args.steps):
+            be.rollout_host(N_TICKS, r_out, reset_mask=r_mask)  # returns after the stream sync: host buffers are final
+            roll_steps += int(r_out["stats"][0])
+        r1.record()
+        barrier()
+        t = torch.tensor([r0.elapsed_time(r1), float(roll_steps)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tm = t.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t[0] = tm[0]
+        roll_val = float(t[1]) / (float(t[0]) * 1e-3)
+
         # ------------------------------------------------------------- end-to-end arm ("e2e"): host buffers
         # The reference-facing call: lcsim_b200_env_step == BicycleSingleEnv.step for all S scenarios.  Every tick the
         # normalised ADS action of every scenario goes host -> device from pinned memory and reward / terms / route /
@@ -285,10 +318,15 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": _config(args, "inputs 1.3 GB/GPU > 126 MB L2; L2 flushed between timed rollouts"),
             "clocks": clocks,
-            "e2e": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "lcsim_b200_env_step per tick (pinned H2D of the ADS action of every scenario, tick, reward kernel, "
-                            "D2H of reward/terms/route/flags, stream sync); per rollout: D2H of pose32/status/collision "
-                            "counts/nearest-edge + episode stats"},
+            "e2e": {"value": roll_val, "unit": "agent-steps/s", "h2d_bytes_per_step": roll_h2d, "d2h_bytes_per_step": roll_d2h,
+                    "what": "lcsim_b200_rollout_host, one call per rollout with pinned host buffers: H2D reset mask, reset + 91 "
+                            "ticks, D2H of the per-tick log [91][S][4], pose32, status, collision counts, nearest edge, "
+                            "off-road flags, statistics; stream sync before the host reads them"},
+            "e2e_env_step": {"value": e2e_val, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                             "what": "RL-style loop (configs[2] call pattern on the same batch): lcsim_b200_env_step per tick "
+                                     "(pinned H2D of every scenario's ADS action, tick, reward kernel, D2H of reward/terms/"
+                                     "route/flags, stream sync every tick) + per rollout D2H of pose32/status/collision "
+                                     "counts/nearest-edge/statistics"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": which,

@@ -171,6 +171,24 @@ int lcsim_b200_rollout(lcsim_b200_engine* e, int n_ticks, void* stream);
  * sum(check_collision_all()) and the number of off-road agents (manager.py:313-345); needs desc.with_metrics. */
 int lcsim_b200_rollout_log(lcsim_b200_engine* e, int n_ticks, int32_t* tick_log, void* stream);
 
+/* A whole rollout with HOST buffers, one call: Engine.reset() for the scenarios whose byte in reset_mask_host is
+ * non-zero (NULL = all; engine.py:132-143), n_ticks x Engine.step() (engine.py:145-158), then everything a caller of
+ * the reference reads back from the engines, copied to host memory (any pointer may be NULL; [S][A_stride] pitch):
+ * the per-tick log of lcsim_b200_rollout_log, float32 poses, status, check_collision_all() counts, nearest edge
+ * point, off-road flags and the batch statistics.  H2D: the mask; D2H: the outputs; sync != 0 waits for the stream.
+ * Use pinned host memory for asynchronous copies. */
+typedef struct {
+    int32_t* tick_log; /* [n_ticks][S][4] */
+    float* pose32; /* [S][A_stride][4] */
+    int32_t* status; /* [S][A_stride] */
+    int32_t* coll_count;
+    int32_t* nearest_edge;
+    uint8_t* offroad;
+    int64_t* stats; /* [LCSIM_B200_N_STATS] */
+} lcsim_b200_rollout_out;
+int lcsim_b200_rollout_host(lcsim_b200_engine* e, const uint8_t* reset_mask_host, int n_ticks,
+                            const lcsim_b200_rollout_out* out, int sync, void* stream);
+
 /* Agent.set_ref_trajectory (agent.py:462-466) as called from Engine._plan_trajectory
  * (engine.py:286-297): n (scenario, agent) pairs receive float32 (T,2) xy, (T,2) vel, (T,) heading
  * straight from device memory; cursor <- 0.  All pointers device. */

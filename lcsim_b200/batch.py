@@ -130,6 +130,21 @@ class BatchEngine:
                     "rollout_log")
         return out
 
+    def rollout_host(self, n_ticks: int, out: dict, reset_mask=None, sync: bool = True):
+        """reset + n_ticks steps + read-back into HOST buffers in one call (lcsim_b200_rollout_host).  ``out`` maps the
+        field names of lcsim_b200_rollout_out to host arrays / pinned tensors: tick_log (n_ticks,S,4) i32, pose32
+        (S,A_stride,4) f32, status / coll_count / nearest_edge (S,A_stride) i32, offroad (S,A_stride) u8, stats (8,) i64;
+        ``reset_mask`` a host (S,) uint8 array or None."""
+        def host_ptr(x):
+            return x.ctypes.data if isinstance(x, np.ndarray) else int(x.data_ptr())
+
+        ro = native.RolloutOut()
+        for k, v in out.items():
+            setattr(ro, k, host_ptr(v))
+        self._check(self.lib.lcsim_b200_rollout_host(self._h, None if reset_mask is None else host_ptr(reset_mask), int(n_ticks),
+                                                     C.byref(ro), int(sync), self.backend.stream()), "rollout_host")
+        self._keep = (out, reset_mask)
+
     # ------------------------------------------------------------------ diffusion-action ingest
     def set_ref_trajectory(self, scenario, agent, xy, vel, heading):
         """Agent.set_ref_trajectory for n (scenario, agent) pairs: xy/vel (n,T,2), heading (n,T) float32."""

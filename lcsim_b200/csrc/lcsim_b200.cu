@@ -503,6 +503,9 @@ struct lcsim_b200_engine {
     double* env_act = nullptr; // [S][2] staging of env_step actions
     lcsim_b200_env_out* env_out = nullptr; // [S] staging of env_step outputs
     LcsWpRec* wp_rec = nullptr;
+    uint8_t* host_mask = nullptr; // rollout_host staging
+    int32_t* tick_log = nullptr;
+    size_t log_ticks = 0;
     float* lane_pts = nullptr; // [S][N][4] centreline points x, y, theta, 0 (upload_centrelines)
     int32_t *lane_ids = nullptr, *lane_n = nullptr;
     int lane_N = 0;
@@ -1065,6 +1068,51 @@ extern "C" int lcsim_b200_rollout(lcsim_b200_engine* e, int n_ticks, void* strea
 extern "C" int lcsim_b200_rollout_log(lcsim_b200_engine* e, int n_ticks, int32_t* tick_log, void* stream) {
     if (!e || n_ticks < 0) return LCSIM_B200_ERR_ARG;
     return lcs_rollout(e, n_ticks, tick_log, stream);
+}
+
+// Host-buffer form of a whole rollout: what a caller of the reference does with `engine.reset(); for _ in range(n):
+// engine.step()` and then reads from the engine, for every scenario of the batch, in ONE call.
+extern "C" int lcsim_b200_rollout_host(lcsim_b200_engine* e, const uint8_t* reset_mask_host, int n_ticks,
+                                       const lcsim_b200_rollout_out* out, int sync, void* stream) {
+    if (!e || n_ticks < 0 || !out) return LCSIM_B200_ERR_ARG;
+    if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "rollout_host before upload_static");
+    cudaStream_t st = (cudaStream_t)stream;
+    const LcsParams& p = e->p;
+    const size_t S = p.S, SA = S * p.Ap;
+    if (!e->host_mask) LCS_ALLOC(e, e->host_mask, S);
+    if (out->tick_log && (size_t)n_ticks > e->log_ticks) {
+        LCS_ALLOC(e, e->tick_log, (size_t)n_ticks * S * 4); // grows only; the old block is freed at destroy
+        e->log_ticks = n_ticks;
+    }
+    if (reset_mask_host) LCS_CUDA(e, cudaMemcpyAsync(e->host_mask, reset_mask_host, S, cudaMemcpyHostToDevice, st));
+    int rc = lcsim_b200_reset(e, reset_mask_host ? e->host_mask : nullptr, stream);
+    if (rc) return rc;
+    rc = lcs_rollout(e, n_ticks, out->tick_log ? e->tick_log : nullptr, stream);
+    if (rc) return rc;
+#ifndef LCSIM_HOSTEMU
+    if (out->stats) lcs_stats_kernel<<<1, 256, 0, st>>>(p.stats, p.S, (int64_t*)e->env_act); // env_act doubles as 64-byte scratch
+#else
+    if (out->stats)
+        for (int k = 0; k < LCS_NSTAT; k++) {
+            int64_t acc = 0;
+            for (size_t s = 0; s < S; s++) acc += p.stats[s * LCS_NSTAT + k];
+            ((int64_t*)e->env_act)[k] = acc;
+        }
+#endif
+#define LCS_D2H(dst, src, bytes) \
+    if (dst) LCS_CUDA(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st))
+    LCS_D2H(out->tick_log, e->tick_log, sizeof(int32_t) * (size_t)n_ticks * S * 4);
+    LCS_D2H(out->pose32, p.pose32, sizeof(float) * 4 * SA);
+    LCS_D2H(out->status, p.status, sizeof(int32_t) * SA);
+    LCS_D2H(out->coll_count, p.coll_count, sizeof(int32_t) * SA);
+    LCS_D2H(out->nearest_edge, p.nearest_edge, sizeof(int32_t) * SA);
+    LCS_D2H(out->offroad, p.offroad, SA);
+    LCS_D2H(out->stats, e->env_act, sizeof(int64_t) * LCS_NSTAT);
+#undef LCS_D2H
+#ifndef LCSIM_HOSTEMU
+    if (sync) LCS_CUDA(e, cudaStreamSynchronize(st));
+#endif
+    return 0;
 }
 
 extern "C" int lcsim_b200_set_ref_trajectory(lcsim_b200_engine* e, const int32_t* scenario, const int32_t* agent,

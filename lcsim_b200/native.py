@@ -102,6 +102,10 @@ class ObsDesc(C.Structure):
                 ("n_nbr_poly", C.c_void_p), ("history", C.c_void_p), ("history_agent", C.c_void_p)]
 
 
+class RolloutOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("tick_log", "pose32", "status", "coll_count", "nearest_edge", "offroad", "stats")]
+
+
 class LaneDesc(C.Structure):
     _fields_ = [("top_k", C.c_int32), ("lane_pt", C.c_void_p), ("lane_id", C.c_void_p), ("lane_dist", C.c_void_p),
                 ("onlane_dist", C.c_void_p), ("heading_diff", C.c_void_p)]
@@ -134,7 +138,7 @@ class CityViews(C.Structure):
 
 
 EXPORTS = ("lcsim_b200_abi_version", "lcsim_b200_create", "lcsim_b200_upload_static", "lcsim_b200_reset",
-           "lcsim_b200_step", "lcsim_b200_rollout", "lcsim_b200_rollout_log", "lcsim_b200_set_ref_trajectory", "lcsim_b200_rewards",
+           "lcsim_b200_step", "lcsim_b200_rollout", "lcsim_b200_rollout_log", "lcsim_b200_rollout_host", "lcsim_b200_set_ref_trajectory", "lcsim_b200_rewards",
            "lcsim_b200_env_step", "lcsim_b200_upload_polylines", "lcsim_b200_build_obs",
            "lcsim_b200_upload_centrelines", "lcsim_b200_project_lanes", "lcsim_b200_views", "lcsim_b200_episode_stats",
            "lcsim_b200_launch_count", "lcsim_b200_last_error", "lcsim_b200_destroy",
@@ -156,6 +160,7 @@ def bind(path: str) -> C.CDLL:
     lib.lcsim_b200_step.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.lcsim_b200_rollout.argtypes = [vp, i32, vp]
     lib.lcsim_b200_rollout_log.argtypes = [vp, i32, vp, vp]
+    lib.lcsim_b200_rollout_host.argtypes = [vp, vp, i32, C.POINTER(RolloutOut), i32, vp]
     lib.lcsim_b200_set_ref_trajectory.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp]
     lib.lcsim_b200_rewards.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.lcsim_b200_env_step.argtypes = [vp, vp, vp, vp, i32, vp]

@@ -103,6 +103,30 @@ def test_fused_rollout_matches_oracle(backend, synth8, reactive, fused, monkeypa
     be.close()
 
 
+def test_rollout_host_buffers(backend, synth8):
+    """lcsim_b200_rollout_host: reset + 91 ticks + read-back into host memory equals the device views and the log"""
+    sb = synth8.scenario_slice(0, 4)
+    be = BatchEngine(sb, reactive=False, with_metrics=True, backend=backend)
+    tn = be.backend.to_numpy
+    want_log = tn(be.rollout(91, log=True)).copy()
+    Ap = be.A_stride
+    out = dict(tick_log=np.zeros((91, sb.S, 4), np.int32), pose32=np.zeros((sb.S, Ap, 4), np.float32),
+               status=np.zeros((sb.S, Ap), np.int32), coll_count=np.zeros((sb.S, Ap), np.int32),
+               nearest_edge=np.zeros((sb.S, Ap), np.int32), offroad=np.zeros((sb.S, Ap), np.uint8), stats=np.zeros(8, np.int64))
+    be.rollout(7)  # dirty state: rollout_host resets first
+    be.rollout_host(91, out)
+    np.testing.assert_array_equal(out["tick_log"], want_log)
+    for k in ("pose32", "status", "coll_count", "nearest_edge", "offroad"):
+        np.testing.assert_array_equal(out[k][:, : be.A], tn(getattr(be, k)), err_msg=k)
+    np.testing.assert_array_equal(out["stats"], tn(be.stats).sum(axis=0))
+    assert out["stats"][0] == want_log[:, :, 0].sum()
+    # masked: only scenario 2 restarts, the others continue from tick 91
+    mask = np.array([0, 0, 1, 0], np.uint8)
+    be.rollout_host(5, dict(stats=out["stats"]), reset_mask=mask)
+    assert tn(be.tick).tolist() == [96, 96, 5, 96]
+    be.close()
+
+
 def test_external_actions_all_types(backend, synth8):
     """BICYCLE / DELTA / STATE actions for several agents per scenario (policy-action mode, agent.py:377-416)."""
     sb = synth8.scenario_slice(0, 4)
