@@ -161,9 +161,8 @@ int lcsim_b200_step(lcsim_b200_engine* e, const int32_t* act_agent, const int32_
 
 /* n_ticks consecutive Engine.step() calls without external actions (engine.py:145-158), i.e. the reference's
  * `for _ in range(n): engine.step()` loop for every scenario of the batch; state and outputs afterwards are those
- * of the last tick.  Batches that need more than one wave of CTAs run as ONE launch (the CTA of a scenario runs all
- * n_ticks ticks back to back; scenarios are independent); batches that are fully co-resident run one launch per
- * tick (measured faster there).  LCSIM_B200_FUSED=0/1 in the environment of create() forces either form. */
+ * of the last tick.  One launch per tick by default; LCSIM_B200_FUSED=1 in the environment of create() selects the
+ * fused kernel in which the CTA of a scenario runs all n_ticks ticks back to back (measured slower on B200). */
 int lcsim_b200_rollout(lcsim_b200_engine* e, int n_ticks, void* stream);
 
 /* Same, and additionally records per tick and scenario what the reference's caller could have read between the

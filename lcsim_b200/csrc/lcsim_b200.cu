@@ -509,7 +509,7 @@ struct lcsim_b200_engine {
     float* lane_pts = nullptr; // [S][N][4] centreline points x, y, theta, 0 (upload_centrelines)
     int32_t *lane_ids = nullptr, *lane_n = nullptr;
     int lane_N = 0;
-    int fused = -1; // rollout(): 1 = one launch for all ticks, 0 = one launch per tick, -1 = by batch size
+    int fused = 0; // rollout(): 1 = one launch for all ticks (LCSIM_B200_FUSED=1), 0 = one launch per tick
     int n_groups = 1; // rollout() splits the batch into this many scenario groups, one stream each
 #ifndef LCSIM_HOSTEMU
     cudaStream_t gstream[8] = {};
@@ -633,11 +633,11 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
             LCS_ALLOC(e, e->wp_rec, SAT);
             p.wp_rec = e->wp_rec;
         }
-        // rollout(): -1 = pick per batch (fused when the batch needs more than one wave of CTAs: no tail per tick;
-        // per-tick launches when all scenarios are co-resident: lock-step phases share the instruction cache and
-        // measured 7 % faster at S = 1024), 0 / 1 = force
+        // rollout(): one launch per tick unless LCSIM_B200_FUSED=1 asks for the fused multi-tick kernel.  Measured on
+        // B200 (profiles/NOTES_r1.md): lock-step per-tick launches are 7-15 % faster at S = 1024 and at S = 4096 (the
+        // fused loop costs registers -> spills, and de-synchronised CTAs thrash the instruction cache)
         env = getenv("LCSIM_B200_FUSED");
-        e->fused = env ? (env[0] == '0' ? 0 : 1) : -1;
+        e->fused = env && env[0] == '1' ? 1 : 0;
     }
     p.n_ticks = 1;
     LCS_ALLOC(e, p.traj_len, SA);
@@ -1018,8 +1018,7 @@ static int lcs_rollout(lcsim_b200_engine* e, int n_ticks, int32_t* tick_log, voi
     q.mode = 0;
     q.K = 0;
     q.tick_log = tick_log;
-    const int fused = e->fused >= 0 ? e->fused : (q.S > 148 * LCS_MIN_CTAS || q.Ap > 128);
-    if (fused && !q.dbg) {
+    if (e->fused && !q.dbg) {
         q.n_ticks = n_ticks;
         lcs_launch_tick(q, (cudaStream_t)stream);
         e->launches++;

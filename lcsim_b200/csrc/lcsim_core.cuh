@@ -262,6 +262,26 @@ LCS_D int lcs_prefix(const uint32_t* words, int tid) { // number of set flags be
     for (int k = 0; k < w; k++) r += lcs_popc(words[k]);
     return r;
 }
+// index of the k-th set flag (k = 0 .. total-1)
+LCS_D int lcs_select(const uint32_t* words, int nwords, int k) {
+    int w = 0;
+    for (; w < nwords - 1; w++) {
+        const int c = lcs_popc(words[w]);
+        if (k < c) break;
+        k -= c;
+    }
+#ifdef LCSIM_HOSTEMU
+    uint32_t x = words[w];
+    for (int b = 0; b < 32; b++)
+        if ((x >> b) & 1u) {
+            if (k == 0) return 32 * w + b;
+            k--;
+        }
+    return 32 * w + 31;
+#else
+    return 32 * w + (int)__fns(words[w], 0, k + 1);
+#endif
+}
 LCS_D int lcs_total(const uint32_t* words, int nwords) {
     int r = 0;
     for (int k = 0; k < nwords; k++) r += lcs_popc(words[k]);
@@ -1131,6 +1151,11 @@ LCS_D void lcs_phase_publish(const LcsParams& p, LcsSmem& sm, int s, int tid) {
     const size_t is = (size_t)s * p.Ap + tid;
     const int n_new = sm.misc[1];
     p.stale_valid[is] = 0; // prepare_obs refreshed every observation (manager.py:98-103)
+    // slots whose agent needs a road-edge search this tick (moved, or new in the list): ballot word row 0, free by now
+#ifdef LCSIM_HOSTEMU
+    if ((tid & 31) == 0) sm.mask[tid >> 5] = 0; // the emulated ballot only sets bits; the device one overwrites the word
+#endif
+    lcs_set_flag(sm.mask, tid, tid < n_new && sm.moved[sm.act2[tid < n_new ? tid : 0]] != 0);
     if (tid >= n_new) {
         p.active[is] = -1;
         return;
@@ -1282,31 +1307,34 @@ LCS_D void lcs_phase_collision_drain(const LcsParams& p, LcsSmem& sm, int s, int
 
 // Phase E3: off-road / nearest edge of every active agent (manager.py:337-345 -> junction.py:387-409)
 LCS_D void lcs_phase_offroad(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
-    t.off = 0;
-    if (tid >= sm.misc[1]) return;
-    const int a = sm.act2[tid];
-    const size_t ia = (size_t)s * p.Ap + a;
-    if (!sm.moved[a]) {
+    t.off = 0; // off-road agents this thread accounts for (summed in lcs_phase_metrics_out)
+    if (tid < sm.misc[1]) {
+        const int a = sm.act2[tid];
         // same query as the tick before (parked / waiting agents, exact-duplicate waypoints): the stored nearest
         // point and side flag were computed for exactly this position and stay as they are
-        t.off = p.offroad[ia];
-        return;
+        if (!sm.moved[a]) t.off = p.offroad[(size_t)s * p.Ap + a];
     }
+    // the searches run on DENSE lanes: thread k takes the k-th slot that needs one (about half of the list moves in
+    // a tick, and a warp pays for the longest search among its lanes whatever their number)
+    const int nw = (p.Ap + 31) >> 5;
+    if (tid >= lcs_total(sm.mask, nw)) return;
+    const int a = sm.act2[lcs_select(sm.mask, nw, tid)];
+    const size_t ia = (size_t)s * p.Ap + a;
     bool off;
     const int k = lcs_nearest_edge_hint(p, s, sm.ex[8 * a], sm.ex[8 * a + 1], p.edge_hint[ia], &off);
     p.nearest_edge[ia] = k;
     p.edge_hint[ia] = k;
     p.offroad[ia] = off ? 1 : 0;
-    t.off = off ? 1 : 0;
+    t.off += off ? 1 : 0;
 }
 
 // Phase F: collision counts out, per-scenario sums.
 LCS_D void lcs_phase_metrics_out(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
+    if (t.off) lcs_atomic_add(&sm.misc[3], t.off); // counted by whichever thread ran that slot's edge search
     if (tid >= sm.misc[1]) return;
     const int c = sm.cnt[tid];
     p.coll_count[(size_t)s * p.Ap + sm.act2[tid]] = c;
     if (c) lcs_atomic_add(&sm.misc[2], c);
-    if (t.off) lcs_atomic_add(&sm.misc[3], 1);
 }
 LCS_D void lcs_phase_stats_out(const LcsParams& p, LcsSmem& sm, int s, int tid, const LcsThread& t) {
     if (tid == 0 && p.mode == 0) {
