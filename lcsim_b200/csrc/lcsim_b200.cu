@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(128) lcs_tick_kernel_clk(const LcsParams p) {
     if (a >= 0) lcs_update_pre(p, s, a, u);
     __syncthreads();
     STAMP(); // 1: pre done
-    if (a >= 0) {
+    if (a >= 0 && u.direct < 0) {
         lcs_scan_begin(p, s, u.qx, u.qy, sc);
         lcs_scan_global(p, s, a, u.len, sc);
     }

@@ -127,6 +127,40 @@ def test_rollout_host_buffers(backend, synth8):
     be.close()
 
 
+def test_oversized_boxes_collision_counts(backend, synth8):
+    """boxes larger than a cell of the collision grid (articulated trucks, 18-30 m) take the all-partners path;
+    far-away agents (external STATE actions outside the grid) are clamped into border cells"""
+    import dataclasses
+
+    sb = synth8.scenario_slice(0, 3)
+    length, width = sb.length.copy(), sb.width.copy()
+    rng = np.random.default_rng(21)
+    for s in range(sb.S):
+        big = rng.choice(sb.A, 12, replace=False)
+        length[s, big] = rng.uniform(18.0, 30.0, 12)
+        width[s, big] = rng.uniform(2.5, 9.0, 12)
+    sb = dataclasses.replace(sb, length=length, width=width)
+    be = BatchEngine(sb, reactive=False, with_metrics=True, backend=backend)
+    o = orc.Oracle(sb, reactive=False)
+    total = 0
+    for k in range(60):
+        aa = np.full((sb.S, 2), -1, np.int32)
+        at = np.zeros((sb.S, 2), np.int32)
+        ad = np.zeros((sb.S, 2, 5))
+        if k % 7 == 3:  # two agents jump far outside the 256 m grid, next to each other
+            aa[:, 0], aa[:, 1] = 5, 9
+            at[:] = native.ACT_STATE
+            ad[:, 0, :2] = [900.0, -700.0]
+            ad[:, 1, :2] = [901.0, -700.5]
+        be.step(aa, at, ad)
+        o.step(aa, at, ad)
+        o.metrics()
+        compare_engine_with_oracle(be, o, POSE_TOL)
+        total += int(o.coll_count.sum())
+    assert total > 500
+    be.close()
+
+
 def test_external_actions_all_types(backend, synth8):
     """BICYCLE / DELTA / STATE actions for several agents per scenario (policy-action mode, agent.py:377-416)."""
     sb = synth8.scenario_slice(0, 4)
