@@ -258,6 +258,8 @@ class CityStatic:
     lane_junction: np.ndarray  # (NL,) i32 parent junction index or -1
     lane_offset: np.ndarray  # (NL,) i32 offset_in_road
     lane_succ0: np.ndarray  # (NL,) i32 first successor (unique_successor for junction lanes) or -1
+    lane_left: np.ndarray  # (NL,) i32 Lane.left_neighbor() or -1 (lane.py:96-98,195-205)
+    lane_right: np.ndarray  # (NL,) i32 Lane.right_neighbor() or -1
     lane_node_start: np.ndarray  # (NL+1,) i32
     node_xy: np.ndarray  # (NN,2) f64 raw centre-line nodes
     node_cum: np.ndarray  # (NN,) f64 Lane.line_lengths
@@ -341,7 +343,9 @@ def pack_city(raw: dict, start: float = 0.0, interval: float = 0.1, max_ticks: i
         lane_pbid=i32(range(NL)), lane_length=lane_len, lane_max_speed=np.asarray([l["max_speed"] for l in lanes], float),
         lane_width=np.asarray([l["width"] for l in lanes], float), lane_road=i32([l["road"] for l in lanes]),
         lane_junction=i32([l["junction"] for l in lanes]), lane_offset=i32([l["offset"] for l in lanes]),
-        lane_succ0=i32([l["succ"][0] if l["succ"] else -1 for l in lanes]), lane_node_start=i32(node_start),
+        lane_succ0=i32([l["succ"][0] if l["succ"] else -1 for l in lanes]),
+        lane_left=i32([l["left"][-1] if l["left"] else -1 for l in lanes]),  # pb lists leftmost first; the reference reverses
+        lane_right=i32([l["right"][0] if l["right"] else -1 for l in lanes]), lane_node_start=i32(node_start),
         node_xy=np.concatenate(nodes), node_cum=np.asarray(cum), node_dir=np.asarray(ndir), lane_eset=lane_eset,
         eset_start=i32(eset_start), edge_xy=np.concatenate(exy) if exy else np.zeros((0, 2)),
         edge_dir=np.concatenate(edir) if edir else np.zeros((0, 2)), grp_start=i32(grp_start), grp_lane=i32(grp_lane),

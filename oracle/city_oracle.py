@@ -4,8 +4,10 @@ Pure-Python loops over the CSR arrays of lcsim_b200.city.CityStatic (small cases
 holds per-tick outputs of the REAL reference engine on MOSS-shaped cities (oracle/gen_golden_city.py);
 tests/test_city.py holds this restatement to them (integers bit-exact, floats 1e-9).  Only tests/ imports this module.
 
-Every method cites the reference lines it follows.  The forced-lane-change branch (idm_policy.py:118-167,
-agent.py:331-368) is NOT restated: `lc_required` is raised instead when Route.get_lc says a change is due.
+Every method cites the reference lines it follows, including the forced-lane-change branch
+(idm_policy.py:64-84,118-167, agent.py:331-368) with its order-dependent reads of already-updated neighbours
+(the loop below runs in list order and updates `v` in place, exactly like AgentManager.update).
+`lc_required` records that some agent needed a lane change (the CUDA engine of round 1 flags instead of changing).
 """
 from __future__ import annotations
 
@@ -94,25 +96,46 @@ class CityOracle:
                 best, index = d, i
         return int(st.grp_lane[index])
 
-    def lc_in_candidate(self, a, lane):  # route.py:138-189, only the in_candidate decision
+    def get_lc(self, a, lane):  # route.py:138-189 -> (in_candidate, side, count, force_lc_length)
         st = self.st
         off = int(st.lane_offset[lane])
         g = self._group(a, 0)
         if g is None:
-            return int(st.end_offset[a]) - off == 0
-        lo, hi = int(st.grp_pre_offset[st.grp_start[g]]), int(st.grp_pre_offset[st.grp_start[g + 1] - 1])
-        return not (lo - off > 0 or hi - off < 0)
+            delta = int(st.end_offset[a]) - off
+            if delta == 0:
+                return True, 0, 0, 0.0
+            return (False, 0, -delta, 0.0) if delta < 0 else (False, 1, delta, 0.0)
+        pre = [int(x) for x in st.grp_pre_offset[st.grp_start[g]:st.grp_start[g + 1]]]
+        if pre[0] - off > 0 or pre[-1] - off < 0:
+            min_delta, cnt = 1e6, 0
+            for po in pre:
+                delta = po - off
+                if abs(delta) < abs(min_delta):
+                    min_delta, cnt = delta, abs(delta)
+            force = min(max(st.lane_max_speed[lane] * 3, 10.0), 50.0)  # LC_FACTOR, MIN/MAX_FORCE_LC_LENGTH
+            return False, (0 if min_delta < 0 else 1), cnt, force
+        return True, 0, 0, 0.0
+
+    def lc_in_candidate(self, a, lane):
+        return self.get_lc(a, lane)[0]
+
+    def project_from_lane(self, lane, other, other_s):  # lane.py:293-300
+        assert self.st.lane_road[lane] == self.st.lane_road[other] and self.st.lane_road[lane] >= 0, "not on the same road"
+        s = other_s / self.st.lane_length[other] * self.st.lane_length[lane]
+        return max(0.0, min(s, self.st.lane_length[lane]))
 
     def route_next(self, a, lane):  # route.py:102-136
         st = self.st
         if self.at_road[a]:
             if self._group(a, 0) is None:
                 return None
-            if self.lc_in_candidate(a, lane):
+            in_cand, side, _, _ = self.get_lc(a, lane)
+            g = self._group(a, 0)
+            if in_cand:
                 nxt = self.junc_lane_by_pre_lane(a, lane, 0)
-            else:
-                self.lc_required = True  # reference: group.lanes[-1] / [0] by lc.side; not restated
-                nxt = self.junc_lane_by_pre_lane(a, lane, 0)
+            else:  # left change pending: the group's rightmost lane is the nearest; right change: the leftmost
+                self.lc_required = True
+                nxt = int(st.grp_lane[st.grp_start[g + 1] - 1] if side == 0 else st.grp_lane[st.grp_start[g]])
             self.r_pop[a] += 1
         else:
             nxt = int(st.lane_succ0[lane])
@@ -151,6 +174,11 @@ class CityOracle:
         self.lead_valid = np.zeros(N, np.uint8)
         self.lead_dis = np.zeros(N)
         self.lead_v = np.zeros(N)
+        self.is_lc = np.zeros(N, np.uint8)  # LaneIDM.LCRuntime (idm_policy.py:18-27)
+        self.lc_total = np.zeros(N)
+        self.lc_completed = np.zeros(N)
+        self.lc_target = np.full(N, -1, np.int32)
+        self.lc_target_s = np.zeros(N)
         self.ring = np.zeros((N, H, 5))
         self.ring_valid = np.zeros(N, np.int32)
         for a in range(N):
@@ -247,8 +275,29 @@ class CityOracle:
             lane = int(self.lane[a])
             distance, ahead_v = (self.lead_dis[a], self.lead_v[a]) if self.lead_valid[a] else (math.inf, 0.0)
             acc = self._car_follow(a, self.v[a], min(st.idm[a][3], st.lane_max_speed[lane]), ahead_v, distance)
-            if st.lane_road[lane] >= 0 and not self.lc_in_candidate(a, lane):
-                self.lc_required = True  # _policy_lane_change (idm_policy.py:118-167) would start a forced change
+            if self.is_lc[a]:  # lane changing: also follow the leader on the target lane (idm_policy.py:67-84)
+                tl = int(self.lc_target[a])
+                ahead = self._next_agent_by_s(tl, float(self.lc_target_s[a]))
+                if ahead is not None:
+                    # ahead_a.runtime.v is read LIVE: already this tick's value if that agent precedes a in the list
+                    d2 = ahead[0] - (st.length[a] + st.length[ahead[1]]) / 2.0
+                    acc = min(acc, self._car_follow(a, self.v[a], st.lane_max_speed[tl], self.v[ahead[1]], d2))
+            if not self.is_lc[a] and st.lane_road[lane] >= 0:  # _policy_lane_change (idm_policy.py:118-167)
+                cur_s, cur_v = float(self.s[a]), float(self.v[a])
+                reverse_s = st.lane_length[lane] - cur_s
+                lc_length = max(3 * cur_v, st.length[a])  # LC_LENGTH_FACTOR
+                in_cand, side, count, force = self.get_lc(a, lane)
+                if not in_cand and reverse_s - force <= lc_length * count:
+                    self.lc_required = True
+                    tl = int(st.lane_left[lane] if side == 0 else st.lane_right[lane])
+                    assert tl >= 0
+                    neighbor_s = self.project_from_lane(tl, lane, cur_s)
+                    ahead = self._next_agent_by_s(tl, neighbor_s)
+                    if ahead is not None:
+                        d2 = ahead[0] - (st.length[a] + st.length[ahead[1]]) / 2.0
+                        acc = min(acc, self._car_follow(a, cur_v, st.lane_max_speed[tl], self.v[ahead[1]], d2))
+                    self.is_lc[a], self.lc_total[a], self.lc_completed[a] = 1, lc_length, 0.0
+                    self.lc_target[a], self.lc_target_s[a] = tl, neighbor_s
             # update_runtime_by_action, LANE branch (agent.py:314-376) + _compute_v_and_dis (:496-501)
             v0 = float(self.v[a])
             dv = acc * dt
@@ -267,8 +316,35 @@ class CityOracle:
                         break
                     cur = nxt
             self.lane[a], self.s[a] = cur, s
-            self.xy[a] = self.position(cur, s)
-            self.h[a] = self.direction(cur, s)
+            if self.is_lc[a]:  # agent.py:331-346
+                tl = int(self.lc_target[a])
+                if self.lc_completed[a] + ds >= self.lc_total[a]:
+                    self.s[a] = self.project_from_lane(tl, cur, s)
+                    self.lane[a] = tl
+                    self.is_lc[a], self.lc_total[a], self.lc_completed[a], self.lc_target[a], self.lc_target_s[a] = 0, 0.0, 0.0, -1, 0.0
+                else:
+                    self.lc_completed[a] += ds
+                    self.lc_target_s[a] = self.project_from_lane(tl, cur, s)
+                    self.lane_new[tl][float(self.lc_target_s[a])] = a
+            xy = self.position(cur, s)  # the lane walked on, even when the change just completed (agent.py:347-348)
+            heading = self.direction(cur, s)
+            if self.is_lc[a]:  # agent.py:349-369: blend towards the target lane
+                tl = int(self.lc_target[a])
+                xy_lc = self.position(tl, float(self.lc_target_s[a]))
+                ratio = self.lc_completed[a] / self.lc_total[a]
+                xy = xy * (1 - ratio) + xy_lc * ratio
+                bias = np.arctan2((st.lane_width[cur] + st.lane_width[tl]) / 2.0, self.lc_total[a]) * (1 - abs(ratio * 2 - 1))
+                if tl == st.lane_left[cur]:
+                    heading += bias
+                elif tl == st.lane_right[cur]:
+                    heading -= bias
+                else:
+                    raise ValueError("lane changing error")
+                heading = float(np.arctan2(np.sin(heading), np.cos(heading)))
+            self.xy[a] = xy
+            self.h[a] = heading
+            cur = int(self.lane[a])
+            s = float(self.s[a])
             # check_close_to_end (agent.py:434-441): returns before add_to_lane and the history append
             if st.lane_road[cur] >= 0 and st.lane_road[cur] == st.end_road[a] and st.end_s[a] - s < CLOSE_TO_END:
                 self.status[a] = FINISHED

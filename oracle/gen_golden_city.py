@@ -22,6 +22,9 @@ CASES = {
     "city_g3_a60": dict(seed=1, grid=3, n_agents=60, n_ticks=260),
     "city_g2_a24": dict(seed=2, grid=2, n_agents=24, n_ticks=200, max_hops=5),
     "city_g4_a150_dense": dict(seed=3, grid=4, n_agents=150, n_ticks=180, depart_window=5.0),
+    # movements that only some lanes offer + random end lanes: forced lane changes (idm_policy.py:118-167)
+    "city_g3_a80_lc": dict(seed=5, grid=3, n_agents=80, n_ticks=280, require_lc=True, max_hops=5),
+    "city_g4_a120_lc": dict(seed=7, grid=4, n_agents=120, n_ticks=240, require_lc=True, max_hops=5, depart_window=8.0),
 }
 
 

@@ -27,6 +27,8 @@ def test_city_oracle_matches_reference(name):
     for k in range(c.n_ticks):
         o.step()
         check_against_ref(c.ref, k + 1, get)
-    assert not o.lc_required
+        np.testing.assert_array_equal(o.is_lc, c.ref["is_lc"][k + 1], err_msg=f"tick {k + 1}: is_lc")
+    assert o.lc_required == name.endswith("_lc")
+    np.testing.assert_array_equal(o.is_lc, c.ref["is_lc"][-1])
     np.testing.assert_array_equal(o.ring_valid, c.ref["ring_valid"])
     np.testing.assert_allclose(o.ring, c.ref["ring"], rtol=0, atol=1e-9)
