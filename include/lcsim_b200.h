@@ -298,8 +298,9 @@ void lcsim_b200_destroy(lcsim_b200_engine* e);
  * (manager.py:50-115), the LaneIDM branch of Agent.prepare_obs (agent.py:198-243), LaneIDM.get_action
  * (policy/idm_policy.py:53-116), the LANE branch of update_runtime_by_action (agent.py:314-376), Lane.* (lane/lane.py:
  * 171-300), Route.* (agent/route.py:102-203), check_collision_all (manager.py:313-327, via a spatial hash) and
- * Agent.is_offroad (agent.py:482-494).  NOT built: the forced-lane-change branch (idm_policy.py:118-167,
- * agent.py:331-368): scalars[6] becomes 1 when the reference would start a lane change.
+ * Agent.is_offroad (agent.py:482-494), including the forced-lane-change branch (idm_policy.py:64-84,118-167,
+ * agent.py:331-368) with its order-dependent reads of already-updated neighbours.  scalars[6] tells that a lane
+ * change was started, scalars[7] that the reference would have raised (target lane missing / not on the same road).
  * Static arrays: lcsim_b200.city.CityStatic / pack_city (dense indices in pb order), host pointers. */
 typedef struct {
     double start, interval;
@@ -310,6 +311,9 @@ typedef struct {
     const int32_t* lane_junction; /* [NL] parent junction index or -1 */
     const int32_t* lane_offset; /* [NL] offset_in_road */
     const int32_t* lane_succ0; /* [NL] first successor (unique_successor of junction lanes) or -1 */
+    const int32_t* lane_left; /* [NL] Lane.left_neighbor() or -1 */
+    const int32_t* lane_right; /* [NL] Lane.right_neighbor() or -1 */
+    const double* lane_width; /* [NL] */
     const int32_t* lane_node_start; /* [NL+1] */
     const double* node_xy; /* [NN][2] raw centre-line nodes */
     const double* node_cum; /* [NN] Lane.line_lengths */
@@ -337,7 +341,8 @@ typedef struct {
 
 typedef struct {
     int32_t N, n_lanes, H;
-    int32_t* scalars; /* [16] 0: n_active, 1: waiting-list pointer, 2: current_step, 6: lane change required (unsupported) */
+    int32_t* scalars; /* [16] 0: n_active, 1: waiting-list pointer, 2: current_step, 6: a lane change was started, 7: lane-change error */
+    int32_t* is_lc; /* [N] LaneIDM.lc_runtime.is_lc */
     int32_t* active; /* [N] active_agents, list order */
     int32_t* status; /* [N] */
     int32_t* lane; /* [N] runtime.lane (dense index) */

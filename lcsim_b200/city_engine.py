@@ -14,7 +14,7 @@ import numpy as np
 from . import native
 from .city import CityStatic
 
-SCALARS = {"n_active": 0, "wait_ptr": 1, "tick": 2, "lc_required": 6}
+SCALARS = {"n_active": 0, "wait_ptr": 1, "tick": 2, "lc_required": 6, "lc_error": 7}
 
 
 class CityEngine:
@@ -43,7 +43,7 @@ class CityEngine:
         v = native.CityViews()
         self._check(self.lib.lcsim_b200_city_views(self._h, C.byref(v)), "views")
         N, H = self.N, native.H_STEPS
-        shapes = {"scalars": (16,), "active": (N,), "status": (N,), "lane": (N,), "s": (N,), "v": (N,), "xy": (N, 2),
+        shapes = {"scalars": (16,), "is_lc": (N,), "active": (N,), "status": (N,), "lane": (N,), "s": (N,), "v": (N,), "xy": (N, 2),
                   "heading": (N,), "lead_valid": (N,), "lead_dis": (N,), "lead_v": (N,), "coll_count": (N,),
                   "offroad": (N,), "ring": (N, H, 5), "ring_head": (N,), "ring_count": (N,), "stats": (native.N_STATS,)}
         for name, typestr in native.CITY_VIEW_FIELDS:

@@ -1714,6 +1714,7 @@ __global__ void lcc_scan_add(int32_t* data, int n, const int32_t* tile_sum) {
 }
 #endif
 
+#define LCC_READER_ROUNDS 2
 struct lcsim_b200_city {
     LccP c;
     std::vector<void*> allocs;
@@ -1801,6 +1802,7 @@ extern "C" int lcsim_b200_city_create(const lcsim_b200_city_static* st, int devi
         if ((st->lane_road[l] >= 0) == (st->lane_junction[l] >= 0)) return lcc_fail(e, LCSIM_B200_ERR_ARG, "lane must belong to exactly one road or junction");
         if (st->lane_junction[l] >= 0 && (st->lane_succ0[l] < 0 || st->lane_succ0[l] >= NL)) return lcc_fail(e, LCSIM_B200_ERR_ARG, "junction lane without successor");
         if (st->lane_eset[l] < 0 || st->lane_eset[l] >= st->n_esets) return lcc_fail(e, LCSIM_B200_ERR_ARG, "lane_eset out of range");
+        if (st->lane_left[l] >= NL || st->lane_right[l] >= NL) return lcc_fail(e, LCSIM_B200_ERR_ARG, "lane neighbour out of range");
     }
     const int n_route = st->route_start[N];
     for (int a = 0; a < N; a++) {
@@ -1828,6 +1830,9 @@ extern "C" int lcsim_b200_city_create(const lcsim_b200_city_static* st, int devi
     // ---- static
     LCC_TRY(lcc_upload(e, &c.lane_length, st->lane_length, NL));
     LCC_TRY(lcc_upload(e, &c.lane_max_speed, st->lane_max_speed, NL));
+    LCC_TRY(lcc_upload(e, &c.lane_width, st->lane_width, NL));
+    LCC_TRY(lcc_upload(e, &c.lane_left, st->lane_left, NL));
+    LCC_TRY(lcc_upload(e, &c.lane_right, st->lane_right, NL));
     LCC_TRY(lcc_upload(e, &c.lane_road, st->lane_road, NL));
     LCC_TRY(lcc_upload(e, &c.lane_junction, st->lane_junction, NL));
     LCC_TRY(lcc_upload(e, &c.lane_offset, st->lane_offset, NL));
@@ -1863,6 +1868,10 @@ extern "C" int lcsim_b200_city_create(const lcsim_b200_city_static* st, int devi
     LCC_TRY(lcc_alloc(e, &c.h, N)); LCC_TRY(lcc_alloc(e, &c.lead_dis, N)); LCC_TRY(lcc_alloc(e, &c.lead_v, N));
     LCC_TRY(lcc_alloc(e, &c.ring, (size_t)N * LCS_H * 5));
     LCC_TRY(lcc_alloc(e, &c.lead_valid, N)); LCC_TRY(lcc_alloc(e, &c.offroad, N));
+    LCC_TRY(lcc_alloc(e, &c.is_lc, N)); LCC_TRY(lcc_alloc(e, &c.lc_target, N)); LCC_TRY(lcc_alloc(e, &c.slot_of, N));
+    LCC_TRY(lcc_alloc(e, &c.rd_ahead, N)); LCC_TRY(lcc_alloc(e, &c.rd_lane, N)); LCC_TRY(lcc_alloc(e, &c.done_round, N));
+    LCC_TRY(lcc_alloc(e, &c.lc_total, N)); LCC_TRY(lcc_alloc(e, &c.lc_completed, N)); LCC_TRY(lcc_alloc(e, &c.lc_target_s, N));
+    LCC_TRY(lcc_alloc(e, &c.v2, N)); LCC_TRY(lcc_alloc(e, &c.acc, N)); LCC_TRY(lcc_alloc(e, &c.rd_dist, N));
     LCC_TRY(lcc_alloc(e, &c.active, N)); LCC_TRY(lcc_alloc(e, &c.active2, N)); LCC_TRY(lcc_alloc(e, &c.fin, N));
     LCC_TRY(lcc_alloc(e, &c.rank, N)); LCC_TRY(lcc_alloc(e, &c.scal, 16)); LCC_TRY(lcc_alloc(e, &c.stats, LCS_NSTAT));
     LCC_TRY(lcc_alloc(e, &c.ent_lane, (size_t)2 * N)); LCC_TRY(lcc_alloc(e, &c.ent_agent, (size_t)2 * N));
@@ -1936,9 +1945,16 @@ extern "C" int lcsim_b200_city_step(lcsim_b200_city* e, int n_ticks, void* strea
     c.mode = 0;
     for (int k = 0; k < n_ticks; k++) {
         LCC_RUN(lcc_update, c, c.N, st);
+        for (int r = 1; r <= LCC_READER_ROUNDS; r++) { // readers of live speeds (lane changes), by dependency depth
+            LccP cr = c;
+            cr.mode = r;
+            LCC_RUN(lcc_update_round, cr, c.N, st);
+        }
+        LCC_RUN(lcc_update_serial, c, 1, st);
+        LCC_RUN(lcc_commit_v, c, c.N, st);
         lcc_prepare(e, c, true, st);
         LCC_RUN(lcc_tick_end, c, 1, st);
-        e->launches += 2;
+        e->launches += 4 + LCC_READER_ROUNDS;
     }
     if (cudaGetLastError() != cudaSuccess) return lcc_fail(e, LCSIM_B200_ERR_CUDA, "city step launch failed");
     return 0;
@@ -1948,7 +1964,7 @@ extern "C" int lcsim_b200_city_views(lcsim_b200_city* e, lcsim_b200_city_state_v
     if (!e || !v) return LCSIM_B200_ERR_ARG;
     const LccP& c = e->c;
     v->N = c.N; v->n_lanes = c.NL; v->H = LCS_H;
-    v->scalars = c.scal; v->active = c.active; v->status = c.status; v->lane = c.lane; v->s = c.s; v->v = c.v; v->xy = c.xy;
+    v->scalars = c.scal; v->is_lc = c.is_lc; v->active = c.active; v->status = c.status; v->lane = c.lane; v->s = c.s; v->v = c.v; v->xy = c.xy;
     v->heading = c.h; v->lead_valid = c.lead_valid; v->lead_dis = c.lead_dis; v->lead_v = c.lead_v;
     v->coll_count = c.coll_count; v->offroad = c.offroad; v->ring = c.ring; v->ring_head = c.ring_head;
     v->ring_count = c.ring_count; v->stats = c.stats;

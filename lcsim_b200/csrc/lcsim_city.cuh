@@ -7,8 +7,10 @@
 //   SortedDict, rebuilt per tick as a counting sort by lane) -> observations (leader search) -> metrics (uniform
 //   spatial hash + float64 SAT, per-lane edge sets) -> clock.
 // Every decision is the reference's float64 expression with pinned roundings (lcs_dmul / lcs_dadd / ...).
-// Not built: the forced-lane-change branch (idm_policy.py:118-167, agent.py:331-368); `flags[0]` is raised when the
-// reference would start one.
+// The forced-lane-change branch (idm_policy.py:64-84,118-167, agent.py:331-368) reads neighbours' runtime.v LIVE
+// (already updated when the neighbour precedes the agent in the list).  Agents without such a read are
+// finished by the first update kernel; the few "readers" are resolved in dependency rounds (a reader waits only for
+// readers that precede it in the list), then by a serial pass for whatever chain is left.
 #pragma once
 
 struct LccP {
@@ -16,8 +18,8 @@ struct LccP {
     double dt, cell_x0, cell_y0, cell_inv;
     int32_t with_metrics;
     // ---- static: lanes
-    const double *lane_length, *lane_max_speed;
-    const int32_t *lane_road, *lane_junction, *lane_offset, *lane_succ0, *lane_node_start, *lane_eset;
+    const double *lane_length, *lane_max_speed, *lane_width;
+    const int32_t *lane_road, *lane_junction, *lane_offset, *lane_succ0, *lane_node_start, *lane_eset, *lane_left, *lane_right;
     const double *node_xy, *node_cum, *node_dir;
     const int32_t* eset_start;
     const double *edge_xy, *edge_dir;
@@ -28,6 +30,9 @@ struct LccP {
     // ---- state: agents
     int32_t *status, *lane, *r_pop, *g_pop, *at_road, *ring_head, *ring_count, *coll_count;
     double *s, *v, *xy, *h, *lead_dis, *lead_v, *ring;
+    // lane change runtime (LaneIDM.LCRuntime, idm_policy.py:18-27) and the update's scratch
+    int32_t *is_lc, *lc_target, *slot_of, *rd_ahead, *rd_lane, *done_round;
+    double *lc_total, *lc_completed, *lc_target_s, *v2, *acc, *rd_dist;
     uint8_t *lead_valid, *offroad;
     // ---- state: lists
     int32_t *active, *active2, *fin, *rank; // [N]
@@ -43,7 +48,7 @@ struct LccP {
     int32_t *cell_start, *cell_cur, *cell_agent; // [n_cells+1], [n_cells+1], [N]
     int32_t mode; // 1 = reset
 };
-enum { LCC_N_ACTIVE = 0, LCC_WAIT_PTR, LCC_TICK, LCC_N_ENT, LCC_N_ARR, LCC_M_POP, LCC_LC_REQUIRED, LCC_N_BKT, LCC_N_OLD };
+enum { LCC_N_ACTIVE = 0, LCC_WAIT_PTR, LCC_TICK, LCC_N_ENT, LCC_N_ARR, LCC_M_POP, LCC_LC_REQUIRED, LCC_LC_ERROR, LCC_N_OLD, LCC_N_PENDING };
 
 #ifndef LCSIM_HOSTEMU
 #define LCC_KERNEL(name)                                          \
@@ -106,19 +111,52 @@ LCS_D int lcc_junc_lane_by_pre_lane(const LccP& c, int a, int pre_lane, int k) {
     }
     return c.grp_lane[index];
 }
-LCS_D bool lcc_in_candidate(const LccP& c, int a, int lane) { // route.py:138-189, the in_candidate decision
+// Route.get_lc (route.py:138-189): in_candidate, else side (0 left, 1 right), count and force_lc_length
+struct LccLC {
+    bool in_candidate;
+    int side, count;
+    double force_len;
+};
+LCS_D LccLC lcc_get_lc(const LccP& c, int a, int lane) {
+    LccLC r;
+    r.in_candidate = true; r.side = 0; r.count = 0; r.force_len = 0.0;
     const int off = c.lane_offset[lane];
     const int g = lcc_group(c, a, 0);
-    if (g < 0) return c.end_offset[a] - off == 0;
-    const int lo = c.grp_pre_offset[c.grp_start[g]], hi = c.grp_pre_offset[c.grp_start[g + 1] - 1];
-    return !(lo - off > 0 || hi - off < 0);
+    if (g < 0) { // reach the end: compare with the end lane
+        const int delta = c.end_offset[a] - off;
+        if (delta != 0) { r.in_candidate = false; r.side = delta < 0 ? 0 : 1; r.count = delta < 0 ? -delta : delta; }
+        return r;
+    }
+    const int b = c.grp_start[g], e = c.grp_start[g + 1];
+    if (c.grp_pre_offset[b] - off > 0 || c.grp_pre_offset[e - 1] - off < 0) {
+        int min_delta = 1000000, cnt = 0;
+        for (int i = b; i < e; i++) {
+            const int delta = c.grp_pre_offset[i] - off, ad = delta < 0 ? -delta : delta;
+            if (ad < (min_delta < 0 ? -min_delta : min_delta)) { min_delta = delta; cnt = ad; }
+        }
+        r.in_candidate = false;
+        r.count = cnt;
+        r.side = min_delta < 0 ? 0 : 1;
+        r.force_len = lcs_pymin(lcs_pymax(lcs_dmul(c.lane_max_speed[lane], 3.0), 10.0), 50.0);
+    }
+    return r;
+}
+// Lane.project_from_lane (lane.py:293-300); the reference raises when the lanes are not on the same road
+LCS_D double lcc_project_from_lane(const LccP& c, int lane, int other, double other_s) {
+    if (c.lane_road[lane] < 0 || c.lane_road[lane] != c.lane_road[other]) c.scal[LCC_LC_ERROR] = 1;
+    const double s = lcs_dmul(lcc_div(other_s, c.lane_length[other]), c.lane_length[lane]);
+    return lcs_pymax(0.0, lcs_pymin(s, c.lane_length[lane]));
 }
 LCS_D int lcc_route_next(const LccP& c, int a, int lane) { // route.py:102-136
     int nxt;
     if (c.at_road[a]) {
-        if (lcc_group(c, a, 0) < 0) return -1;
-        if (!lcc_in_candidate(c, a, lane)) c.scal[LCC_LC_REQUIRED] = 1; // reference: group.lanes[-1] / [0] by lc.side
-        nxt = lcc_junc_lane_by_pre_lane(c, a, lane, 0);
+        const int g = lcc_group(c, a, 0);
+        if (g < 0) return -1;
+        const LccLC lc = lcc_get_lc(c, a, lane);
+        if (lc.in_candidate)
+            nxt = lcc_junc_lane_by_pre_lane(c, a, lane, 0);
+        else // a left change is pending: the group's rightmost lane is the nearest; a right change: its leftmost
+            nxt = lc.side == 0 ? c.grp_lane[c.grp_start[g + 1] - 1] : c.grp_lane[c.grp_start[g]];
         c.r_pop[a] += 1;
     } else {
         nxt = c.lane_succ0[lane];
@@ -136,15 +174,15 @@ LCS_D void lcc_add_to_lane(const LccP& c, int lane, double s, int a, int order) 
     c.ent_agent[e] = a;
     c.ent_order[e] = order;
 }
-LCS_D void lcc_ring_push(const LccP& c, int a) { // agent.py:67-84,159-165,419-426 (circular instead of shifting)
+LCS_D void lcc_ring_push(const LccP& c, int a, double v) { // agent.py:67-84,159-165,419-426 (circular instead of shifting)
     const int head = c.ring_head[a];
     double* r = c.ring + ((size_t)a * LCS_H + head) * 5;
     double sh, ch;
     lcs_sincos(c.h[a], &sh, &ch);
     r[0] = c.xy[2 * a];
     r[1] = c.xy[2 * a + 1];
-    r[2] = lcs_dmul(c.v[a], ch);
-    r[3] = lcs_dmul(c.v[a], sh);
+    r[2] = lcs_dmul(v, ch);
+    r[3] = lcs_dmul(v, sh);
     r[4] = c.h[a];
     c.ring_head[a] = head + 1 == LCS_H ? 0 : head + 1;
     if (c.ring_count[a] < LCS_H) c.ring_count[a] += 1;
@@ -167,12 +205,19 @@ LCS_D void lcc_reset_agent(const LccP& c, int a) {
     c.lead_valid[a] = 0;
     c.lead_dis[a] = lcs_inf_d();
     c.lead_v[a] = 0.0;
+    c.is_lc[a] = 0;
+    c.lc_total[a] = 0.0;
+    c.lc_completed[a] = 0.0;
+    c.lc_target[a] = -1;
+    c.lc_target_s[a] = 0.0;
+    c.slot_of[a] = -1;
+    c.v2[a] = 0.0;
     c.coll_count[a] = 0;
     c.offroad[a] = 0;
     c.ring_head[a] = 0;
     c.ring_count[a] = 0;
     for (int k = 0; k < LCS_H * 5; k++) c.ring[(size_t)a * LCS_H * 5 + k] = 0.0;
-    lcc_ring_push(c, a);
+    lcc_ring_push(c, a, 0.0);
     c.fin[a] = 0;
     c.active[a] = -1;
 }
@@ -194,7 +239,90 @@ LCS_D double lcc_car_follow(const double* idm, double self_v, double target_v, d
     }
     return lcs_pymax(mb, lcs_pymin(ma, acc));
 }
-// slot i of the active list: manager.py:105-115 -> idm_policy.py:53-90 -> agent.py:314-376, 419-426
+// forward declarations of the bucket lookups (lane.py:210-234), defined with the lane buckets below
+LCS_D bool lcc_next_agent(const LccP& c, int lane, double s, double* ks, int* agent);
+
+// everything after the action is known: update_runtime_by_action, LANE branch (agent.py:314-376, 419-426)
+LCS_D void lcc_finalize(const LccP& c, int i, int a, double acc) {
+    const int lane = c.lane[a];
+    const double v0 = c.v[a];
+    // _compute_v_and_dis (agent.py:496-501)
+    const double dt = c.dt, dv = lcs_dmul(acc, dt);
+    double v, ds;
+    if (lcs_dadd(v0, dv) < 0) {
+        v = 0.0;
+        ds = lcc_div(lcs_dmul(-v0, v0), lcs_dmul(2.0, acc));
+    } else {
+        v = lcs_dadd(v0, dv);
+        ds = lcs_dmul(lcs_dadd(v0, lcs_dmul(0.5, dv)), dt);
+    }
+    c.v2[a] = v; // c.v keeps the value of the tick start until lcc_commit_v: other agents may still have to read it
+    double s = lcs_dadd(c.s[a], ds);
+    int cur = lane;
+    if (s > c.lane_length[lane]) {
+        while (s > c.lane_length[cur]) {
+            s = lcs_dsub(s, c.lane_length[cur]);
+            const int nxt = lcc_route_next(c, a, cur);
+            if (nxt < 0) break;
+            cur = nxt;
+        }
+    }
+    int new_lane = cur;
+    double new_s = s;
+    bool lc = c.is_lc[a] != 0;
+    const int tl = c.lc_target[a];
+    if (lc) { // agent.py:331-346
+        if (lcs_dadd(c.lc_completed[a], ds) >= c.lc_total[a]) {
+            new_s = lcc_project_from_lane(c, tl, cur, s);
+            new_lane = tl;
+            c.is_lc[a] = 0; c.lc_total[a] = 0.0; c.lc_completed[a] = 0.0; c.lc_target[a] = -1; c.lc_target_s[a] = 0.0;
+            lc = false;
+        } else {
+            c.lc_completed[a] = lcs_dadd(c.lc_completed[a], ds);
+            const double ts = lcc_project_from_lane(c, tl, cur, s);
+            c.lc_target_s[a] = ts;
+            lcc_add_to_lane(c, tl, ts, a, (1 << 28) | (i << 1)); // target_lane.add_agent, before the own lane's entry
+        }
+    }
+    c.lane[a] = new_lane;
+    c.s[a] = new_s;
+    double x, y, dir;
+    lcc_position(c, cur, s, &x, &y, &dir); // the lane walked on, even when the change just completed (agent.py:347-348)
+    if (lc) { // agent.py:349-369: blend towards the target lane
+        double xl, yl, dl;
+        lcc_position(c, tl, c.lc_target_s[a], &xl, &yl, &dl);
+        const double ratio = lcc_div(c.lc_completed[a], c.lc_total[a]), om = lcs_dsub(1.0, ratio);
+        x = lcs_dadd(lcs_dmul(x, om), lcs_dmul(xl, ratio));
+        y = lcs_dadd(lcs_dmul(y, om), lcs_dmul(yl, ratio));
+        const double bias = lcs_dmul(atan2(lcc_div(lcs_dadd(c.lane_width[cur], c.lane_width[tl]), 2.0), c.lc_total[a]),
+                                     lcs_dsub(1.0, fabs(lcs_dsub(lcs_dmul(ratio, 2.0), 1.0))));
+        if (tl == c.lane_left[cur])
+            dir = lcs_dadd(dir, bias);
+        else if (tl == c.lane_right[cur])
+            dir = lcs_dsub(dir, bias);
+        else
+            c.scal[LCC_LC_ERROR] = 1; // reference: ValueError("lane changing error")
+        double sh, ch;
+        lcs_sincos(dir, &sh, &ch);
+        dir = atan2(sh, ch);
+    }
+    c.xy[2 * a] = x;
+    c.xy[2 * a + 1] = y;
+    c.h[a] = dir;
+    // check_close_to_end (agent.py:434-441): returns before add_to_lane and the history append (SURVEY Q21)
+    if (c.lane_road[new_lane] >= 0 && c.lane_road[new_lane] == c.end_road[a] && lcs_dsub(c.end_s[a], new_s) < 5.0) {
+        c.status[a] = LCS_IDLE; // FINISHED now, IDLE after this tick's check_departure_and_arrival (single-trip schedules)
+        c.fin[i] = 1;
+        c.coll_count[a] = 0;
+        c.offroad[a] = 0;
+        return;
+    }
+    c.fin[i] = 0;
+    lcc_add_to_lane(c, new_lane, new_s, a, (1 << 28) | (i << 1) | 1);
+    lcc_ring_push(c, a, v); // history append with the new speed (agent.py:419-426 reads runtime.v after the update)
+}
+// slot i of the active list: manager.py:105-115 -> LaneIDM.get_action (idm_policy.py:53-90).  Agents whose action
+// needs no live read of another agent are finished here; the others leave (acc, whom to read) for the rounds.
 LCS_D void lcc_update(const LccP& c, int i) {
     const int n = c.scal[LCC_N_ACTIVE];
     if (i >= n) {
@@ -208,48 +336,88 @@ LCS_D void lcc_update(const LccP& c, int i) {
     const double distance = lv ? c.lead_dis[a] : lcs_inf_d(), ahead_v = lv ? c.lead_v[a] : 0.0;
     const double v0 = c.v[a];
     const double acc = lcc_car_follow(idm, v0, lcs_pymin(idm[3], c.lane_max_speed[lane]), ahead_v, distance);
-    if (c.lane_road[lane] >= 0 && !lcc_in_candidate(c, a, lane)) c.scal[LCC_LC_REQUIRED] = 1; // _policy_lane_change would act
-    // _compute_v_and_dis (agent.py:496-501)
-    const double dt = c.dt, dv = lcs_dmul(acc, dt);
-    double v, ds;
-    if (lcs_dadd(v0, dv) < 0) {
-        v = 0.0;
-        ds = lcc_div(lcs_dmul(-v0, v0), lcs_dmul(2.0, acc));
-    } else {
-        v = lcs_dadd(v0, dv);
-        ds = lcs_dmul(lcs_dadd(v0, lcs_dmul(0.5, dv)), dt);
-    }
-    c.v[a] = v;
-    double s = lcs_dadd(c.s[a], ds);
-    int cur = lane;
-    if (s > c.lane_length[lane]) {
-        while (s > c.lane_length[cur]) {
-            s = lcs_dsub(s, c.lane_length[cur]);
-            const int nxt = lcc_route_next(c, a, cur);
-            if (nxt < 0) break;
-            cur = nxt;
+    int tl = -1;
+    double ts = 0.0;
+    if (c.is_lc[a]) { // lane changing: also follow the leader on the target lane (idm_policy.py:67-84)
+        tl = c.lc_target[a];
+        ts = c.lc_target_s[a];
+    } else if (c.lane_road[lane] >= 0) { // _policy_lane_change (idm_policy.py:118-167)
+        const double cur_s = c.s[a];
+        const double reverse_s = lcs_dsub(c.lane_length[lane], cur_s);
+        const double lc_length = lcs_pymax(lcs_dmul(3.0, v0), c.length[a]);
+        const LccLC lc = lcc_get_lc(c, a, lane);
+        if (!lc.in_candidate && lcs_dsub(reverse_s, lc.force_len) <= lcs_dmul(lc_length, (double)lc.count)) {
+            c.scal[LCC_LC_REQUIRED] = 1; // informational: this scenario exercises lane changes
+            tl = lc.side == 0 ? c.lane_left[lane] : c.lane_right[lane];
+            if (tl < 0) {
+                c.scal[LCC_LC_ERROR] = 1; // reference: assert target_lane is not None
+            } else {
+                ts = lcc_project_from_lane(c, tl, lane, cur_s);
+                c.is_lc[a] = 1;
+                c.lc_total[a] = lc_length;
+                c.lc_completed[a] = 0.0;
+                c.lc_target[a] = tl;
+                c.lc_target_s[a] = ts;
+            }
         }
     }
-    c.lane[a] = cur;
-    c.s[a] = s;
-    double x, y, dir;
-    lcc_position(c, cur, s, &x, &y, &dir);
-    c.xy[2 * a] = x;
-    c.xy[2 * a + 1] = y;
-    c.h[a] = dir;
-    // check_close_to_end (agent.py:434-441): returns before add_to_lane and the history append (SURVEY Q21)
-    if (c.lane_road[cur] >= 0 && c.lane_road[cur] == c.end_road[a] && lcs_dsub(c.end_s[a], s) < 5.0) {
-        c.status[a] = LCS_IDLE; // FINISHED now, IDLE after this tick's check_departure_and_arrival (single-trip schedules)
-        c.fin[i] = 1;
-        c.coll_count[a] = 0;
-        c.offroad[a] = 0;
-        return;
+    c.acc[a] = acc;
+    c.rd_ahead[a] = -1;
+    if (tl >= 0) {
+        double ks;
+        int other;
+        if (lcc_next_agent(c, tl, ts, &ks, &other)) { // NB the reference uses the leader's absolute s (idm_policy.py:77,157)
+            c.rd_ahead[a] = other;
+            c.rd_dist[a] = lcs_dsub(ks, lcc_div(lcs_dadd(c.length[a], c.length[other]), 2.0));
+            c.rd_lane[a] = tl;
+        }
     }
-    c.fin[i] = 0;
-    lcc_add_to_lane(c, cur, s, a, (1 << 24) | i);
-    lcc_ring_push(c, a);
+    if (c.rd_ahead[a] < 0) {
+        c.done_round[a] = 0;
+        lcc_finalize(c, i, a, acc);
+    } else {
+        c.done_round[a] = 0x7fffffff;
+        lcs_atomic_add(&c.scal[LCC_N_PENDING], 1);
+    }
 }
 LCC_KERNEL(lcc_update)
+// reader of slot i: ahead_a.runtime.v is this tick's value if that agent precedes it in the list, else last tick's
+LCS_D bool lcc_reader_step(const LccP& c, int i, int round, bool serial) {
+    const int a = c.active[i];
+    if (c.done_round[a] != 0x7fffffff) return false;
+    const int x = c.rd_ahead[a];
+    const int sx = c.slot_of[x];
+    double vx;
+    if (sx >= 0 && sx < i) {
+        if (!serial && c.done_round[x] >= round) return false; // not finished in an EARLIER launch: wait
+        vx = c.v2[x];
+    } else {
+        vx = c.v[x];
+    }
+    const double acc2 = lcc_car_follow(c.idm + 5 * (size_t)a, c.v[a], c.lane_max_speed[c.rd_lane[a]], vx, c.rd_dist[a]);
+    lcc_finalize(c, i, a, lcs_pymin(c.acc[a], acc2));
+    c.done_round[a] = round;
+    return true;
+}
+LCS_D void lcc_update_round(const LccP& c, int i) {
+    if (c.scal[LCC_N_PENDING] == 0 || i >= c.scal[LCC_N_ACTIVE]) return;
+    if (lcc_reader_step(c, i, c.mode /* round number travels in mode */, false)) lcs_atomic_add(&c.scal[LCC_N_PENDING], -1);
+}
+LCC_KERNEL(lcc_update_round)
+// whatever dependency chain is longer than the rounds: one thread, list order (normally no work at all)
+LCS_D void lcc_update_serial(const LccP& c, int unused) {
+    if (c.scal[LCC_N_PENDING] == 0) return;
+    const int n = c.scal[LCC_N_ACTIVE];
+    for (int i = 0; i < n; i++)
+        if (lcc_reader_step(c, i, 0x7ffffffe, true)) c.scal[LCC_N_PENDING] -= 1; // list order: predecessors are finished
+}
+LCC_KERNEL(lcc_update_serial)
+LCS_D void lcc_commit_v(const LccP& c, int i) {
+    if (i >= c.scal[LCC_N_ACTIVE]) return;
+    const int a = c.active[i];
+    c.v[a] = c.v2[a];
+}
+LCC_KERNEL(lcc_commit_v)
 
 // ------------------------------------------------------------------ arrivals / departures (manager.py:50-96)
 // waiting offset j: the popped entries are a prefix of the (sorted) waiting list; the last popped one reports m
@@ -269,22 +437,33 @@ LCS_D void lcc_place(const LccP& c, int i) {
     const int n = c.scal[LCC_N_ACTIVE], n_arr = c.scal[LCC_N_ARR], m = c.scal[LCC_M_POP], wp = c.scal[LCC_WAIT_PTR];
     if (i < n) {
         const int r = c.rank[i]; // finished slots before i
-        if (!c.fin[i])
-            c.active2[i - (r > m ? r - m : 0)] = c.active[i];
-        else if (r < m)
-            c.active2[i] = c.wait_order[wp + r]; // departure r takes the slot of the r-th finished agent
+        if (!c.fin[i]) {
+            const int pos = i - (r > m ? r - m : 0);
+            c.active2[pos] = c.active[i];
+            c.slot_of[c.active[i]] = pos;
+        } else {
+            c.slot_of[c.active[i]] = -1;
+            if (r < m) { // departure r takes the slot of the r-th finished agent
+                c.active2[i] = c.wait_order[wp + r];
+                c.slot_of[c.wait_order[wp + r]] = i;
+            }
+        }
     }
     if (i < m) {
         const int a = c.wait_order[wp + i];
         c.status[a] = LCS_ACTIVE;
-        if (i >= n_arr) c.active2[n + (i - n_arr)] = a;
-        lcc_add_to_lane(c, c.lane[a], c.s[a], a, ((c.mode == 1 ? 0 : 2) << 24) | i); // add_to_lane at the home position
+        if (i >= n_arr) {
+            c.active2[n + (i - n_arr)] = a;
+            c.slot_of[a] = n + (i - n_arr);
+        }
+        lcc_add_to_lane(c, c.lane[a], c.s[a], a, ((c.mode == 1 ? 0 : 2) << 28) | i); // add_to_lane at the home position
     }
 }
 LCC_KERNEL(lcc_place)
 LCS_D void lcc_place_end(const LccP& c, int i) {
     const int n = c.scal[LCC_N_ACTIVE], n_arr = c.scal[LCC_N_ARR], m = c.scal[LCC_M_POP];
     c.scal[LCC_N_OLD] = n;
+    c.scal[LCC_N_PENDING] = 0;
     c.scal[LCC_N_ACTIVE] = n - n_arr + m;
     c.scal[LCC_WAIT_PTR] += m;
     if (c.mode == 0) {

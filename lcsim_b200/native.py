@@ -113,7 +113,8 @@ class LaneDesc(C.Structure):
 
 CITY_STATIC_FIELDS = (
     ("lane_length", np.float64), ("lane_max_speed", np.float64), ("lane_road", np.int32), ("lane_junction", np.int32),
-    ("lane_offset", np.int32), ("lane_succ0", np.int32), ("lane_node_start", np.int32), ("node_xy", np.float64),
+    ("lane_offset", np.int32), ("lane_succ0", np.int32), ("lane_left", np.int32), ("lane_right", np.int32),
+    ("lane_width", np.float64), ("lane_node_start", np.int32), ("node_xy", np.float64),
     ("node_cum", np.float64), ("node_dir", np.float64), ("lane_eset", np.int32), ("eset_start", np.int32),
     ("edge_xy", np.float64), ("edge_dir", np.float64), ("grp_start", np.int32), ("grp_lane", np.int32),
     ("grp_pre_offset", np.int32), ("length", np.float64), ("width", np.float64), ("idm", np.float64),
@@ -127,7 +128,7 @@ class CityStaticC(C.Structure):
                  ("n_esets", C.c_int32), ("n_groups", C.c_int32)] + [(n, C.c_void_p) for n, _ in CITY_STATIC_FIELDS])
 
 
-CITY_VIEW_FIELDS = (("scalars", "<i4"), ("active", "<i4"), ("status", "<i4"), ("lane", "<i4"), ("s", "<f8"), ("v", "<f8"),
+CITY_VIEW_FIELDS = (("scalars", "<i4"), ("is_lc", "<i4"), ("active", "<i4"), ("status", "<i4"), ("lane", "<i4"), ("s", "<f8"), ("v", "<f8"),
                     ("xy", "<f8"), ("heading", "<f8"), ("lead_valid", "|u1"), ("lead_dis", "<f8"), ("lead_v", "<f8"),
                     ("coll_count", "<i4"), ("offroad", "|u1"), ("ring", "<f8"), ("ring_head", "<i4"),
                     ("ring_count", "<i4"), ("stats", "<i8"))
