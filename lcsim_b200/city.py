@@ -10,9 +10,9 @@ Structure follows what the reference expects of a MOSS map (lcsim/scripts/scenar
 lane/lane.py:93-106, road/road.py:90-95, junction/junction.py:90-103, agent/route.py:56-100): roads own 2-3 parallel
 lanes (left to right = offset_in_road), junction lanes connect lane k of an in-road to lane k of an out-road and
 are grouped per (in_road, out_road); every road carries one BOUNDARY edge 3 m right of its rightmost lane, every
-junction the edges of its right-turn lanes.  Because every movement connects ALL lanes of the in-road, routes never
-require a lane change (route.py:148-189 `in_candidate` is always true) — the forced-lane-change branch of LaneIDM
-is not built yet; `require_lc=True` narrows some movements so tests can check that the engine flags it.
+junction the edges of its right-turn lanes.  By default every movement connects ALL lanes of the in-road, so routes
+never require a lane change (route.py:148-189 `in_candidate` is always true); `require_lc=True` narrows left turns to
+the leftmost lane and picks random end lanes, which makes LaneIDM force lane changes (idm_policy.py:118-167).
 """
 from __future__ import annotations
 

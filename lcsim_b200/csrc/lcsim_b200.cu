@@ -1722,6 +1722,11 @@ struct lcsim_b200_city {
     int with_metrics = 1;
     bool fresh_reset = false;
     int64_t launches = 0;
+    int launches_per_tick = 0;
+#ifndef LCSIM_HOSTEMU
+    cudaGraphExec_t tick_graph = nullptr; // one tick's launch sequence, captured once (LCSIM_B200_CITY_GRAPH=0: off)
+    int use_graph = 1;
+#endif
     std::string err;
 };
 
@@ -1775,6 +1780,9 @@ extern "C" const char* lcsim_b200_city_last_error(const lcsim_b200_city* e) { re
 extern "C" int64_t lcsim_b200_city_launch_count(const lcsim_b200_city* e) { return e ? e->launches : 0; }
 extern "C" void lcsim_b200_city_destroy(lcsim_b200_city* e) {
     if (!e) return;
+#ifndef LCSIM_HOSTEMU
+    if (e->tick_graph) cudaGraphExecDestroy(e->tick_graph);
+#endif
     for (void* q : e->allocs) cudaFree(q);
     delete e;
 }
@@ -1795,6 +1803,12 @@ extern "C" int lcsim_b200_city_create(const lcsim_b200_city_static* st, int devi
     c.NL = NL;
     c.dt = st->interval;
     c.with_metrics = e->with_metrics = with_metrics;
+#ifndef LCSIM_HOSTEMU
+    {
+        const char* env = getenv("LCSIM_B200_CITY_GRAPH");
+        e->use_graph = !(env && env[0] == '0');
+    }
+#endif
     const int NN = st->lane_node_start[NL];
     // ---- validation of the graph indices the kernels follow
     for (int l = 0; l < NL; l++) {
@@ -1938,24 +1952,57 @@ extern "C" int lcsim_b200_city_reset(lcsim_b200_city* e, void* stream) {
     return 0;
 }
 
+// one Engine.step(): update (+ the readers' rounds) -> prepare -> clock
+static void lcc_tick(lcsim_b200_city* e, LccP& c, cudaStream_t st) {
+    LCC_RUN(lcc_update, c, c.N, st);
+    for (int r = 1; r <= LCC_READER_ROUNDS; r++) { // readers of live speeds (lane changes), by dependency depth
+        LccP cr = c;
+        cr.mode = r;
+        LCC_RUN(lcc_update_round, cr, c.N, st);
+    }
+    LCC_RUN(lcc_update_serial, c, 1, st);
+    LCC_RUN(lcc_commit_v, c, c.N, st);
+    lcc_prepare(e, c, true, st);
+    LCC_RUN(lcc_tick_end, c, 1, st);
+    e->launches += 4 + LCC_READER_ROUNDS;
+}
+
 extern "C" int lcsim_b200_city_step(lcsim_b200_city* e, int n_ticks, void* stream) {
     if (!e || n_ticks < 0) return LCSIM_B200_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     LccP c = e->c;
     c.mode = 0;
-    for (int k = 0; k < n_ticks; k++) {
-        LCC_RUN(lcc_update, c, c.N, st);
-        for (int r = 1; r <= LCC_READER_ROUNDS; r++) { // readers of live speeds (lane changes), by dependency depth
-            LccP cr = c;
-            cr.mode = r;
-            LCC_RUN(lcc_update_round, cr, c.N, st);
+#ifndef LCSIM_HOSTEMU
+    // The launch sequence of a tick is static (all state lives in device memory), and at ~25 short launches per
+    // tick the host's launch rate is the limit: capture it once into a CUDA graph and replay that.
+    if (e->use_graph && !e->tick_graph && n_ticks > 0) {
+        cudaStream_t cs = nullptr;
+        cudaGraph_t g = nullptr;
+        const int64_t before = e->launches;
+        bool ok = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            lcc_tick(e, c, cs);
+            ok = cudaStreamEndCapture(cs, &g) == cudaSuccess && g && cudaGraphInstantiate(&e->tick_graph, g, 0) == cudaSuccess;
         }
-        LCC_RUN(lcc_update_serial, c, 1, st);
-        LCC_RUN(lcc_commit_v, c, c.N, st);
-        lcc_prepare(e, c, true, st);
-        LCC_RUN(lcc_tick_end, c, 1, st);
-        e->launches += 4 + LCC_READER_ROUNDS;
+        e->launches_per_tick = (int)(e->launches - before);
+        e->launches = before;
+        if (g) cudaGraphDestroy(g);
+        if (cs) cudaStreamDestroy(cs);
+        if (!ok) {
+            cudaGetLastError();
+            e->tick_graph = nullptr;
+            e->use_graph = 0;
+        }
     }
+    if (e->tick_graph) {
+        for (int k = 0; k < n_ticks; k++)
+            if (cudaGraphLaunch(e->tick_graph, st) != cudaSuccess) return lcc_fail(e, LCSIM_B200_ERR_CUDA, "city tick graph launch failed");
+        e->launches += (int64_t)n_ticks * e->launches_per_tick;
+        return 0;
+    }
+#endif
+    for (int k = 0; k < n_ticks; k++) lcc_tick(e, c, st);
     if (cudaGetLastError() != cudaSuccess) return lcc_fail(e, LCSIM_B200_ERR_CUDA, "city step launch failed");
     return 0;
 }
