@@ -112,7 +112,7 @@ def run_reference(args):
     steps, secs = cpu_rollouts(sb, cores, args.steps)
     val = steps / secs
     sample = f"{n_sample} of the {args.scenarios} scenarios per step, 91 ticks with collision/off-road metrics"
-    print(json.dumps({
+    print_json({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "agent-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -121,7 +121,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is pure Python and cannot travel; timed arm is oracle/lcsim_oracle.c (pinned to the real "
                 "engine's golden vectors) on all host cores",
-    }))
+    })
 
 
 def _config(args, l2):
@@ -339,13 +339,25 @@ def run_b200(args):
             "agent_steps_per_rollout": agent_steps_all // max(args.steps, 1),
             "episode": shard.rates(total),
         }
-        print(json.dumps(out))
+        print_json(out)
     be.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Libraries (NCCL's version banner, torchrun warnings) write to fd 1; the contract is ONE JSON line on stdout.
+    Everything else goes to stderr: fd 1 is pointed at stderr and the JSON line is written to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(saved, "w")
+    global print_json
+    print_json = lambda obj: (out.write(json.dumps(obj) + "\n"), out.flush())  # noqa: E731
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
