@@ -232,6 +232,76 @@ def to_pb(raw: dict):
     return m, ag
 
 
+def raw_from_pb(map_pb, agents_pb) -> dict:
+    """map.pb / agents.pb of a MOSS-shaped scenario -> the raw structure `pack_city` lowers (dense indices in pb order).
+    What Engine.__init__ derives from the same bytes: LaneManager / RoadManager / JunctionManager wiring
+    (lane/lane.py:55-106, road/road.py:90-95, junction/junction.py:90-103) and, per agent, Schedule / Route inputs
+    (agent/agent.py:106-125, agent/route.py:56-100, agent/schedule.py:51-64)."""
+    lane_ix = {l.id: i for i, l in enumerate(map_pb.lanes)}
+    road_ix = {r.id: i for i, r in enumerate(map_pb.roads)}
+    lanes = []
+    for l in map_pb.lanes:
+        pts = np.array([[p.x, p.y] for p in l.center_line.nodes], float)
+        lanes.append(dict(id=int(l.id), pts=pts, max_speed=float(l.max_speed), width=float(l.width), road=-1, junction=-1,
+                          offset=0, pred=[lane_ix[c.id] for c in l.predecessors], succ=[lane_ix[c.id] for c in l.successors],
+                          left=[lane_ix[x] for x in l.left_lane_ids], right=[lane_ix[x] for x in l.right_lane_ids],
+                          length=_plen(pts)))
+    roads = []
+    for ri, r in enumerate(map_pb.roads):
+        ids = [lane_ix[x] for x in r.lane_ids]
+        for k, li in enumerate(ids):
+            lanes[li]["road"], lanes[li]["offset"] = ri, k
+        roads.append(dict(id=int(r.id), lane_ids=ids,
+                          edges=[(np.array([[p.x, p.y] for p in e.nodes], float), int(e.type)) for e in r.road_edges]))
+    juncs = []
+    for ji, j in enumerate(map_pb.junctions):
+        ids = [lane_ix[x] for x in j.lane_ids]
+        for li in ids:
+            lanes[li]["junction"] = ji
+        groups = [dict(in_road=road_ix[g.in_road_id], out_road=road_ix[g.out_road_id], lane_ids=[lane_ix[x] for x in g.lane_ids])
+                  for g in j.driving_lane_groups]
+        juncs.append(dict(id=int(j.id), lane_ids=ids, groups=groups,
+                          edges=[(np.array([[p.x, p.y] for p in e.nodes], float), int(e.type)) for e in j.road_edges]))
+    agents = []
+    for a in agents_pb.agents:
+        if a.home.lane_position.ByteSize() == 0:
+            raise NotImplementedError("city scenarios hold lane-position homes only (xy homes: lcsim_b200.packer)")
+        if len(a.schedules) != 1 or len(a.schedules[0].trips) != 1 or a.schedules[0].loop_count != 1:
+            raise NotImplementedError("lane agents are expected to carry one schedule x one trip, loop_count=1")
+        sch, trip = a.schedules[0], a.schedules[0].trips[0]
+        if trip.HasField("departure_time"):
+            dep = trip.departure_time
+        elif sch.HasField("departure_time"):
+            dep = sch.departure_time
+        elif trip.HasField("wait_time"):
+            dep = 0.0 + trip.wait_time
+        else:
+            dep = 0.0
+        if len(trip.routes) == 0:
+            raise ValueError(f"agent {a.id}: no route (reference: Route.valid is False)")
+        at = a.attribute
+        agents.append(dict(
+            id=int(a.id), length=float(at.length), width=float(at.width), max_speed=float(at.max_speed),
+            max_acc=float(at.max_acceleration), usual_acc=float(at.usual_acceleration),
+            max_brake=float(at.max_braking_acceleration), usual_brake=float(at.usual_braking_acceleration),
+            min_gap=float(a.vehicle_attribute.min_gap), home_lane=lane_ix[a.home.lane_position.lane_id],
+            home_s=float(a.home.lane_position.s), end_lane=lane_ix[trip.end.lane_position.lane_id],
+            end_s=float(trip.end.lane_position.s), route=[road_ix[x] for x in trip.routes[0].driving.road_ids],
+            departure_time=float(dep)))
+    return dict(seed=-1, lanes=lanes, roads=roads, juncs=juncs, agents=agents, ads_index=int(agents_pb.ads_index))
+
+
+def pack_dir(data_dir: str, **kw) -> "CityStatic":
+    return pack_city(raw_from_pb(proto.load_map(os.path.join(data_dir, "map.pb")),
+                                 proto.load_agents(os.path.join(data_dir, "agents.pb"))), **kw)
+
+
+def is_city_dir(data_dir: str) -> bool:
+    """True when the scenario's agents have lane-position homes (LaneIDM agents, agent.py:121-131,167-171)."""
+    ag = proto.load_agents(os.path.join(data_dir, "agents.pb"))
+    return len(ag.agents) > 0 and ag.agents[0].home.lane_position.ByteSize() > 0
+
+
 def write_city(out_dir: str, raw: dict):
     m, ag = to_pb(raw)
     os.makedirs(out_dir, exist_ok=True)
@@ -340,7 +410,7 @@ def pack_city(raw: dict, start: float = 0.0, interval: float = 0.1, max_ticks: i
     i32 = lambda x: np.asarray(x, np.int32)  # noqa: E731
     return CityStatic(
         start=start, interval=interval, n_lanes=NL, n_agents=N,
-        lane_pbid=i32(range(NL)), lane_length=lane_len, lane_max_speed=np.asarray([l["max_speed"] for l in lanes], float),
+        lane_pbid=i32([l.get("id", i) for i, l in enumerate(lanes)]), lane_length=lane_len, lane_max_speed=np.asarray([l["max_speed"] for l in lanes], float),
         lane_width=np.asarray([l["width"] for l in lanes], float), lane_road=i32([l["road"] for l in lanes]),
         lane_junction=i32([l["junction"] for l in lanes]), lane_offset=i32([l["offset"] for l in lanes]),
         lane_succ0=i32([l["succ"][0] if l["succ"] else -1 for l in lanes]),

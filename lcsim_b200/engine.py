@@ -410,6 +410,18 @@ class ScenarioEngine:
 class Engine(ScenarioEngine):
     """reference: lcsim/engine/engine.py:22-260"""
 
+    def __new__(cls, config: dict):
+        # a scenario of lane-position agents (LaneIDM, agent.py:121-131,167-171) goes to the city engine's face
+        data_dir = config["input"]["data_dir"]
+        if isinstance(data_dir, (str, os.PathLike)) and os.path.exists(os.path.join(data_dir, "agents.pb")):
+            from . import city
+
+            if city.is_city_dir(data_dir):
+                from .city_facade import CityFacadeEngine
+
+                return CityFacadeEngine(config)
+        return super().__new__(cls)
+
     def __init__(self, config: dict):
         self.config = config
         step = config["control"]["step"]

@@ -107,6 +107,46 @@ def test_city_lane_changes_match_oracle(backend):
     ce.close()
 
 
+def test_city_through_facade(tmp_path, backend):
+    """Engine(config) on a MOSS-shaped map.pb / agents.pb directory, driven like the reference (reset, step, manager and
+    agent attributes), against the golden vectors of the real engine for the same city"""
+    from lcsim_b200.engine import Engine
+
+    c = CityCase("city_g2_a24")
+    raw = city.make_city(seed=2, grid=2, n_agents=24, max_hops=5)  # the generator call that produced the golden case
+    d = str(tmp_path / "city")
+    city.write_city(d, raw)
+    cfg = {"input": {"data_dir": d, "model_path": "none", "model_config_path": "none"},
+           "control": {"step": {"start": 0, "total": 100000, "interval": 0.1}, "enable_poly_emb": False, "enable_plan": False,
+                       "plan_interval": 80, "plan_init_step": 10, "device": "cuda:0", "allow_new_obj": True, "reactive": False,
+                       "no_static": False, "guidance": False},
+           "reward": {}, "render": {}, "_backend": backend}
+    eng = Engine(cfg)
+    eng.reset()
+    am = eng.agent_manager
+    ids = list(am.agents.keys())
+    assert ids == [int(x) for x in c.static.agent_id] and am.ads_id == ids[int(c.static.ads_index)]
+    ref = c.ref
+    for k in range(120):
+        eng.step()
+        t = k + 1
+        act = am.active_agents
+        n = int(ref["n_active"][t])
+        assert [ids.index(a.id) for a in act] == list(ref["active"][t, :n]) and eng.current_step == t
+        np.testing.assert_array_equal(am.check_collision_all(), ref["coll"][t][ref["active"][t, :n]])
+        for a in act[:: max(1, n // 5)]:
+            i = ids.index(a.id)
+            assert a.runtime.lane.id == int(ref["lane"][t, i]) and a.runtime.status.value == int(ref["status"][t, i])
+            np.testing.assert_allclose([a.runtime.s, a.v, a.heading], [ref["s"][t, i], ref["v"][t, i], ref["h"][t, i]], rtol=0, atol=1e-9)
+            np.testing.assert_allclose(a.runtime.xy, [ref["x"][t, i], ref["y"][t, i]], rtol=0, atol=1e-9)
+            assert a.is_offroad() == bool(ref["offroad"][t, i])
+            assert (a.obs.ahead_vehicle is not None) == bool(ref["lead_valid"][t, i])
+        if n:
+            assert am.get_collision_rate() == pytest.approx(ref["coll"][t].sum() / n)
+            assert am.get_offroad_rate() == pytest.approx(ref["offroad"][t].sum() / n)
+    eng.close()
+
+
 def test_city_rejects_bad_static(backend):
     raw = city.make_city(seed=6, grid=2, n_agents=10)
     st = city.pack_city(raw)
