@@ -1708,9 +1708,13 @@ __global__ void __launch_bounds__(1024) lcc_scan_sums(int32_t* tile_sum, int n_t
     }
     if (threadIdx.x == 0 && total) *total = carry;
 }
-__global__ void lcc_scan_add(int32_t* data, int n, const int32_t* tile_sum) {
+__global__ void lcc_scan_add(int32_t* data, int n, const int32_t* tile_sum, int32_t* copy) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) data[i] += tile_sum[i / LCC_SCAN_TILE];
+    if (i < n) {
+        const int32_t v = data[i] + tile_sum[i / LCC_SCAN_TILE];
+        data[i] = v;
+        if (copy) copy[i] = v; // the scatter's cursor array, written in the same pass
+    }
 }
 #endif
 
@@ -1730,18 +1734,19 @@ struct lcsim_b200_city {
     std::string err;
 };
 
-static void lcc_scan(lcsim_b200_city* e, int32_t* data, int n, int32_t* total, cudaStream_t st) {
+static void lcc_scan(lcsim_b200_city* e, int32_t* data, int n, int32_t* total, int32_t* copy, cudaStream_t st) {
 #ifndef LCSIM_HOSTEMU
     const int tiles = (n + LCC_SCAN_TILE - 1) / LCC_SCAN_TILE;
     lcc_scan_tiles<<<tiles, 1024, 0, st>>>(data, n, e->tile_sum);
     lcc_scan_sums<<<1, 1024, 0, st>>>(e->tile_sum, tiles, total);
-    lcc_scan_add<<<(n + 255) / 256, 256, 0, st>>>(data, n, e->tile_sum);
+    lcc_scan_add<<<(n + 255) / 256, 256, 0, st>>>(data, n, e->tile_sum, copy);
     e->launches += 3;
 #else
     int32_t acc = 0;
     for (int i = 0; i < n; i++) {
         const int32_t v = data[i];
         data[i] = acc;
+        if (copy) copy[i] = acc;
         acc += v;
     }
     if (total) *total = acc;
@@ -1895,6 +1900,7 @@ extern "C" int lcsim_b200_city_create(const lcsim_b200_city_static* st, int devi
     LCC_TRY(lcc_alloc(e, &c.bkt_s, (size_t)2 * N));
     LCC_TRY(lcc_alloc(e, &c.cell_start, c.n_cells + 1)); LCC_TRY(lcc_alloc(e, &c.cell_cur, c.n_cells + 1));
     LCC_TRY(lcc_alloc(e, &c.cell_agent, N));
+    LCC_TRY(lcc_alloc(e, &c.cell_rec, (size_t)N * 8));
     const int max_scan = std::max(std::max(N, NL + 1), c.n_cells + 1);
     LCC_TRY(lcc_alloc(e, &e->tile_sum, max_scan / 2048 + 2));
     int rc = lcsim_b200_city_reset(e, nullptr);
@@ -1909,14 +1915,13 @@ static void lcc_prepare(lcsim_b200_city* e, LccP& c, bool swap_lanes, cudaStream
     const int N = c.N;
     LCC_RUN(lcc_pop_count, c, N, st);
     cudaMemcpyAsync(c.rank, c.fin, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, st);
-    lcc_scan(e, c.rank, N, c.scal + LCC_N_ARR, st);
+    lcc_scan(e, c.rank, N, c.scal + LCC_N_ARR, nullptr, st);
     LCC_RUN(lcc_place, c, N, st);
     LCC_RUN(lcc_place_end, c, 1, st);
     if (swap_lanes) { // Lane.prepare: agents <- new_agents (lane.py:171-175)
         cudaMemsetAsync(c.lane_start, 0, sizeof(int32_t) * (c.NL + 1), st);
         LCC_RUN(lcc_bucket_count, c, 2 * N, st);
-        lcc_scan(e, c.lane_start, c.NL + 1, nullptr, st);
-        cudaMemcpyAsync(c.lane_cur, c.lane_start, sizeof(int32_t) * (c.NL + 1), cudaMemcpyDeviceToDevice, st);
+        lcc_scan(e, c.lane_start, c.NL + 1, nullptr, c.lane_cur, st);
         LCC_RUN(lcc_bucket_scatter, c, 2 * N, st);
         LCC_RUN(lcc_bucket_end, c, 1, st);
         e->launches += 3;
@@ -1926,8 +1931,7 @@ static void lcc_prepare(lcsim_b200_city* e, LccP& c, bool swap_lanes, cudaStream
     if (c.with_metrics) {
         cudaMemsetAsync(c.cell_start, 0, sizeof(int32_t) * (c.n_cells + 1), st);
         LCC_RUN(lcc_cell_count, c, N, st);
-        lcc_scan(e, c.cell_start, c.n_cells + 1, nullptr, st);
-        cudaMemcpyAsync(c.cell_cur, c.cell_start, sizeof(int32_t) * (c.n_cells + 1), cudaMemcpyDeviceToDevice, st);
+        lcc_scan(e, c.cell_start, c.n_cells + 1, nullptr, c.cell_cur, st);
         LCC_RUN(lcc_cell_scatter, c, N, st);
         LCC_RUN(lcc_collide, c, N, st);
         LCC_RUN(lcc_offroad, c, N, st);

@@ -46,6 +46,7 @@ struct LccP {
     double* bkt_s;
     // spatial hash of the active agents
     int32_t *cell_start, *cell_cur, *cell_agent; // [n_cells+1], [n_cells+1], [N]
+    double* cell_rec; // [N][8] collision records in cell order
     int32_t mode; // 1 = reset
 };
 enum { LCC_N_ACTIVE = 0, LCC_WAIT_PTR, LCC_TICK, LCC_N_ENT, LCC_N_ARR, LCC_M_POP, LCC_LC_REQUIRED, LCC_LC_ERROR, LCC_N_OLD, LCC_N_PENDING };
@@ -575,40 +576,46 @@ LCS_D void lcc_cell_count(const LccP& c, int i) {
     if (i < c.scal[LCC_N_ACTIVE]) lcs_atomic_add(&c.cell_start[lcc_cell_of(c, c.active2[i])], 1);
 }
 LCC_KERNEL(lcc_cell_count)
+// slot -> its cell, as a 64-byte record {x, y, heading, length, width, bounding radius, agent}: the collision kernel
+// then reads its candidates from three contiguous runs (the three cells of a grid row are neighbours in the table)
 LCS_D void lcc_cell_scatter(const LccP& c, int i) {
     if (i >= c.scal[LCC_N_ACTIVE]) return;
     const int a = c.active2[i];
-    c.cell_agent[lcs_atomic_add(&c.cell_cur[lcc_cell_of(c, a)], 1)] = a;
+    const int e = lcs_atomic_add(&c.cell_cur[lcc_cell_of(c, a)], 1);
+    c.cell_agent[e] = a;
+    double* r = c.cell_rec + 8 * (size_t)e;
+    const double L = c.length[a], W = c.width[a];
+    r[0] = c.xy[2 * a]; r[1] = c.xy[2 * a + 1]; r[2] = c.h[a]; r[3] = L; r[4] = W;
+    r[5] = 0.5 * sqrt(L * L + W * W);
+    r[6] = (double)a;
 }
 LCC_KERNEL(lcc_cell_scatter)
-LCS_D void lcc_box(const LccP& c, int a, double* ex) {
-    double sh, ch;
-    lcs_sincos(c.h[a], &sh, &ch);
-    ex[0] = c.xy[2 * a]; ex[1] = c.xy[2 * a + 1]; ex[2] = c.v[a]; ex[3] = ch; ex[4] = sh; ex[5] = c.length[a]; ex[6] = c.width[a]; ex[7] = c.h[a];
-}
 LCS_D void lcc_collide(const LccP& c, int i) {
     if (i >= c.scal[LCC_N_ACTIVE]) return;
     const int a = c.active2[i];
     double ea[8], eb[8];
-    lcc_box(c, a, ea);
+    {
+        double sh, ch;
+        lcs_sincos(c.h[a], &sh, &ch);
+        ea[0] = c.xy[2 * a]; ea[1] = c.xy[2 * a + 1]; ea[2] = 0.0; ea[3] = ch; ea[4] = sh; ea[5] = c.length[a]; ea[6] = c.width[a]; ea[7] = c.h[a];
+    }
     const double ra = 0.5 * sqrt(ea[5] * ea[5] + ea[6] * ea[6]);
     const int cell = lcc_cell_of(c, a), cx = cell % c.cell_w, cy = cell / c.cell_w;
+    const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx < c.cell_w - 1 ? cx + 1 : c.cell_w - 1;
     int cnt = 0;
     for (int y = cy - 1; y <= cy + 1; y++) {
         if (y < 0 || y >= c.cell_h) continue;
-        for (int x = cx - 1; x <= cx + 1; x++) {
-            if (x < 0 || x >= c.cell_w) continue;
-            const int q = y * c.cell_w + x;
-            for (int e = c.cell_start[q]; e < c.cell_start[q + 1]; e++) {
-                const int b = c.cell_agent[e];
-                if (b == a) continue;
-                const double dx = c.xy[2 * b] - ea[0], dy = c.xy[2 * b + 1] - ea[1];
-                const double rb = 0.5 * sqrt(c.length[b] * c.length[b] + c.width[b] * c.width[b]);
-                const double rr = (ra + rb) * 1.000001 + 1e-6; // bounding circles apart: the SAT cannot overlap
-                if (dx * dx + dy * dy > rr * rr) continue;
-                lcc_box(c, b, eb);
-                if (lcs_collide(ea, eb)) cnt++;
-            }
+        const int b0 = c.cell_start[y * c.cell_w + x0], b1 = c.cell_start[y * c.cell_w + x1 + 1];
+        for (int e = b0; e < b1; e++) {
+            const double* r = c.cell_rec + 8 * (size_t)e;
+            const double dx = r[0] - ea[0], dy = r[1] - ea[1];
+            const double rr = (ra + r[5]) * 1.000001 + 1e-6; // bounding circles apart: the SAT cannot overlap
+            if (dx * dx + dy * dy > rr * rr) continue;
+            if ((int)r[6] == a) continue;
+            double sh, ch;
+            lcs_sincos(r[2], &sh, &ch);
+            eb[0] = r[0]; eb[1] = r[1]; eb[2] = 0.0; eb[3] = ch; eb[4] = sh; eb[5] = r[3]; eb[6] = r[4]; eb[7] = r[2];
+            if (lcs_collide(ea, eb)) cnt++;
         }
     }
     c.coll_count[a] = cnt;
