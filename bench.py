@@ -130,7 +130,11 @@ def _config(args, l2):
                         f"(BASELINE configs[1])",
             "scenarios_per_gpu": args.scenarios, "agents": args.agents, "ticks": N_TICKS,
             "mode": "log-replay" if args.mode == "replay" else "reactive (TrajIDM + bicycle)",
-            "l2": l2}
+            "l2": l2,
+            "exact_shortcuts": "replay records (cursor of a replayed waypoint from a canonical-index table instead of the "
+                               "trajectory scan; LCSIM_B200_RECORDS=0 disables), edge search skipped for agents whose position "
+                               "did not change, per-cell candidate lists for the nearest road-edge point "
+                               "(LCSIM_B200_CAND_CELL=0 disables); results bit-identical either way (tests/test_parity.py)"}
 
 
 def run_b200(args):
@@ -316,7 +320,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": _config(args, "inputs 1.3 GB/GPU > 126 MB L2; L2 flushed between timed rollouts"),
+            "config": _config(args, "inputs 5.6 GB/GPU > 126 MB L2; L2 flushed between timed rollouts"),
             "clocks": clocks,
             "e2e": {"value": roll_val, "unit": "agent-steps/s", "h2d_bytes_per_step": roll_h2d, "d2h_bytes_per_step": roll_d2h,
                     "what": "lcsim_b200_rollout_host, one call per rollout with pinned host buffers: H2D reset mask, reset + 91 "

@@ -421,7 +421,7 @@ LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s) {
     bool off;
     if (have_metrics)
         off = p.offroad[ia] != 0;
-    else
+    else if (lcs_nearest_edge_cell(p, s, x, y, &off) == -2)
         lcs_nearest_edge_hint(p, s, x, y, p.edge_hint[ia], &off);
     terms[4] = off ? -1.0 : 0.0;
     if (status == LCS_IDLE || status == LCS_FINISHED) {
@@ -503,6 +503,7 @@ struct lcsim_b200_engine {
     double* env_act = nullptr; // [S][2] staging of env_step actions
     lcsim_b200_env_out* env_out = nullptr; // [S] staging of env_step outputs
     LcsWpRec* wp_rec = nullptr;
+    int64_t cand_entries = 0; // total length of the candidate lists
     uint8_t* host_mask = nullptr; // rollout_host staging
     int32_t* tick_log = nullptr;
     size_t log_ticks = 0;
@@ -695,6 +696,10 @@ struct Staging {
     std::vector<uint8_t> dynamic;
     std::vector<double> length, width, home_xy, traj_xy, traj_vel, traj_h, s_tab, edge_xy, edge_dir;
     std::vector<lcs_f2> tf_xy, ge_xy;
+    std::vector<float> cl_geom;
+    std::vector<int32_t> cl_dim;
+    std::vector<std::vector<int32_t>> cl_start, cl_idx; // per scenario
+    std::vector<std::vector<lcs_f2>> cl_xy;
     std::vector<LcsWpRec> wp_rec;
     std::vector<float> grid_geom, eta;
 };
@@ -788,6 +793,16 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     g.grid_dim.assign((size_t)S * 2, 1);
     g.eta.assign(S, 0.f);
     g.home_edge.assign(SA, -1);
+    g.cl_geom.assign((size_t)S * 4, 0.f);
+    g.cl_dim.assign((size_t)S * 2, 0);
+    g.cl_start.resize(S);
+    g.cl_idx.resize(S);
+    g.cl_xy.resize(S);
+    float cl_cell = 2.0f; // LCSIM_B200_CAND_CELL: cell of the candidate lists in metres, 0 = no lists (hinted search only)
+    {
+        const char* env = getenv("LCSIM_B200_CAND_CELL");
+        if (env) cl_cell = (float)atof(env);
+    }
     const float cell = e->desc.grid_cell > 0 ? e->desc.grid_cell : 4.0f;
     std::vector<std::vector<int32_t>> cell_starts(S);
 
@@ -924,6 +939,72 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
                 }
                 g.home_edge[(size_t)s * Ap + a] = bi;
             }
+            // ---- candidate lists (lcs_nearest_edge_cell): fine grid over the edge points' box + 12 m, at most 192 x 192
+            if (cl_cell > 0.f && !keep.empty()) {
+                const float mg = 12.0f;
+                const float cx0 = minx - mg, cy0 = miny - mg;
+                int cw = (int)std::ceil((maxx + mg - cx0) / cl_cell), ch = (int)std::ceil((maxy + mg - cy0) / cl_cell);
+                cw = std::min(std::max(cw, 1), 192);
+                ch = std::min(std::max(ch, 1), 192);
+                const float cinv = 1.0f / cl_cell;
+                g.cl_geom[4 * s] = cx0; g.cl_geom[4 * s + 1] = cy0; g.cl_geom[4 * s + 2] = cinv; g.cl_geom[4 * s + 3] = cl_cell;
+                g.cl_dim[2 * s] = cw; g.cl_dim[2 * s + 1] = ch;
+                const size_t np_ = keep.size();
+                std::vector<double> px(np_), py(np_);
+                for (size_t q = 0; q < np_; q++) { // local float64 coordinates of the kept points
+                    px[q] = exy[2 * keep[q]] - ox;
+                    py[q] = exy[2 * keep[q] + 1] - oy;
+                }
+                std::vector<int32_t>& cst = g.cl_start[s];
+                std::vector<int32_t>& cidx = g.cl_idx[s];
+                std::vector<lcs_f2>& cxy = g.cl_xy[s];
+                cst.assign((size_t)cw * ch + 1, 0);
+                // the kernel finds the cell with float32 arithmetic: widen every cell by 2 cm against its rounding
+                const double infl = 0.02;
+                // K(box) = points with mindist(point, box) <= U(box) + 1 cm, U(box) = min over points of maxdist(point, box).
+                // For a box inside a larger one, K(box) is a subset of K(larger) and so is the point that attains
+                // U(box): the fine cells are therefore built from the list of their 8 x 8 block, not from all points.
+                auto select = [&](double x0, double x1, double y0, double y1, const std::vector<int>& from, std::vector<int>& out) {
+                    double U2 = 1e300; // squared distance to the farthest corner, minimised over the points
+                    for (int q : from) {
+                        const double fx = std::max(px[q] - x0, x1 - px[q]), fy = std::max(py[q] - y0, y1 - py[q]);
+                        U2 = std::min(U2, fx * fx + fy * fy);
+                    }
+                    const double U = std::sqrt(U2) + 0.01, lim = U * U;
+                    out.clear();
+                    for (int q : from) {
+                        const double nx = std::max(std::max(x0 - px[q], px[q] - x1), 0.0), ny = std::max(std::max(y0 - py[q], py[q] - y1), 0.0);
+                        if (nx * nx + ny * ny <= lim) out.push_back(q);
+                    }
+                };
+                std::vector<int> all(np_), coarse, fine;
+                for (size_t q = 0; q < np_; q++) all[q] = (int)q;
+                const int CB = 8;
+                std::vector<std::vector<int>> row_lists((cw + CB - 1) / CB);
+                for (int cyy = 0; cyy < ch; cyy++) {
+                    if (cyy % CB == 0) // the coarse blocks of this band of rows
+                        for (int bx = 0; bx * CB < cw; bx++) {
+                            const int xe = std::min(cw, (bx + 1) * CB), ye = std::min(ch, cyy + CB);
+                            select((double)cx0 + (double)(bx * CB) * cl_cell - infl, (double)cx0 + (double)xe * cl_cell + infl,
+                                   (double)cy0 + (double)cyy * cl_cell - infl, (double)cy0 + (double)ye * cl_cell + infl, all, row_lists[bx]);
+                        }
+                    for (int cxx = 0; cxx < cw; cxx++) {
+                        select((double)cx0 + (double)cxx * cl_cell - infl, (double)cx0 + (double)(cxx + 1) * cl_cell + infl,
+                               (double)cy0 + (double)cyy * cl_cell - infl, (double)cy0 + (double)(cyy + 1) * cl_cell + infl,
+                               row_lists[cxx / CB], fine);
+                        cst[(size_t)cyy * cw + cxx] = (int32_t)cxy.size();
+                        for (int q : fine) { // ascending original index (keep[] is sorted)
+                            cxy.push_back(pts[q]);
+                            cidx.push_back(keep[q]);
+                        }
+                        while (cxy.size() % 4) { // whole 32-byte blocks
+                            cxy.push_back(far);
+                            cidx.push_back(0);
+                        }
+                    }
+                }
+                cst[(size_t)cw * ch] = (int32_t)cxy.size();
+            }
         }
     });
     int GC = 2;
@@ -932,6 +1013,42 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     for (int s = 0; s < S; s++) {
         std::copy(cell_starts[s].begin(), cell_starts[s].end(), g.grid_start.begin() + (size_t)s * GC);
         for (size_t c = cell_starts[s].size(); c < (size_t)GC; c++) g.grid_start[(size_t)s * GC + c] = cell_starts[s].back();
+    }
+    // candidate lists: concatenate the scenarios' runs
+    {
+        int nc = 1;
+        for (int s = 0; s < S; s++) nc = std::max<int>(nc, (int)g.cl_start[s].size() - 1);
+        std::vector<int32_t> cstart((size_t)S * (nc + 1), 0);
+        std::vector<long long> cbase(S, 0);
+        size_t total = 0;
+        for (int s = 0; s < S; s++) {
+            cbase[s] = (long long)total;
+            const std::vector<int32_t>& c = g.cl_start[s];
+            for (size_t k = 0; k < (size_t)nc + 1; k++) cstart[(size_t)s * (nc + 1) + k] = c.empty() ? 0 : c[std::min(k, c.size() - 1)];
+            total += g.cl_xy[s].size();
+        }
+        std::vector<lcs_f2> cxy(std::max<size_t>(total, 4), far);
+        std::vector<int32_t> cidx(std::max<size_t>(total, 4), 0);
+        for (int s = 0; s < S; s++) {
+            std::copy(g.cl_xy[s].begin(), g.cl_xy[s].end(), cxy.begin() + cbase[s]);
+            std::copy(g.cl_idx[s].begin(), g.cl_idx[s].end(), cidx.begin() + cbase[s]);
+            std::vector<lcs_f2>().swap(g.cl_xy[s]);
+            std::vector<int32_t>().swap(g.cl_idx[s]);
+        }
+        p.cl_nc = nc;
+        LCS_ALLOC(e, p.cl_geom, (size_t)S * 4);
+        LCS_ALLOC(e, p.cl_dim, (size_t)S * 2);
+        LCS_ALLOC(e, p.cl_start, cstart.size());
+        LCS_ALLOC(e, p.cl_base, S);
+        LCS_ALLOC(e, p.cl_xy, cxy.size());
+        LCS_ALLOC(e, p.cl_idx, cidx.size());
+        LCS_CUDA(e, cudaMemcpy((void*)p.cl_geom, g.cl_geom.data(), g.cl_geom.size() * sizeof(float), cudaMemcpyHostToDevice));
+        LCS_CUDA(e, cudaMemcpy((void*)p.cl_dim, g.cl_dim.data(), g.cl_dim.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        LCS_CUDA(e, cudaMemcpy((void*)p.cl_start, cstart.data(), cstart.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        LCS_CUDA(e, cudaMemcpy((void*)p.cl_base, cbase.data(), cbase.size() * sizeof(long long), cudaMemcpyHostToDevice));
+        LCS_CUDA(e, cudaMemcpy((void*)p.cl_xy, cxy.data(), cxy.size() * sizeof(lcs_f2), cudaMemcpyHostToDevice));
+        LCS_CUDA(e, cudaMemcpy((void*)p.cl_idx, cidx.data(), cidx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        e->cand_entries = (int64_t)total;
     }
     if (p.grid_start) { /* re-upload: keep the old block alive until destroy */ }
     p.GC = GC;

@@ -128,6 +128,14 @@ struct LcsParams {
     int32_t GC;
     const lcs_f2* ge_xy; // [S][E] points sorted by cell, float32 relative to origin
     const int32_t* ge_idx; // [S][E] original index of each sorted point
+    // candidate lists: for every cell of a fine grid, ALL edge points that can be nearest to some position in the cell
+    const float* cl_geom; // [S][4] x0, y0, 1 / cell, cell (float32 local frame)
+    const int32_t* cl_dim; // [S][2] W, H (0, 0: no lists for this scenario)
+    const int32_t* cl_start; // [S][cl_nc + 1] offsets into the scenario's run of cl_xy / cl_idx, multiples of 4
+    const long long* cl_base; // [S] first entry of the scenario in cl_xy / cl_idx
+    const lcs_f2* cl_xy; // filter coordinates, 32-byte blocks, padded with LCS_FAR
+    const int32_t* cl_idx; // original index
+    int32_t cl_nc;
     // ---- state, per scenario
     int32_t *tick, *n_active, *wait_ptr;
     int64_t* stats; // [S][LCS_NSTAT]
@@ -516,6 +524,62 @@ LCS_D int lcs_nearest_edge(const LcsParams& p, int s, double qx, double qy, bool
     if (m2 <= thr) {
         double bd;
         lcs_edge_lane_exact(p, s, q, qx, qy, thr, 0, 1, bd, best);
+    }
+    *offroad = lcs_edge_side(p, s, qx, qy, best);
+    return best;
+}
+
+// Nearest edge point through the candidate lists.  List K(C) of cell C holds every edge point p with
+// mindist(p, C) <= U(C) + 1 cm, U(C) = min over all points of maxdist(point, C): for a query anywhere in C the nearest
+// point is no farther than U(C), so K(C) contains every point that can attain (or tie within the filter's error band)
+// the minimum.  The search is one header load and a contiguous run of 32-byte blocks, four in flight; the float32
+// filter / float64 tie-break logic is the one of the other searches.  Returns -2 when the query lies outside the grid.
+LCS_D int lcs_nearest_edge_cell(const LcsParams& p, int s, double qx, double qy, bool* offroad) {
+    const int W = p.cl_dim[2 * s], H = p.cl_dim[2 * s + 1];
+    if (W <= 0) return -2;
+    const float fqx = (float)(qx - p.origin[2 * s]), fqy = (float)(qy - p.origin[2 * s + 1]);
+    const float gx0 = p.cl_geom[4 * s], gy0 = p.cl_geom[4 * s + 1], inv = p.cl_geom[4 * s + 2];
+    const float fx = floorf((fqx - gx0) * inv), fy = floorf((fqy - gy0) * inv);
+    if (!(fx >= 0.0f && fy >= 0.0f && fx < (float)W && fy < (float)H)) return -2;
+    const int cell = (int)fy * W + (int)fx;
+    const int32_t* cs = p.cl_start + (size_t)s * (p.cl_nc + 1);
+    const int b = cs[cell], e = cs[cell + 1];
+    if (e <= b) return -2; // no edge point at all in this scenario
+    const size_t base = (size_t)p.cl_base[s];
+    const lcs_f2* gp = p.cl_xy + base;
+    float m = lcs_inf_f(), m2 = lcs_inf_f();
+    int j = -1;
+    for (int k0 = b; k0 < e; k0 += 16) {
+        lcs_f8 v[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (k0 + 4 * r < e) v[r] = lcs_ld32((const lcs_f8*)(gp + k0 + 4 * r));
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            if (k0 + 4 * r < e) {
+                const int k = k0 + 4 * r;
+                LCS_SCAN_POINT(v[r].v[0], v[r].v[1], k)
+                LCS_SCAN_POINT(v[r].v[2], v[r].v[3], k + 1)
+                LCS_SCAN_POINT(v[r].v[4], v[r].v[5], k + 2)
+                LCS_SCAN_POINT(v[r].v[6], v[r].v[7], k + 3)
+            }
+    }
+    const int32_t* gi = p.cl_idx + base;
+    const float thr = lcs_filter_thr(m, lcs_filter_eta(p.eta_pts[s], fqx, fqy, m));
+    int best = gi[j];
+    if (m2 <= thr) { // near-tie: float64 on every candidate, (distance, original index) minimum
+        const double* e64 = p.edge_xy + (size_t)s * p.E * 2;
+        double bd = lcs_inf_d();
+        best = 0x7fffffff;
+        for (int k = b; k < e; k++) {
+            const lcs_f2 pt = gp[k];
+            const float dx = pt.x - fqx, dy = pt.y - fqy;
+            if (dx * dx + dy * dy <= thr) {
+                const int idx = gi[k];
+                const double ee = lcs_norm2_axis(lcs_dsub(e64[2 * idx], qx), lcs_dsub(e64[2 * idx + 1], qy));
+                if (ee < bd || (ee == bd && idx < best)) { bd = ee; best = idx; }
+            }
+        }
     }
     *offroad = lcs_edge_side(p, s, qx, qy, best);
     return best;
@@ -1320,8 +1384,9 @@ LCS_D void lcs_phase_offroad(const LcsParams& p, LcsSmem& sm, int s, int tid, Lc
     if (tid >= lcs_total(sm.mask, nw)) return;
     const int a = sm.act2[lcs_select(sm.mask, nw, tid)];
     const size_t ia = (size_t)s * p.Ap + a;
-    bool off;
-    const int k = lcs_nearest_edge_hint(p, s, sm.ex[8 * a], sm.ex[8 * a + 1], p.edge_hint[ia], &off);
+    bool off = false;
+    int k = lcs_nearest_edge_cell(p, s, sm.ex[8 * a], sm.ex[8 * a + 1], &off);
+    if (k == -2) k = lcs_nearest_edge_hint(p, s, sm.ex[8 * a], sm.ex[8 * a + 1], p.edge_hint[ia], &off); // outside the lists' grid
     p.nearest_edge[ia] = k;
     p.edge_hint[ia] = k;
     p.offroad[ia] = off ? 1 : 0;
