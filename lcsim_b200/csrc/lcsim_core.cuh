@@ -181,7 +181,8 @@ struct LcsSmem {
     uint32_t* queue; // [LCS_QPER * Ap] candidate pairs (slot_i << 16 | slot_j)
     uint16_t* cand; // [LCS_CAND][Ap] per-thread broadphase survivors
     uint32_t* mask; // [3][32] ballot words: finished, popped, activated
-    int32_t* misc; // [8] n_old, n_new, collision sum, off-road sum, tick, wait_ptr, queue length
+    int32_t* misc; // [16] n_old, n_new, collision sum, off-road sum, tick, wait_ptr, queue length, -, then [8..11]:
+                   // number of set flags of the ballot rows finished / popped / activated / moved
     uint8_t* moved; // [Ap] 0: the agent's position is bit-identical to the one its edge outputs were computed for (agent index)
 };
 
@@ -191,7 +192,7 @@ static inline
 __host__ __device__ inline
 #endif
 size_t lcs_smem_bytes(int Ap) {
-    return (size_t)Ap * (64 + 8 + 32 + 4 * 4 + 4 * LCS_QPER + 2 * LCS_CAND + 1) + 3 * 32 * 4 + 8 * 4 + 64;
+    return (size_t)Ap * (64 + 8 + 32 + 4 * 4 + 4 * LCS_QPER + 2 * LCS_CAND + 1) + 3 * 32 * 4 + 16 * 4 + 64;
 }
 
 LCS_D void lcs_smem_carve(LcsSmem& sm, unsigned char* base, int Ap) {
@@ -206,7 +207,7 @@ LCS_D void lcs_smem_carve(LcsSmem& sm, unsigned char* base, int Ap) {
     sm.cnt = (int32_t*)p; p += (size_t)Ap * 4;
     sm.queue = (uint32_t*)p; p += (size_t)Ap * 4 * LCS_QPER;
     sm.mask = (uint32_t*)p; p += 3 * 32 * 4;
-    sm.misc = (int32_t*)p; p += 8 * 4;
+    sm.misc = (int32_t*)p; p += 16 * 4;
     sm.cand = (uint16_t*)p; p += (size_t)Ap * 2 * LCS_CAND;
     sm.moved = (uint8_t*)p;
 }
@@ -263,6 +264,22 @@ LCS_D void lcs_set_flag(uint32_t* words, int tid, bool f) {
 #else
     uint32_t b = __ballot_sync(0xffffffffu, f);
     if ((tid & 31) == 0) words[tid >> 5] = b;
+#endif
+}
+// same, and the number of set flags of the whole row accumulates in *total (zeroed at tick start): every thread
+// needs the totals afterwards, and popcounting all words again in every thread was 9 % of the kernel's instructions
+LCS_D void lcs_set_flag_count(uint32_t* words, int tid, bool f, int32_t* total) {
+#ifdef LCSIM_HOSTEMU
+    if (f) {
+        words[tid >> 5] |= 1u << (tid & 31);
+        *total += 1;
+    }
+#else
+    uint32_t b = __ballot_sync(0xffffffffu, f);
+    if ((tid & 31) == 0) {
+        words[tid >> 5] = b;
+        if (b) atomicAdd(total, __popc(b));
+    }
 #endif
 }
 LCS_D int lcs_prefix(const uint32_t* words, int tid) { // number of set flags below tid
@@ -1114,6 +1131,7 @@ LCS_D int lcs_phase_init(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThr
         sm.misc[4] = p.mode == 1 ? 0 : p.tick[s];
         sm.misc[5] = p.mode == 1 ? 0 : p.wait_ptr[s];
         sm.misc[6] = 0; // pair-queue length
+        sm.misc[8] = sm.misc[9] = sm.misc[10] = sm.misc[11] = 0; // flag totals
     }
     sm.cnt[tid] = 0;
     sm.moved[tid] = 1; // agents that enter the list this tick have no edge outputs yet
@@ -1154,17 +1172,16 @@ LCS_D void lcs_phase_depart_flags(const LcsParams& p, LcsSmem& sm, int s, int ti
         t.pop = p.depart_tick[(size_t)s * p.Ap + aw] <= tick;
         t.act = t.pop && !(p.no_static && !p.dynamic[(size_t)s * p.Ap + aw] && aw != p.ads_index[s]);
     }
-    lcs_set_flag(sm.mask, tid, t.fin);
-    lcs_set_flag(sm.mask + 32, tid, t.pop);
-    lcs_set_flag(sm.mask + 64, tid, t.act);
+    lcs_set_flag_count(sm.mask, tid, t.fin, &sm.misc[8]);
+    lcs_set_flag_count(sm.mask + 32, tid, t.pop, &sm.misc[9]);
+    lcs_set_flag_count(sm.mask + 64, tid, t.act, &sm.misc[10]);
 }
 
 // Phase B2: new active list — departures reuse the finished slots in order, else append; leftover
 // finished slots are dropped preserving order.  Departing agents publish their record.
 LCS_D void lcs_phase_depart_place(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
-    const int nw = (p.Ap + 31) >> 5;
     const int n = sm.misc[0];
-    const int n_arr = lcs_total(sm.mask, nw), m = lcs_total(sm.mask + 64, nw);
+    const int n_arr = sm.misc[8], m = sm.misc[10];
     if (tid < n && !t.fin) {
         const int r = lcs_prefix(sm.mask, tid);
         sm.act2[tid - (r > m ? r - m : 0)] = sm.act[tid];
@@ -1182,9 +1199,8 @@ LCS_D void lcs_phase_depart_place(const LcsParams& p, LcsSmem& sm, int s, int ti
     }
 }
 LCS_D void lcs_phase_depart_fill(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
-    const int nw = (p.Ap + 31) >> 5;
     const int n = sm.misc[0];
-    const int n_arr = lcs_total(sm.mask, nw), n_pop = lcs_total(sm.mask + 32, nw), m = lcs_total(sm.mask + 64, nw);
+    const int n_arr = sm.misc[8], n_pop = sm.misc[9], m = sm.misc[10];
     if (tid < n && t.fin) {
         const int r = lcs_prefix(sm.mask, tid);
         if (r < m) sm.act2[tid] = sm.dlist[r]; // no slot before this one was dropped when r < m
@@ -1219,7 +1235,7 @@ LCS_D void lcs_phase_publish(const LcsParams& p, LcsSmem& sm, int s, int tid) {
 #ifdef LCSIM_HOSTEMU
     if ((tid & 31) == 0) sm.mask[tid >> 5] = 0; // the emulated ballot only sets bits; the device one overwrites the word
 #endif
-    lcs_set_flag(sm.mask, tid, tid < n_new && sm.moved[sm.act2[tid < n_new ? tid : 0]] != 0);
+    lcs_set_flag_count(sm.mask, tid, tid < n_new && sm.moved[sm.act2[tid < n_new ? tid : 0]] != 0, &sm.misc[11]);
     if (tid >= n_new) {
         p.active[is] = -1;
         return;
@@ -1381,7 +1397,7 @@ LCS_D void lcs_phase_offroad(const LcsParams& p, LcsSmem& sm, int s, int tid, Lc
     // the searches run on DENSE lanes: thread k takes the k-th slot that needs one (about half of the list moves in
     // a tick, and a warp pays for the longest search among its lanes whatever their number)
     const int nw = (p.Ap + 31) >> 5;
-    if (tid >= lcs_total(sm.mask, nw)) return;
+    if (tid >= sm.misc[11]) return;
     const int a = sm.act2[lcs_select(sm.mask, nw, tid)];
     const size_t ia = (size_t)s * p.Ap + a;
     bool off = false;
