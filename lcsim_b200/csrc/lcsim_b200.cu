@@ -350,7 +350,25 @@ LCS_D int lcs_argmin_exact(const double* pts, int n, double px, double py) {
 
 // reference: engine.py:301-357 _compute_rewards, agent.py:468-480 get_route, manager.py:289-311
 // check_collision (lane=None agents: all active), agent.py:482-494 is_offroad
-LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s) {
+// One WARP per scenario on the device (lane = 0 .. 31; the host emulation calls it with nlanes = 1): the two frenet
+// scans over the reference trajectory are split over the lanes and merged with shuffles, everything else is
+// computed redundantly by all lanes (same addresses: broadcast loads) and stored by lane 0.
+LCS_D void lcs_scan_lanes(const LcsParams& p, int s, int a, int len, LcsScan& sc, int lane, int nlanes) {
+    const lcs_f8* tf = (const lcs_f8*)(p.tf_xy + lcs_tf_index(p, s, 0, a));
+    const int n4 = (len + 3) >> 2;
+    for (int k4 = lane; k4 < n4; k4 += nlanes) lcs_scan_quad(sc, lcs_ld32(tf + k4), 4 * k4);
+#ifndef LCSIM_HOSTEMU
+    if (nlanes > 1) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, sc.m, d), om2 = __shfl_xor_sync(0xffffffffu, sc.m2, d);
+            const int oj = __shfl_xor_sync(0xffffffffu, sc.j, d);
+            lcs_edge_merge(sc.m, sc.m2, sc.j, om, om2, oj);
+        }
+    }
+#endif
+}
+LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s, int lane, int nlanes) {
     const int a = r.agent ? r.agent[s] : p.ads_index[s];
     const size_t ia = (size_t)s * p.Ap + a;
     double terms[6] = {0, 0, 0, 0, 0, 0};
@@ -368,9 +386,9 @@ LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s) {
         // frenet_projection index = the same first-index argmin the tick uses for the cursor (filter + exact ties)
         LcsScan sc0, sc1;
         lcs_scan_begin(p, s, p0[0], p0[1], sc0);
-        lcs_scan_global(p, s, a, n, sc0);
+        lcs_scan_lanes(p, s, a, n, sc0, lane, nlanes);
         lcs_scan_begin(p, s, p1[0], p1[1], sc1);
-        lcs_scan_global(p, s, a, n, sc1);
+        lcs_scan_lanes(p, s, a, n, sc1, lane, nlanes);
         const int i0 = lcs_scan_finish(p, s, a, n, p0[0], p0[1], sc0), i1 = lcs_scan_finish(p, s, a, n, p1[0], p1[1], sc1);
         const double d0 = lcs_norm2_vec(lcs_dsub(p0[0], xy[2 * i0]), lcs_dsub(p0[1], xy[2 * i0 + 1]));
         const double d1 = lcs_norm2_vec(lcs_dsub(p1[0], xy[2 * i1]), lcs_dsub(p1[1], xy[2 * i1 + 1]));
@@ -451,6 +469,7 @@ LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s) {
             }
         }
     }
+    if (lane != 0) return;
     if (r.env) {
         lcsim_b200_env_out* o = r.env + s;
         o->reward = rew;
@@ -470,8 +489,8 @@ LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s) {
 }
 #ifndef LCSIM_HOSTEMU
 __global__ void lcs_rewards_kernel(const LcsParams p, const LcsRewardArgs r) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < p.S) lcs_rewards_one(p, r, s);
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s < p.S) lcs_rewards_one(p, r, s, threadIdx.x & 31, 32);
 }
 __global__ void lcs_stats_kernel(const int64_t* stats, int S, int64_t* out) {
     __shared__ long long acc[LCS_NSTAT];
@@ -1268,10 +1287,10 @@ extern "C" int lcsim_b200_rewards(lcsim_b200_engine* e, const int32_t* agent, co
     r.truncated = truncated;
     r.s_tab0 = e->s_tab0;
 #ifndef LCSIM_HOSTEMU
-    lcs_rewards_kernel<<<(e->p.S + 63) / 64, 64, 0, (cudaStream_t)stream>>>(e->p, r);
+    lcs_rewards_kernel<<<(e->p.S + 3) / 4, 128, 0, (cudaStream_t)stream>>>(e->p, r);
     LCS_CUDA(e, cudaGetLastError());
 #else
-    for (int s = 0; s < e->p.S; s++) lcs_rewards_one(e->p, r, s);
+    for (int s = 0; s < e->p.S; s++) lcs_rewards_one(e->p, r, s, 0, 1);
 #endif
     return 0;
 }
@@ -1297,12 +1316,12 @@ extern "C" int lcsim_b200_env_step(lcsim_b200_engine* e, const double* actions_h
     r.env = e->env_out;
     r.s_tab0 = e->s_tab0;
 #ifndef LCSIM_HOSTEMU
-    lcs_rewards_kernel<<<(q.S + 63) / 64, 64, 0, st>>>(e->p, r);
+    lcs_rewards_kernel<<<(q.S + 3) / 4, 128, 0, st>>>(e->p, r);
     LCS_CUDA(e, cudaGetLastError());
     LCS_CUDA(e, cudaMemcpyAsync(out_host, e->env_out, sizeof(lcsim_b200_env_out) * q.S, cudaMemcpyDeviceToHost, st));
     if (sync) LCS_CUDA(e, cudaStreamSynchronize(st));
 #else
-    for (int s = 0; s < q.S; s++) lcs_rewards_one(e->p, r, s);
+    for (int s = 0; s < q.S; s++) lcs_rewards_one(e->p, r, s, 0, 1);
     memcpy(out_host, e->env_out, sizeof(lcsim_b200_env_out) * q.S);
 #endif
     return 0;

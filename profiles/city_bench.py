@@ -37,7 +37,24 @@ print(f"{ticks} ticks in {ms:.1f} ms ({1e3 * ms / ticks:.1f} us/tick, {(ce.launc
 xy, h = ce.xy.cpu().numpy(), ce.heading.cpu().numpy()
 status, cc = ce.status.cpu().numpy(), ce.coll_count.cpu().numpy()
 act = np.nonzero(status == 1)[0]
-from oracle.city_oracle import _overlap_a_over_b  # checker only
+
+
+def _corners(b):  # polygon.py:238-268 corners_from_bboxes
+    x, y, length, width, yaw = b[..., 0], b[..., 1], b[..., 2], b[..., 3], b[..., 4]
+    cos, sin = np.cos(yaw), np.sin(yaw)
+    xc = np.stack([x + length / 2 * cos + width / 2 * sin, x - length / 2 * cos + width / 2 * sin,
+                   x - length / 2 * cos - width / 2 * sin, x + length / 2 * cos - width / 2 * sin], axis=-1)
+    yc = np.stack([y + length / 2 * sin - width / 2 * cos, y - length / 2 * sin - width / 2 * cos,
+                   y - length / 2 * sin + width / 2 * cos, y + length / 2 * sin + width / 2 * cos], axis=-1)
+    return np.stack([xc, yc], axis=-1)
+
+
+def _overlap_a_over_b(first, second):  # polygon.py:206-230 (brute-force checker of this script)
+    c, s_ = np.cos(first[..., 4]), np.sin(first[..., 4])
+    normals_t = np.stack([np.stack([c, -s_], axis=-1), np.stack([s_, c], axis=-1)], axis=-2)
+    pa, pb = np.matmul(_corners(first), normals_t), np.matmul(_corners(second), normals_t)
+    return np.all(np.minimum(pa.max(axis=-2), pb.max(axis=-2)) - np.maximum(pa.min(axis=-2), pb.min(axis=-2)) > 0, axis=-1)
+
 
 rng = np.random.default_rng(0)
 sample = rng.choice(act, size=min(300, len(act)), replace=False)
