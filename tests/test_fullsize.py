@@ -1,0 +1,93 @@
+"""BASELINE.json sizes on the GPU (configs[1]: 1024 scenarios x 128 agents; configs[3]: one city, here 20k vehicles):
+the oracle cannot run these in seconds, so the checks are size-independent properties plus the oracle on a sample.
+  * the 91-tick rollout is deterministic (same bits twice) and the fused multi-tick kernel lands on the same bits as
+    per-tick launches;
+  * list bookkeeping is conserved every tick (active after = updated - arrivals + departures) and the statistics
+    equal the sums of the per-tick log;
+  * 16 scenarios drawn from the batch equal the CPU oracle's state after its own 91 steps, integers bit-exact;
+  * city: collision counts equal a brute-force numpy SAT on a sample of vehicles, agents are conserved."""
+import numpy as np
+import pytest
+
+from lcsim_b200 import city, native, workload
+from lcsim_b200.batch import BatchEngine
+from lcsim_b200.city_engine import CityEngine
+from oracle import oracle as orc
+from oracle.city_oracle import _overlap_a_over_b
+
+pytestmark = pytest.mark.gpu
+KEYS = ("pose64", "status", "cursor", "active", "coll_count", "nearest_edge", "offroad", "ring", "ring_head", "stats")
+
+
+@pytest.fixture(scope="module")
+def batch1024():
+    return workload.synthetic_batch(0, 1024, 128, workers=16)
+
+
+def test_full_batch_rollout_properties(batch1024, monkeypatch):
+    sb = batch1024
+    be = BatchEngine(sb, reactive=False, with_metrics=True, device=0)
+    tn = be.backend.to_numpy
+    log = tn(be.rollout(91, log=True)).astype(np.int64)
+    snap = {k: tn(getattr(be, k)).copy() for k in KEYS}
+    st = snap["stats"]
+    # statistics == sums of the log; conservation of the active list
+    np.testing.assert_array_equal(st[:, 0], log[:, :, 0].sum(axis=0))
+    np.testing.assert_array_equal(st[:, 1], log[:, :, 1].sum(axis=0))
+    np.testing.assert_array_equal(st[:, 2], log[:, :, 2].sum(axis=0))
+    np.testing.assert_array_equal(st[:, 3], log[:, :, 3].sum(axis=0))
+    np.testing.assert_array_equal(log[1:, :, 0], log[:-1, :, 1])  # updated at tick k+1 == active after tick k
+    assert (st[:, 5] - st[:, 4] == log[-1, :, 1]).all()  # departures - arrivals == active at the end
+    assert int(st[:, 0].sum()) > 6_000_000
+    # determinism
+    be.reset()
+    log2 = tn(be.rollout(91, log=True)).astype(np.int64)
+    np.testing.assert_array_equal(log2, log)
+    for k, v in snap.items():
+        np.testing.assert_array_equal(tn(getattr(be, k)), v, err_msg=k)
+    be.close()
+    # fused multi-tick kernel: same bits
+    monkeypatch.setenv("LCSIM_B200_FUSED", "1")
+    bf = BatchEngine(sb, reactive=False, with_metrics=True, device=0)
+    np.testing.assert_array_equal(tn(bf.rollout(91, log=True)).astype(np.int64), log)
+    for k, v in snap.items():
+        np.testing.assert_array_equal(tn(getattr(bf, k)), v, err_msg="fused " + k)
+    bf.close()
+    # the oracle on a sample of the batch
+    pick = np.sort(np.random.default_rng(0).choice(sb.S, 16, replace=False))
+    for s in pick:
+        sub = sb.scenario_slice(int(s), int(s) + 1)
+        o = orc.Oracle(sub, reactive=False)
+        for _ in range(91):
+            o.step()
+        o.metrics()
+        np.testing.assert_array_equal(snap["status"][s], o.status[0], err_msg=f"scenario {s}: status")
+        np.testing.assert_array_equal(snap["cursor"][s], o.cursor[0], err_msg=f"scenario {s}: cursor")
+        np.testing.assert_array_equal(snap["coll_count"][s], o.coll_count[0], err_msg=f"scenario {s}: collisions")
+        np.testing.assert_array_equal(snap["nearest_edge"][s], o.nearest_edge[0], err_msg=f"scenario {s}: nearest edge")
+        np.testing.assert_array_equal(snap["offroad"][s], o.offroad[0], err_msg=f"scenario {s}: offroad")
+        np.testing.assert_allclose(snap["pose64"][s][:, 0], o.x[0], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(snap["pose64"][s][:, 2], o.h[0], rtol=0, atol=1e-9)
+        assert int(snap["stats"][s, 0]) == int(o.agent_steps[0])
+
+
+def test_city_20k_properties():
+    raw = city.make_city(seed=77, grid=24, n_agents=20000, depart_window=10.0, max_hops=6)
+    st = city.pack_city(raw)
+    ce = CityEngine(st, device=0)
+    ce.step(150)
+    tn = ce.backend.to_numpy
+    stats, status = tn(ce.stats), tn(ce.status)
+    n_active = ce.scalar("n_active")
+    assert stats[5] - stats[4] == n_active == int((status == native.ACTIVE).sum())
+    assert ce.scalar("lc_error") == 0 and ce.scalar("tick") == 150
+    act = tn(ce.active)[:n_active]
+    assert len(set(act.tolist())) == n_active and (status[act] == native.ACTIVE).all()
+    xy, h, cc = tn(ce.xy), tn(ce.heading), tn(ce.coll_count)
+    boxes = np.stack([xy[act, 0], xy[act, 1], st.length[act], st.width[act], h[act]], axis=1)
+    for a in np.random.default_rng(1).choice(act, 200, replace=False):
+        me = np.asarray([[xy[a, 0], xy[a, 1], st.length[a], st.width[a], h[a]]])
+        near = np.nonzero((np.abs(boxes[:, 0] - me[0, 0]) < 12) & (np.abs(boxes[:, 1] - me[0, 1]) < 12) & (act != a))[0]
+        n = int(np.logical_and(_overlap_a_over_b(me, boxes[near]), _overlap_a_over_b(boxes[near], me)).sum()) if len(near) else 0
+        assert n == cc[a], (a, n, cc[a])
+    ce.close()
