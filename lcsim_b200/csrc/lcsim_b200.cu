@@ -597,7 +597,8 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || d->device < 0 || d->device >= ndev) return LCSIM_B200_ERR_CUDA;
     if (cudaSetDevice(d->device) != cudaSuccess) return LCSIM_B200_ERR_CUDA;
     if (lcs_configure_kernels() != cudaSuccess) return LCSIM_B200_ERR_CUDA;
-    int n_groups = 1;
+    // sub-batches on separate streams in rollout(): two as soon as the batch does not fit the chip in one wave
+    int n_groups = d->S > 148 * LCS_MIN_CTAS && d->A <= 128 ? 2 : 1;
     {
         const char* env = getenv("LCSIM_B200_GROUPS");
         if (env) n_groups = std::min(8, std::max(1, atoi(env)));
@@ -1161,6 +1162,32 @@ static int lcs_rollout(lcsim_b200_engine* e, int n_ticks, int32_t* tick_log, voi
         LCS_CUDA(e, cudaGetLastError());
         return 0;
     }
+#ifndef LCSIM_HOSTEMU
+    if (e->n_groups > 1 && !q.dbg) {
+        // Scenarios are independent, so a batch that needs more than one wave of CTAs is stepped as sub-batches on
+        // their own streams: while one group drains the tail of its tick, the other group's CTAs take the free
+        // slots (measured on B200: 2.55e9 -> 3.1e9 agent-steps/s at S = 4096, 2.36e9 -> 3.0e9 at S = 2048; no gain
+        // when the whole batch is co-resident).  The caller's stream waits for all groups.
+        const int G = e->n_groups;
+        cudaStream_t us = (cudaStream_t)stream;
+        LCS_CUDA(e, cudaEventRecord(e->gevent[G], us));
+        for (int g = 0; g < G; g++) {
+            const int s0 = (int)((long long)q.S * g / G), s1 = (int)((long long)q.S * (g + 1) / G);
+            LCS_CUDA(e, cudaStreamWaitEvent(e->gstream[g], e->gevent[G], 0));
+            if (s1 > s0)
+                for (int k = 0; k < n_ticks; k++) {
+                    q.n_ticks = 1;
+                    if (tick_log) q.tick_log = tick_log + (size_t)k * q.S * 4;
+                    lcs_launch_tick(q, e->gstream[g], s0, s1 - s0);
+                }
+            LCS_CUDA(e, cudaEventRecord(e->gevent[g], e->gstream[g]));
+            LCS_CUDA(e, cudaStreamWaitEvent(us, e->gevent[g], 0));
+        }
+        e->launches += (int64_t)n_ticks * G;
+        LCS_CUDA(e, cudaGetLastError());
+        return 0;
+    }
+#endif
     for (int k = 0; k < n_ticks; k++) {
         q.n_ticks = 1;
         if (tick_log) q.tick_log = tick_log + (size_t)k * q.S * 4;
@@ -1173,30 +1200,6 @@ static int lcs_rollout(lcsim_b200_engine* e, int n_ticks, int32_t* tick_log, voi
 
 extern "C" int lcsim_b200_rollout(lcsim_b200_engine* e, int n_ticks, void* stream) {
     if (!e || n_ticks < 0) return LCSIM_B200_ERR_ARG;
-#ifndef LCSIM_HOSTEMU
-    if (e->n_groups > 1 && e->uploaded && n_ticks > 0) {
-        // Scenarios are independent, so the batch is stepped as n_groups sub-batches on their own streams:
-        // their ticks drift apart in time and the memory-bound and compute-bound phases of different groups
-        // overlap instead of every CTA of the chip hitting the same phase at once.
-        const int G = e->n_groups;
-        cudaStream_t us = (cudaStream_t)stream;
-        LCS_CUDA(e, cudaEventRecord(e->gevent[G], us));
-        LcsParams q = e->p;
-        q.mode = 0;
-        q.K = 0;
-        for (int g = 0; g < G; g++) {
-            const int s0 = (int)((long long)q.S * g / G), s1 = (int)((long long)q.S * (g + 1) / G);
-            LCS_CUDA(e, cudaStreamWaitEvent(e->gstream[g], e->gevent[G], 0));
-            if (s1 > s0)
-                for (int k = 0; k < n_ticks; k++) lcs_launch_tick(q, e->gstream[g], s0, s1 - s0);
-            LCS_CUDA(e, cudaEventRecord(e->gevent[g], e->gstream[g]));
-            LCS_CUDA(e, cudaStreamWaitEvent(us, e->gevent[g], 0));
-        }
-        e->launches += (int64_t)n_ticks * G;
-        LCS_CUDA(e, cudaGetLastError());
-        return 0;
-    }
-#endif
     return lcs_rollout(e, n_ticks, nullptr, stream);
 }
 

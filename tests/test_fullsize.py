@@ -71,6 +71,21 @@ def test_full_batch_rollout_properties(batch1024, monkeypatch):
         assert int(snap["stats"][s, 0]) == int(o.agent_steps[0])
 
 
+def test_stream_groups_same_bits(batch1024, monkeypatch):
+    """rollout() of a batch larger than one wave runs as sub-batches on separate streams (forced here with three groups
+    of the 1024-scenario batch): same log, statistics and state as the single-stream rollout, bit for bit"""
+    sb = batch1024
+    out = {}
+    for g in ("1", "3"):
+        monkeypatch.setenv("LCSIM_B200_GROUPS", g)
+        be = BatchEngine(sb, reactive=True, with_metrics=True, device=0)
+        tn = be.backend.to_numpy
+        out[g] = [tn(be.rollout(40, log=True)).copy()] + [tn(getattr(be, k)).copy() for k in KEYS]
+        be.close()
+    for a, b in zip(out["1"], out["3"]):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_city_20k_properties():
     raw = city.make_city(seed=77, grid=24, n_agents=20000, depart_window=10.0, max_hops=6)
     st = city.pack_city(raw)
