@@ -161,8 +161,12 @@ int lcsim_b200_step(lcsim_b200_engine* e, const int32_t* act_agent, const int32_
 
 /* n_ticks consecutive Engine.step() calls without external actions (engine.py:145-158), i.e. the reference's
  * `for _ in range(n): engine.step()` loop for every scenario of the batch; state and outputs afterwards are those
- * of the last tick.  One launch per tick by default; LCSIM_B200_FUSED=1 in the environment of create() selects the
- * fused kernel in which the CTA of a scenario runs all n_ticks ticks back to back (measured slower on B200). */
+ * of the last tick.  One launch per tick.  When the whole batch is co-resident on the device, consecutive ticks go to
+ * two alternating internal streams and the CTA of a scenario starts as soon as that scenario's previous tick is done
+ * (a release/acquire flag per scenario), so the next tick fills the slots idle behind the slowest scenarios; larger
+ * batches run as two sub-batches on separate streams.  The caller's stream waits for all of it.  Environment of
+ * create(): LCSIM_B200_PIPELINE=0 / LCSIM_B200_GROUPS=1 switch these off, LCSIM_B200_FUSED=1 selects the fused
+ * kernel in which the CTA of a scenario runs all n_ticks ticks back to back (measured slower on B200). */
 int lcsim_b200_rollout(lcsim_b200_engine* e, int n_ticks, void* stream);
 
 /* Same, and additionally records per tick and scenario what the reference's caller could have read between the

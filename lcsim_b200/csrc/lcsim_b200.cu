@@ -83,6 +83,22 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_ti
     extern __shared__ __align__(128) unsigned char lcs_smem_raw[];
     const int s = blockIdx.x + p.s0, tid = threadIdx.x;
     if (p.mode == 1 && p.reset_mask && !p.reset_mask[s]) return;
+    if (p.wait_seq) {
+        // Pipelined rollout: this launch was started while the previous tick's launch may still be running.  A
+        // scenario only depends on its own previous tick: wait for that CTA's release, then one acquire fence (it
+        // also drops this SM's stale L1 lines) and the barrier hand the data to the whole CTA.
+        if (tid == 0) {
+            int v;
+            for (unsigned spins = 0;; spins++) {
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.done_seq + s) : "memory");
+                if (v - p.wait_seq >= 0) break;
+                if (spins > 40000000u) __trap(); // ~10 s: the producer cannot run (should be impossible): fail, do not hang
+                __nanosleep(200);
+            }
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        }
+        __syncthreads();
+    }
     LcsSmem sm;
     lcs_smem_carve(sm, lcs_smem_raw, p.Ap);
     LcsThread th;
@@ -92,6 +108,10 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_ti
 #define TH th
     LCS_TICK_REST(__syncthreads(), )
 #undef TH
+    if (p.set_seq) {
+        __syncthreads(); // every thread's stores precede the release (cumulativity through the barrier)
+        if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.done_seq + s), "r"(p.set_seq) : "memory");
+    }
 }
 
 // Fused rollout: the CTA of a scenario runs p.n_ticks consecutive ticks in ONE launch.  Scenarios never exchange
@@ -530,6 +550,8 @@ struct lcsim_b200_engine {
     int32_t *lane_ids = nullptr, *lane_n = nullptr;
     int lane_N = 0;
     int fused = 0; // rollout(): 1 = one launch for all ticks (LCSIM_B200_FUSED=1), 0 = one launch per tick
+    int pipeline = 0; // rollout(): consecutive ticks on alternating streams, per-scenario hand-over (LCSIM_B200_PIPELINE=0: off)
+    int32_t seq = 0; // last published sequence number
     int n_groups = 1; // rollout() splits the batch into this many scenario groups, one stream each
 #ifndef LCSIM_HOSTEMU
     cudaStream_t gstream[8] = {};
@@ -627,6 +649,18 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     *out = e; // returned even on failure below so the caller can read last_error and destroy
     e->n_groups = n_groups;
 #ifndef LCSIM_HOSTEMU
+    {
+        // Pipelining needs every CTA of a tick to be resident when the next tick's CTAs start to wait for them
+        // (otherwise waiting CTAs could hold the slots the CTAs they wait for need): whole batch <= one wave.
+        int per_sm = 0, n_sm = 0;
+        const char* env = getenv("LCSIM_B200_PIPELINE");
+        if (!(env && env[0] == '0') && n_groups == 1 && p.Ap <= 128 &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcs_tick_kernel_ldg<128>, p.Ap, lcs_smem_bytes(p.Ap)) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d->device) == cudaSuccess && p.S <= per_sm * n_sm) {
+            e->pipeline = 1;
+            n_groups = 2; // two streams, three events
+        }
+    }
     if (n_groups > 1) {
         for (int g = 0; g < n_groups; g++) LCS_CUDA(e, cudaStreamCreateWithFlags(&e->gstream[g], cudaStreamNonBlocking));
         for (int g = 0; g <= n_groups; g++) LCS_CUDA(e, cudaEventCreateWithFlags(&e->gevent[g], cudaEventDisableTiming));
@@ -677,6 +711,7 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     LCS_ALLOC(e, p.grid_dim, S * 2);
     LCS_ALLOC(e, p.ge_xy, SE);
     LCS_ALLOC(e, p.ge_idx, SE);
+    LCS_ALLOC(e, p.done_seq, S);
     LCS_ALLOC(e, p.tick, S);
     LCS_ALLOC(e, p.n_active, S);
     LCS_ALLOC(e, p.wait_ptr, S);
@@ -1163,7 +1198,32 @@ static int lcs_rollout(lcsim_b200_engine* e, int n_ticks, int32_t* tick_log, voi
         return 0;
     }
 #ifndef LCSIM_HOSTEMU
-    if (e->n_groups > 1 && !q.dbg) {
+    if (e->pipeline && !q.dbg && n_ticks > 1) {
+        // Whole batch co-resident: tick k+1 is launched on the other stream while tick k runs, and the CTA of a
+        // scenario starts as soon as ITS previous tick is done (done_seq) — the slots that the fast scenarios of a
+        // tick leave idle while the slowest one finishes are used by the next tick.  Tick k+2 follows tick k on
+        // the same stream, so at most two ticks are in flight and all CTAs of the older one are always resident.
+        cudaStream_t us = (cudaStream_t)stream;
+        LCS_CUDA(e, cudaEventRecord(e->gevent[2], us));
+        LCS_CUDA(e, cudaStreamWaitEvent(e->gstream[0], e->gevent[2], 0));
+        LCS_CUDA(e, cudaStreamWaitEvent(e->gstream[1], e->gevent[2], 0));
+        for (int k = 0; k < n_ticks; k++) {
+            q.n_ticks = 1;
+            if (tick_log) q.tick_log = tick_log + (size_t)k * q.S * 4;
+            q.wait_seq = k == 0 ? 0 : e->seq;
+            e->seq = e->seq == 0x7ffffff0 ? 1 : e->seq + 1;
+            q.set_seq = e->seq;
+            lcs_launch_tick(q, e->gstream[k & 1]);
+        }
+        e->launches += n_ticks;
+        for (int g = 0; g < 2; g++) {
+            LCS_CUDA(e, cudaEventRecord(e->gevent[g], e->gstream[g]));
+            LCS_CUDA(e, cudaStreamWaitEvent(us, e->gevent[g], 0));
+        }
+        LCS_CUDA(e, cudaGetLastError());
+        return 0;
+    }
+    if (e->n_groups > 1 && !e->pipeline && !q.dbg) {
         // Scenarios are independent, so a batch that needs more than one wave of CTAs is stepped as sub-batches on
         // their own streams: while one group drains the tail of its tick, the other group's CTAs take the free
         // slots (measured on B200: 2.55e9 -> 3.1e9 agent-steps/s at S = 4096, 2.36e9 -> 3.0e9 at S = 2048; no gain

@@ -160,6 +160,10 @@ struct LcsParams {
     long long* dbg; // [S][16] phase clocks (debug builds of the launch only)
     int32_t prefetch; // LCSIM_B200_PREFETCH=1 (default off): early L2 prefetch of the per-agent lines
     int32_t s0; // first scenario of this launch (sub-batch launches)
+    // tick pipelining (rollout): the launch of tick k+1 may start while tick k still runs; the CTA of scenario s
+    // waits until done_seq[s] reached wait_seq (0 = do not wait) and publishes set_seq when it is done (0 = do not)
+    int32_t* done_seq; // [S]
+    int32_t wait_seq, set_seq;
     int32_t mode; // 0 = step, 1 = reset
     int32_t n_ticks; // ticks per launch of the fused rollout kernel (1 for the per-tick kernel)
     int32_t* tick_log; // [n_ticks][S][4] agents updated, active after, collision sum, off-road sum (or null)
