@@ -1710,7 +1710,6 @@ __global__ void __launch_bounds__(128) lcs_lane_kernel(const LcsParams p, const 
         }
         int bi = -1, hn = 0, hmax_q = 0;
         float bd2 = lcs_inf_f(), on_d2 = lcs_inf_f(), hmax = lcs_inf_f();
-        int hmax_i = 0x7fffffff;
         for (int t0 = 0; t0 < n; t0 += LCS_LANE_TILE) {
             __syncthreads();
             for (int k = tid; k < LCS_LANE_TILE && t0 + k < n; k += 128) tile[k] = P[t0 + k];
@@ -1732,7 +1731,7 @@ __global__ void __launch_bounds__(128) lcs_lane_kernel(const LcsParams p, const 
                                 const float dq = hd[q * 128 + tid], dm = hd[hmax_q * 128 + tid];
                                 if (dq > dm || (dq == dm && hi[q * 128 + tid] > hi[hmax_q * 128 + tid])) hmax_q = q;
                             }
-                            hmax = hd[hmax_q * 128 + tid]; hmax_i = hi[hmax_q * 128 + tid];
+                            hmax = hd[hmax_q * 128 + tid];
                         }
                     } else if (d2 < hmax) {
                         hd[hmax_q * 128 + tid] = d2; hi[hmax_q * 128 + tid] = t0 + k;
@@ -1741,12 +1740,11 @@ __global__ void __launch_bounds__(128) lcs_lane_kernel(const LcsParams p, const 
                             const float dq = hd[q * 128 + tid], dm = hd[hmax_q * 128 + tid];
                             if (dq > dm || (dq == dm && hi[q * 128 + tid] > hi[hmax_q * 128 + tid])) hmax_q = q;
                         }
-                        hmax = hd[hmax_q * 128 + tid]; hmax_i = hi[hmax_q * 128 + tid];
+                        hmax = hd[hmax_q * 128 + tid];
                     }
                 }
             }
         }
-        (void)hmax_i;
         if (a >= 0) {
             float hdiff = -1.0f;
             if (K > 0 && hn == K) {
