@@ -196,7 +196,6 @@ def run_b200(args):
         stats_acc += be.episode_stats()
     barrier()
     t_wall1 = time.time()
-    clocks = sampler.stop(t_wall0, t_wall1)
     ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = be.launches - launches0
     total = shard.reduce_episode_stats(stats_acc)  # the one collective of the path: NCCL all-reduce over NVLink
@@ -299,6 +298,8 @@ def run_b200(args):
             e2e_ms, e2e_steps = float(tm[0]), int(t[1])
         e2e_val = e2e_steps / (e2e_ms * 1e-3)
 
+    # clocks / throttle reasons over everything timed on the GPU (the device-resident leg and both end-to-end legs)
+    clocks = sampler.stop(t_wall0, time.time() if not args.kernel_only else t_wall1)
     if rank == 0:
         peak, which = _peaks()
         # dominant kernel: the stepping launches of a rollout (one fused lcs_rollout_kernel launch of 91 ticks, or 91
