@@ -1036,7 +1036,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
                 for (size_t q = 0; q < np_; q++) all[q] = (int)q;
                 const int CB = 8;
                 std::vector<std::vector<int>> row_lists((cw + CB - 1) / CB);
-                for (int cyy = 0; cyy < ch; cyy++) {
+                for (int cyy = 0; cyy < ch && cxy.size() <= ((size_t)4 << 20); cyy++) {
                     if (cyy % CB == 0) // the coarse blocks of this band of rows
                         for (int bx = 0; bx * CB < cw; bx++) {
                             const int xe = std::min(cw, (bx + 1) * CB), ye = std::min(ch, cyy + CB);
@@ -1059,6 +1059,14 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
                     }
                 }
                 cst[(size_t)cw * ch] = (int32_t)cxy.size();
+                if (cxy.size() > (size_t)4 << 20) {
+                    // degenerate geometry (e.g. many points equidistant from a region): lists of this scenario would
+                    // take > 48 MB — drop them, its searches use the hinted hash grid
+                    g.cl_dim[2 * s] = g.cl_dim[2 * s + 1] = 0;
+                    std::vector<int32_t>().swap(cst);
+                    std::vector<int32_t>().swap(cidx);
+                    std::vector<lcs_f2>().swap(cxy);
+                }
             }
         }
     });

@@ -235,6 +235,26 @@ def test_ragged_and_empty_inputs(backend):
         be.close()
 
 
+def test_degenerate_edge_geometry_falls_back(backend):
+    """road edge = one circle around the scene: every cell near the centre is (almost) equidistant from all points, the
+    candidate lists would explode and are dropped for that scenario; its searches take the hinted hash-grid path"""
+    from lcsim_b200 import packer, proto, synth
+
+    raw = synth.make_raw_scenario(31, 48)
+    ang = np.linspace(0, 2 * np.pi, 2600)
+    raw["edges"] = [(np.stack([150.0 * np.cos(ang), 150.0 * np.sin(ang)], axis=1).astype(np.float32).astype(np.float64),
+                     proto.ROAD_EDGE_TYPE_BOUNDARY)]
+    sb = packer.pack([packer.scenario_from_raw(raw), packer.scenario_from_raw(synth.make_raw_scenario(32, 48))])
+    be = BatchEngine(sb, reactive=True, with_metrics=True, backend=backend)
+    o = orc.Oracle(sb, reactive=True)
+    for k in range(40):
+        be.step()
+        o.step()
+        o.metrics()
+        compare_engine_with_oracle(be, o, POSE_TOL, near_duplicate_edges=sb.edge_xy)
+    be.close()
+
+
 def test_abi_rejects_bad_calls(backend, synth8):
     import ctypes as C
 
