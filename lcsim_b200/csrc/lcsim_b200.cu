@@ -41,132 +41,104 @@ struct alignas(16) float4 { float x, y, z, w; };
 
 #include "lcsim_core.cuh"
 
+#ifndef LCS_MC_CTAS
+#define LCS_MC_CTAS 8 // resident CTAs per SM the 128-thread collision / edge kernels are compiled for
+#endif
+#ifndef LCS_ME_CTAS
+#define LCS_ME_CTAS 8
+#endif
+#define LCS_SNAP_MAX 8 // largest depth of the snapshot ring
 #ifndef LCS_MIN_CTAS
 #define LCS_MIN_CTAS 7 // resident CTAs per SM the 128-thread tick kernel is compiled for (register cap)
 #endif
 
 // ------------------------------------------------------------------------------------ kernels
 
-// One CTA per scenario, one thread per active-list slot; the whole tick in one launch (reference:
-// engine.py:145-158 Engine.step, plus manager.py:313-345 when with_metrics).
-#define LCS_TICK_REST(SYNC, FOR_T)                                                  \
+// ---- the engine kernel ------------------------------------------------------------------------------------------
+// A launch covers n_ticks ticks of all S scenarios as a queue of work items, processed by a grid of persistent CTAs
+// (one thread per active-list slot):
+//   tick item   T(k, s): Engine.step for scenario s (engine.py:145-158: update -> check_departure_and_arrival ->
+//                        prepare_obs -> clock); leaves a snapshot of the new list in ring slot k % D
+//   metric item M(k, s): check_collision_all / check_offroads of that snapshot (manager.py:313-345); nothing a later
+//                        tick reads, so it is off the scenario's serial chain and runs whenever a CTA is free
+// Ticket order: T(0, 0..S-1), M(0, 0..S-1), T(1, ...), ...  T(k, s) needs T(k-1, s) and M(k-D, s) (its ring slot is
+// free again), M(k, s) needs T(k, s) and M(k-1, s): always SMALLER tickets.  Tickets are claimed by running CTAs (atomic counter),
+// so the item a CTA waits for was claimed by a CTA that already runs — forward progress holds for any grid size, with
+// or without other work on the GPU; nothing depends on the order in which the hardware dispatches blocks.
+#define LCS_TICK_PHASES(SYNC, FOR_T)                                                \
+    FOR_T lcs_phase_update(p, sm, s, tid, TH);                                      \
+    SYNC;                                                                           \
     FOR_T lcs_phase_depart_flags(p, sm, s, tid, TH);                                \
     SYNC;                                                                           \
     FOR_T lcs_phase_depart_place(p, sm, s, tid, TH);                                \
     SYNC;                                                                           \
     FOR_T lcs_phase_depart_fill(p, sm, s, tid, TH);                                 \
     SYNC;                                                                           \
-    FOR_T lcs_phase_publish(p, sm, s, tid);                                         \
-    SYNC;                                                                           \
+    FOR_T lcs_phase_publish(p, sm, s, tid, TH);                                     \
     if (p.reactive) {                                                               \
-        FOR_T lcs_phase_lead_filter(p, sm, s, tid);                                 \
         SYNC;                                                                       \
-        FOR_T lcs_phase_lead_drain(p, sm, s, tid);                                  \
-        SYNC;                                                                       \
-        FOR_T lcs_phase_lead_out(p, sm, s, tid);                                    \
-        SYNC;                                                                       \
-    }                                                                               \
-    if (p.with_metrics) {                                                           \
-        FOR_T lcs_phase_collision_filter(p, sm, s, tid);                            \
-        FOR_T lcs_phase_offroad(p, sm, s, tid, TH);                                 \
-        SYNC;                                                                       \
-        FOR_T lcs_phase_collision_drain(p, sm, s, tid);                             \
-        SYNC;                                                                       \
-        FOR_T lcs_phase_metrics_out(p, sm, s, tid, TH);                             \
-        SYNC;                                                                       \
-        FOR_T lcs_phase_stats_out(p, sm, s, tid, TH);                               \
+        FOR_T lcs_phase_lead(p, sm, s, tid);                                        \
     }
+// AG: per-thread agent of the slot (device: a register; host emulation: an array)
+#define LCS_METRIC_PHASES(SYNC, FOR_T, AG)                                          \
+    FOR_T { if (tid < 2) sm.misc[12 + tid] = 0; }                                   \
+    SYNC;                                                                           \
+    FOR_T { AG = lcs_mc_load(p, sm, s, tid, TH); lcs_me_flags(p, s, tid, sm.mask, sm.misc + 12, TH); } \
+    SYNC;                                                                           \
+    FOR_T { lcs_phase_collision_filter(p, sm, s, tid); lcs_me_search(p, s, tid, sm.mask, sm.misc + 12, TH); } \
+    SYNC;                                                                           \
+    FOR_T lcs_phase_collision_drain(p, sm, s, tid);                                 \
+    SYNC;                                                                           \
+    FOR_T lcs_mc_out(p, sm, s, tid, AG);                                            \
+    SYNC;                                                                           \
+    FOR_T { lcs_mc_stats(p, sm, s, tid, TH); lcs_me_stats(p, s, tid, sm.misc + 12, TH); }
 
 #ifndef LCSIM_HOSTEMU
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_tick_kernel_ldg(const LcsParams p) {
-    extern __shared__ __align__(128) unsigned char lcs_smem_raw[];
-    const int s = blockIdx.x + p.s0, tid = threadIdx.x;
-    if (p.mode == 1 && p.reset_mask && !p.reset_mask[s]) return;
-    if (p.wait_seq) {
-        // Pipelined rollout: this launch was started while the previous tick's launch may still be running.  A
-        // scenario only depends on its own previous tick: wait for that CTA's release, then one acquire fence (it
-        // also drops this SM's stale L1 lines) and the barrier hand the data to the whole CTA.
-        if (tid == 0) {
-            int v;
-            for (unsigned spins = 0;; spins++) {
-                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.done_seq + s) : "memory");
-                if (v - p.wait_seq >= 0) break;
-                if (spins > 40000000u) __trap(); // ~10 s: the producer cannot run (should be impossible): fail, do not hang
-                __nanosleep(200);
-            }
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        }
-        __syncthreads();
-    }
-    LcsSmem sm;
-    lcs_smem_carve(sm, lcs_smem_raw, p.Ap);
-    LcsThread th;
-    th.k = 0;
-    lcs_phase_update(p, sm, s, tid, th);
-    __syncthreads();
-#define TH th
-    LCS_TICK_REST(__syncthreads(), )
-#undef TH
-    if (p.set_seq) {
-        __syncthreads(); // every thread's stores precede the release (cumulativity through the barrier)
-        if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.done_seq + s), "r"(p.set_seq) : "memory");
+LCS_D void lcs_wait_seq(const int32_t* addr, int want) {
+    int v;
+    for (;;) {
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+        if (v >= want) break;
+        __nanosleep(100);
     }
 }
 
-// Fused rollout: the CTA of a scenario runs p.n_ticks consecutive ticks in ONE launch.  Scenarios never exchange
-// anything, so nothing forces them to advance in lock step: without a launch boundary per tick there is no wave
-// tail (the slowest scenario of every tick), the CTAs drift apart so that memory-bound and shared-memory-bound
-// phases of different scenarios overlap, and a scenario's working set (state lines, replay records, the edge-grid
-// cells around its agents) is still in L1/L2 when the next tick asks for it.  State written by one thread and read
-// by another one tick later is ordered by the __syncthreads() between the phases (same CTA, same SM).
-template <int MAXT>
-__global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_rollout_kernel(const LcsParams p) {
-    extern __shared__ __align__(128) unsigned char lcs_smem_raw[];
-    const int s0 = blockIdx.x + p.s0, tid0 = threadIdx.x;
-#pragma unroll 1
-    for (int k = 0; k < p.n_ticks; k++) {
-        const int s = s0, tid = tid0;
-        LcsSmem sm;
-        lcs_smem_carve(sm, lcs_smem_raw, p.Ap);
-        LcsThread th;
-        th.k = k;
-        lcs_phase_update(p, sm, s, tid, th);
-        __syncthreads();
-#define TH th
-        LCS_TICK_REST(__syncthreads(), )
-#undef TH
-        __syncthreads();
-    }
-}
-
-// Instrumented copy of the plain kernel (LCSIM_B200_CLOCKS=1): thread 0 stamps clock64() at every phase
-// boundary into p.dbg[s][*]; used only by profiles/phase_clocks.py.
-__global__ void __launch_bounds__(128) lcs_tick_kernel_clk(const LcsParams p) {
-    extern __shared__ __align__(128) unsigned char lcs_smem_raw[];
-    const int s = blockIdx.x + p.s0, tid = threadIdx.x;
-    if (p.mode == 1) return;
+// The two item bodies are separate functions (not inlined into the queue loop: the loop's live state would push
+// the 72-register kernel into kilobytes of spills).  CLK: instrumented instantiation (LCSIM_B200_CLOCKS=1), thread 0
+// stamps clock64() at phase boundaries into p.dbg[s][*] (tick item: 0..6, metric item: 8..12); used only by
+// profiles/phase_clocks.py.
+#ifndef LCS_ITEM_INLINE
+#define LCS_ITEM_INLINE __forceinline__
+#endif
+#define STAMP() do { if (CLK) { if (tid == 0) dbg[kk] = clock64(); kk++; } } while (0)
+template <int MAXT, bool CLK>
+__device__ LCS_ITEM_INLINE void lcs_item_tick(const LcsParams& p, unsigned char* smem_raw, int s, int k) {
+    const int tid = threadIdx.x;
     LcsSmem sm;
-    lcs_smem_carve(sm, lcs_smem_raw, p.Ap);
+    lcs_smem_carve(sm, smem_raw, p.Ap);
     LcsThread th;
-    th.k = 0;
-    long long* dbg = p.dbg + (size_t)s * 16;
-    int k = 0;
-#define STAMP() do { if (tid == 0) dbg[k] = clock64(); k++; } while (0)
+    th.k = k;
+    th.snap = k % p.snap_depth;
+    long long* dbg = CLK ? p.dbg + (size_t)s * 16 : nullptr;
+    int kk = 0;
     STAMP();
-    const int a = lcs_phase_init(p, sm, s, tid, th);
-    LcsUpd u;
-    LcsScan sc;
-    if (a >= 0) lcs_update_pre(p, s, a, u);
-    __syncthreads();
-    STAMP(); // 1: pre done
-    if (a >= 0 && u.direct < 0) {
-        lcs_scan_begin(p, s, u.qx, u.qy, sc);
-        lcs_scan_global(p, s, a, u.len, sc);
+    if (CLK) {
+        const int a = lcs_phase_init(p, sm, s, tid, th);
+        LcsUpd u;
+        LcsScan sc;
+        bool whole_row = false;
+        u.len = 0;
+        if (a >= 0) lcs_update_pre(p, s, a, u);
+        __syncthreads();
+        STAMP(); // 1: pre done
+        if (a >= 0 && u.direct < 0) whole_row = !lcs_scan_first(p, s, a, u.len, u.cursor, u.qx, u.qy, sc);
+        lcs_scan_rows_warp(p, s, whole_row, a, u.len, sc);
+        __syncthreads();
+        STAMP(); // 2: scan done
+        if (a >= 0) th.fin = lcs_update_post(p, sm, s, a, u, sc);
+    } else {
+        lcs_phase_update(p, sm, s, tid, th);
     }
-    __syncthreads();
-    STAMP(); // 2: scan done
-    if (a >= 0) th.fin = lcs_update_post(p, sm, s, a, u, sc);
     __syncthreads();
     STAMP(); // 3: post done
     lcs_phase_depart_flags(p, sm, s, tid, th);
@@ -175,87 +147,134 @@ __global__ void __launch_bounds__(128) lcs_tick_kernel_clk(const LcsParams p) {
     __syncthreads();
     lcs_phase_depart_fill(p, sm, s, tid, th);
     __syncthreads();
-    lcs_phase_publish(p, sm, s, tid);
-    __syncthreads();
+    lcs_phase_publish(p, sm, s, tid, th);
     STAMP(); // 4: departures + publish
     if (p.reactive) {
-        lcs_phase_lead_filter(p, sm, s, tid);
         __syncthreads();
-        lcs_phase_lead_drain(p, sm, s, tid);
-        __syncthreads();
-        lcs_phase_lead_out(p, sm, s, tid);
-        __syncthreads();
+        lcs_phase_lead(p, sm, s, tid);
+        if (CLK) __syncthreads();
+        STAMP(); // 5: lead search
     }
-    STAMP(); // 5: lead
-    if (p.with_metrics) {
-        lcs_phase_collision_filter(p, sm, s, tid);
+}
+template <int MAXT, bool CLK>
+__device__ LCS_ITEM_INLINE void lcs_item_metric(const LcsParams& p, unsigned char* smem_raw, int s, int k) {
+    const int tid = threadIdx.x;
+    LcsSmem sm;
+    lcs_smem_carve(sm, smem_raw, p.Ap);
+    LcsThread th;
+    th.k = k;
+    th.snap = k % p.snap_depth;
+    long long* dbg = CLK ? p.dbg + (size_t)s * 16 + 8 : nullptr;
+    int kk = 0;
+    STAMP(); // 8
+    if (tid < 2) sm.misc[12 + tid] = 0;
+    __syncthreads();
+    const int ag = lcs_mc_load(p, sm, s, tid, th);
+    lcs_me_flags(p, s, tid, sm.mask, sm.misc + 12, th);
+    __syncthreads();
+    STAMP(); // 9: load
+    lcs_phase_collision_filter(p, sm, s, tid);
+    if (CLK) {
         __syncthreads();
-        STAMP(); // 6: collision filter
-        lcs_phase_offroad(p, sm, s, tid, th);
-        __syncthreads();
-        STAMP(); // 7: offroad
-        lcs_phase_collision_drain(p, sm, s, tid);
-        __syncthreads();
-        STAMP(); // 8: collision drain
-        lcs_phase_metrics_out(p, sm, s, tid, th);
-        __syncthreads();
-        lcs_phase_stats_out(p, sm, s, tid, th);
+        STAMP(); // 10: collision filter
     }
-    STAMP(); // 9: end
+    lcs_me_search(p, s, tid, sm.mask, sm.misc + 12, th);
+    __syncthreads();
+    STAMP(); // 11 (10 without CLK): edge search
+    lcs_phase_collision_drain(p, sm, s, tid);
+    __syncthreads();
+    lcs_mc_out(p, sm, s, tid, ag);
+    __syncthreads();
+    lcs_mc_stats(p, sm, s, tid, th);
+    lcs_me_stats(p, s, tid, sm.misc + 12, th);
+    STAMP(); // 12: drain + out
+}
 #undef STAMP
+
+template <int MAXT, bool CLK>
+__global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_engine_kernel(const LcsParams p) {
+    extern __shared__ __align__(128) unsigned char lcs_smem_raw[];
+    __shared__ int s_item;
+    const int tid = threadIdx.x;
+    const int per_tick = p.with_metrics ? 2 * p.S : p.S, D = p.snap_depth;
+    // one item per CTA; the ticket is claimed when the CTA RUNS (not blockIdx): see the forward-progress argument above
+    if (tid == 0) s_item = atomicAdd(p.q_ticket, 1);
+    __syncthreads();
+    const int item = s_item;
+    const int k = item / per_tick, r = item - k * per_tick;
+    const bool metric = r >= p.S;
+    const int s = metric ? r - p.S : r;
+    long long t_wait = 0;
+    if (CLK && tid == 0) t_wait = clock64();
+    if (tid == 0) {
+        // the scenario's previous items (claimed earlier, hence running or done): wait for their release, then one
+        // acquire fence (it also drops this SM's stale L1 lines); the barrier hands the data to the whole CTA
+        if (!metric) {
+            if (k > 0) lcs_wait_seq(p.q_seq_t + s, k);
+            if (k >= D && p.with_metrics) lcs_wait_seq(p.q_seq_m + s, k - D + 1);
+        } else {
+            lcs_wait_seq(p.q_seq_t + s, k + 1);
+            // metric items of a scenario run in order: they update the same per-agent outputs, and an agent that did
+            // not move keeps the flag its previous metric item stored
+            if (k > 0) lcs_wait_seq(p.q_seq_m + s, k);
+        }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (CLK) p.dbg[(size_t)s * 16 + (metric ? 15 : 7)] = clock64() - t_wait; // cycles spent waiting for the dependencies
+    }
+    __syncthreads();
+    if (!(p.mode == 1 && p.reset_mask && !p.reset_mask[s])) {
+        if (!metric)
+            lcs_item_tick<MAXT, CLK>(p, lcs_smem_raw, s, k);
+        else
+            lcs_item_metric<MAXT, CLK>(p, lcs_smem_raw, s, k);
+    }
+    __syncthreads(); // every thread's stores precede the release (cumulativity through the barrier)
+    if (tid == 0)
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"((metric ? p.q_seq_m : p.q_seq_t) + s), "r"(k + 1) : "memory");
 }
 #endif
 
-static cudaError_t lcs_configure_kernels() { return cudaSuccess; }
-
-static void lcs_launch_tick(const LcsParams& pfull, cudaStream_t stream, int s0 = 0, int ns = -1) {
-    LcsParams p = pfull;
+// Runs p.n_ticks ticks (or the reset) of all scenarios.  grid_cap: CTAs the device holds at once (create()).
+static void lcs_launch(const LcsParams& p, int grid_cap, cudaStream_t stream) {
 #ifndef LCSIM_HOSTEMU
-    p.s0 = s0;
-    const int nblk = ns < 0 ? p.S : ns;
-    if (p.dbg && p.Ap == 128 && p.mode == 0) {
-        lcs_tick_kernel_clk<<<nblk, p.Ap, lcs_smem_bytes(p.Ap), stream>>>(p);
-        return;
-    }
-    const size_t smem = lcs_smem_bytes(p.Ap);
-    if (p.n_ticks > 1 && p.mode == 0) {
-        if (p.Ap <= 128)
-            lcs_rollout_kernel<128><<<nblk, p.Ap, smem, stream>>>(p);
-        else if (p.Ap <= 256)
-            lcs_rollout_kernel<256><<<nblk, p.Ap, smem, stream>>>(p);
-        else if (p.Ap <= 512)
-            lcs_rollout_kernel<512><<<nblk, p.Ap, smem, stream>>>(p);
-        else
-            lcs_rollout_kernel<1024><<<nblk, p.Ap, smem, stream>>>(p);
-        return;
-    }
-    if (p.Ap <= 128)
-        lcs_tick_kernel_ldg<128><<<nblk, p.Ap, smem, stream>>>(p);
-    else if (p.Ap <= 256)
-        lcs_tick_kernel_ldg<256><<<nblk, p.Ap, smem, stream>>>(p);
-    else if (p.Ap <= 512)
-        lcs_tick_kernel_ldg<512><<<nblk, p.Ap, smem, stream>>>(p);
+    const int Ap = p.Ap;
+    const size_t smem = lcs_smem_bytes(Ap);
+    const long long total = (long long)p.n_ticks * (p.with_metrics ? 2 : 1) * p.S;
+    const int nblk = (int)total; // one CTA per item (n_ticks * 2 * S <= 2^31 - 1 is checked by the callers)
+    (void)grid_cap;
+    cudaMemsetAsync(p.q_ticket, 0, sizeof(int32_t) * (1 + 2 * (size_t)p.S), stream); // ticket, seq_t, seq_m are one block
+    if (p.dbg && Ap == 128 && p.mode == 0)
+        lcs_engine_kernel<128, true><<<nblk, Ap, smem, stream>>>(p);
+    else if (Ap <= 128)
+        lcs_engine_kernel<128, false><<<nblk, Ap, smem, stream>>>(p);
+    else if (Ap <= 256)
+        lcs_engine_kernel<256, false><<<nblk, Ap, smem, stream>>>(p);
+    else if (Ap <= 512)
+        lcs_engine_kernel<512, false><<<nblk, Ap, smem, stream>>>(p);
     else
-        lcs_tick_kernel_ldg<1024><<<nblk, p.Ap, smem, stream>>>(p);
+        lcs_engine_kernel<1024, false><<<nblk, Ap, smem, stream>>>(p);
 #else
+    (void)grid_cap;
     const int Ap = p.Ap;
     std::vector<unsigned char> raw(lcs_smem_bytes(Ap) + 16);
     std::vector<LcsThread> ths(Ap);
-    const int n_ticks = p.mode == 0 && p.n_ticks > 1 ? p.n_ticks : 1;
-    for (int s = 0; s < p.S; s++) {
-        if (p.mode == 1 && p.reset_mask && !p.reset_mask[s]) continue;
-        LcsSmem sm;
-        lcs_smem_carve(sm, (unsigned char*)(((uintptr_t)raw.data() + 15) & ~(uintptr_t)15), Ap);
+    std::vector<int> agent_of(Ap);
+    for (int k = 0; k < p.n_ticks; k++)
+        for (int s = 0; s < p.S; s++) {
+            if (p.mode == 1 && p.reset_mask && !p.reset_mask[s]) continue;
+            LcsSmem sm;
+            lcs_smem_carve(sm, (unsigned char*)(((uintptr_t)raw.data() + 15) & ~(uintptr_t)15), Ap);
 #define TH ths[tid]
 #define LCS_FOR_T for (int tid = 0; tid < Ap; tid++)
-        for (int k = 0; k < n_ticks; k++) {
-            LCS_FOR_T ths[tid].k = k;
-            LCS_FOR_T lcs_phase_update(p, sm, s, tid, TH);
-            LCS_TICK_REST((void)0, LCS_FOR_T)
-        }
+            LCS_FOR_T { ths[tid].k = k; ths[tid].snap = k % p.snap_depth; }
+            LCS_TICK_PHASES((void)0, LCS_FOR_T)
+            if (p.with_metrics) {
+                for (int w = 0; w < 32; w++) sm.mask[w] = 0; // the emulated ballot only sets bits
+                LCS_METRIC_PHASES((void)0, LCS_FOR_T, agent_of[tid])
+            }
 #undef LCS_FOR_T
 #undef TH
-    }
+        }
 #endif
 }
 
@@ -299,9 +318,31 @@ LCS_D void lcs_replan_copy(const LcsParams& p, const LcsReplanArgs& r, int e, in
         v.y = LCS_FAR;
         p.tf_xy[f] = v;
     }
+    // safe radius of the new point (lcs_scan_window): every point of a re-plan is live
+    float rho = 0.f;
+    if (k < Tn) {
+        const size_t q0 = (size_t)e * r.Tn;
+        const double x = (double)r.xy[2 * (q0 + k)], y = (double)r.xy[2 * (q0 + k) + 1];
+        double d2 = lcs_inf_d();
+        for (int m = 0; m < Tn; m++)
+            if (m < k - LCS_SCAN_W || m > k + LCS_SCAN_W) {
+                const double dx = (double)r.xy[2 * (q0 + m)] - x, dy = (double)r.xy[2 * (q0 + m) + 1] - y;
+                const double dd = dx * dx + dy * dy;
+                d2 = dd < d2 ? dd : d2;
+            }
+        if (d2 == lcs_inf_d()) {
+            rho = lcs_inf_f();
+        } else {
+            const double h = 0.5 * sqrt(d2) * (1.0 - 1e-9);
+            rho = (float)h;
+            if ((double)rho > h) rho = nextafterf(rho, 0.0f); // round down
+        }
+    }
+    p.tf_rho[f] = rho;
     if (k == 0) {
         p.traj_len[ia] = Tn;
         p.traj_f32[ia] = 1;
+        p.traj_blob[ia] = 0;
         p.cursor[ia] = 0;
     }
 }
@@ -544,19 +585,13 @@ struct lcsim_b200_engine {
     LcsWpRec* wp_rec = nullptr;
     int64_t cand_entries = 0; // total length of the candidate lists
     uint8_t* host_mask = nullptr; // rollout_host staging
-    int32_t* tick_log = nullptr;
+    int32_t* tick_log = nullptr; // per-tick log of the last rollout (a stable address for the captured graphs)
     size_t log_ticks = 0;
     float* lane_pts = nullptr; // [S][N][4] centreline points x, y, theta, 0 (upload_centrelines)
     int32_t *lane_ids = nullptr, *lane_n = nullptr;
     int lane_N = 0;
-    int fused = 0; // rollout(): 1 = one launch for all ticks (LCSIM_B200_FUSED=1), 0 = one launch per tick
-    int pipeline = 0; // rollout(): consecutive ticks on alternating streams, per-scenario hand-over (LCSIM_B200_PIPELINE=0: off)
-    int32_t seq = 0; // last published sequence number
-    int n_groups = 1; // rollout() splits the batch into this many scenario groups, one stream each
-#ifndef LCSIM_HOSTEMU
-    cudaStream_t gstream[8] = {};
-    cudaEvent_t gevent[9] = {};
-#endif
+    int device = 0;
+    int grid_cap = 1; // CTAs of the engine kernel the device holds at once (occupancy x SMs)
     std::string err;
 };
 
@@ -592,6 +627,37 @@ static int lcs_alloc(lcsim_b200_engine* e, Tp** out, size_t count) {
         if (_rc) return _rc;                                                  \
     } while (0)
 
+// Every entry point runs with the engine's device current and restores the caller's on return (two engines on
+// different GPUs in one process, or a caller whose current device is another one).
+struct LcsDeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit LcsDeviceGuard(int dev) {
+#ifndef LCSIM_HOSTEMU
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+        else prev = -1;
+#endif
+    }
+    ~LcsDeviceGuard() {
+#ifndef LCSIM_HOSTEMU
+        if (prev >= 0) cudaSetDevice(prev);
+#endif
+    }
+};
+#define LCS_GUARD(e) LcsDeviceGuard _guard((e)->device)
+
+// frees one of the engine's device blocks now (re-uploads replace their buffers instead of piling them up)
+template <typename Tp>
+static void lcs_release(lcsim_b200_engine* e, Tp*& ptr) {
+    if (!ptr) return;
+    void* raw = const_cast<void*>(static_cast<const void*>(ptr));
+    auto it = std::find(e->allocs.begin(), e->allocs.end(), raw);
+    if (it != e->allocs.end()) e->allocs.erase(it);
+    cudaFree(raw);
+    ptr = nullptr;
+}
+
 extern "C" int lcsim_b200_abi_version(void) { return LCSIM_B200_ABI_VERSION; }
 
 extern "C" const char* lcsim_b200_last_error(const lcsim_b200_engine* e) { return e ? e->err.c_str() : "null engine"; }
@@ -601,12 +667,6 @@ extern "C" int64_t lcsim_b200_launch_count(const lcsim_b200_engine* e) { return 
 extern "C" void lcsim_b200_destroy(lcsim_b200_engine* e) {
     if (!e) return;
     for (void* q : e->allocs) cudaFree(q);
-#ifndef LCSIM_HOSTEMU
-    for (int g = 0; g < 8; g++)
-        if (e->gstream[g]) cudaStreamDestroy(e->gstream[g]);
-    for (int g = 0; g < 9; g++)
-        if (e->gevent[g]) cudaEventDestroy(e->gevent[g]);
-#endif
     delete e;
 }
 
@@ -617,14 +677,8 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     if (d->S < 1 || d->A < 1 || d->A > 1024 || d->T < 1 || d->E < 0) return LCSIM_B200_ERR_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || d->device < 0 || d->device >= ndev) return LCSIM_B200_ERR_CUDA;
-    if (cudaSetDevice(d->device) != cudaSuccess) return LCSIM_B200_ERR_CUDA;
-    if (lcs_configure_kernels() != cudaSuccess) return LCSIM_B200_ERR_CUDA;
-    // sub-batches on separate streams in rollout(): two as soon as the batch does not fit the chip in one wave
-    int n_groups = d->S > 148 * LCS_MIN_CTAS && d->A <= 128 ? 2 : 1;
-    {
-        const char* env = getenv("LCSIM_B200_GROUPS");
-        if (env) n_groups = std::min(8, std::max(1, atoi(env)));
-    }
+    LcsDeviceGuard guard(d->device); // the caller's current device is restored on return
+    if (!guard.ok) return LCSIM_B200_ERR_CUDA;
 
     lcsim_b200_engine* e = new lcsim_b200_engine();
     e->desc = *d;
@@ -642,28 +696,34 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     p.no_static = d->no_static;
     p.allow_new_obj = d->allow_new_obj;
     p.with_metrics = d->with_metrics;
-    {
-        const char* env = getenv("LCSIM_B200_PREFETCH");
-        p.prefetch = env && env[0] == '1'; // measured neutral-to-negative on B200 (profiles/NOTES_r1.md): off by default
-    }
     *out = e; // returned even on failure below so the caller can read last_error and destroy
-    e->n_groups = n_groups;
+    e->device = d->device;
+    {
+        const char* env = getenv("LCSIM_B200_SNAP_DEPTH");
+        p.snap_depth = env ? std::min(LCS_SNAP_MAX, std::max(1, atoi(env))) : 2;
+        if (!p.with_metrics) p.snap_depth = 1;
+    }
+    p.n_ticks = 1;
 #ifndef LCSIM_HOSTEMU
     {
-        // Pipelining needs every CTA of a tick to be resident when the next tick's CTAs start to wait for them
-        // (otherwise waiting CTAs could hold the slots the CTAs they wait for need): whole batch <= one wave.
         int per_sm = 0, n_sm = 0;
-        const char* env = getenv("LCSIM_B200_PIPELINE");
-        if (!(env && env[0] == '0') && n_groups == 1 && p.Ap <= 128 &&
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcs_tick_kernel_ldg<128>, p.Ap, lcs_smem_bytes(p.Ap)) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d->device) == cudaSuccess && p.S <= per_sm * n_sm) {
-            e->pipeline = 1;
-            n_groups = 2; // two streams, three events
+        const size_t smem = lcs_smem_bytes(p.Ap);
+        cudaError_t st = cudaSuccess;
+        if (smem > 48 * 1024) {
+            st = cudaFuncSetAttribute(lcs_engine_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (st == cudaSuccess) st = cudaFuncSetAttribute(lcs_engine_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
-    }
-    if (n_groups > 1) {
-        for (int g = 0; g < n_groups; g++) LCS_CUDA(e, cudaStreamCreateWithFlags(&e->gstream[g], cudaStreamNonBlocking));
-        for (int g = 0; g <= n_groups; g++) LCS_CUDA(e, cudaEventCreateWithFlags(&e->gevent[g], cudaEventDisableTiming));
+        if (st == cudaSuccess) {
+            if (p.Ap <= 128) st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcs_engine_kernel<128, false>, p.Ap, smem);
+            else if (p.Ap <= 256) st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcs_engine_kernel<256, false>, p.Ap, smem);
+            else if (p.Ap <= 512) st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcs_engine_kernel<512, false>, p.Ap, smem);
+            else st = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcs_engine_kernel<1024, false>, p.Ap, smem);
+        }
+        if (st == cudaSuccess) st = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d->device);
+        if (st != cudaSuccess || per_sm < 1) return lcs_fail(e, LCSIM_B200_ERR_CUDA, "engine kernel cannot be resident (A=%d): %s", d->A, cudaGetErrorString(st));
+        e->grid_cap = per_sm * n_sm;
+        const char* env = getenv("LCSIM_B200_GRID"); // experiments: CTAs of the persistent grid
+        if (env && atoi(env) > 0) e->grid_cap = atoi(env);
     }
 #endif
     const size_t S = p.S, SA = S * p.Ap, SAT = SA * p.T, SE = S * p.E;
@@ -673,6 +733,7 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     LCS_ALLOC(e, p.eta_pts, S);
     LCS_ALLOC(e, p.depart_tick, SA);
     LCS_ALLOC(e, p.wait_order, SA);
+    LCS_ALLOC(e, p.depart_sorted, SA);
     LCS_ALLOC(e, p.dynamic, SA);
     LCS_ALLOC(e, p.length, SA);
     LCS_ALLOC(e, p.width, SA);
@@ -682,24 +743,22 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     LCS_ALLOC(e, p.traj_vel0, SAT * 2);
     LCS_ALLOC(e, p.traj_h0, SAT);
     LCS_ALLOC(e, p.tf_xy0, SA * p.Tp);
+    LCS_ALLOC(e, p.tf_rho0, SA * p.Tp);
+    LCS_ALLOC(e, p.traj_blob0, SA);
     {
         const char* env = getenv("LCSIM_B200_RECORDS"); // =0: experiments without the replay records
         if (!(env && env[0] == '0')) {
             LCS_ALLOC(e, e->wp_rec, SAT);
             p.wp_rec = e->wp_rec;
         }
-        // rollout(): one launch per tick unless LCSIM_B200_FUSED=1 asks for the fused multi-tick kernel.  Measured on
-        // B200 (profiles/NOTES_r1.md): lock-step per-tick launches are 7-15 % faster at S = 1024 and at S = 4096 (the
-        // fused loop costs registers -> spills, and de-synchronised CTAs thrash the instruction cache)
-        env = getenv("LCSIM_B200_FUSED");
-        e->fused = env && env[0] == '1' ? 1 : 0;
     }
-    p.n_ticks = 1;
     LCS_ALLOC(e, p.traj_len, SA);
     LCS_ALLOC(e, p.traj_xy, SAT * 2);
     LCS_ALLOC(e, p.traj_vel, SAT * 2);
     LCS_ALLOC(e, p.traj_h, SAT);
     LCS_ALLOC(e, p.tf_xy, SA * p.Tp);
+    LCS_ALLOC(e, p.tf_rho, SA * p.Tp);
+    LCS_ALLOC(e, p.traj_blob, SA);
     LCS_ALLOC(e, p.traj_f32, SA);
     LCS_ALLOC(e, p.stale_valid, SA);
     LCS_ALLOC(e, p.stale_f32, SA);
@@ -711,7 +770,16 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     LCS_ALLOC(e, p.grid_dim, S * 2);
     LCS_ALLOC(e, p.ge_xy, SE);
     LCS_ALLOC(e, p.ge_idx, SE);
-    LCS_ALLOC(e, p.done_seq, S);
+    LCS_ALLOC(e, p.q_ticket, 1 + 2 * S);
+    p.q_seq_t = p.q_ticket + 1;
+    p.q_seq_m = p.q_seq_t + S;
+    if (p.with_metrics) {
+        const size_t D = p.snap_depth;
+        LCS_ALLOC(e, p.snap_hdr, D * S * 4);
+        LCS_ALLOC(e, p.snap_agent, D * SA);
+        LCS_ALLOC(e, p.snap_rec, D * SA * 6);
+        LCS_ALLOC(e, p.snap_fin, D * SA);
+    }
     LCS_ALLOC(e, p.tick, S);
     LCS_ALLOC(e, p.n_active, S);
     LCS_ALLOC(e, p.wait_ptr, S);
@@ -746,11 +814,20 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
 
 namespace {
 
+// largest float not above x (x >= 0)
+float lcs_round_down_f32(double x) {
+    float f = (float)x;
+    if ((double)f > x) f = std::nextafterf(f, 0.0f);
+    return f;
+}
+
 struct Staging {
-    std::vector<int32_t> depart_tick, wait_order, traj_len, ge_idx, grid_dim, grid_start, home_edge;
+    std::vector<int32_t> depart_sorted, depart_tick, wait_order, traj_len, ge_idx, grid_dim, grid_start, home_edge;
     std::vector<uint8_t> dynamic;
     std::vector<double> length, width, home_xy, traj_xy, traj_vel, traj_h, s_tab, edge_xy, edge_dir;
     std::vector<lcs_f2> tf_xy, ge_xy;
+    std::vector<float> tf_rho;
+    std::vector<uint8_t> traj_blob;
     std::vector<float> cl_geom;
     std::vector<int32_t> cl_dim;
     std::vector<std::vector<int32_t>> cl_start, cl_idx; // per scenario
@@ -799,6 +876,7 @@ static void lcs_parallel_range(int n, const std::function<void(int, int)>& fn) {
 
 extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_static_host* st) {
     if (!e || !st) return LCSIM_B200_ERR_ARG;
+    LCS_GUARD(e);
     LcsParams& p = e->p;
     const int S = p.S, A = p.A, Ap = p.Ap, T = p.T, E = e->desc.E;
     const size_t SA = (size_t)S * Ap, SAT = SA * T;
@@ -821,6 +899,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     Staging g;
     g.depart_tick.assign(SA, 0x7fffffff);
     g.wait_order.assign(SA, 0);
+    g.depart_sorted.assign(SA, 0x7fffffff);
     g.traj_len.assign(SA, 1);
     g.dynamic.assign(SA, 0);
     g.length.assign(SA, 0.0);
@@ -839,6 +918,8 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     far.x = LCS_FAR;
     far.y = LCS_FAR;
     g.tf_xy.assign(SA * p.Tp, far);
+    g.tf_rho.assign(SA * p.Tp, 0.f);
+    g.traj_blob.assign(SA, 0);
     const size_t Ed = (size_t)p.E;
     g.edge_xy.assign((size_t)S * Ed * 2, 0.0);
     g.edge_dir.assign((size_t)S * Ed * 2, 0.0);
@@ -863,6 +944,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
 
     lcs_parallel_range(S, [&](int s0, int s1) {
         std::vector<double> seg(T);
+        std::vector<char> live;
         std::vector<std::pair<std::pair<double, double>, int>> keyed;
         for (int s = s0; s < s1; s++) {
             const double ox = st->origin[2 * s], oy = st->origin[2 * s + 1];
@@ -894,10 +976,31 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
                 keyed.clear();
                 for (int k = 0; k < n; k++) keyed.push_back({{xy[2 * k], xy[2 * k + 1]}, k});
                 std::sort(keyed.begin(), keyed.end());
+                live.assign(n, 0);
                 for (int q = 0; q < n; q++) {
                     const bool dup = q > 0 && keyed[q].first == keyed[q - 1].first;
                     const int k = keyed[q].second;
-                    if (!dup) g.tf_xy[lcs_tf_index(p, s, k, a)] = to_f32(xy[2 * k], xy[2 * k + 1]);
+                    if (!dup) {
+                        g.tf_xy[lcs_tf_index(p, s, k, a)] = to_f32(xy[2 * k], xy[2 * k + 1]);
+                        live[k] = 1;
+                    }
+                }
+                // safe radii of the live points (lcs_scan_window)
+                {
+                    float best = 0.f;
+                    for (int k = 0; k < n; k++) {
+                        if (!live[k]) continue;
+                        double d2 = 1e300;
+                        for (int m = 0; m < n; m++)
+                            if (live[m] && (m < k - LCS_SCAN_W || m > k + LCS_SCAN_W)) {
+                                const double dx = xy[2 * m] - xy[2 * k], dy = xy[2 * m + 1] - xy[2 * k + 1];
+                                d2 = std::min(d2, dx * dx + dy * dy);
+                            }
+                        const float rho = d2 > 1e290 ? INFINITY : lcs_round_down_f32(0.5 * std::sqrt(d2) * (1.0 - 1e-9));
+                        g.tf_rho[lcs_tf_index(p, s, k, a)] = rho;
+                        best = std::max(best, rho);
+                    }
+                    g.traj_blob[dst] = best < 0.05f ? 1 : 0; // radii of a few cm: a moving query never fits, skip the window
                 }
                 // Trajectory.s table: s_tab[k] = np.sum(seg[:k]) (polygon.py:287-292)
                 for (int k = 0; k + 1 < n; k++) {
@@ -930,6 +1033,8 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
                 }
             }
             for (int i = 0; i < A; i++) g.wait_order[(size_t)s * Ap + i] = st->wait_order[(size_t)s * A + i];
+            for (int i = 0; i < st->n_agents[s]; i++)
+                g.depart_sorted[(size_t)s * Ap + i] = st->depart_tick[(size_t)s * A + st->wait_order[(size_t)s * A + i]];
             // ---- road edges: exact arrays + hash grid over the de-duplicated float32 points
             const int ne = st->n_edge[s];
             const double* exy = st->edge_xy + (size_t)s * E * 2;
@@ -1077,6 +1182,32 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
         std::copy(cell_starts[s].begin(), cell_starts[s].end(), g.grid_start.begin() + (size_t)s * GC);
         for (size_t c = cell_starts[s].size(); c < (size_t)GC; c++) g.grid_start[(size_t)s * GC + c] = cell_starts[s].back();
     }
+    // batch-wide bound of the candidate lists (12 bytes per entry): at most half of the free device memory (and
+    // LCSIM_B200_CAND_MAX_MB when set); beyond it the largest scenarios fall back to the hinted hash-grid search
+    {
+        size_t budget = (size_t)64 << 30;
+#ifndef LCSIM_HOSTEMU
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = free_b / 2;
+#endif
+        const char* env = getenv("LCSIM_B200_CAND_MAX_MB");
+        if (env) budget = std::min<size_t>(budget, (size_t)atoll(env) << 20);
+        size_t total = 0;
+        for (int s = 0; s < S; s++) total += g.cl_xy[s].size();
+        if (total * 12 > budget) {
+            std::vector<int> order(S);
+            for (int s = 0; s < S; s++) order[s] = s;
+            std::sort(order.begin(), order.end(), [&](int a, int b) { return g.cl_xy[a].size() > g.cl_xy[b].size(); });
+            for (int s : order) {
+                if (total * 12 <= budget) break;
+                total -= g.cl_xy[s].size();
+                g.cl_dim[2 * s] = g.cl_dim[2 * s + 1] = 0;
+                std::vector<int32_t>().swap(g.cl_start[s]);
+                std::vector<int32_t>().swap(g.cl_idx[s]);
+                std::vector<lcs_f2>().swap(g.cl_xy[s]);
+            }
+        }
+    }
     // candidate lists: concatenate the scenarios' runs
     {
         int nc = 1;
@@ -1099,6 +1230,13 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
             std::vector<int32_t>().swap(g.cl_idx[s]);
         }
         p.cl_nc = nc;
+        lcs_release(e, p.cl_geom); // a second upload replaces the first one's lists
+        lcs_release(e, p.cl_dim);
+        lcs_release(e, p.cl_start);
+        lcs_release(e, p.cl_base);
+        lcs_release(e, p.cl_xy);
+        lcs_release(e, p.cl_idx);
+        lcs_release(e, p.grid_start);
         LCS_ALLOC(e, p.cl_geom, (size_t)S * 4);
         LCS_ALLOC(e, p.cl_dim, (size_t)S * 2);
         LCS_ALLOC(e, p.cl_start, cstart.size());
@@ -1113,7 +1251,6 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
         LCS_CUDA(e, cudaMemcpy((void*)p.cl_idx, cidx.data(), cidx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         e->cand_entries = (int64_t)total;
     }
-    if (p.grid_start) { /* re-upload: keep the old block alive until destroy */ }
     p.GC = GC;
     LCS_ALLOC(e, p.grid_start, (size_t)S * GC);
 
@@ -1125,6 +1262,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     LCS_UP(p.eta_pts, g.eta);
     LCS_UP(p.depart_tick, g.depart_tick);
     LCS_UP(p.wait_order, g.wait_order);
+    LCS_UP(p.depart_sorted, g.depart_sorted);
     LCS_UP(p.dynamic, g.dynamic);
     LCS_UP(p.length, g.length);
     LCS_UP(p.width, g.width);
@@ -1134,6 +1272,10 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     LCS_UP(p.traj_vel0, g.traj_vel);
     LCS_UP(p.traj_h0, g.traj_h);
     LCS_UP(p.tf_xy0, g.tf_xy);
+    LCS_UP(p.tf_rho0, g.tf_rho);
+    LCS_UP(p.tf_rho, g.tf_rho);
+    LCS_UP(p.traj_blob0, g.traj_blob);
+    LCS_UP(p.traj_blob, g.traj_blob);
     LCS_UP(p.traj_len, g.traj_len);
     LCS_UP(p.traj_xy, g.traj_xy);
     LCS_UP(p.traj_vel, g.traj_vel);
@@ -1159,15 +1301,21 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     return 0;
 }
 
+static void lcs_launch_ticks(lcsim_b200_engine* e, LcsParams& q, int n_ticks, cudaStream_t st) {
+    q.n_ticks = n_ticks;
+    lcs_launch(q, e->grid_cap, st);
+    e->launches += 1;
+}
+
 extern "C" int lcsim_b200_reset(lcsim_b200_engine* e, const uint8_t* reset_mask, void* stream) {
     if (!e) return LCSIM_B200_ERR_ARG;
     if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "reset before upload_static");
+    LCS_GUARD(e);
     LcsParams q = e->p;
     q.mode = 1;
     q.reset_mask = reset_mask;
     q.K = 0;
-    lcs_launch_tick(q, (cudaStream_t)stream);
-    e->launches++;
+    lcs_launch_ticks(e, q, 1, (cudaStream_t)stream);
     LCS_CUDA(e, cudaGetLastError());
     return 0;
 }
@@ -1177,103 +1325,56 @@ extern "C" int lcsim_b200_step(lcsim_b200_engine* e, const int32_t* act_agent, c
     if (!e) return LCSIM_B200_ERR_ARG;
     if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "step before upload_static");
     if (K < 0 || (K > 0 && (!act_agent || !act_type || !act_data))) return lcs_fail(e, LCSIM_B200_ERR_ARG, "K=%d with null action arrays", K);
+    LCS_GUARD(e);
     LcsParams q = e->p;
     q.mode = 0;
     q.act_agent = act_agent;
     q.act_type = act_type;
     q.act_data = act_data;
     q.K = K;
-    lcs_launch_tick(q, (cudaStream_t)stream);
-    e->launches++;
+    lcs_launch_ticks(e, q, 1, (cudaStream_t)stream);
     LCS_CUDA(e, cudaGetLastError());
     return 0;
 }
 
-// n_ticks steps without external actions; tick_log (device, [n_ticks][S][4], may be null) receives per tick and
-// scenario: agents updated, active agents after the tick, collision-count sum, off-road count (with_metrics only)
-static int lcs_rollout(lcsim_b200_engine* e, int n_ticks, int32_t* tick_log, void* stream) {
+// n_ticks steps without external actions in ONE launch.  want_log: per tick and scenario the engine's own buffer
+// e->tick_log ([n_ticks][S][4]) receives agents updated, active agents after the tick, collision-count sum, off-road
+// count (the last two with_metrics only); log_out (device, may be null) gets a copy.
+static int lcs_rollout(lcsim_b200_engine* e, int n_ticks, bool want_log, int32_t* log_out, void* stream) {
     if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "rollout before upload_static");
     if (n_ticks == 0) return 0;
+    if ((long long)n_ticks * 2 * e->p.S > 0x7fffffffLL) return lcs_fail(e, LCSIM_B200_ERR_ARG, "rollout: n_ticks * 2 * S exceeds the grid limit");
     LcsParams q = e->p;
     q.mode = 0;
     q.K = 0;
-    q.tick_log = tick_log;
-    if (e->fused && !q.dbg) {
-        q.n_ticks = n_ticks;
-        lcs_launch_tick(q, (cudaStream_t)stream);
-        e->launches++;
-        LCS_CUDA(e, cudaGetLastError());
-        return 0;
+    if (want_log && (size_t)n_ticks > e->log_ticks) {
+        lcs_release(e, e->tick_log);
+        LCS_ALLOC(e, e->tick_log, (size_t)n_ticks * q.S * 4);
+        e->log_ticks = n_ticks;
     }
-#ifndef LCSIM_HOSTEMU
-    if (e->pipeline && !q.dbg && n_ticks > 1) {
-        // Whole batch co-resident: tick k+1 is launched on the other stream while tick k runs, and the CTA of a
-        // scenario starts as soon as ITS previous tick is done (done_seq) — the slots that the fast scenarios of a
-        // tick leave idle while the slowest one finishes are used by the next tick.  Tick k+2 follows tick k on
-        // the same stream, so at most two ticks are in flight and all CTAs of the older one are always resident.
-        cudaStream_t us = (cudaStream_t)stream;
-        LCS_CUDA(e, cudaEventRecord(e->gevent[2], us));
-        LCS_CUDA(e, cudaStreamWaitEvent(e->gstream[0], e->gevent[2], 0));
-        LCS_CUDA(e, cudaStreamWaitEvent(e->gstream[1], e->gevent[2], 0));
-        for (int k = 0; k < n_ticks; k++) {
-            q.n_ticks = 1;
-            if (tick_log) q.tick_log = tick_log + (size_t)k * q.S * 4;
-            q.wait_seq = k == 0 ? 0 : e->seq;
-            e->seq = e->seq == 0x7ffffff0 ? 1 : e->seq + 1;
-            q.set_seq = e->seq;
-            lcs_launch_tick(q, e->gstream[k & 1]);
-        }
-        e->launches += n_ticks;
-        for (int g = 0; g < 2; g++) {
-            LCS_CUDA(e, cudaEventRecord(e->gevent[g], e->gstream[g]));
-            LCS_CUDA(e, cudaStreamWaitEvent(us, e->gevent[g], 0));
-        }
-        LCS_CUDA(e, cudaGetLastError());
-        return 0;
-    }
-    if (e->n_groups > 1 && !e->pipeline && !q.dbg) {
-        // Scenarios are independent, so a batch that needs more than one wave of CTAs is stepped as sub-batches on
-        // their own streams: while one group drains the tail of its tick, the other group's CTAs take the free
-        // slots (measured on B200: 2.55e9 -> 3.1e9 agent-steps/s at S = 4096, 2.36e9 -> 3.0e9 at S = 2048; no gain
-        // when the whole batch is co-resident).  The caller's stream waits for all groups.
-        const int G = e->n_groups;
-        cudaStream_t us = (cudaStream_t)stream;
-        LCS_CUDA(e, cudaEventRecord(e->gevent[G], us));
-        for (int g = 0; g < G; g++) {
-            const int s0 = (int)((long long)q.S * g / G), s1 = (int)((long long)q.S * (g + 1) / G);
-            LCS_CUDA(e, cudaStreamWaitEvent(e->gstream[g], e->gevent[G], 0));
-            if (s1 > s0)
-                for (int k = 0; k < n_ticks; k++) {
-                    q.n_ticks = 1;
-                    if (tick_log) q.tick_log = tick_log + (size_t)k * q.S * 4;
-                    lcs_launch_tick(q, e->gstream[g], s0, s1 - s0);
-                }
-            LCS_CUDA(e, cudaEventRecord(e->gevent[g], e->gstream[g]));
-            LCS_CUDA(e, cudaStreamWaitEvent(us, e->gevent[g], 0));
-        }
-        e->launches += (int64_t)n_ticks * G;
-        LCS_CUDA(e, cudaGetLastError());
-        return 0;
-    }
-#endif
-    for (int k = 0; k < n_ticks; k++) {
-        q.n_ticks = 1;
-        if (tick_log) q.tick_log = tick_log + (size_t)k * q.S * 4;
-        lcs_launch_tick(q, (cudaStream_t)stream);
-        e->launches++;
+    q.tick_log = want_log ? e->tick_log : nullptr;
+    cudaStream_t us = (cudaStream_t)stream;
+    if (q.dbg) { // phase clocks: one tick per launch, so that the stamps are those of the last tick
+        for (int k = 0; k < n_ticks; k++) lcs_launch_ticks(e, q, 1, us);
+    } else {
+        lcs_launch_ticks(e, q, n_ticks, us);
     }
     LCS_CUDA(e, cudaGetLastError());
+    if (log_out)
+        LCS_CUDA(e, cudaMemcpyAsync(log_out, e->tick_log, sizeof(int32_t) * (size_t)n_ticks * q.S * 4, cudaMemcpyDeviceToDevice, us));
     return 0;
 }
 
 extern "C" int lcsim_b200_rollout(lcsim_b200_engine* e, int n_ticks, void* stream) {
     if (!e || n_ticks < 0) return LCSIM_B200_ERR_ARG;
-    return lcs_rollout(e, n_ticks, nullptr, stream);
+    LCS_GUARD(e);
+    return lcs_rollout(e, n_ticks, false, nullptr, stream);
 }
 
 extern "C" int lcsim_b200_rollout_log(lcsim_b200_engine* e, int n_ticks, int32_t* tick_log, void* stream) {
     if (!e || n_ticks < 0) return LCSIM_B200_ERR_ARG;
-    return lcs_rollout(e, n_ticks, tick_log, stream);
+    LCS_GUARD(e);
+    return lcs_rollout(e, n_ticks, tick_log != nullptr, tick_log, stream);
 }
 
 // Host-buffer form of a whole rollout: what a caller of the reference does with `engine.reset(); for _ in range(n):
@@ -1282,18 +1383,15 @@ extern "C" int lcsim_b200_rollout_host(lcsim_b200_engine* e, const uint8_t* rese
                                        const lcsim_b200_rollout_out* out, int sync, void* stream) {
     if (!e || n_ticks < 0 || !out) return LCSIM_B200_ERR_ARG;
     if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "rollout_host before upload_static");
+    LCS_GUARD(e);
     cudaStream_t st = (cudaStream_t)stream;
     const LcsParams& p = e->p;
     const size_t S = p.S, SA = S * p.Ap;
     if (!e->host_mask) LCS_ALLOC(e, e->host_mask, S);
-    if (out->tick_log && (size_t)n_ticks > e->log_ticks) {
-        LCS_ALLOC(e, e->tick_log, (size_t)n_ticks * S * 4); // grows only; the old block is freed at destroy
-        e->log_ticks = n_ticks;
-    }
     if (reset_mask_host) LCS_CUDA(e, cudaMemcpyAsync(e->host_mask, reset_mask_host, S, cudaMemcpyHostToDevice, st));
     int rc = lcsim_b200_reset(e, reset_mask_host ? e->host_mask : nullptr, stream);
     if (rc) return rc;
-    rc = lcs_rollout(e, n_ticks, out->tick_log ? e->tick_log : nullptr, stream);
+    rc = lcs_rollout(e, n_ticks, out->tick_log != nullptr, nullptr, stream);
     if (rc) return rc;
 #ifndef LCSIM_HOSTEMU
     if (out->stats) lcs_stats_kernel<<<1, 256, 0, st>>>(p.stats, p.S, (int64_t*)e->env_act); // env_act doubles as 64-byte scratch
@@ -1326,6 +1424,7 @@ extern "C" int lcsim_b200_set_ref_trajectory(lcsim_b200_engine* e, const int32_t
                                              void* stream) {
     if (!e) return LCSIM_B200_ERR_ARG;
     if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "set_ref_trajectory before upload_static");
+    LCS_GUARD(e);
     if (n < 0 || T < 1 || (n > 0 && (!scenario || !agent || !xy || !vel || !heading))) return lcs_fail(e, LCSIM_B200_ERR_ARG, "bad re-plan arguments");
     if (T > 128) return lcs_fail(e, LCSIM_B200_ERR_ARG, "re-plan length %d > 128", T);
     if (n == 0) return 0;
@@ -1346,6 +1445,7 @@ extern "C" int lcsim_b200_rewards(lcsim_b200_engine* e, const int32_t* agent, co
                                   double* terms, uint8_t* terminated, uint8_t* truncated, double* route, void* stream) {
     if (!e) return LCSIM_B200_ERR_ARG;
     if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "rewards before upload_static");
+    LCS_GUARD(e);
     LcsRewardArgs r;
     memset(&r, 0, sizeof r);
     r.agent = agent;
@@ -1370,6 +1470,7 @@ extern "C" int lcsim_b200_env_step(lcsim_b200_engine* e, const double* actions_h
                                    lcsim_b200_env_out* out_host, int sync, void* stream) {
     if (!e || !out_host) return LCSIM_B200_ERR_ARG;
     if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "env_step before upload_static");
+    LCS_GUARD(e);
     cudaStream_t st = (cudaStream_t)stream;
     LcsParams q = e->p;
     q.mode = 0;
@@ -1378,8 +1479,7 @@ extern "C" int lcsim_b200_env_step(lcsim_b200_engine* e, const double* actions_h
         LCS_CUDA(e, cudaMemcpyAsync(e->env_act, actions_host, sizeof(double) * 2 * q.S, cudaMemcpyHostToDevice, st));
         q.ads_action = e->env_act;
     }
-    lcs_launch_tick(q, st);
-    e->launches++;
+    lcs_launch_ticks(e, q, 1, st);
     LcsRewardArgs r;
     memset(&r, 0, sizeof r);
     r.has_coef = coef6 != nullptr;
@@ -1586,12 +1686,15 @@ __global__ void __launch_bounds__(128) lcs_obs_kernel(const LcsParams p, const L
 
 extern "C" int lcsim_b200_upload_polylines(lcsim_b200_engine* e, const int32_t* n_poly, const double* poly_xyh, int P) {
     if (!e || !n_poly || !poly_xyh || P < 1) return LCSIM_B200_ERR_ARG;
+    LCS_GUARD(e);
     const int S = e->p.S;
     std::vector<float> f((size_t)S * P * 3, 0.f);
     for (int s = 0; s < S; s++) {
         if (n_poly[s] < 0 || n_poly[s] > P) return lcs_fail(e, LCSIM_B200_ERR_ARG, "scenario %d: n_poly %d out of [0,%d]", s, n_poly[s], P);
         for (size_t k = 0; k < (size_t)n_poly[s] * 3; k++) f[(size_t)s * P * 3 + k] = (float)poly_xyh[(size_t)s * P * 3 + k];
     }
+    lcs_release(e, e->poly); // a second upload replaces the first
+    lcs_release(e, e->n_poly);
     LCS_ALLOC(e, e->poly, (size_t)S * P * 3);
     LCS_ALLOC(e, e->n_poly, S);
     LCS_CUDA(e, cudaMemcpy(e->poly, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1603,6 +1706,7 @@ extern "C" int lcsim_b200_upload_polylines(lcsim_b200_engine* e, const int32_t* 
 extern "C" int lcsim_b200_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_desc* obs, void* stream) {
     if (!e || !obs) return LCSIM_B200_ERR_ARG;
     if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "build_obs before upload_static");
+    LCS_GUARD(e);
     if (obs->k_agents < 0 || obs->k_polys < 0 || obs->k_agents > LCS_OBS_CAP || obs->k_polys > LCS_OBS_CAP || !(obs->radius > 0))
         return lcs_fail(e, LCSIM_B200_ERR_ARG, "build_obs: k_agents/k_polys must be in [0,%d], radius > 0", LCS_OBS_CAP);
     if ((obs->nbr_poly || obs->nbr_poly_feat) && !e->poly)
@@ -1768,6 +1872,7 @@ __global__ void __launch_bounds__(128) lcs_lane_kernel(const LcsParams p, const 
 extern "C" int lcsim_b200_upload_centrelines(lcsim_b200_engine* e, const int32_t* n_pts, const float* xy_theta,
                                              const int32_t* ids, int N) {
     if (!e || !n_pts || !xy_theta || !ids || N < 1) return LCSIM_B200_ERR_ARG;
+    LCS_GUARD(e);
     const int S = e->p.S;
     std::vector<float> f((size_t)S * N * 4, 0.f);
     for (int s = 0; s < S; s++) {
@@ -1775,6 +1880,9 @@ extern "C" int lcsim_b200_upload_centrelines(lcsim_b200_engine* e, const int32_t
         for (int k = 0; k < n_pts[s]; k++)
             for (int c = 0; c < 3; c++) f[((size_t)s * N + k) * 4 + c] = xy_theta[((size_t)s * N + k) * 3 + c];
     }
+    lcs_release(e, e->lane_pts); // a second upload replaces the first
+    lcs_release(e, e->lane_ids);
+    lcs_release(e, e->lane_n);
     LCS_ALLOC(e, e->lane_pts, (size_t)S * N * 4);
     LCS_ALLOC(e, e->lane_ids, (size_t)S * N);
     LCS_ALLOC(e, e->lane_n, S);
@@ -1788,6 +1896,7 @@ extern "C" int lcsim_b200_upload_centrelines(lcsim_b200_engine* e, const int32_t
 extern "C" int lcsim_b200_project_lanes(lcsim_b200_engine* e, const lcsim_b200_lane_desc* d, void* stream) {
     if (!e || !d) return LCSIM_B200_ERR_ARG;
     if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "project_lanes before upload_static");
+    LCS_GUARD(e);
     if (!e->lane_pts) return lcs_fail(e, LCSIM_B200_ERR_STATE, "project_lanes before upload_centrelines");
     if (d->top_k < 0 || d->top_k > LCS_LANE_KMAX) return lcs_fail(e, LCSIM_B200_ERR_ARG, "top_k must be in [0,%d]", LCS_LANE_KMAX);
     LcsLaneArgs o;
@@ -1838,6 +1947,7 @@ extern "C" int lcsim_b200_views(lcsim_b200_engine* e, lcsim_b200_state_views* v)
 
 extern "C" int lcsim_b200_episode_stats(lcsim_b200_engine* e, int64_t* stats_device, void* stream) {
     if (!e || !stats_device) return LCSIM_B200_ERR_ARG;
+    LCS_GUARD(e);
 #ifndef LCSIM_HOSTEMU
     lcs_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(e->p.stats, e->p.S, stats_device);
     LCS_CUDA(e, cudaGetLastError());
@@ -1851,6 +1961,9 @@ extern "C" int lcsim_b200_episode_stats(lcsim_b200_engine* e, int64_t* stats_dev
     return 0;
 }
 
+#ifdef LCSIM_HOSTEMU
+extern "C" long long* lcsim_hostemu_counters(void) { return lcs_dbg_count; }
+#endif
 // not part of the public ABI: device pointer of the phase-clock buffer ([S][16] int64) or NULL
 extern "C" void* lcsim_b200_debug_clocks(lcsim_b200_engine* e) { return e ? (void*)e->p.dbg : nullptr; }
 

@@ -31,6 +31,9 @@ LCS_D int lcs_popc(uint32_t x) { return __builtin_popcount(x); }
 LCS_D int lcs_atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
 LCS_D void lcs_atomic_min_u64(unsigned long long* p, unsigned long long v) { if (v < *p) *p = v; }
 LCS_D unsigned long long lcs_d2u(double d) { unsigned long long u; memcpy(&u, &d, 8); return u; }
+LCS_D int lcs_f2i(float f) { int i; memcpy(&i, &f, 4); return i; }
+LCS_D float lcs_i2f(int i) { float f; memcpy(&f, &i, 4); return f; }
+LCS_D void lcs_atomic_max(int* p, int v) { if (v > *p) *p = v; }
 #else
 #define LCS_D __device__ __forceinline__
 #define LCS_HD __host__ __device__ __forceinline__
@@ -47,6 +50,17 @@ LCS_D int lcs_popc(uint32_t x) { return __popc(x); }
 LCS_D int lcs_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 LCS_D void lcs_atomic_min_u64(unsigned long long* p, unsigned long long v) { atomicMin(p, v); }
 LCS_D unsigned long long lcs_d2u(double d) { return (unsigned long long)__double_as_longlong(d); }
+LCS_D int lcs_f2i(float f) { return __float_as_int(f); }
+LCS_D float lcs_i2f(int i) { return __int_as_float(i); }
+LCS_D void lcs_atomic_max(int* p, int v) { atomicMax(p, v); }
+#endif
+
+// host emulation only: counters of the fast / fallback paths (tests read them to see how often a shortcut applies)
+#ifdef LCSIM_HOSTEMU
+static long long lcs_dbg_count[8]; // 0 window ok, 1 window rejected, 2 blob (no window), 3 lead decided, 4 lead fallback, 5 lead none
+#define LCS_COUNT(i) (lcs_dbg_count[i]++)
+#else
+#define LCS_COUNT(i) ((void)0)
 #endif
 
 #define LCS_WAITING 0
@@ -102,6 +116,7 @@ struct LcsParams {
     const float* eta_pts; // [S] bound on |fl32(p - origin) - (p - origin)| over all static points
     // ---- static, per agent [S][Ap]
     const int32_t *depart_tick, *wait_order;
+    const int32_t* depart_sorted; // [S][Ap] depart_tick along wait_order (one coalesced load in the departure test)
     const uint8_t* dynamic;
     const double *length, *width; // [S][Ap]
     const double* home_xy; // [S][Ap][2]
@@ -115,6 +130,14 @@ struct LcsParams {
     int32_t* traj_len;
     double *traj_xy, *traj_vel, *traj_h;
     lcs_f2* tf_xy;
+    // safe radius of every live filter point: half the distance to the nearest live point of the same trajectory more
+    // than LCS_SCAN_W indices away (+inf if none), rounded down.  A query closer than that to point j has its nearest
+    // point within LCS_SCAN_W indices of j (triangle inequality), so a scan of a window around the previous cursor is
+    // enough (lcs_scan_window); traj_blob = 1 marks trajectories whose radii are too small to ever help.
+    const float* tf_rho0; // [S][Ap][Tp]
+    float* tf_rho;
+    const uint8_t* traj_blob0; // [S][Ap]
+    uint8_t* traj_blob;
     uint8_t* traj_f32; // 1: arrays came from a float32 re-plan (engine.py:290-297)
     uint8_t *stale_valid, *stale_f32; // obs.ref_trajectory still points at the old Trajectory
     double* stale_wp; // [S][Ap][5]
@@ -156,16 +179,24 @@ struct LcsParams {
     const double* act_data; // [S][K][5]
     int32_t K;
     const double* ads_action; // [S][2] normalised (acc, steer) of every scenario's ADS, or null (env_step)
+    // ---- per-tick snapshot handed from the tick kernel to the metric kernels (ring of snap_depth ticks): collision
+    // counts and nearest-edge / off-road are OUTPUTS that no later tick reads, so they are computed by their own
+    // kernels, which overlap with the following ticks instead of lengthening every scenario's serial chain
+    int32_t* snap_hdr; // [D][S][4] n_old, n_new, n_fin, -
+    int32_t* snap_agent; // [D][S][Ap] agent of every new-list slot | (needs an edge search) << 30
+    double* snap_rec; // [D][S][Ap][6] x, y, cos h, sin h, length, width of that agent
+    int32_t* snap_fin; // [D][S][Ap] agents that left the list in this tick (dense)
+    int32_t snap_depth; // D
+    // ---- work queue of the engine kernel: tickets are claimed at run time, in an order in which every item depends
+    // only on items with smaller tickets (tick k of scenario s on its tick k-1 and on the metric item of tick k-D;
+    // the metric item on its tick item) -> a running CTA can only wait for work that is already running or done
+    int32_t* q_ticket; // [1] next ticket
+    int32_t* q_seq_t; // [S] tick items of this launch completed for the scenario
+    int32_t* q_seq_m; // [S] metric items completed
+    int32_t n_ticks; // ticks of this launch
     // ---- launch mode
-    long long* dbg; // [S][16] phase clocks (debug builds of the launch only)
-    int32_t prefetch; // LCSIM_B200_PREFETCH=1 (default off): early L2 prefetch of the per-agent lines
-    int32_t s0; // first scenario of this launch (sub-batch launches)
-    // tick pipelining (rollout): the launch of tick k+1 may start while tick k still runs; the CTA of scenario s
-    // waits until done_seq[s] reached wait_seq (0 = do not wait) and publishes set_seq when it is done (0 = do not)
-    int32_t* done_seq; // [S]
-    int32_t wait_seq, set_seq;
+    long long* dbg; // [S][16] phase clocks (instrumented instantiation of the tick kernel only)
     int32_t mode; // 0 = step, 1 = reset
-    int32_t n_ticks; // ticks per launch of the fused rollout kernel (1 for the per-tick kernel)
     int32_t* tick_log; // [n_ticks][S][4] agents updated, active after, collision sum, off-road sum (or null)
     const uint8_t* reset_mask; // [S] or null
 };
@@ -222,12 +253,24 @@ LCS_D void lcs_smem_carve(LcsSmem& sm, unsigned char* base, int Ap) {
 // modulo of Python/NumPy.  fmod is exact in IEEE arithmetic on both sides.
 LCS_D double lcs_wrap_angle(double a) {
     const double two_pi = 2 * LCS_PI;
-    double t = lcs_dadd(a, LCS_PI);
-    double r = fmod(t, two_pi);
-    if (r != 0.0) {
-        if (r < 0.0) r = lcs_dadd(r, two_pi);
+    const double t = lcs_dadd(a, LCS_PI);
+    double r;
+    // fmod is exact; for |t| < 4 pi it is t itself or ONE exact subtraction (Sterbenz: 2 pi <= t < 4 pi), and Python's
+    // floored modulo then adds 2 pi (rounded) to a negative remainder.  Headings live in this range; the library
+    // fmod (a long division loop on the device) is kept for everything else.
+    if (t >= 0.0 && t < two_pi) {
+        r = t;
+    } else if (t >= two_pi && t < 2 * two_pi) {
+        r = lcs_dsub(t, two_pi);
+    } else if (t < 0.0 && t > -two_pi) {
+        r = lcs_dadd(t, two_pi);
     } else {
-        r = 0.0;
+        r = fmod(t, two_pi);
+        if (r != 0.0) {
+            if (r < 0.0) r = lcs_dadd(r, two_pi);
+        } else {
+            r = 0.0;
+        }
     }
     return lcs_dsub(r, LCS_PI);
 }
@@ -387,6 +430,106 @@ LCS_D void lcs_scan_global(const LcsParams& p, int s, int a, int len, LcsScan& s
             if (k4 + r < n4) lcs_scan_quad(sc, v[r], 4 * (k4 + r));
     }
 }
+// Windowed scan: 16 points around the previous cursor (4 sectors in flight), accepted when the safe radius of the
+// window's best point proves that no point outside the window can be nearer; otherwise the caller
+// scans the whole row.  Agents move a few waypoints per tick at most, so this replaces ~23 sector loads by 5.
+#define LCS_SCAN_W 4
+LCS_D bool lcs_scan_window(const LcsParams& p, int s, int a, int len, int cursor, LcsScan& sc) {
+    const size_t row = lcs_tf_index(p, s, 0, a);
+    const int q0 = (cursor >> 2) - 1, w0 = q0 > 0 ? 4 * q0 : 0, n4 = (len + 3) >> 2;
+    const lcs_f8* tf = (const lcs_f8*)(p.tf_xy + row) + (w0 >> 2);
+    lcs_f8 v[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        if ((w0 >> 2) + r < n4) v[r] = lcs_ld32(tf + r);
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        if ((w0 >> 2) + r < n4) lcs_scan_quad(sc, v[r], w0 + 4 * r);
+    const int j = sc.j;
+    if (!(sc.m < 1.0e30f)) return false; // no live point in the window
+    if (!((j - LCS_SCAN_W >= w0 || w0 == 0) && (j + LCS_SCAN_W <= w0 + 15 || w0 + 16 >= len))) return false;
+    const float rho = p.tf_rho[row + j];
+    const float eta = lcs_filter_eta(p.eta_pts[s], sc.fqx, sc.fqy, sc.m);
+    return sqrtf(sc.m) * 1.00001f + 1.5f * eta + 1e-6f < rho;
+}
+// merge of two lanes' filter results (best, second best, index of best)
+LCS_D void lcs_edge_merge(float& m, float& m2, int& j, float om, float om2, int oj) {
+    if (om < m) {
+        m2 = fminf(m, om2);
+        m = om;
+        j = oj;
+    } else {
+        if (om == m && oj < j) j = oj;
+        m2 = fminf(m2, om); // om == m counts as a tie: m2 == m sends the query to the exact phase
+    }
+}
+
+// first stage of the cursor scan: true when the window settled it, false when the whole row has to be scanned
+LCS_D bool lcs_scan_first(const LcsParams& p, int s, int a, int len, int cursor, double qx, double qy, LcsScan& sc) {
+    lcs_scan_begin(p, s, qx, qy, sc);
+    if (p.traj_blob[(size_t)s * p.Ap + a]) {
+        LCS_COUNT(2);
+        return false;
+    }
+    if (lcs_scan_window(p, s, a, len, cursor, sc)) {
+        LCS_COUNT(0);
+        return true;
+    }
+    LCS_COUNT(1);
+    lcs_scan_begin(p, s, qx, qy, sc);
+    return false;
+}
+#ifndef LCSIM_HOSTEMU
+// Second stage on the device: the lanes of a warp that need a whole-row scan are served four at a time, each row by
+// a group of 8 lanes (lane i of the group takes the 32-byte entries i, i + 8, i + 16, ... : the group's loads are
+// contiguous 256-byte pieces, a quarter of the L1 wavefronts of private row walks, and three loads per lane are in
+// flight); a butterfly inside the group merges best / second best / index (ties keep the lower index and force the
+// exact pass, like the serial scan).  Every lane of the warp must call this.
+LCS_D void lcs_scan_rows_warp(const LcsParams& p, int s, bool need, int a, int len, LcsScan& sc) {
+    unsigned todo = __ballot_sync(0xffffffffu, need);
+    const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
+    while (todo) {
+        // the next (up to) four flagged lanes; group g serves the g-th of them
+        int src = -1, mine = -1;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int l = todo ? __ffs(todo) - 1 : -1;
+            if (todo) todo &= todo - 1;
+            if (g == grp) src = l;
+            if (l == lane) mine = g;
+        }
+        const int srcl = src < 0 ? 0 : src;
+        LcsScan t;
+        t.fqx = __shfl_sync(0xffffffffu, sc.fqx, srcl);
+        t.fqy = __shfl_sync(0xffffffffu, sc.fqy, srcl);
+        t.m = t.m2 = lcs_inf_f();
+        t.j = 0x7fffffff;
+        const int ar = __shfl_sync(0xffffffffu, a, srcl);
+        const int n4 = src < 0 ? 0 : (__shfl_sync(0xffffffffu, len, srcl) + 3) >> 2;
+        const lcs_f8* row = (const lcs_f8*)(p.tf_xy + lcs_tf_index(p, s, 0, ar < 0 ? 0 : ar));
+        for (int k4 = sub; k4 < n4; k4 += 24) {
+            lcs_f8 v[3];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                if (k4 + 8 * r < n4) v[r] = lcs_ld32(row + k4 + 8 * r);
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                if (k4 + 8 * r < n4) lcs_scan_quad(t, v[r], 4 * (k4 + 8 * r));
+        }
+#pragma unroll
+        for (int d = 4; d > 0; d >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, t.m, d), om2 = __shfl_xor_sync(0xffffffffu, t.m2, d);
+            const int oj = __shfl_xor_sync(0xffffffffu, t.j, d);
+            lcs_edge_merge(t.m, t.m2, t.j, om, om2, oj);
+        }
+        // hand the group's result to the lane it belongs to
+        const int from = mine < 0 ? 0 : 8 * mine;
+        const float rm = __shfl_sync(0xffffffffu, t.m, from), rm2 = __shfl_sync(0xffffffffu, t.m2, from);
+        const int rj = __shfl_sync(0xffffffffu, t.j, from);
+        if (mine >= 0) { sc.m = rm; sc.m2 = rm2; sc.j = rj; }
+    }
+}
+#endif
 // the cursor from a finished scan: unique candidate -> done; near-tie -> float64 on every candidate,
 // first minimum wins (np.argmin)
 LCS_D int lcs_scan_finish(const LcsParams& p, int s, int a, int len, double qx, double qy, const LcsScan& sc) {
@@ -515,18 +658,6 @@ LCS_D bool lcs_edge_side(const LcsParams& p, int s, double qx, double qy, int be
     const double cross = lcs_dsub(lcs_dmul(ax, d64[2 * best + 1]), lcs_dmul(ay, d64[2 * best])); // np.cross, 2-vectors
     return cross < 0;
 }
-// merge of two lanes' filter results (best, second best, index of best)
-LCS_D void lcs_edge_merge(float& m, float& m2, int& j, float om, float om2, int oj) {
-    if (om < m) {
-        m2 = fminf(m, om2);
-        m = om;
-        j = oj;
-    } else {
-        if (om == m && oj < j) j = oj;
-        m2 = fminf(m2, om); // om == m counts as a tie: m2 == m sends the query to the exact phase
-    }
-}
-
 // single-thread driver (rewards kernel)
 LCS_D int lcs_nearest_edge(const LcsParams& p, int s, double qx, double qy, bool* offroad) {
     *offroad = false;
@@ -815,8 +946,8 @@ LCS_D bool lcs_policy_waypoint(const LcsParams& p, size_t ia, int cursor, int le
 }
 
 // reference: agent/agent.py:67-84 HistoryState.update + :419-426; circular instead of shifting
-LCS_D void lcs_ring_push(const LcsParams& p, size_t ia, double x, double y, double h, double v, double ch, double sh, bool f32) {
-    int head = p.ring_head[ia];
+LCS_D void lcs_ring_push_at(const LcsParams& p, size_t ia, int head, int c, double x, double y, double h, double v, double ch,
+                            double sh, bool f32) {
     double* r = p.ring + (ia * LCS_H + head) * 5;
     r[0] = x;
     r[1] = y;
@@ -829,8 +960,10 @@ LCS_D void lcs_ring_push(const LcsParams& p, size_t ia, double x, double y, doub
     }
     r[4] = h;
     p.ring_head[ia] = head + 1 == LCS_H ? 0 : head + 1;
-    int c = p.ring_count[ia];
     if (c < LCS_H) p.ring_count[ia] = c + 1;
+}
+LCS_D void lcs_ring_push(const LcsParams& p, size_t ia, double x, double y, double h, double v, double ch, double sh, bool f32) {
+    lcs_ring_push_at(p, ia, p.ring_head[ia], p.ring_count[ia], x, y, h, v, ch, sh, f32);
 }
 
 
@@ -866,8 +999,9 @@ LCS_D int lcs_sat_f32(const double* ea, const double* eb) {
 
 struct LcsThread { // per-thread values that live across phases (registers on the device)
     bool fin, pop, act;
-    int aw, off;
-    int k; // tick index inside the launch (fused rollout kernel)
+    int aw;
+    int snap; // ring slot of the snapshot this item writes / reads
+    int k; // tick index inside the launch (row of tick_log)
 };
 
 LCS_D void lcs_store_ex(LcsSmem& sm, int a, double x, double y, double v, double ch, double sh, double L, double W, double h) {
@@ -918,7 +1052,9 @@ LCS_D void lcs_reset_agent(const LcsParams& p, int s, int a) {
         for (int k = 0; k < p.Tp; k++) {
             const size_t f = lcs_tf_index(p, s, k, a);
             p.tf_xy[f] = p.tf_xy0[f];
+            p.tf_rho[f] = p.tf_rho0[f];
         }
+        p.traj_blob[ia] = p.traj_blob0[ia];
         p.traj_f32[ia] = 0;
     }
     const double vx = p.traj_vel[2 * ia * p.T], vy = p.traj_vel[2 * ia * p.T + 1];
@@ -938,7 +1074,9 @@ LCS_D void lcs_reset_agent(const LcsParams& p, int s, int a) {
 //   post : cursor, history ring, stores; returns true when the agent reached the end of its trajectory
 struct LcsUpd {
     double x, y, h, v, ch, sh, qx, qy;
-    int len;
+    int len, cursor;
+    int ring_head, ring_count; // loaded with the rest of the state (the post part would otherwise wait for them)
+    double L, W;
     int direct; // >= 0: the cursor is known without a scan (replay record)
     bool ring_f32;
     bool moved; // new position differs from the old one
@@ -971,6 +1109,11 @@ LCS_D void lcs_update_pre(const LcsParams& p, int s, int a, LcsUpd& u) {
         d1 = lcs_dmul(p.ads_action[2 * s + 1], 0.3);
     }
     u.direct = -1;
+    u.cursor = cursor;
+    u.ring_head = p.ring_head[ia];
+    u.ring_count = p.ring_count[ia];
+    u.L = p.length[ia];
+    u.W = p.width[ia];
     const double x_old = x, y_old = y;
     if (type == LCS_ACT_NONE) {
         double wp[5];
@@ -1067,64 +1210,21 @@ LCS_D bool lcs_update_post(const LcsParams& p, LcsSmem& sm, int s, int a, const 
     const int cursor = u.direct >= 0 ? u.direct : lcs_scan_finish(p, s, a, u.len, u.qx, u.qy, sc);
     p.cursor[ia] = cursor;
     sm.moved[a] = u.moved ? 1 : 0;
-    lcs_ring_push(p, ia, u.x, u.y, u.h, u.v, u.ch, u.sh, u.ring_f32);
+    lcs_ring_push_at(p, ia, u.ring_head, u.ring_count, u.x, u.y, u.h, u.v, u.ch, u.sh, u.ring_f32);
     lcs_store_pose(p, s, ia, u.x, u.y, u.h, u.v);
-    lcs_store_ex(sm, a, u.x, u.y, u.v, u.ch, u.sh, p.length[ia], p.width[ia], u.h);
+    lcs_store_ex(sm, a, u.x, u.y, u.v, u.ch, u.sh, u.L, u.W, u.h);
     const bool fin = cursor >= u.len - 1; // type.py:50-51 reach_end
     if (fin) {
         // FINISHED now, IDLE after this tick's check_departure_and_arrival (single-trip schedules:
         // schedule.py:22-40 next_trip() is False); the agent leaves the list, its metric outputs reset
-        p.status[ia] = LCS_IDLE;
-        if (p.with_metrics) {
-            p.coll_count[ia] = 0;
-            p.nearest_edge[ia] = -1;
-            p.offroad[ia] = 0;
-        }
+        p.status[ia] = LCS_IDLE; // (the metric kernels reset its collision / edge outputs: lcs_mc_load, lcs_me_run)
     }
     return fin;
 }
 
 // Phase A: shared-memory init + update (step mode: thread = old list slot) or reset (thread = agent).
 // lcs_phase_init returns the agent this thread updates (-1: none).
-#ifndef LCSIM_HOSTEMU
-LCS_D void lcs_pf(const void* q) { asm volatile("prefetch.global.L2 [%0];" ::"l"(q)); }
-// Thread = agent index: start every cache line this tick will need for the agent on its way to L2 now, so the
-// dependent loads of the slot-mapped phases (state -> waypoint -> filter row -> ring -> edge hint) hit L2
-// instead of paying a DRAM round trip each.
-LCS_D void lcs_prefetch_agent(const LcsParams& p, int s, int a) {
-    const size_t ia = (size_t)s * p.Ap + a;
-    if (a >= p.A || p.status[ia] != LCS_ACTIVE) return;
-    const int cur = p.cursor[ia], hint = p.edge_hint[ia], head = p.ring_head[ia];
-    lcs_pf(p.pose64 + 4 * ia);
-    lcs_pf(p.traj_len + ia);
-    lcs_pf(p.ring_count + ia);
-    lcs_pf(p.traj_f32 + ia);
-    lcs_pf(p.stale_valid + ia);
-    lcs_pf(p.length + ia);
-    lcs_pf(p.width + ia);
-    if (p.reactive) {
-        lcs_pf(p.lead_valid + ia);
-        lcs_pf(p.lead_dis + ia);
-        lcs_pf(p.lead_v + ia);
-    }
-    const char* row = (const char*)(p.tf_xy + lcs_tf_index(p, s, 0, a));
-    for (int b = 0; b < p.Tp * 8; b += 128) lcs_pf(row + b);
-    const size_t t = ia * p.T + (cur + 1 < p.T ? cur + 1 : cur);
-    lcs_pf(p.traj_xy + 2 * t);
-    lcs_pf(p.traj_vel + 2 * t);
-    lcs_pf(p.traj_h + t);
-    lcs_pf(p.ring + (ia * LCS_H + head) * 5);
-    if (p.with_metrics && hint >= 0) {
-        lcs_pf(p.edge_xy + ((size_t)s * p.E + hint) * 2);
-        lcs_pf(p.edge_dir + ((size_t)s * p.E + hint) * 2);
-    }
-}
-#endif
-
 LCS_D int lcs_phase_init(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
-#ifndef LCSIM_HOSTEMU
-    if (p.mode == 0 && p.prefetch) lcs_prefetch_agent(p, s, tid);
-#endif
     for (int k = tid; k < 96; k += p.Ap) sm.mask[k] = 0;
     const int n_old = p.mode == 1 ? 0 : p.n_active[s];
     if (tid == 0) {
@@ -1136,12 +1236,12 @@ LCS_D int lcs_phase_init(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThr
         sm.misc[5] = p.mode == 1 ? 0 : p.wait_ptr[s];
         sm.misc[6] = 0; // pair-queue length
         sm.misc[8] = sm.misc[9] = sm.misc[10] = sm.misc[11] = 0; // flag totals
+        sm.misc[14] = sm.misc[15] = 0; // largest bounding radius / coordinate slack of the new list (float bits)
     }
     sm.cnt[tid] = 0;
     sm.moved[tid] = 1; // agents that enter the list this tick have no edge outputs yet
     sm.lead_key[tid] = ~0ull;
     t.fin = false;
-    t.off = 0;
     int a = -1;
     if (p.mode == 1)
         lcs_reset_agent(p, s, tid);
@@ -1152,16 +1252,26 @@ LCS_D int lcs_phase_init(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThr
 }
 LCS_D void lcs_phase_update(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
     const int a = lcs_phase_init(p, sm, s, tid, t);
-    if (a < 0) return;
     LcsUpd u;
     LcsScan sc;
-    lcs_update_pre(p, s, a, u);
-    if (u.direct < 0) {
-        lcs_scan_begin(p, s, u.qx, u.qy, sc);
-        lcs_scan_global(p, s, a, u.len, sc);
+    bool whole_row = false;
+    u.len = 0;
+    if (a >= 0) {
+        lcs_update_pre(p, s, a, u);
+        if (u.direct < 0) whole_row = !lcs_scan_first(p, s, a, u.len, u.cursor, u.qx, u.qy, sc);
     }
-    t.fin = lcs_update_post(p, sm, s, a, u, sc);
+#ifndef LCSIM_HOSTEMU
+    lcs_scan_rows_warp(p, s, whole_row, a, u.len, sc);
+#else
+    if (whole_row) lcs_scan_global(p, s, a, u.len, sc);
+#endif
+    if (a >= 0) t.fin = lcs_update_post(p, sm, s, a, u, sc);
 }
+
+// snapshot ring: entry of (this launch's ring slot, scenario s)
+LCS_HD size_t lcs_snap_base(const LcsParams& p, int snap, int s) { return ((size_t)snap * p.S + s) * p.Ap; }
+LCS_HD size_t lcs_snap_hdr(const LcsParams& p, int snap, int s) { return ((size_t)snap * p.S + s) * 4; }
+#define LCS_SNAP_MOVED 0x40000000
 
 // Phase B1: AgentManager.check_departure_and_arrival (manager.py:50-96), flags.  tid = list slot and,
 // independently, offset into the waiting list (sorted by departure time, manager.py:33-35).
@@ -1171,10 +1281,12 @@ LCS_D void lcs_phase_depart_flags(const LcsParams& p, LcsSmem& sm, int s, int ti
     t.pop = t.act = false;
     t.aw = -1;
     if (allow && wp + tid < p.n_agents[s]) {
-        const int aw = p.wait_order[(size_t)s * p.Ap + wp + tid];
-        t.aw = aw;
-        t.pop = p.depart_tick[(size_t)s * p.Ap + aw] <= tick;
-        t.act = t.pop && !(p.no_static && !p.dynamic[(size_t)s * p.Ap + aw] && aw != p.ads_index[s]);
+        t.pop = p.depart_sorted[(size_t)s * p.Ap + wp + tid] <= tick;
+        if (t.pop) {
+            const int aw = p.wait_order[(size_t)s * p.Ap + wp + tid];
+            t.aw = aw;
+            t.act = !(p.no_static && !p.dynamic[(size_t)s * p.Ap + aw] && aw != p.ads_index[s]);
+        }
     }
     lcs_set_flag_count(sm.mask, tid, t.fin, &sm.misc[8]);
     lcs_set_flag_count(sm.mask + 32, tid, t.pop, &sm.misc[9]);
@@ -1186,9 +1298,12 @@ LCS_D void lcs_phase_depart_flags(const LcsParams& p, LcsSmem& sm, int s, int ti
 LCS_D void lcs_phase_depart_place(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
     const int n = sm.misc[0];
     const int n_arr = sm.misc[8], m = sm.misc[10];
-    if (tid < n && !t.fin) {
+    if (tid < n) {
         const int r = lcs_prefix(sm.mask, tid);
-        sm.act2[tid - (r > m ? r - m : 0)] = sm.act[tid];
+        if (!t.fin)
+            sm.act2[tid - (r > m ? r - m : 0)] = sm.act[tid];
+        else if (p.with_metrics)
+            p.snap_fin[lcs_snap_base(p, t.snap, s) + r] = sm.act[tid]; // the metric kernels reset this agent's outputs
     }
     if (t.act) {
         const int q = lcs_prefix(sm.mask + 64, tid), aw = t.aw;
@@ -1226,40 +1341,74 @@ LCS_D void lcs_phase_depart_fill(const LcsParams& p, LcsSmem& sm, int s, int tid
             st[5] += m;
             st[6] += 1;
             p.tick[s] = sm.misc[4] + 1;
+            if (p.tick_log) {
+                int32_t* lg = p.tick_log + ((size_t)t.k * p.S + s) * 4;
+                lg[0] = n;
+                lg[1] = n_new;
+                if (!p.with_metrics) lg[2] = lg[3] = 0;
+            }
+        }
+        if (p.with_metrics) {
+            int32_t* h = p.snap_hdr + lcs_snap_hdr(p, t.snap, s);
+            h[0] = n;
+            h[1] = n_new;
+            h[2] = n_arr;
         }
     }
 }
 
-// Phase C: publish the list; slot-indexed float32 filter records of the new list.
-LCS_D void lcs_phase_publish(const LcsParams& p, LcsSmem& sm, int s, int tid) {
+// float32 filter records of a list slot from its float64 state (bounding circle with the coordinate slack, axes)
+LCS_D void lcs_make_crec(const LcsParams& p, int s, double x, double y, double ch, double sh, double L64, double W64, lcs_f4* c1,
+                         lcs_f4* c2) {
+    lcs_f4 r;
+    r.x = (float)(x - p.origin[2 * s]);
+    r.y = (float)(y - p.origin[2 * s + 1]);
+    const float L = (float)L64, W = (float)W64;
+    r.w = 5e-5f + 1.2e-7f * (fabsf(r.x) + fabsf(r.y)); // float32 coordinate error
+    r.z = 0.5f * sqrtf(L * L + W * W) * 1.00001f + r.w; // half diagonal, rounded up
+    *c1 = r;
+    lcs_f4 r2;
+    r2.x = (float)ch;
+    r2.y = (float)sh;
+    r2.z = 0.5f * L;
+    r2.w = 0.5f * W;
+    *c2 = r2;
+}
+
+// Phase C: publish the list; snapshot of the new list for the metric kernels; slot-indexed float32 filter records
+// for the lead search.
+LCS_D void lcs_phase_publish(const LcsParams& p, LcsSmem& sm, int s, int tid, const LcsThread& t) {
     const size_t is = (size_t)s * p.Ap + tid;
     const int n_new = sm.misc[1];
     p.stale_valid[is] = 0; // prepare_obs refreshed every observation (manager.py:98-103)
-    // slots whose agent needs a road-edge search this tick (moved, or new in the list): ballot word row 0, free by now
-#ifdef LCSIM_HOSTEMU
-    if ((tid & 31) == 0) sm.mask[tid >> 5] = 0; // the emulated ballot only sets bits; the device one overwrites the word
-#endif
-    lcs_set_flag_count(sm.mask, tid, tid < n_new && sm.moved[sm.act2[tid < n_new ? tid : 0]] != 0, &sm.misc[11]);
     if (tid >= n_new) {
         p.active[is] = -1;
+        if (p.reactive) {
+            float* sx = (float*)sm.queue;
+            sx[tid] = sx[p.Ap + tid] = LCS_FAR; // never inside a corridor
+        }
         return;
     }
     const int a = sm.act2[tid];
     p.active[is] = a;
     const double* ex = sm.ex + 8 * a;
-    lcs_f4 r;
-    r.x = (float)(ex[0] - p.origin[2 * s]);
-    r.y = (float)(ex[1] - p.origin[2 * s + 1]);
-    const float L = (float)ex[5], W = (float)ex[6];
-    r.w = 5e-5f + 1.2e-7f * (fabsf(r.x) + fabsf(r.y)); // float32 coordinate error
-    r.z = 0.5f * sqrtf(L * L + W * W) * 1.00001f + r.w; // half diagonal, rounded up
-    sm.crec[tid] = r;
-    lcs_f4 r2;
-    r2.x = (float)ex[3];
-    r2.y = (float)ex[4];
-    r2.z = 0.5f * L;
-    r2.w = 0.5f * W;
-    sm.crec2[tid] = r2;
+    if (p.with_metrics) {
+        // an agent whose position is bit-identical to the one its edge outputs were computed for keeps them
+        const size_t q = lcs_snap_base(p, t.snap, s) + tid;
+        p.snap_agent[q] = a | (sm.moved[a] ? LCS_SNAP_MOVED : 0);
+        double* r = p.snap_rec + 6 * q;
+        r[0] = ex[0]; r[1] = ex[1]; r[2] = ex[3]; r[3] = ex[4]; r[4] = ex[5]; r[5] = ex[6];
+    }
+    if (p.reactive) {
+        lcs_make_crec(p, s, ex[0], ex[1], ex[3], ex[4], ex[5], ex[6], &sm.crec[tid], &sm.crec2[tid]);
+        // coordinates once more as two float arrays for the lead search's first test (four partners per load), and the
+        // largest bounding radius / coordinate slack of the list (positive floats order like their bit patterns)
+        float* sx = (float*)sm.queue;
+        sx[tid] = sm.crec[tid].x;
+        sx[p.Ap + tid] = sm.crec[tid].y;
+        lcs_atomic_max(&sm.misc[14], lcs_f2i(sm.crec[tid].z));
+        lcs_atomic_max(&sm.misc[15], lcs_f2i(sm.crec[tid].w));
+    }
 }
 
 LCS_D void lcs_push_pair(LcsSmem& sm, int cap, int i, int j, bool* overflow) {
@@ -1268,53 +1417,97 @@ LCS_D void lcs_push_pair(LcsSmem& sm, int cap, int i, int j, bool* overflow) {
     if (q < cap) sm.queue[q] = ((uint32_t)i << 16) | (uint32_t)j;
 }
 
-// lead candidate (ego slot i, other slot j): exact evaluation, packed (distance, slot) minimum.
-// The low 10 bits of the float64 distance make room for the slot: distances that agree to 2^-42
-// relative are ordered by list position, exact ties included (reference: strict <, list order).
-LCS_D void lcs_lead_eval(LcsSmem& sm, int i, int j) {
-    double dis, vl;
-    if (lcs_lead_pair(sm.ex + 8 * sm.act2[i], sm.ex + 8 * sm.act2[j], &dis, &vl))
-        lcs_atomic_min_u64(&sm.lead_key[i], (lcs_d2u(dis) & ~0x3ffull) | (unsigned long long)j);
-}
-
-// Phase D1: TrajIDM branch of Agent.prepare_obs (agent.py:249-299), float32 filter over all ordered pairs
-LCS_D void lcs_phase_lead_filter(const LcsParams& p, LcsSmem& sm, int s, int tid) {
-    const int n_new = sm.misc[1], cap = LCS_QPER * p.Ap;
+// TrajIDM branch of Agent.prepare_obs (agent.py:249-299): the nearest agent ahead in the ego's corridor.  The
+// reference walks the active list and keeps the strict minimum of dis = min(corner x) - length / 2 among the agents
+// that pass its two tests (corner y range meets [-w/2, w/2]; min corner x >= length / 2).
+// One pass in float32 over the slot records RANKS the partners: min corner x = rx - (|hl cos| + |hw sin|), corner
+// y range = ry -+ (|hl sin| + |hw cos|) with rx, ry the partner's centre in the ego frame (the four sign combinations
+// of the reference's corner formulas).  e bounds the float32 error of those quantities, so a partner is certainly
+// out / certainly in / undecided; the float64 restatement (lcs_lead_pair) is evaluated for the unique winner only:
+// it must be certainly in and its error interval must lie below every other possible partner's.  Otherwise
+// (rare: ties, partners on the edge of the corridor) the thread falls back to the float64 evaluation of every partner
+// of the list, in list order with the reference's strict <.
+LCS_D void lcs_phase_lead(const LcsParams& p, LcsSmem& sm, int s, int tid) {
+    const int n_new = sm.misc[1];
     if (tid >= n_new) return;
     const double* eg = sm.ex + 8 * sm.act2[tid];
-    const lcs_f4 me = sm.crec[tid];
-    const float c32 = (float)eg[3], s32 = (float)eg[4];
-    const float hl = 0.5f * (float)eg[5], hw = 0.5f * (float)eg[6];
-    for (int j = 0; j < n_new; j++) {
-        const lcs_f4 ot = sm.crec[j];
-        const float dx = ot.x - me.x, dy = ot.y - me.y;
-        const float rx = dx * c32 + dy * s32, ry = dy * c32 - dx * s32;
-        // error of rx, ry: coordinate rounding (slack) + float32 trig / arithmetic
-        const float err = ot.w + me.w + 1e-6f * (fabsf(dx) + fabsf(dy));
-        // every corner lies within the other's half diagonal of its centre; min corner x <= centre x
-        if (j != tid && fabsf(ry) <= hw + ot.z + err && rx >= hl - err) {
-            bool overflow;
-            lcs_push_pair(sm, cap, tid, j, &overflow);
-            if (overflow) lcs_lead_eval(sm, tid, j);
+    const lcs_f4 me = sm.crec[tid], me2 = sm.crec2[tid];
+    const float c32 = me2.x, s32 = me2.y, hl = me2.z, hw = me2.w;
+    // possible partners as intervals [d - e, d + e] of their true distance: the one with the smallest upper end (h1)
+    // wins outright when it is certainly in and h1 lies below the lower ends of all others (lo2 = their minimum)
+    float h1 = lcs_inf_f(), lo2 = lcs_inf_f();
+    float l1 = 0.f;
+    int j1 = -1;
+    bool sure1 = false;
+    // First test, four partners per step on the coordinate arrays: the centre must lie in the corridor widened by the
+    // largest bounding radius of the list and not behind the ego (conservative: rmax, emax bound every partner's radius
+    // and error); only the few survivors go through the full classification.
+    const float* sx = (const float*)sm.queue;
+    const float* sy = sx + p.Ap;
+    const float rmax = lcs_i2f(sm.misc[14]), wmax = lcs_i2f(sm.misc[15]);
+    // e <= 2 wmax + 3e-6 (|dx| + |dy|) + 2e-5 with |dx| + |dy| <= 2 (wmax - 5e-5) / 1.2e-7; 1e-4 more for a differently
+    // contracted evaluation of rx, ry here and below
+    const float emax = 52.0f * wmax + 1.2e-4f;
+    const float cy = hw + rmax + emax, cx = hl - emax;
+    for (int j4 = 0; j4 < n_new; j4 += 4) {
+        const lcs_f4 X = *(const lcs_f4*)(sx + j4), Y = *(const lcs_f4*)(sy + j4);
+        const float dx0 = X.x - me.x, dx1 = X.y - me.x, dx2 = X.z - me.x, dx3 = X.w - me.x;
+        const float dy0 = Y.x - me.y, dy1 = Y.y - me.y, dy2 = Y.z - me.y, dy3 = Y.w - me.y;
+        const bool q0 = fabsf(dy0 * c32 - dx0 * s32) <= cy && dx0 * c32 + dy0 * s32 >= cx;
+        const bool q1 = fabsf(dy1 * c32 - dx1 * s32) <= cy && dx1 * c32 + dy1 * s32 >= cx;
+        const bool q2 = fabsf(dy2 * c32 - dx2 * s32) <= cy && dx2 * c32 + dy2 * s32 >= cx;
+        const bool q3 = fabsf(dy3 * c32 - dx3 * s32) <= cy && dx3 * c32 + dy3 * s32 >= cx;
+        if (!(q0 || q1 || q2 || q3)) continue;
+        for (int r = 0; r < 4; r++) {
+            const int j = j4 + r;
+            if (!(r == 0 ? q0 : r == 1 ? q1 : r == 2 ? q2 : q3) || j >= n_new || j == tid) continue;
+            const lcs_f4 ot = sm.crec[j];
+            const float dx = ot.x - me.x, dy = ot.y - me.y;
+            const float rx = dx * c32 + dy * s32, ry = dy * c32 - dx * s32;
+            // error of rx, ry and of the corner extents: coordinate rounding (slack) + float32 trig / arithmetic
+            const float e = ot.w + me.w + 3e-6f * (fabsf(dx) + fabsf(dy)) + 2e-5f;
+            // every corner lies within the other's half diagonal (ot.z) of its centre; a partner whose interval lies
+            // above both h1 and lo2 changes neither
+            if (fabsf(ry) > hw + ot.z + e || rx < hl - e || rx - ot.z - hl - e > fmaxf(h1, lo2)) continue;
+            const lcs_f4 o2 = sm.crec2[j];
+            const float cr = o2.x * c32 + o2.y * s32, sr = o2.y * c32 - o2.x * s32; // cos / sin of the relative heading
+            const float ex = fabsf(o2.z * cr) + fabsf(o2.w * sr), ey = fabsf(o2.z * sr) + fabsf(o2.w * cr);
+            const float xmin = rx - ex, ymax = ry + ey, ymin = ry - ey;
+            if (ymax < -hw - e || ymin > hw + e || xmin < hl - e) continue; // certainly not a lead vehicle
+            const bool sure = ymax >= -hw + e && ymin <= hw - e && xmin >= hl + e;
+            const float d = xmin - hl, lo = d - e, hi = d + e;
+            if (hi < h1) {
+                if (j1 >= 0) lo2 = fminf(lo2, l1);
+                h1 = hi; l1 = lo; j1 = j; sure1 = sure;
+            } else {
+                lo2 = fminf(lo2, lo);
+            }
         }
     }
-}
-LCS_D void lcs_phase_lead_drain(const LcsParams& p, LcsSmem& sm, int s, int tid) {
-    const int cap = LCS_QPER * p.Ap;
-    const int n = sm.misc[6] < cap ? sm.misc[6] : cap;
-    for (int q = tid; q < n; q += p.Ap) {
-        const uint32_t e = sm.queue[q];
-        lcs_lead_eval(sm, (int)(e >> 16), (int)(e & 0xffff));
-    }
-}
-LCS_D void lcs_phase_lead_out(const LcsParams& p, LcsSmem& sm, int s, int tid) {
-    if (tid == 0) sm.misc[6] = 0; // the queue is reused by the collision phase
-    if (tid >= sm.misc[1]) return;
     const size_t ia = (size_t)s * p.Ap + sm.act2[tid];
-    const unsigned long long key = sm.lead_key[tid];
     double dis = lcs_inf_d(), vl = 0.0;
     bool valid = false;
-    if (key != ~0ull) valid = lcs_lead_pair(sm.ex + 8 * sm.act2[tid], sm.ex + 8 * sm.act2[(int)(key & 0x3ffull)], &dis, &vl);
+    if (j1 >= 0) {
+        bool decided = false;
+        if (sure1 && h1 < lo2) {
+            decided = lcs_lead_pair(eg, sm.ex + 8 * sm.act2[j1], &dis, &vl);
+            valid = decided;
+        }
+        LCS_COUNT(decided ? 3 : 4);
+        if (!decided) { // exact fallback
+            dis = lcs_inf_d();
+            vl = 0.0;
+            valid = false;
+            for (int j = 0; j < n_new; j++) {
+                if (j == tid) continue;
+                double d64, v64;
+                if (lcs_lead_pair(eg, sm.ex + 8 * sm.act2[j], &d64, &v64) && d64 < dis) {
+                    dis = d64; vl = v64; valid = true;
+                }
+            }
+        }
+    }
+    if (j1 < 0) LCS_COUNT(5);
     p.lead_valid[ia] = valid ? 1 : 0;
     p.lead_dis[ia] = valid ? dis : lcs_inf_d();
     p.lead_v[ia] = valid ? vl : 0.0;
@@ -1389,49 +1582,87 @@ LCS_D void lcs_phase_collision_drain(const LcsParams& p, LcsSmem& sm, int s, int
     }
 }
 
-// Phase E3: off-road / nearest edge of every active agent (manager.py:337-345 -> junction.py:387-409)
-LCS_D void lcs_phase_offroad(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
-    t.off = 0; // off-road agents this thread accounts for (summed in lcs_phase_metrics_out)
-    if (tid < sm.misc[1]) {
-        const int a = sm.act2[tid];
+// ------------------------------------------------------------------ metric kernels (collision / nearest edge)
+// They read the snapshot the tick kernel wrote for its ring slot (p.snap): the new list, and per slot the float64
+// state x, y, cos h, sin h, length, width.  Nothing they write is read by a later tick (the outputs are metrics,
+// manager.py:313-345), so the host lets them run beside the following ticks.
+
+// Collision kernel, load phase: thread = list slot; shared-memory records are SLOT-indexed here (act2 = identity).
+// Returns the agent of this thread's slot (-1: none).
+LCS_D int lcs_mc_load(const LcsParams& p, LcsSmem& sm, int s, int tid, const LcsThread& t) {
+    const int32_t* h = p.snap_hdr + lcs_snap_hdr(p, t.snap, s);
+    const int n_new = h[1], n_fin = h[2];
+    const size_t base = lcs_snap_base(p, t.snap, s);
+    if (tid == 0) {
+        sm.misc[0] = h[0];
+        sm.misc[1] = n_new;
+        sm.misc[2] = 0; // collision sum
+        sm.misc[6] = 0; // pair-queue length
+    }
+    sm.cnt[tid] = 0;
+    sm.act2[tid] = tid;
+    if (tid < n_fin) p.coll_count[(size_t)s * p.Ap + p.snap_fin[base + tid]] = 0; // left the list: outputs reset
+    if (tid >= n_new) return -1;
+    const int a = p.snap_agent[base + tid] & (LCS_SNAP_MOVED - 1);
+    const double* r = p.snap_rec + 6 * (base + tid);
+    lcs_store_ex(sm, tid, r[0], r[1], 0.0, r[2], r[3], r[4], r[5], 0.0);
+    lcs_make_crec(p, s, r[0], r[1], r[2], r[3], r[4], r[5], &sm.crec[tid], &sm.crec2[tid]);
+    return a;
+}
+LCS_D void lcs_mc_out(const LcsParams& p, LcsSmem& sm, int s, int tid, int a) {
+    if (a < 0) return;
+    const int c = sm.cnt[tid];
+    p.coll_count[(size_t)s * p.Ap + a] = c;
+    if (c) lcs_atomic_add(&sm.misc[2], c);
+}
+LCS_D void lcs_mc_stats(const LcsParams& p, LcsSmem& sm, int s, int tid, const LcsThread& t) {
+    if (tid == 0 && p.mode == 0) {
+        p.stats[(size_t)s * LCS_NSTAT + 2] += sm.misc[2];
+        if (p.tick_log) p.tick_log[((size_t)t.k * p.S + s) * 4 + 2] = sm.misc[2];
+    }
+}
+
+// Edge kernel (manager.py:337-345 -> junction.py:387-409): nearest road-edge point and side flag of every listed
+// agent whose position changed.  words: [32] ballot words, cnt: [2] = {searches, off-road agents} (shared memory).
+// Part 1: flags; the agents that keep last tick's outputs contribute their stored flag to the off-road sum.
+LCS_D void lcs_me_flags(const LcsParams& p, int s, int tid, uint32_t* words, int32_t* cnt, const LcsThread& t) {
+    const int32_t* h = p.snap_hdr + lcs_snap_hdr(p, t.snap, s);
+    const int n_new = h[1], n_fin = h[2];
+    const size_t base = lcs_snap_base(p, t.snap, s);
+    bool need = false;
+    if (tid < n_new) {
+        const int v = p.snap_agent[base + tid];
+        need = (v & LCS_SNAP_MOVED) != 0;
         // same query as the tick before (parked / waiting agents, exact-duplicate waypoints): the stored nearest
         // point and side flag were computed for exactly this position and stay as they are
-        if (!sm.moved[a]) t.off = p.offroad[(size_t)s * p.Ap + a];
+        if (!need && p.offroad[(size_t)s * p.Ap + (v & (LCS_SNAP_MOVED - 1))]) lcs_atomic_add(&cnt[1], 1);
     }
-    // the searches run on DENSE lanes: thread k takes the k-th slot that needs one (about half of the list moves in
-    // a tick, and a warp pays for the longest search among its lanes whatever their number)
-    const int nw = (p.Ap + 31) >> 5;
-    if (tid >= sm.misc[11]) return;
-    const int a = sm.act2[lcs_select(sm.mask, nw, tid)];
+    lcs_set_flag_count(words, tid, need, &cnt[0]);
+    if (tid < n_fin) {
+        const size_t ia = (size_t)s * p.Ap + p.snap_fin[base + tid];
+        p.nearest_edge[ia] = -1;
+        p.offroad[ia] = 0;
+    }
+}
+// Part 2: the searches run on DENSE lanes: thread k takes the k-th slot that needs one (a warp pays for the longest
+// search among its lanes whatever their number)
+LCS_D void lcs_me_search(const LcsParams& p, int s, int tid, const uint32_t* words, int32_t* cnt, const LcsThread& t) {
+    if (tid >= cnt[0]) return;
+    const size_t q = lcs_snap_base(p, t.snap, s) + lcs_select(words, (p.Ap + 31) >> 5, tid);
+    const int a = p.snap_agent[q] & (LCS_SNAP_MOVED - 1);
     const size_t ia = (size_t)s * p.Ap + a;
+    const double qx = p.snap_rec[6 * q], qy = p.snap_rec[6 * q + 1];
     bool off = false;
-    int k = lcs_nearest_edge_cell(p, s, sm.ex[8 * a], sm.ex[8 * a + 1], &off);
-    if (k == -2) k = lcs_nearest_edge_hint(p, s, sm.ex[8 * a], sm.ex[8 * a + 1], p.edge_hint[ia], &off); // outside the lists' grid
+    int k = lcs_nearest_edge_cell(p, s, qx, qy, &off);
+    if (k == -2) k = lcs_nearest_edge_hint(p, s, qx, qy, p.edge_hint[ia], &off); // outside the lists' grid
     p.nearest_edge[ia] = k;
     p.edge_hint[ia] = k;
     p.offroad[ia] = off ? 1 : 0;
-    t.off += off ? 1 : 0;
+    if (off) lcs_atomic_add(&cnt[1], 1);
 }
-
-// Phase F: collision counts out, per-scenario sums.
-LCS_D void lcs_phase_metrics_out(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThread& t) {
-    if (t.off) lcs_atomic_add(&sm.misc[3], t.off); // counted by whichever thread ran that slot's edge search
-    if (tid >= sm.misc[1]) return;
-    const int c = sm.cnt[tid];
-    p.coll_count[(size_t)s * p.Ap + sm.act2[tid]] = c;
-    if (c) lcs_atomic_add(&sm.misc[2], c);
-}
-LCS_D void lcs_phase_stats_out(const LcsParams& p, LcsSmem& sm, int s, int tid, const LcsThread& t) {
+LCS_D void lcs_me_stats(const LcsParams& p, int s, int tid, const int32_t* cnt, const LcsThread& t) {
     if (tid == 0 && p.mode == 0) {
-        int64_t* st = p.stats + (size_t)s * LCS_NSTAT;
-        st[2] += sm.misc[2];
-        st[3] += sm.misc[3];
-        if (p.tick_log) {
-            int32_t* lg = p.tick_log + ((size_t)t.k * p.S + s) * 4;
-            lg[0] = sm.misc[0];
-            lg[1] = sm.misc[1];
-            lg[2] = sm.misc[2];
-            lg[3] = sm.misc[3];
-        }
+        p.stats[(size_t)s * LCS_NSTAT + 3] += cnt[1];
+        if (p.tick_log) p.tick_log[((size_t)t.k * p.S + s) * 4 + 3] = cnt[1];
     }
 }

@@ -20,19 +20,28 @@ be.lib.lcsim_b200_debug_clocks.argtypes = [C.c_void_p]
 ptr = be.lib.lcsim_b200_debug_clocks(be._h)
 assert ptr, "run with LCSIM_B200_CLOCKS=1"
 dbg = be.backend.view(ptr, (S, 16), "<i8")
-names = ["pre", "scan", "post", "depart+publish", "lead", "coll filter", "offroad", "coll drain", "out"]
-acc = np.zeros(9)
+tnames = ["pre", "scan", "post", "depart+publish"] + (["lead search"] if reactive else [])
+mnames = ["load snapshot", "collision filter", "edge search", "drain + out"]
+NT, NM = len(tnames), len(mnames)
+acc_t, acc_m, acc_w = np.zeros(NT), np.zeros(NM), np.zeros(2)
 n = 0
 be.rollout(20)
 for _ in range(40):
     be.step()
     torch.cuda.synchronize()
     d = dbg.cpu().numpy()
-    acc += np.diff(d[:, :10], axis=1).mean(axis=0)
-    tot = (d[:, 9] - d[:, 0])
+    acc_t += np.diff(d[:, : NT + 1], axis=1).mean(axis=0)
+    acc_m += np.diff(d[:, 8 : 8 + NM + 1], axis=1).mean(axis=0)
+    acc_w += np.array([d[:, 7].mean(), d[:, 15].mean()])
+    tot_t, tot_m = d[:, NT] - d[:, 0], d[:, 8 + NM] - d[:, 8]
     n += 1
-acc /= n
-print(f"S={S} reactive={reactive}: mean per-CTA cycles by phase (thread 0 view, includes barrier waits)")
-for nm, v in zip(names, acc):
-    print(f"  {nm:16s} {v:9.0f} cyc  {100 * v / acc.sum():5.1f}%")
-print(f"  total            {acc.sum():9.0f} cyc = {acc.sum() / 1.965e3:.1f} us @1965 MHz; CTA total min/max last tick {tot.min()}/{tot.max()}")
+acc_t /= n; acc_m /= n; acc_w /= n
+print(f"S={S} reactive={reactive}: mean per-item cycles by phase (thread 0 view, includes barrier waits); one tick per launch")
+print(" tick item")
+for nm, v in zip(tnames, acc_t):
+    print(f"  {nm:18s} {v:9.0f} cyc  {100 * v / acc_t.sum():5.1f}%")
+print(f"  total              {acc_t.sum():9.0f} cyc = {acc_t.sum() / 1.965e3:.1f} us @1965 MHz; min/max last tick {tot_t.min()}/{tot_t.max()}; ticket+dependency wait {acc_w[0]:.0f}")
+print(" metric item")
+for nm, v in zip(mnames, acc_m):
+    print(f"  {nm:18s} {v:9.0f} cyc  {100 * v / acc_m.sum():5.1f}%")
+print(f"  total              {acc_m.sum():9.0f} cyc = {acc_m.sum() / 1.965e3:.1f} us; min/max last tick {tot_m.min()}/{tot_m.max()}; ticket+dependency wait {acc_w[1]:.0f}")
