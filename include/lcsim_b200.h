@@ -159,6 +159,12 @@ int lcsim_b200_reset(lcsim_b200_engine* e, const uint8_t* reset_mask, void* stre
 int lcsim_b200_step(lcsim_b200_engine* e, const int32_t* act_agent, const int32_t* act_type, const double* act_data,
                     int K, void* stream);
 
+/* Same for the scenarios whose byte in step_mask (device, [S]) is non-zero only; the others keep their state and
+ * clock.  This is `engine_list[i].step(actions)` of lcsim/envs/gym_warpper.py:78-87, where every scenario of a worker
+ * is an Engine of its own and only the current one advances.  NULL steps all. */
+int lcsim_b200_step_masked(lcsim_b200_engine* e, const uint8_t* step_mask, const int32_t* act_agent, const int32_t* act_type,
+                           const double* act_data, int K, void* stream);
+
 /* n_ticks consecutive Engine.step() calls without external actions (engine.py:145-158), i.e. the reference's
  * `for _ in range(n): engine.step()` loop for every scenario of the batch; state and outputs afterwards are those
  * of the last tick.  One launch per tick.  When the whole batch is co-resident on the device, consecutive ticks go to

@@ -104,20 +104,24 @@ class BatchEngine:
         self._check(self.lib.lcsim_b200_reset(self._h, self.backend.ptr(m), self.backend.stream()), "reset")
         self._keep = m
 
-    def step(self, act_agent=None, act_type=None, act_data=None):
+    def step(self, act_agent=None, act_type=None, act_data=None, mask=None):
         """Engine.step(actions).  act_agent/act_type: (S,K) int32, act_data: (S,K,5) float64 (device tensors or
-        arrays); None lets every agent use its own policy."""
+        arrays); None lets every agent use its own policy.  mask: (S,) bool/uint8, only those scenarios advance
+        (None = all)."""
+        m = None if mask is None else self.backend.to_device(mask, np.uint8)
+        mp = None if m is None else self.backend.ptr(m)
         if act_agent is None:
-            self._check(self.lib.lcsim_b200_step(self._h, None, None, None, 0, self.backend.stream()), "step")
+            self._check(self.lib.lcsim_b200_step_masked(self._h, mp, None, None, None, 0, self.backend.stream()), "step")
+            self._keep = m
             return
         aa = self.backend.to_device(act_agent, np.int32)
         at = self.backend.to_device(act_type, np.int32)
         ad = self.backend.to_device(act_data, np.float64)
         K = int(aa.shape[1])
         assert tuple(aa.shape) == tuple(at.shape) == (self.S, K) and tuple(ad.shape) == (self.S, K, 5)
-        self._check(self.lib.lcsim_b200_step(self._h, self.backend.ptr(aa), self.backend.ptr(at), self.backend.ptr(ad),
-                                             K, self.backend.stream()), "step")
-        self._keep = (aa, at, ad)  # the launch is asynchronous: keep the buffers alive until the next call
+        self._check(self.lib.lcsim_b200_step_masked(self._h, mp, self.backend.ptr(aa), self.backend.ptr(at),
+                                                    self.backend.ptr(ad), K, self.backend.stream()), "step")
+        self._keep = (aa, at, ad, m)  # the launch is asynchronous: keep the buffers alive until the next call
 
     def rollout(self, n_ticks: int, log: bool = False):
         """``for _ in range(n_ticks): engine.step()`` for the whole batch in one launch.  With ``log`` returns the

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
         if (CLK) p.dbg[(size_t)s * 16 + (metric ? 15 : 7)] = clock64() - t_wait; // cycles spent waiting for the dependencies
     }
     __syncthreads();
-    if (!(p.mode == 1 && p.reset_mask && !p.reset_mask[s])) {
+    if (!(p.reset_mask && !p.reset_mask[s])) { // a masked-out scenario: nothing to do, but its items still count as done
         if (!metric)
             lcs_item_tick<MAXT, CLK>(p, lcs_smem_raw, s, k);
         else
@@ -261,7 +261,7 @@ static void lcs_launch(const LcsParams& p, int grid_cap, cudaStream_t stream) {
     std::vector<int> agent_of(Ap);
     for (int k = 0; k < p.n_ticks; k++)
         for (int s = 0; s < p.S; s++) {
-            if (p.mode == 1 && p.reset_mask && !p.reset_mask[s]) continue;
+            if (p.reset_mask && !p.reset_mask[s]) continue;
             LcsSmem sm;
             lcs_smem_carve(sm, (unsigned char*)(((uintptr_t)raw.data() + 15) & ~(uintptr_t)15), Ap);
 #define TH ths[tid]
@@ -1322,12 +1322,18 @@ extern "C" int lcsim_b200_reset(lcsim_b200_engine* e, const uint8_t* reset_mask,
 
 extern "C" int lcsim_b200_step(lcsim_b200_engine* e, const int32_t* act_agent, const int32_t* act_type,
                                const double* act_data, int K, void* stream) {
+    return lcsim_b200_step_masked(e, nullptr, act_agent, act_type, act_data, K, stream);
+}
+
+extern "C" int lcsim_b200_step_masked(lcsim_b200_engine* e, const uint8_t* step_mask, const int32_t* act_agent,
+                                      const int32_t* act_type, const double* act_data, int K, void* stream) {
     if (!e) return LCSIM_B200_ERR_ARG;
     if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "step before upload_static");
     if (K < 0 || (K > 0 && (!act_agent || !act_type || !act_data))) return lcs_fail(e, LCSIM_B200_ERR_ARG, "K=%d with null action arrays", K);
     LCS_GUARD(e);
     LcsParams q = e->p;
     q.mode = 0;
+    q.reset_mask = step_mask;
     q.act_agent = act_agent;
     q.act_type = act_type;
     q.act_data = act_data;

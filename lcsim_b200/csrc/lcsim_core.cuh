@@ -198,7 +198,7 @@ struct LcsParams {
     long long* dbg; // [S][16] phase clocks (instrumented instantiation of the tick kernel only)
     int32_t mode; // 0 = step, 1 = reset
     int32_t* tick_log; // [n_ticks][S][4] agents updated, active after, collision sum, off-road sum (or null)
-    const uint8_t* reset_mask; // [S] or null
+    const uint8_t* reset_mask; // [S] or null: scenarios this launch touches (reset launch: which are reset; step: which are stepped)
 };
 
 // Shared memory of one CTA (Ap threads).  Carved from one dynamic allocation.
@@ -505,7 +505,8 @@ LCS_D void lcs_scan_rows_warp(const LcsParams& p, int s, bool need, int a, int l
         t.m = t.m2 = lcs_inf_f();
         t.j = 0x7fffffff;
         const int ar = __shfl_sync(0xffffffffu, a, srcl);
-        const int n4 = src < 0 ? 0 : (__shfl_sync(0xffffffffu, len, srcl) + 3) >> 2;
+        const int len_r = __shfl_sync(0xffffffffu, len, srcl); // every lane takes part in every shuffle
+        const int n4 = src < 0 ? 0 : (len_r + 3) >> 2;
         const lcs_f8* row = (const lcs_f8*)(p.tf_xy + lcs_tf_index(p, s, 0, ar < 0 ? 0 : ar));
         for (int k4 = sub; k4 < n4; k4 += 24) {
             lcs_f8 v[3];

@@ -24,7 +24,7 @@ from typing import Dict, List, Optional, Sequence, Union
 
 import numpy as np
 
-from . import native, packer, proto
+from . import mapview, native, packer, proto
 from .batch import BatchEngine
 
 
@@ -357,7 +357,8 @@ class ScenarioEngine:
     def __init__(self, root: "Engine", s: int):
         self._root, self._s = root, s
         self.agent_manager = AgentManager(self)
-        self.lane_manager = self.road_manager = self.junction_manager = None  # map objects are not rebuilt
+        # read-only views with the reference's manager surface (the engine itself works on packed arrays)
+        self.lane_manager, self.road_manager, self.junction_manager = mapview.build(root._scenario_arrays[s])
         self.motion_diffuser = None
         self.guidance = None
         self._pending: Dict[int, Action] = {}
@@ -381,6 +382,19 @@ class ScenarioEngine:
     @property
     def current_time(self) -> float:
         return self._root._time[self._s]
+
+    # ---- this scenario only (lcsim/envs/gym_warpper.py keeps one Engine per scenario and advances the current one)
+    def reset(self):
+        self._root._reset_scenarios([self._s])
+
+    def step(self, actions: Dict[int, "Action"] = {}):
+        self._root._step_scenarios({self._s: dict(actions)})
+
+    def release_deep_models(self):
+        self.motion_diffuser = None
+
+    def load_deep_models(self):
+        self.motion_diffuser = None
 
     def get_step_return(self, agent_id: int):
         """reference: engine.py:160-201"""
@@ -450,8 +464,9 @@ class Engine(ScenarioEngine):
         dev = 0
         if isinstance(self.device, str) and self.device.startswith("cuda:"):
             dev = int(self.device.split(":")[1])
-        static = packer.pack_dirs(dirs, start=float(self.start_time), interval=float(self.step_interval),
-                                  total_steps=int(self.total_steps))
+        self._scenario_arrays = packer.scenarios_from_dirs(dirs)
+        static = packer.pack(self._scenario_arrays, start=float(self.start_time), interval=float(self.step_interval),
+                             total_steps=int(self.total_steps))
         self._batch = BatchEngine(static, reactive=self.reactive, no_static=self.no_static,
                                   allow_new_obj=self.allow_new_obj, with_metrics=True, device=dev,
                                   backend=config.get("_backend"))
@@ -481,6 +496,51 @@ class Engine(ScenarioEngine):
             self._rew_cache[key] = {k: be.backend.to_numpy(v) for k, v in r.items()}
         c = self._rew_cache[key]
         return {k: v[s] for k, v in c.items()}
+
+    def _reset_scenarios(self, which: Sequence[int]):
+        """Engine.reset of the scenarios `which` only (masked reset launch)."""
+        mask = np.zeros(self._batch.S, np.uint8)
+        mask[list(which)] = 1
+        self._batch.reset(mask)
+        for s in which:
+            self._step_count[s] = 0
+            self._time[s] = self.start_time
+            self.scenarios[s]._pending = {}
+        self._invalidate()
+
+    def _step_scenarios(self, actions_by_scenario: Dict[int, Dict[int, Action]]):
+        """Engine.step(actions) of the given scenarios only (masked tick launch); the others keep state and clock."""
+        be = self._batch
+        mask = np.zeros(be.S, np.uint8)
+        K = max((len(a) for a in actions_by_scenario.values()), default=0)
+        aa = np.full((be.S, max(K, 1)), -1, np.int32)
+        at = np.zeros((be.S, max(K, 1)), np.int32)
+        ad = np.zeros((be.S, max(K, 1), 5))
+        for s, acts in actions_by_scenario.items():
+            mask[s] = 1
+            am = self.scenarios[s].agent_manager
+            for k, (aid, act) in enumerate(acts.items()):
+                a = am.get_agent_by_id(aid)
+                if a is not None:
+                    aa[s, k], at[s, k], ad[s, k] = a._i, act.type.value, act._row()
+        if K == 0:
+            be.step(mask=mask)
+        else:
+            be.step(aa, at, ad, mask=mask)
+        for s in actions_by_scenario:
+            self._time[s] += self.step_interval
+            self._step_count[s] += 1
+        self._invalidate()
+
+    def scenario_view(self, s: int) -> ScenarioEngine:
+        """The reference's per-scenario Engine surface for scenario s whose reset()/step() touch that scenario only
+        (``engine.scenarios[0]`` is this object, whose reset()/step() drive the whole batch)."""
+        if not hasattr(self, "_views"):
+            self._views = [ScenarioEngine(self, i) for i in range(self._batch.S)]
+            for v in self._views:
+                v.config, v.total_steps, v.step_interval = self.config, self.total_steps, self.step_interval
+                v.reward_config, v.start_time = self.reward_config, self.start_time
+        return self._views[s]
 
     # ---- reference API
     def reset(self):

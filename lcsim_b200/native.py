@@ -139,7 +139,7 @@ class CityViews(C.Structure):
 
 
 EXPORTS = ("lcsim_b200_abi_version", "lcsim_b200_create", "lcsim_b200_upload_static", "lcsim_b200_reset",
-           "lcsim_b200_step", "lcsim_b200_rollout", "lcsim_b200_rollout_log", "lcsim_b200_rollout_host", "lcsim_b200_set_ref_trajectory", "lcsim_b200_rewards",
+           "lcsim_b200_step", "lcsim_b200_step_masked", "lcsim_b200_rollout", "lcsim_b200_rollout_log", "lcsim_b200_rollout_host", "lcsim_b200_set_ref_trajectory", "lcsim_b200_rewards",
            "lcsim_b200_env_step", "lcsim_b200_upload_polylines", "lcsim_b200_build_obs",
            "lcsim_b200_upload_centrelines", "lcsim_b200_project_lanes", "lcsim_b200_views", "lcsim_b200_episode_stats",
            "lcsim_b200_launch_count", "lcsim_b200_last_error", "lcsim_b200_destroy",
@@ -159,6 +159,7 @@ def bind(path: str) -> C.CDLL:
     lib.lcsim_b200_upload_static.argtypes = [vp, C.POINTER(StaticHost)]
     lib.lcsim_b200_reset.argtypes = [vp, vp, vp]
     lib.lcsim_b200_step.argtypes = [vp, vp, vp, vp, i32, vp]
+    lib.lcsim_b200_step_masked.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     lib.lcsim_b200_rollout.argtypes = [vp, i32, vp]
     lib.lcsim_b200_rollout_log.argtypes = [vp, i32, vp, vp]
     lib.lcsim_b200_rollout_host.argtypes = [vp, vp, i32, C.POINTER(RolloutOut), i32, vp]

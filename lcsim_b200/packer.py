@@ -98,6 +98,7 @@ class ScenarioArrays:
     lanes: list = field(default_factory=list)  # raw centrelines [(pts, lane_id)]
     lines: list = field(default_factory=list)
     edges_raw: list = field(default_factory=list)
+    junction_id: int = 0
 
 
 def _edges_to_arrays(edge_polys: Sequence[np.ndarray]):
@@ -158,6 +159,7 @@ def scenario_from_pb(map_pb, agents_pb) -> ScenarioArrays:
         lanes=[(np.array([[p.x, p.y] for p in l.center_line.nodes]), l.id) for l in map_pb.lanes],
         lines=[(np.array([[p.x, p.y] for p in l.nodes]), l.type) for l in junc.road_lines],
         edges_raw=[(p, e.type) for p, e in zip(edge_polys, junc.road_edges)],
+        junction_id=int(junc.id),
     )
 
 
@@ -175,7 +177,7 @@ def scenario_from_raw(raw: dict) -> ScenarioArrays:
         traj_xy=[a["xy"] for a in ag], traj_vel=[a["vel"] for a in ag], traj_h=[a["heading"] for a in ag],
         ads_index=int(raw["ads_index"]), edge_xy=edge_xy, edge_dir=edge_dir, edge_poly_start=starts,
         lanes=[(ln["pts"], i) for i, ln in enumerate(raw["lanes"])],
-        lines=list(raw["lines"]), edges_raw=list(raw["edges"]),
+        lines=list(raw["lines"]), edges_raw=list(raw["edges"]), junction_id=300000000,
     )
 
 
@@ -334,11 +336,12 @@ def pack_raw(raws: Sequence[dict], **kw) -> StaticBatch:
     return pack([scenario_from_raw(r) for r in raws], **kw)
 
 
-def pack_dirs(dirs: Sequence[str], **kw) -> StaticBatch:
+def scenarios_from_dirs(dirs: Sequence[str]) -> List[ScenarioArrays]:
     import os
 
-    scs = []
-    for d in dirs:
-        scs.append(scenario_from_pb(proto.load_map(os.path.join(d, "map.pb")),
-                                    proto.load_agents(os.path.join(d, "agents.pb"))))
-    return pack(scs, **kw)
+    return [scenario_from_pb(proto.load_map(os.path.join(d, "map.pb")), proto.load_agents(os.path.join(d, "agents.pb")))
+            for d in dirs]
+
+
+def pack_dirs(dirs: Sequence[str], **kw) -> StaticBatch:
+    return pack(scenarios_from_dirs(dirs), **kw)
