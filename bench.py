@@ -239,19 +239,22 @@ def measure_traffic(args):
         with tempfile.TemporaryDirectory() as tmp:
             log = os.path.join(tmp, "t.csv")
             cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
-                   "regex:lcs_engine_kernel", "--launch-skip", "3", "--launch-count", "1", "--csv", "--log-file", log,
+                   "regex:lcs_engine_kernel", "--launch-skip", "3", "--launch-count", "2", "--csv", "--log-file", log,
                    sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "replay", "--kernel-only", "--steps", "1",
                    "--warmup", "1", "--rollouts-per-step", "1", "--scenarios", str(args.scenarios), "--no-ncu"]
             env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK=os.environ.get("LOCAL_RANK", "0"))
             subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=240, env=env, check=True)
-            total = 0.0
+            # launches alternate reset (1 tick) / rollout (91 ticks): two consecutive ones are captured, the rollout is
+            # the one with the larger traffic
+            per_launch = {}
             for line in open(log):
                 parts = [x.strip('"') for x in line.strip().split('","')]
                 if len(parts) > 3 and parts[-3].startswith("dram__bytes"):
                     v, unit = float(parts[-1].replace(",", "")), parts[-2]
-                    total += v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+                    per_launch[parts[0]] = per_launch.get(parts[0], 0.0) + v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+            total = max(per_launch.values()) if per_launch else 0.0
             if total > 0:
-                return total, "ncu child run of this bench (launch 4 of the engine kernel: a 91-tick rollout)"
+                return total, "ncu child run of this bench (dram__bytes_read.sum + dram__bytes_write.sum of one 91-tick rollout launch)"
     except Exception:
         pass
     return fallback

@@ -81,7 +81,7 @@ struct alignas(16) float4 { float x, y, z, w; };
     }
 // AG: per-thread agent of the slot (device: a register; host emulation: an array)
 #define LCS_METRIC_PHASES(SYNC, FOR_T, AG)                                          \
-    FOR_T { if (tid < 2) sm.misc[12 + tid] = 0; }                                   \
+    FOR_T { if (tid < 3) sm.misc[12 + tid] = 0; }                                   \
     SYNC;                                                                           \
     FOR_T { AG = lcs_mc_load(p, sm, s, tid, TH); lcs_me_flags(p, s, tid, sm.mask, sm.misc + 12, TH); } \
     SYNC;                                                                           \
@@ -94,11 +94,12 @@ struct alignas(16) float4 { float x, y, z, w; };
     FOR_T { lcs_mc_stats(p, sm, s, tid, TH); lcs_me_stats(p, s, tid, sm.misc + 12, TH); }
 
 #ifndef LCSIM_HOSTEMU
-LCS_D void lcs_wait_seq(const int32_t* addr, int want) {
-    int v;
+// waits until scenario's pair of counters (tick items done, metric items done) reached (want_t, want_m): one 8-byte load per poll
+LCS_D void lcs_wait_seq(const int32_t* pair, int want_t, int want_m) {
+    int vt, vm;
     for (;;) {
-        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
-        if (v >= want) break;
+        asm volatile("ld.relaxed.gpu.global.v2.s32 {%0, %1}, [%2];" : "=r"(vt), "=r"(vm) : "l"(pair) : "memory");
+        if (vt >= want_t && vm >= want_m) break;
         __nanosleep(100);
     }
 }
@@ -167,7 +168,7 @@ __device__ LCS_ITEM_INLINE void lcs_item_metric(const LcsParams& p, unsigned cha
     long long* dbg = CLK ? p.dbg + (size_t)s * 16 + 8 : nullptr;
     int kk = 0;
     STAMP(); // 8
-    if (tid < 2) sm.misc[12 + tid] = 0;
+    if (tid < 3) sm.misc[12 + tid] = 0; // edge-search counters, largest radius (float bits)
     __syncthreads();
     const int ag = lcs_mc_load(p, sm, s, tid, th);
     lcs_me_flags(p, s, tid, sm.mask, sm.misc + 12, th);
@@ -209,14 +210,12 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
     if (tid == 0) {
         // the scenario's previous items (claimed earlier, hence running or done): wait for their release, then one
         // acquire fence (it also drops this SM's stale L1 lines); the barrier hands the data to the whole CTA
+        // (metric items of a scenario run in order: they update the same per-agent outputs, and an agent that did not
+        // move keeps the flag its previous metric item stored)
         if (!metric) {
-            if (k > 0) lcs_wait_seq(p.q_seq_t + s, k);
-            if (k >= D && p.with_metrics) lcs_wait_seq(p.q_seq_m + s, k - D + 1);
+            if (k > 0) lcs_wait_seq(p.q_seq + 2 * s, k, p.with_metrics ? k - D + 1 : 0);
         } else {
-            lcs_wait_seq(p.q_seq_t + s, k + 1);
-            // metric items of a scenario run in order: they update the same per-agent outputs, and an agent that did
-            // not move keeps the flag its previous metric item stored
-            if (k > 0) lcs_wait_seq(p.q_seq_m + s, k);
+            lcs_wait_seq(p.q_seq + 2 * s, k + 1, k);
         }
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
         if (CLK) p.dbg[(size_t)s * 16 + (metric ? 15 : 7)] = clock64() - t_wait; // cycles spent waiting for the dependencies
@@ -230,7 +229,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
     }
     __syncthreads(); // every thread's stores precede the release (cumulativity through the barrier)
     if (tid == 0)
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"((metric ? p.q_seq_m : p.q_seq_t) + s), "r"(k + 1) : "memory");
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.q_seq + 2 * s + (metric ? 1 : 0)), "r"(k + 1) : "memory");
 }
 #endif
 
@@ -242,7 +241,7 @@ static void lcs_launch(const LcsParams& p, int grid_cap, cudaStream_t stream) {
     const long long total = (long long)p.n_ticks * (p.with_metrics ? 2 : 1) * p.S;
     const int nblk = (int)total; // one CTA per item (n_ticks * 2 * S <= 2^31 - 1 is checked by the callers)
     (void)grid_cap;
-    cudaMemsetAsync(p.q_ticket, 0, sizeof(int32_t) * (1 + 2 * (size_t)p.S), stream); // ticket, seq_t, seq_m are one block
+    cudaMemsetAsync(p.q_ticket, 0, sizeof(int32_t) * (2 + 2 * (size_t)p.S), stream); // ticket and the counter pairs are one block
     if (p.dbg && Ap == 128 && p.mode == 0)
         lcs_engine_kernel<128, true><<<nblk, Ap, smem, stream>>>(p);
     else if (Ap <= 128)
@@ -770,9 +769,8 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     LCS_ALLOC(e, p.grid_dim, S * 2);
     LCS_ALLOC(e, p.ge_xy, SE);
     LCS_ALLOC(e, p.ge_idx, SE);
-    LCS_ALLOC(e, p.q_ticket, 1 + 2 * S);
-    p.q_seq_t = p.q_ticket + 1;
-    p.q_seq_m = p.q_seq_t + S;
+    LCS_ALLOC(e, p.q_ticket, 2 + 2 * S);
+    p.q_seq = p.q_ticket + 2; // 8-byte aligned pairs
     if (p.with_metrics) {
         const size_t D = p.snap_depth;
         LCS_ALLOC(e, p.snap_hdr, D * S * 4);

@@ -28,6 +28,7 @@ LCS_D void lcs_sincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a)
 LCS_D float lcs_fmul(float a, float b) { return a * b; }
 LCS_D float lcs_fadd(float a, float b) { return a + b; }
 LCS_D int lcs_popc(uint32_t x) { return __builtin_popcount(x); }
+LCS_D int lcs_ffs0(uint32_t x) { return __builtin_ctz(x); } // index of the lowest set bit (x != 0)
 LCS_D int lcs_atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
 LCS_D void lcs_atomic_min_u64(unsigned long long* p, unsigned long long v) { if (v < *p) *p = v; }
 LCS_D unsigned long long lcs_d2u(double d) { unsigned long long u; memcpy(&u, &d, 8); return u; }
@@ -47,6 +48,7 @@ LCS_D void lcs_sincos(double a, double* s, double* c) { sincos(a, s, c); }
 LCS_D float lcs_fmul(float a, float b) { return __fmul_rn(a, b); }
 LCS_D float lcs_fadd(float a, float b) { return __fadd_rn(a, b); }
 LCS_D int lcs_popc(uint32_t x) { return __popc(x); }
+LCS_D int lcs_ffs0(uint32_t x) { return __ffs((int)x) - 1; }
 LCS_D int lcs_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 LCS_D void lcs_atomic_min_u64(unsigned long long* p, unsigned long long v) { atomicMin(p, v); }
 LCS_D unsigned long long lcs_d2u(double d) { return (unsigned long long)__double_as_longlong(d); }
@@ -63,6 +65,7 @@ static long long lcs_dbg_count[8]; // 0 window ok, 1 window rejected, 2 blob (no
 #define LCS_COUNT(i) ((void)0)
 #endif
 
+#define LCS_SOA_Y(Ap) (2 * (Ap) + 4) // offset of the y array inside LcsSmem::soa
 #define LCS_WAITING 0
 #define LCS_ACTIVE 1
 #define LCS_FINISHED 2
@@ -191,8 +194,7 @@ struct LcsParams {
     // only on items with smaller tickets (tick k of scenario s on its tick k-1 and on the metric item of tick k-D;
     // the metric item on its tick item) -> a running CTA can only wait for work that is already running or done
     int32_t* q_ticket; // [1] next ticket
-    int32_t* q_seq_t; // [S] tick items of this launch completed for the scenario
-    int32_t* q_seq_m; // [S] metric items completed
+    int32_t* q_seq; // [S][2] tick items / metric items of this launch completed for the scenario
     int32_t n_ticks; // ticks of this launch
     // ---- launch mode
     long long* dbg; // [S][16] phase clocks (instrumented instantiation of the tick kernel only)
@@ -218,6 +220,8 @@ struct LcsSmem {
     uint32_t* mask; // [3][32] ballot words: finished, popped, activated
     int32_t* misc; // [16] n_old, n_new, collision sum, off-road sum, tick, wait_ptr, queue length, -, then [8..11]:
                    // number of set flags of the ballot rows finished / popped / activated / moved
+    float* soa; // [2][2 Ap + 4] x and y of the list slots once more as float arrays, each written twice (slot i at i and
+                // i + n) so that the partner range i+1 .. i+n/2 of the pair loops is contiguous: four partners per load
     uint8_t* moved; // [Ap] 0: the agent's position is bit-identical to the one its edge outputs were computed for (agent index)
 };
 
@@ -227,7 +231,7 @@ static inline
 __host__ __device__ inline
 #endif
 size_t lcs_smem_bytes(int Ap) {
-    return (size_t)Ap * (64 + 8 + 32 + 4 * 4 + 4 * LCS_QPER + 2 * LCS_CAND + 1) + 3 * 32 * 4 + 16 * 4 + 64;
+    return (size_t)Ap * (64 + 8 + 32 + 4 * 4 + 4 * LCS_QPER + 2 * LCS_CAND + 16 + 1) + 32 + 3 * 32 * 4 + 16 * 4 + 64;
 }
 
 LCS_D void lcs_smem_carve(LcsSmem& sm, unsigned char* base, int Ap) {
@@ -244,6 +248,7 @@ LCS_D void lcs_smem_carve(LcsSmem& sm, unsigned char* base, int Ap) {
     sm.mask = (uint32_t*)p; p += 3 * 32 * 4;
     sm.misc = (int32_t*)p; p += 16 * 4;
     sm.cand = (uint16_t*)p; p += (size_t)Ap * 2 * LCS_CAND;
+    sm.soa = (float*)p; p += ((size_t)Ap * 4 + 8) * 4;
     sm.moved = (uint8_t*)p;
 }
 
@@ -1384,10 +1389,7 @@ LCS_D void lcs_phase_publish(const LcsParams& p, LcsSmem& sm, int s, int tid, co
     p.stale_valid[is] = 0; // prepare_obs refreshed every observation (manager.py:98-103)
     if (tid >= n_new) {
         p.active[is] = -1;
-        if (p.reactive) {
-            float* sx = (float*)sm.queue;
-            sx[tid] = sx[p.Ap + tid] = LCS_FAR; // never inside a corridor
-        }
+        if (p.reactive) sm.soa[tid] = sm.soa[LCS_SOA_Y(p.Ap) + tid] = LCS_FAR; // never inside a corridor
         return;
     }
     const int a = sm.act2[tid];
@@ -1404,9 +1406,8 @@ LCS_D void lcs_phase_publish(const LcsParams& p, LcsSmem& sm, int s, int tid, co
         lcs_make_crec(p, s, ex[0], ex[1], ex[3], ex[4], ex[5], ex[6], &sm.crec[tid], &sm.crec2[tid]);
         // coordinates once more as two float arrays for the lead search's first test (four partners per load), and the
         // largest bounding radius / coordinate slack of the list (positive floats order like their bit patterns)
-        float* sx = (float*)sm.queue;
-        sx[tid] = sm.crec[tid].x;
-        sx[p.Ap + tid] = sm.crec[tid].y;
+        sm.soa[tid] = sm.crec[tid].x;
+        sm.soa[LCS_SOA_Y(p.Ap) + tid] = sm.crec[tid].y;
         lcs_atomic_max(&sm.misc[14], lcs_f2i(sm.crec[tid].z));
         lcs_atomic_max(&sm.misc[15], lcs_f2i(sm.crec[tid].w));
     }
@@ -1442,38 +1443,52 @@ LCS_D void lcs_phase_lead(const LcsParams& p, LcsSmem& sm, int s, int tid) {
     bool sure1 = false;
     // First test, four partners per step on the coordinate arrays: the centre must lie in the corridor widened by the
     // largest bounding radius of the list and not behind the ego (conservative: rmax, emax bound every partner's radius
-    // and error); only the few survivors go through the full classification.
-    const float* sx = (const float*)sm.queue;
-    const float* sy = sx + p.Ap;
+    // and error).  A partner whose CENTRE lies well inside the corridor and whose whole circle is ahead of the ego is
+    // certainly a lead candidate no farther than rx - hl: `bound` (the smallest such value + emax) prunes everybody
+    // whose circle starts beyond it — they can neither win nor touch the winner's error interval.  The few survivors
+    // go through the full classification.
+    const float* sx = sm.soa;
+    const float* sy = sm.soa + LCS_SOA_Y(p.Ap);
     const float rmax = lcs_i2f(sm.misc[14]), wmax = lcs_i2f(sm.misc[15]);
     // e <= 2 wmax + 3e-6 (|dx| + |dy|) + 2e-5 with |dx| + |dy| <= 2 (wmax - 5e-5) / 1.2e-7; 1e-4 more for a differently
     // contracted evaluation of rx, ry here and below
     const float emax = 52.0f * wmax + 1.2e-4f;
-    const float cy = hw + rmax + emax, cx = hl - emax;
+    const float cy = hw + rmax + emax, cx = hl - emax, cy_in = hw - emax, cx_in = hl + rmax + emax;
+    const float off = rmax + hl + emax;
+    float bound = lcs_inf_f();
     for (int j4 = 0; j4 < n_new; j4 += 4) {
         const lcs_f4 X = *(const lcs_f4*)(sx + j4), Y = *(const lcs_f4*)(sy + j4);
-        const float dx0 = X.x - me.x, dx1 = X.y - me.x, dx2 = X.z - me.x, dx3 = X.w - me.x;
-        const float dy0 = Y.x - me.y, dy1 = Y.y - me.y, dy2 = Y.z - me.y, dy3 = Y.w - me.y;
-        const bool q0 = fabsf(dy0 * c32 - dx0 * s32) <= cy && dx0 * c32 + dy0 * s32 >= cx;
-        const bool q1 = fabsf(dy1 * c32 - dx1 * s32) <= cy && dx1 * c32 + dy1 * s32 >= cx;
-        const bool q2 = fabsf(dy2 * c32 - dx2 * s32) <= cy && dx2 * c32 + dy2 * s32 >= cx;
-        const bool q3 = fabsf(dy3 * c32 - dx3 * s32) <= cy && dx3 * c32 + dy3 * s32 >= cx;
-        if (!(q0 || q1 || q2 || q3)) continue;
+        float rx[4], ry[4];
+        {
+            const float dx0 = X.x - me.x, dx1 = X.y - me.x, dx2 = X.z - me.x, dx3 = X.w - me.x;
+            const float dy0 = Y.x - me.y, dy1 = Y.y - me.y, dy2 = Y.z - me.y, dy3 = Y.w - me.y;
+            rx[0] = dx0 * c32 + dy0 * s32; rx[1] = dx1 * c32 + dy1 * s32; rx[2] = dx2 * c32 + dy2 * s32; rx[3] = dx3 * c32 + dy3 * s32;
+            ry[0] = fabsf(dy0 * c32 - dx0 * s32); ry[1] = fabsf(dy1 * c32 - dx1 * s32);
+            ry[2] = fabsf(dy2 * c32 - dx2 * s32); ry[3] = fabsf(dy3 * c32 - dx3 * s32);
+        }
+        unsigned m = 0;
+#pragma unroll
         for (int r = 0; r < 4; r++) {
+            if (ry[r] <= cy_in && rx[r] >= cx_in) bound = fminf(bound, rx[r] - hl + emax); // (the ego itself: rx = 0 < cx_in)
+            if (ry[r] <= cy && rx[r] >= cx && rx[r] - off <= bound) m |= 1u << r;
+        }
+        while (m) {
+            const int r = lcs_ffs0(m);
+            m &= m - 1;
             const int j = j4 + r;
-            if (!(r == 0 ? q0 : r == 1 ? q1 : r == 2 ? q2 : q3) || j >= n_new || j == tid) continue;
+            if (j >= n_new || j == tid) continue;
             const lcs_f4 ot = sm.crec[j];
             const float dx = ot.x - me.x, dy = ot.y - me.y;
-            const float rx = dx * c32 + dy * s32, ry = dy * c32 - dx * s32;
+            const float rxx = dx * c32 + dy * s32, ryy = dy * c32 - dx * s32;
             // error of rx, ry and of the corner extents: coordinate rounding (slack) + float32 trig / arithmetic
             const float e = ot.w + me.w + 3e-6f * (fabsf(dx) + fabsf(dy)) + 2e-5f;
             // every corner lies within the other's half diagonal (ot.z) of its centre; a partner whose interval lies
             // above both h1 and lo2 changes neither
-            if (fabsf(ry) > hw + ot.z + e || rx < hl - e || rx - ot.z - hl - e > fmaxf(h1, lo2)) continue;
+            if (fabsf(ryy) > hw + ot.z + e || rxx < hl - e || rxx - ot.z - hl - e > fmaxf(h1, lo2)) continue;
             const lcs_f4 o2 = sm.crec2[j];
             const float cr = o2.x * c32 + o2.y * s32, sr = o2.y * c32 - o2.x * s32; // cos / sin of the relative heading
             const float ex = fabsf(o2.z * cr) + fabsf(o2.w * sr), ey = fabsf(o2.z * sr) + fabsf(o2.w * cr);
-            const float xmin = rx - ex, ymax = ry + ey, ymin = ry - ey;
+            const float xmin = rxx - ex, ymax = ryy + ey, ymin = ryy - ey;
             if (ymax < -hw - e || ymin > hw + e || xmin < hl - e) continue; // certainly not a lead vehicle
             const bool sure = ymax >= -hw + e && ymin <= hw - e && xmin >= hl + e;
             const float d = xmin - hl, lo = d - e, hi = d + e;
@@ -1555,20 +1570,39 @@ LCS_D void lcs_phase_collision_filter(const LcsParams& p, LcsSmem& sm, int s, in
     if (tid >= n) return;
     const lcs_f4 me = sm.crec[tid], me2 = sm.crec2[tid];
     const int half = n >> 1;
+    // partners tid+1 .. tid+half of the doubled coordinate arrays (no wrap); for even n the pair at distance n/2 is
+    // taken by its lower slot only
+    const int lo = tid + 1, hi = tid + half - ((2 * half == n && tid >= half) ? 1 : 0);
+    const float* sx = sm.soa;
+    const float* sy = sm.soa + LCS_SOA_Y(p.Ap);
+    // first test, four partners per step: squared centre distance against (own radius + largest radius of the list)^2;
+    // survivors get the pair's own radii
+    const float rq = me.z + lcs_i2f(sm.misc[14]), thr2 = rq * rq * 1.00001f;
     int nc = 0;
     // the circle test runs over all partners first; the survivors (a handful per thread) are kept in a private
     // list so that the warp does not serialise a SAT evaluation into almost every iteration of this loop
-    for (int d = 1; d <= half; d++) {
-        int j = tid + d;
-        if (j >= n) j -= n;
-        const lcs_f4 ot = sm.crec[j];
-        const float dx = ot.x - me.x, dy = ot.y - me.y;
-        const float rr = ot.z + me.z; // both radii already include their coordinate slack
-        if (dx * dx + dy * dy <= rr * rr * 1.00001f && !(2 * d == n && tid >= half)) {
-            if (nc < LCS_CAND)
-                sm.cand[nc++ * p.Ap + tid] = (uint16_t)j;
-            else
-                lcs_collision_narrow(sm, cap, tid, j, me, me2);
+    for (int g = lo & ~3; g <= hi; g += 4) {
+        const lcs_f4 X = *(const lcs_f4*)(sx + g), Y = *(const lcs_f4*)(sy + g);
+        const float dx0 = X.x - me.x, dx1 = X.y - me.x, dx2 = X.z - me.x, dx3 = X.w - me.x;
+        const float dy0 = Y.x - me.y, dy1 = Y.y - me.y, dy2 = Y.z - me.y, dy3 = Y.w - me.y;
+        unsigned m = (dx0 * dx0 + dy0 * dy0 <= thr2 ? 1u : 0u) | (dx1 * dx1 + dy1 * dy1 <= thr2 ? 2u : 0u) |
+                     (dx2 * dx2 + dy2 * dy2 <= thr2 ? 4u : 0u) | (dx3 * dx3 + dy3 * dy3 <= thr2 ? 8u : 0u);
+        if (g < lo) m &= 0xFu << (lo - g);
+        if (g + 3 > hi) m &= 0xFu >> (g + 3 - hi);
+        while (m) {
+            const int r = lcs_ffs0(m);
+            m &= m - 1;
+            int j = g + r;
+            if (j >= n) j -= n;
+            const lcs_f4 ot = sm.crec[j];
+            const float dx = ot.x - me.x, dy = ot.y - me.y;
+            const float rr = ot.z + me.z; // both radii already include their coordinate slack
+            if (dx * dx + dy * dy <= rr * rr * 1.00001f) {
+                if (nc < LCS_CAND)
+                    sm.cand[nc++ * p.Ap + tid] = (uint16_t)j;
+                else
+                    lcs_collision_narrow(sm, cap, tid, j, me, me2);
+            }
         }
     }
     for (int k = 0; k < nc; k++) lcs_collision_narrow(sm, cap, tid, sm.cand[k * p.Ap + tid], me, me2);
@@ -1608,6 +1642,10 @@ LCS_D int lcs_mc_load(const LcsParams& p, LcsSmem& sm, int s, int tid, const Lcs
     const double* r = p.snap_rec + 6 * (base + tid);
     lcs_store_ex(sm, tid, r[0], r[1], 0.0, r[2], r[3], r[4], r[5], 0.0);
     lcs_make_crec(p, s, r[0], r[1], r[2], r[3], r[4], r[5], &sm.crec[tid], &sm.crec2[tid]);
+    // coordinates once more as doubled float arrays (collision filter), largest bounding radius of the list
+    sm.soa[tid] = sm.soa[tid + n_new] = sm.crec[tid].x;
+    sm.soa[LCS_SOA_Y(p.Ap) + tid] = sm.soa[LCS_SOA_Y(p.Ap) + tid + n_new] = sm.crec[tid].y;
+    lcs_atomic_max(&sm.misc[14], lcs_f2i(sm.crec[tid].z));
     return a;
 }
 LCS_D void lcs_mc_out(const LcsParams& p, LcsSmem& sm, int s, int tid, int a) {

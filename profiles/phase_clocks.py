@@ -24,6 +24,7 @@ tnames = ["pre", "scan", "post", "depart+publish"] + (["lead search"] if reactiv
 mnames = ["load snapshot", "collision filter", "edge search", "drain + out"]
 NT, NM = len(tnames), len(mnames)
 acc_t, acc_m, acc_w = np.zeros(NT), np.zeros(NM), np.zeros(2)
+heavy_t, heavy_m = np.zeros(NT), np.zeros(NM)
 n = 0
 be.rollout(20)
 for _ in range(40):
@@ -34,14 +35,17 @@ for _ in range(40):
     acc_m += np.diff(d[:, 8 : 8 + NM + 1], axis=1).mean(axis=0)
     acc_w += np.array([d[:, 7].mean(), d[:, 15].mean()])
     tot_t, tot_m = d[:, NT] - d[:, 0], d[:, 8 + NM] - d[:, 8]
+    top = np.argsort(tot_t)[-max(1, S // 20):]  # the heaviest 5 % of the tick items: they set the rollout's serial chain
+    heavy_t += np.diff(d[top, : NT + 1], axis=1).mean(axis=0)
+    heavy_m += np.diff(d[np.argsort(tot_m)[-max(1, S // 20):], 8 : 8 + NM + 1], axis=1).mean(axis=0)
     n += 1
-acc_t /= n; acc_m /= n; acc_w /= n
+acc_t /= n; acc_m /= n; acc_w /= n; heavy_t /= n; heavy_m /= n
 print(f"S={S} reactive={reactive}: mean per-item cycles by phase (thread 0 view, includes barrier waits); one tick per launch")
 print(" tick item")
-for nm, v in zip(tnames, acc_t):
-    print(f"  {nm:18s} {v:9.0f} cyc  {100 * v / acc_t.sum():5.1f}%")
+for nm, v, hv in zip(tnames, acc_t, heavy_t):
+    print(f"  {nm:18s} {v:9.0f} cyc  {100 * v / acc_t.sum():5.1f}%   heaviest 5%: {hv:9.0f}")
 print(f"  total              {acc_t.sum():9.0f} cyc = {acc_t.sum() / 1.965e3:.1f} us @1965 MHz; min/max last tick {tot_t.min()}/{tot_t.max()}; ticket+dependency wait {acc_w[0]:.0f}")
 print(" metric item")
-for nm, v in zip(mnames, acc_m):
-    print(f"  {nm:18s} {v:9.0f} cyc  {100 * v / acc_m.sum():5.1f}%")
+for nm, v, hv in zip(mnames, acc_m, heavy_m):
+    print(f"  {nm:18s} {v:9.0f} cyc  {100 * v / acc_m.sum():5.1f}%   heaviest 5%: {hv:9.0f}")
 print(f"  total              {acc_m.sum():9.0f} cyc = {acc_m.sum() / 1.965e3:.1f} us; min/max last tick {tot_m.min()}/{tot_m.max()}; ticket+dependency wait {acc_w[1]:.0f}")

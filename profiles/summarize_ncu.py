@@ -54,4 +54,16 @@ with open(out + "_hot_lines.txt", "w") as f:
     f.write(f"total inst {tot_i} samples {tot_s}\n")
     for samp, inst, thr, fn, ln, txt in sorted(lines, reverse=True)[:40]:
         f.write(f"{fn[:10]:10s} {ln:5d} samp {100 * samp / tot_s:5.1f}%  inst {inst:9d} ({100 * inst / tot_i:4.1f}%) thr/inst {thr / max(inst, 1):5.1f}  {txt[:110]}\n")
+    f.write("--- by executed instructions\n")
+    for samp, inst, thr, fn, ln, txt in sorted(lines, key=lambda x: -x[1])[:50]:
+        f.write(f"{fn[:10]:10s} {ln:5d} samp {100 * samp / tot_s:5.1f}%  inst {inst:9d} ({100 * inst / tot_i:4.1f}%) thr/inst {thr / max(inst, 1):5.1f}  {txt[:110]}\n")
+    # instructions / stall samples per 25-line bucket of each file: a coarse per-function picture
+    f.write("--- by 25-line bucket\n")
+    buckets = {}
+    for samp, inst, thr, fn, ln, txt in lines:
+        k = (fn, ln // 25 * 25)
+        b = buckets.setdefault(k, [0, 0])
+        b[0] += samp; b[1] += inst
+    for (fn, ln), (samp, inst) in sorted(buckets.items(), key=lambda kv: -kv[1][1])[:40]:
+        f.write(f"{fn[:14]:14s} {ln:5d}-{ln + 24:5d} samp {100 * samp / tot_s:5.1f}%  inst {100 * inst / tot_i:5.1f}%\n")
 print("wrote", out + "_metrics.txt", out + "_hot_lines.txt")
