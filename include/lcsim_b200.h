@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LCSIM_B200_ABI_VERSION 1
+#define LCSIM_B200_ABI_VERSION 2
 
 /* reference: lcsim/entity/agent/agent.py:89-90 */
 #define LCSIM_B200_H_STEPS 11 /* NUM_HISTORICAL_STEPS */
@@ -102,6 +102,9 @@ typedef struct {
     const double* edge_xy; /* [S][E][2] resampled road-edge points, pb order */
     const double* edge_dir; /* [S][E][2] unit direction of the segment ending at the point */
     const double* origin; /* [S][2] origin of the scenario-local fp32 frame */
+    const int32_t* edge_poly_id; /* [S][E] ordinal of the road-edge polyline every point belongs to (the `ids` of
+                                  * Junction.roadgraph_points, junction.py:133-144), or NULL: guidance / plan metrics
+                                  * that need the prior-point rule are then unavailable */
 } lcsim_b200_static_host;
 
 /* Borrowed device pointers into the engine's state (valid until destroy).  A_stride >= A is the
@@ -289,6 +292,27 @@ typedef struct {
     float* heading_diff;
 } lcsim_b200_lane_desc;
 int lcsim_b200_project_lanes(lcsim_b200_engine* e, const lcsim_b200_lane_desc* d, void* stream);
+
+/* Guidance costs over planned trajectories with their analytic gradients, float32 like the reference's
+ * tensors; every scenario is one graph.  xy (device) [S][A][T][2] world-frame positions of the plans (what
+ * diffuser._reconstruct_traj returns), rows a >= n_agents[s] ignored.  Outputs (device, may be NULL): loss [S], grad
+ * [S][A][T][2] = d loss / d xy as torch.autograd gives it for the loss expression.
+ *   which = 0  Repeller.loss  (motion_diff/modules/guidance.py:17-49; radius 6, eps 1e-6 in the reference)
+ *   which = 1  NoOffRoad.loss (guidance.py:52-85 -> metrics/roadgraph.py:160-232; radius 1, eps 1e-6): needs
+ *              static.edge_poly_id; sd (device [S][A][T], may be NULL) receives the signed distances */
+int lcsim_b200_guidance_cost(lcsim_b200_engine* e, int which, const float* xy, int T, float radius, float eps, float* loss,
+                             float* grad, float* sd, void* stream);
+
+/* Batched plan metrics: traj5 (device) [S][A][T][5] = x, y, length, width, yaw; masks (device, [S][A]
+ * u8, NULL = every agent) select the agents that are counted.  Outputs (device, any may be NULL), per scenario:
+ *   overlap_rate / overlap_count  compute_overlap_rate (motion_diff/metrics/overlap.py:7-43: boxes of ALL agents of a
+ *                                 step are tested pairwise, metrics/geometry.py:8-101; an agent counts when it
+ *                                 overlaps anybody), rate = count / sum(mask) / T
+ *   offroad_rate / offroad_count  compute_offroad_rate (metrics/roadgraph.py:36-88; the caller ANDs the vehicle mask
+ *                                 into offroad_mask), signed distance > 0 */
+int lcsim_b200_plan_metrics(lcsim_b200_engine* e, const float* traj5, int T, const uint8_t* overlap_mask,
+                            const uint8_t* offroad_mask, float* overlap_rate, int32_t* overlap_count, float* offroad_rate,
+                            int32_t* offroad_count, void* stream);
 
 int lcsim_b200_views(lcsim_b200_engine* e, lcsim_b200_state_views* out);
 

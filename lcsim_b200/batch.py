@@ -45,7 +45,11 @@ class BatchEngine:
         sh = native.StaticHost()
         keep = []
         for name, dt in native.STATIC_FIELDS:
-            arr = np.ascontiguousarray(getattr(static, name), dtype=dt)
+            val = getattr(static, name, None)
+            if val is None:  # optional arrays (edge_poly_id of batches packed before ABI 2)
+                setattr(sh, name, None)
+                continue
+            arr = np.ascontiguousarray(val, dtype=dt)
             keep.append(arr)
             setattr(sh, name, arr.ctypes.data)
         self._check(self.lib.lcsim_b200_upload_static(self._h, C.byref(sh)), "upload_static")
@@ -266,6 +270,45 @@ class BatchEngine:
             setattr(d, k, b.ptr(v))
         self._check(self.lib.lcsim_b200_project_lanes(self._h, C.byref(d), b.stream()), "project_lanes")
         return {k: v[:, : self.A] for k, v in out.items()}
+
+    # ------------------------------------------------------------------ guidance costs / plan metrics
+    def guidance_cost(self, which: str, xy, radius: Optional[float] = None, eps: float = 1e-6, with_sd: bool = False):
+        """Repeller.loss / NoOffRoad.loss (motion_diff/modules/guidance.py:17-85) of the plans xy (S,A,T,2) float32 with
+        the analytic gradient: dict(loss (S,), grad (S,A,T,2)[, sd (S,A,T)]) device tensors."""
+        b = self.backend
+        idx = {"repeller": 0, "no_offroad": 1}[which]
+        if radius is None:
+            radius = 6.0 if idx == 0 else 1.0
+        x = b.to_device(xy, np.float32)
+        T = int(x.shape[2])
+        assert tuple(x.shape) == (self.S, self.A, T, 2)
+        out = dict(loss=b.empty((self.S,), np.float32), grad=b.empty((self.S, self.A, T, 2), np.float32))
+        if with_sd and idx == 1:
+            out["sd"] = b.empty((self.S, self.A, T), np.float32)
+        self._check(self.lib.lcsim_b200_guidance_cost(self._h, idx, b.ptr(x), T, float(radius), float(eps), b.ptr(out["loss"]),
+                                                      b.ptr(out["grad"]), b.ptr(out["sd"]) if "sd" in out else None,
+                                                      b.stream()), "guidance_cost")
+        self._keep = x
+        return out
+
+    def plan_metrics(self, traj5, overlap_mask=None, offroad_mask=None):
+        """compute_overlap_rate / compute_offroad_rate (motion_diff/metrics/overlap.py:7-43, roadgraph.py:36-88) of the
+        plans traj5 (S,A,T,5) = x, y, length, width, yaw (float32), per scenario: dict(overlap_rate, overlap_count,
+        offroad_rate, offroad_count) device tensors.  The masks are (S,A); offroad_mask should carry the vehicle mask."""
+        b = self.backend
+        x = b.to_device(traj5, np.float32)
+        T = int(x.shape[2])
+        assert tuple(x.shape) == (self.S, self.A, T, 5)
+        m1 = None if overlap_mask is None else b.to_device(overlap_mask, np.uint8)
+        m2 = None if offroad_mask is None else b.to_device(offroad_mask, np.uint8)
+        out = dict(overlap_rate=b.empty((self.S,), np.float32), overlap_count=b.empty((self.S,), np.int32),
+                   offroad_rate=b.empty((self.S,), np.float32), offroad_count=b.empty((self.S,), np.int32))
+        self._check(self.lib.lcsim_b200_plan_metrics(
+            self._h, b.ptr(x), T, None if m1 is None else b.ptr(m1), None if m2 is None else b.ptr(m2),
+            b.ptr(out["overlap_rate"]), b.ptr(out["overlap_count"]), b.ptr(out["offroad_rate"]), b.ptr(out["offroad_count"]),
+            b.stream()), "plan_metrics")
+        self._keep = (x, m1, m2)
+        return out
 
     # ------------------------------------------------------------------ aggregates
     def episode_stats(self):

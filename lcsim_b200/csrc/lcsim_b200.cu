@@ -40,6 +40,7 @@ struct alignas(16) float4 { float x, y, z, w; };
 #endif
 
 #include "lcsim_core.cuh"
+#include "lcsim_plan.cuh"
 
 #ifndef LCS_MC_CTAS
 #define LCS_MC_CTAS 8 // resident CTAs per SM the 128-thread collision / edge kernels are compiled for
@@ -589,6 +590,11 @@ struct lcsim_b200_engine {
     float* lane_pts = nullptr; // [S][N][4] centreline points x, y, theta, 0 (upload_centrelines)
     int32_t *lane_ids = nullptr, *lane_n = nullptr;
     int lane_N = 0;
+    float4* plan_edge = nullptr; // [S][E] road-edge points x, y, dir_x, dir_y in float32 (guidance / plan metrics)
+    int32_t* plan_edge_id = nullptr; // [S][E]
+    float* plan_sum = nullptr; // [S][plan_parts] partial sums of the guidance / metric kernels
+    int32_t* plan_cnt = nullptr;
+    int plan_parts = 0;
     int device = 0;
     int grid_cap = 1; // CTAs of the engine kernel the device holds at once (occupancy x SMs)
     std::string err;
@@ -1290,6 +1296,28 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     LCS_UP(p.ge_idx, g.ge_idx);
     LCS_UP(p.home_edge, g.home_edge);
 #undef LCS_UP
+    {
+        // the road-edge points as the reference's float32 roadgraph tensors hold them (junction.py:133-150: float64
+        // resampled points and get_polyline_dir directions, cast to float32), for the guidance / plan-metric kernels
+        std::vector<float4> pe((size_t)S * Ed);
+        for (int s = 0; s < S; s++)
+            for (int k = 0; k < st->n_edge[s]; k++) {
+                const size_t src = ((size_t)s * E + k) * 2, dst = (size_t)s * Ed + k;
+                pe[dst].x = (float)st->edge_xy[src]; pe[dst].y = (float)st->edge_xy[src + 1];
+                pe[dst].z = (float)st->edge_dir[src]; pe[dst].w = (float)st->edge_dir[src + 1];
+            }
+        lcs_release(e, e->plan_edge);
+        lcs_release(e, e->plan_edge_id);
+        LCS_ALLOC(e, e->plan_edge, pe.size());
+        LCS_CUDA(e, cudaMemcpy(e->plan_edge, pe.data(), pe.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        if (st->edge_poly_id) {
+            std::vector<int32_t> ids((size_t)S * Ed, 0);
+            for (int s = 0; s < S; s++)
+                for (int k = 0; k < st->n_edge[s]; k++) ids[(size_t)s * Ed + k] = st->edge_poly_id[(size_t)s * E + k];
+            LCS_ALLOC(e, e->plan_edge_id, ids.size());
+            LCS_CUDA(e, cudaMemcpy(e->plan_edge_id, ids.data(), ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        }
+    }
     LCS_CUDA(e, cudaMemset(p.traj_f32, 0, SA));
     LCS_CUDA(e, cudaMemset(p.stale_valid, 0, SA));
     e->uploaded = true;
@@ -1932,6 +1960,97 @@ extern "C" int lcsim_b200_project_lanes(lcsim_b200_engine* e, const lcsim_b200_l
                                   &on_d2, &hdiff, hd.data(), hi.data());
             lcs_lane_store(p, o, s, a, bi, bd2, on_d2, hdiff);
         }
+#endif
+    return 0;
+}
+
+// ---- guidance costs / plan metrics: lcsim_plan.cuh ---------------------------------------------
+static int lcs_plan_parts(lcsim_b200_engine* e, int parts) {
+    if (parts <= e->plan_parts) return 0;
+    lcs_release(e, e->plan_sum);
+    lcs_release(e, e->plan_cnt);
+    LCS_ALLOC(e, e->plan_sum, (size_t)e->p.S * parts);
+    LCS_ALLOC(e, e->plan_cnt, (size_t)e->p.S * parts);
+    e->plan_parts = parts;
+    return 0;
+}
+static void lcs_plan_args(lcsim_b200_engine* e, LcpArgs& o, int T) {
+    memset(&o, 0, sizeof o);
+    o.S = e->p.S; o.A = e->p.A; o.T = T;
+    o.n_agents = e->p.n_agents;
+    o.edge = e->plan_edge; o.edge_id = e->plan_edge_id; o.n_edge = e->p.n_edge; o.E = e->p.E;
+    o.part_sum = e->plan_sum; o.part_cnt = e->plan_cnt; o.P = e->plan_parts;
+}
+
+extern "C" int lcsim_b200_guidance_cost(lcsim_b200_engine* e, int which, const float* xy, int T, float radius, float eps,
+                                        float* loss, float* grad, float* sd, void* stream) {
+    if (!e || !xy || T < 1 || !(radius > 0) || (which != 0 && which != 1)) return LCSIM_B200_ERR_ARG;
+    if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "guidance_cost before upload_static");
+    if (which == 1 && !e->plan_edge_id) return lcs_fail(e, LCSIM_B200_ERR_STATE, "guidance_cost: NoOffRoad needs static.edge_poly_id");
+    LCS_GUARD(e);
+    const int A = e->p.A, qblocks = (A * T + 255) / 256;
+    int rc = lcs_plan_parts(e, std::max(T, qblocks));
+    if (rc) return rc;
+    LcpArgs o;
+    lcs_plan_args(e, o, T);
+    o.xy = xy; o.radius = radius; o.eps = eps; o.loss = loss; o.grad = grad; o.sd = sd;
+#ifndef LCSIM_HOSTEMU
+    cudaStream_t st = (cudaStream_t)stream;
+    if (which == 0) {
+        const int nthr = (A + 31) / 32 * 32;
+        lcp_repeller_kernel<<<dim3(T, o.S), nthr, sizeof(float) * 2 * nthr, st>>>(o);
+        lcp_finalize_kernel<<<o.S, 256, 0, st>>>(o, 0, T);
+    } else {
+        lcp_offroad_kernel<<<dim3(qblocks, o.S), 256, 0, st>>>(o, 0);
+        lcp_finalize_kernel<<<o.S, 256, 0, st>>>(o, 1, qblocks);
+    }
+    LCS_CUDA(e, cudaGetLastError());
+#else
+    if (which == 0) lcp_repeller_serial(o);
+    else lcp_offroad_serial(o, 0);
+#endif
+    return 0;
+}
+
+extern "C" int lcsim_b200_plan_metrics(lcsim_b200_engine* e, const float* traj5, int T, const uint8_t* overlap_mask,
+                                       const uint8_t* offroad_mask, float* overlap_rate, int32_t* overlap_count,
+                                       float* offroad_rate, int32_t* offroad_count, void* stream) {
+    if (!e || !traj5 || T < 1) return LCSIM_B200_ERR_ARG;
+    if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "plan_metrics before upload_static");
+    const bool want_off = offroad_rate || offroad_count, want_ovl = overlap_rate || overlap_count;
+    if (want_off && !e->plan_edge_id) return lcs_fail(e, LCSIM_B200_ERR_STATE, "plan_metrics: the off-road rate needs static.edge_poly_id");
+    LCS_GUARD(e);
+    const int A = e->p.A, qblocks = (A * T + 255) / 256;
+    int rc = lcs_plan_parts(e, std::max(T, qblocks));
+    if (rc) return rc;
+    LcpArgs o;
+    lcs_plan_args(e, o, T);
+    o.traj5 = traj5;
+#ifndef LCSIM_HOSTEMU
+    cudaStream_t st = (cudaStream_t)stream;
+    if (want_ovl) {
+        const int nthr = (A + 31) / 32 * 32;
+        const size_t smem = (sizeof(LcpBox) + 3 * sizeof(float)) * nthr;
+        if (smem > 48 * 1024) LCS_CUDA(e, cudaFuncSetAttribute(lcp_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        o.mask = overlap_mask; o.rate = overlap_rate; o.count = overlap_count;
+        lcp_overlap_kernel<<<dim3(T, o.S), nthr, smem, st>>>(o);
+        lcp_finalize_kernel<<<o.S, 256, 0, st>>>(o, 2, T);
+    }
+    if (want_off) {
+        o.mask = offroad_mask; o.rate = offroad_rate; o.count = offroad_count;
+        lcp_offroad_kernel<<<dim3(qblocks, o.S), 256, 0, st>>>(o, 1);
+        lcp_finalize_kernel<<<o.S, 256, 0, st>>>(o, 2, qblocks);
+    }
+    LCS_CUDA(e, cudaGetLastError());
+#else
+    if (want_ovl) {
+        o.mask = overlap_mask; o.rate = overlap_rate; o.count = overlap_count;
+        lcp_overlap_serial(o);
+    }
+    if (want_off) {
+        o.mask = offroad_mask; o.rate = offroad_rate; o.count = offroad_count;
+        lcp_offroad_serial(o, 1);
+    }
 #endif
     return 0;
 }

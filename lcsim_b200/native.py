@@ -18,10 +18,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 SRC = os.path.join(_HERE, "csrc", "lcsim_b200.cu")
 HDRS = [os.path.join(_HERE, "csrc", "lcsim_core.cuh"), os.path.join(_HERE, "csrc", "lcsim_city.cuh"),
+        os.path.join(_HERE, "csrc", "lcsim_plan.cuh"),
         os.path.join(ROOT, "include", "lcsim_b200.h")]
 LIB_PATH = os.path.join(_HERE, "liblcsim_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 H_STEPS, ROUTE_LEN, N_REWARD_TERMS, N_STATS = 11, 10, 6, 8
 WAITING, ACTIVE, FINISHED, IDLE = 0, 1, 2, 3
 ACT_NONE, ACT_BICYCLE, ACT_DELTA, ACT_STATE = 0, 1, 2, 3
@@ -72,7 +73,7 @@ STATIC_FIELDS = (("n_agents", np.int32), ("ads_index", np.int32), ("agent_type",
                  ("width", np.float64), ("dynamic", np.uint8), ("traj_len", np.int32), ("depart_tick", np.int32),
                  ("wait_order", np.int32), ("home_xy", np.float64), ("traj_xy", np.float64), ("traj_vel", np.float64),
                  ("traj_h", np.float64), ("n_edge", np.int32), ("edge_xy", np.float64), ("edge_dir", np.float64),
-                 ("origin", np.float64))
+                 ("origin", np.float64), ("edge_poly_id", np.int32))
 
 
 class StaticHost(C.Structure):
@@ -141,7 +142,8 @@ class CityViews(C.Structure):
 EXPORTS = ("lcsim_b200_abi_version", "lcsim_b200_create", "lcsim_b200_upload_static", "lcsim_b200_reset",
            "lcsim_b200_step", "lcsim_b200_step_masked", "lcsim_b200_rollout", "lcsim_b200_rollout_log", "lcsim_b200_rollout_host", "lcsim_b200_set_ref_trajectory", "lcsim_b200_rewards",
            "lcsim_b200_env_step", "lcsim_b200_upload_polylines", "lcsim_b200_build_obs",
-           "lcsim_b200_upload_centrelines", "lcsim_b200_project_lanes", "lcsim_b200_views", "lcsim_b200_episode_stats",
+           "lcsim_b200_upload_centrelines", "lcsim_b200_project_lanes", "lcsim_b200_guidance_cost",
+           "lcsim_b200_plan_metrics", "lcsim_b200_views", "lcsim_b200_episode_stats",
            "lcsim_b200_launch_count", "lcsim_b200_last_error", "lcsim_b200_destroy",
            "lcsim_b200_city_create", "lcsim_b200_city_reset", "lcsim_b200_city_step", "lcsim_b200_city_views",
            "lcsim_b200_city_launch_count", "lcsim_b200_city_last_error", "lcsim_b200_city_destroy")
@@ -170,6 +172,8 @@ def bind(path: str) -> C.CDLL:
     lib.lcsim_b200_build_obs.argtypes = [vp, C.POINTER(ObsDesc), vp]
     lib.lcsim_b200_upload_centrelines.argtypes = [vp, vp, vp, vp, i32]
     lib.lcsim_b200_project_lanes.argtypes = [vp, C.POINTER(LaneDesc), vp]
+    lib.lcsim_b200_guidance_cost.argtypes = [vp, i32, vp, i32, C.c_float, C.c_float, vp, vp, vp, vp]
+    lib.lcsim_b200_plan_metrics.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.lcsim_b200_views.argtypes = [vp, C.POINTER(StateViews)]
     lib.lcsim_b200_episode_stats.argtypes = [vp, vp, vp]
     lib.lcsim_b200_launch_count.argtypes = [vp]

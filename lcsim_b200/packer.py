@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass, field
-from typing import Dict, List, Sequence, Tuple
+from typing import Optional, Dict, List, Sequence, Tuple
 
 import numpy as np
 
@@ -264,6 +264,7 @@ class StaticBatch:
     edge_xy: np.ndarray  # (S,E,2) f64
     edge_dir: np.ndarray  # (S,E,2) f64
     origin: np.ndarray  # (S,2) f64
+    edge_poly_id: Optional[np.ndarray] = None  # (S,E) i32 ordinal of the road-edge polyline of every point (roadgraph ids)
 
     def scenario_slice(self, s0: int, s1: int) -> "StaticBatch":
         kw = {k: (v[s0:s1] if isinstance(v, np.ndarray) else v) for k, v in self.__dict__.items()}
@@ -288,7 +289,7 @@ def pack(scenarios: Sequence[ScenarioArrays], start: float = 0.0, interval: floa
         wait_order=np.zeros((S, A), np.int32), home_xy=np.zeros((S, A, 2)),
         traj_xy=np.zeros((S, A, T, 2)), traj_vel=np.zeros((S, A, T, 2)), traj_h=np.zeros((S, A, T)),
         n_edge=np.zeros(S, np.int32), edge_xy=np.zeros((S, E, 2)), edge_dir=np.zeros((S, E, 2)),
-        origin=np.zeros((S, 2)),
+        origin=np.zeros((S, 2)), edge_poly_id=np.zeros((S, E), np.int32),
     )
     max_ticks = max(4 * total_steps, 1024)
     for i, sc in enumerate(scenarios):
@@ -324,6 +325,9 @@ def pack(scenarios: Sequence[ScenarioArrays], start: float = 0.0, interval: floa
         b.n_edge[i] = ne
         b.edge_xy[i, :ne] = sc.edge_xy
         b.edge_dir[i, :ne] = sc.edge_dir
+        st = np.asarray(sc.edge_poly_start, np.int64)
+        if len(st) > 1:
+            b.edge_poly_id[i, :ne] = np.repeat(np.arange(len(st) - 1, dtype=np.int32), np.diff(st))
         # origin of the fp32 filter frame: integer metres near the middle of everything
         allp = [sc.edge_xy] if ne else []
         allp += [np.asarray(x, np.float64) for x in sc.traj_xy]
