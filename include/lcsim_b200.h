@@ -314,6 +314,27 @@ int lcsim_b200_plan_metrics(lcsim_b200_engine* e, const float* traj5, int T, con
                             const uint8_t* offroad_mask, float* overlap_rate, int32_t* overlap_count, float* offroad_rate,
                             int32_t* offroad_count, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Scenario loader / packer: reads `map.pb` + `agents.pb` of n_dirs WOMD-shaped scenario directories and
+ * packs them for lcsim_b200_upload_static — the native form of what Engine.__init__ does per scenario (engine.py:84-130:
+ * protobuf parse; junction/junction.py:59-78 -> utils/polygon.py:90-188 0.5 m resampling of the road edges;
+ * polygon.py:78-86 direction vectors; agent/agent.py:106-171 homes, trajectories, dynamic flags; manager.py:33-35
+ * waiting order; lane/lane.py:108-124 polyline centres), threaded over the scenarios (n_threads <= 0: all cores).
+ * Bit-identical to lcsim_b200/packer.py, which is pinned to the real reference.  Host memory only; no GPU needed. */
+typedef struct lcsim_b200_scenarios lcsim_b200_scenarios;
+int lcsim_b200_load_dirs(const char* const* dirs, int n_dirs, double start, double interval, int32_t total_steps, int n_threads,
+                         lcsim_b200_scenarios** out);
+/* dims[5] = S, A, T, E, P (largest number of polyline centres) */
+int lcsim_b200_scenarios_dims(const lcsim_b200_scenarios* sc, int32_t* dims);
+/* the packed arrays (owned by sc, valid until lcsim_b200_scenarios_free), ready for lcsim_b200_upload_static */
+int lcsim_b200_scenarios_static(const lcsim_b200_scenarios* sc, lcsim_b200_static_host* out);
+const int32_t* lcsim_b200_scenarios_agent_id(const lcsim_b200_scenarios* sc); /* [S][A] pb ids, -1 padded */
+const int32_t* lcsim_b200_scenarios_junction_id(const lcsim_b200_scenarios* sc); /* [S] */
+/* polyline centres for lcsim_b200_upload_polylines: *n_poly [S], return [S][P][3] x, y, heading */
+const double* lcsim_b200_scenarios_polylines(const lcsim_b200_scenarios* sc, const int32_t** n_poly);
+const char* lcsim_b200_scenarios_error(const lcsim_b200_scenarios* sc);
+void lcsim_b200_scenarios_free(lcsim_b200_scenarios* sc);
+
 int lcsim_b200_views(lcsim_b200_engine* e, lcsim_b200_state_views* out);
 
 /* Sums the per-scenario statistics into stats_device[LCSIM_B200_N_STATS] (int64, device). */

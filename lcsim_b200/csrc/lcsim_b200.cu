@@ -41,6 +41,7 @@ struct alignas(16) float4 { float x, y, z, w; };
 
 #include "lcsim_core.cuh"
 #include "lcsim_plan.cuh"
+#include "lcsim_loader.hpp"
 
 #ifndef LCS_MC_CTAS
 #define LCS_MC_CTAS 8 // resident CTAs per SM the 128-thread collision / edge kernels are compiled for
@@ -1963,6 +1964,39 @@ extern "C" int lcsim_b200_project_lanes(lcsim_b200_engine* e, const lcsim_b200_l
 #endif
     return 0;
 }
+
+// ---- scenario loader: lcsim_loader.hpp -------------------------------------------------------------
+extern "C" int lcsim_b200_load_dirs(const char* const* dirs, int n_dirs, double start, double interval, int32_t total_steps,
+                                    int n_threads, lcsim_b200_scenarios** out) {
+    if (!dirs || n_dirs < 1 || !out) return LCSIM_B200_ERR_ARG;
+    lcsim_b200_scenarios* sc = new lcsim_b200_scenarios();
+    *out = sc; // returned on failure too: the caller reads the message and frees it
+    return lcs_load_dirs(dirs, n_dirs, start, interval, total_steps, n_threads, sc);
+}
+extern "C" int lcsim_b200_scenarios_dims(const lcsim_b200_scenarios* sc, int32_t* dims) {
+    if (!sc || !dims) return LCSIM_B200_ERR_ARG;
+    dims[0] = sc->S; dims[1] = sc->A; dims[2] = sc->T; dims[3] = sc->E; dims[4] = sc->P;
+    return 0;
+}
+extern "C" int lcsim_b200_scenarios_static(const lcsim_b200_scenarios* sc, lcsim_b200_static_host* o) {
+    if (!sc || !o) return LCSIM_B200_ERR_ARG;
+    o->n_agents = sc->n_agents.data(); o->ads_index = sc->ads_index.data(); o->agent_type = sc->agent_type.data();
+    o->length = sc->length.data(); o->width = sc->width.data(); o->dynamic = sc->dynamic.data(); o->traj_len = sc->traj_len.data();
+    o->depart_tick = sc->depart_tick.data(); o->wait_order = sc->wait_order.data(); o->home_xy = sc->home_xy.data();
+    o->traj_xy = sc->traj_xy.data(); o->traj_vel = sc->traj_vel.data(); o->traj_h = sc->traj_h.data(); o->n_edge = sc->n_edge.data();
+    o->edge_xy = sc->edge_xy.data(); o->edge_dir = sc->edge_dir.data(); o->origin = sc->origin.data();
+    o->edge_poly_id = sc->edge_poly_id.data();
+    return 0;
+}
+extern "C" const int32_t* lcsim_b200_scenarios_agent_id(const lcsim_b200_scenarios* sc) { return sc ? sc->agent_id.data() : nullptr; }
+extern "C" const int32_t* lcsim_b200_scenarios_junction_id(const lcsim_b200_scenarios* sc) { return sc ? sc->junction_id.data() : nullptr; }
+extern "C" const double* lcsim_b200_scenarios_polylines(const lcsim_b200_scenarios* sc, const int32_t** n_poly) {
+    if (!sc) return nullptr;
+    if (n_poly) *n_poly = sc->n_poly.data();
+    return sc->poly.data();
+}
+extern "C" const char* lcsim_b200_scenarios_error(const lcsim_b200_scenarios* sc) { return sc ? sc->err.c_str() : "null"; }
+extern "C" void lcsim_b200_scenarios_free(lcsim_b200_scenarios* sc) { delete sc; }
 
 // ---- guidance costs / plan metrics: lcsim_plan.cuh ---------------------------------------------
 static int lcs_plan_parts(lcsim_b200_engine* e, int parts) {

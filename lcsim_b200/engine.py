@@ -357,8 +357,7 @@ class ScenarioEngine:
     def __init__(self, root: "Engine", s: int):
         self._root, self._s = root, s
         self.agent_manager = AgentManager(self)
-        # read-only views with the reference's manager surface (the engine itself works on packed arrays)
-        self.lane_manager, self.road_manager, self.junction_manager = mapview.build(root._scenario_arrays[s])
+        self._map = None  # (lane_manager, road_manager, junction_manager) views, built on first access
         self.motion_diffuser = None
         self.guidance = None
         self._pending: Dict[int, Action] = {}
@@ -366,6 +365,24 @@ class ScenarioEngine:
     @property
     def _be(self) -> BatchEngine:
         return self._root._batch
+
+    # ---- read-only views with the reference's manager surface (the engine itself works on packed arrays)
+    def _map_views(self):
+        if self._map is None:
+            self._map = mapview.build(self._root._scenario(self._s))
+        return self._map
+
+    @property
+    def lane_manager(self):
+        return self._map_views()[0]
+
+    @property
+    def road_manager(self):
+        return self._map_views()[1]
+
+    @property
+    def junction_manager(self):
+        return self._map_views()[2]
 
     @property
     def _snap(self) -> _Snapshot:
@@ -464,12 +481,15 @@ class Engine(ScenarioEngine):
         dev = 0
         if isinstance(self.device, str) and self.device.startswith("cuda:"):
             dev = int(self.device.split(":")[1])
-        self._scenario_arrays = packer.scenarios_from_dirs(dirs)
-        static = packer.pack(self._scenario_arrays, start=float(self.start_time), interval=float(self.step_interval),
-                             total_steps=int(self.total_steps))
+        # map.pb / agents.pb -> packed arrays by the native loader (lcsim_b200_load_dirs, threaded; bit-identical to
+        # packer.pack_dirs); the Python-side map objects behind lane_manager / junction_manager are parsed on first use
+        backend = config.get("_backend") or native.TorchCudaBackend(dev)
+        self._dirs = dirs
+        self._scenario_arrays: Dict[int, packer.ScenarioArrays] = {}
+        static, self._poly_centres, _ = native.load_dirs(backend.lib, dirs, start=float(self.start_time),
+                                                         interval=float(self.step_interval), total_steps=int(self.total_steps))
         self._batch = BatchEngine(static, reactive=self.reactive, no_static=self.no_static,
-                                  allow_new_obj=self.allow_new_obj, with_metrics=True, device=dev,
-                                  backend=config.get("_backend"))
+                                  allow_new_obj=self.allow_new_obj, with_metrics=True, device=dev, backend=backend)
         self._snapshot = _Snapshot(self._batch)
         self._rew_cache: dict = {}
         self._step_count = [0] * static.S
@@ -478,6 +498,11 @@ class Engine(ScenarioEngine):
         self.scenarios: List[ScenarioEngine] = [self] + [ScenarioEngine(self, s) for s in range(1, static.S)]
 
     # ---- internals
+    def _scenario(self, s: int) -> "packer.ScenarioArrays":
+        if s not in self._scenario_arrays:
+            self._scenario_arrays[s] = packer.scenarios_from_dirs([self._dirs[s]])[0]
+        return self._scenario_arrays[s]
+
     def _invalidate(self):
         self._snapshot.invalidate()
         self._rew_cache = {}

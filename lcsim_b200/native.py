@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 SRC = os.path.join(_HERE, "csrc", "lcsim_b200.cu")
 HDRS = [os.path.join(_HERE, "csrc", "lcsim_core.cuh"), os.path.join(_HERE, "csrc", "lcsim_city.cuh"),
-        os.path.join(_HERE, "csrc", "lcsim_plan.cuh"),
+        os.path.join(_HERE, "csrc", "lcsim_plan.cuh"), os.path.join(_HERE, "csrc", "lcsim_loader.hpp"),
         os.path.join(ROOT, "include", "lcsim_b200.h")]
 LIB_PATH = os.path.join(_HERE, "liblcsim_b200.so")
 
@@ -30,7 +30,7 @@ REWARD_KEYS = ("forward", "route_progress", "smooth", "collision", "offroad", "d
 STAT_KEYS = ("agent_steps", "active_sum", "collision_sum", "offroad_sum", "arrivals", "departures", "ticks", "reserved")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-Xcompiler", "-ffp-contract=off"]
 
 
 class NativeLibraryError(RuntimeError):
@@ -143,7 +143,9 @@ EXPORTS = ("lcsim_b200_abi_version", "lcsim_b200_create", "lcsim_b200_upload_sta
            "lcsim_b200_step", "lcsim_b200_step_masked", "lcsim_b200_rollout", "lcsim_b200_rollout_log", "lcsim_b200_rollout_host", "lcsim_b200_set_ref_trajectory", "lcsim_b200_rewards",
            "lcsim_b200_env_step", "lcsim_b200_upload_polylines", "lcsim_b200_build_obs",
            "lcsim_b200_upload_centrelines", "lcsim_b200_project_lanes", "lcsim_b200_guidance_cost",
-           "lcsim_b200_plan_metrics", "lcsim_b200_views", "lcsim_b200_episode_stats",
+           "lcsim_b200_plan_metrics", "lcsim_b200_load_dirs", "lcsim_b200_scenarios_dims", "lcsim_b200_scenarios_static",
+           "lcsim_b200_scenarios_agent_id", "lcsim_b200_scenarios_junction_id", "lcsim_b200_scenarios_polylines",
+           "lcsim_b200_scenarios_error", "lcsim_b200_scenarios_free", "lcsim_b200_views", "lcsim_b200_episode_stats",
            "lcsim_b200_launch_count", "lcsim_b200_last_error", "lcsim_b200_destroy",
            "lcsim_b200_city_create", "lcsim_b200_city_reset", "lcsim_b200_city_step", "lcsim_b200_city_views",
            "lcsim_b200_city_launch_count", "lcsim_b200_city_last_error", "lcsim_b200_city_destroy")
@@ -174,6 +176,19 @@ def bind(path: str) -> C.CDLL:
     lib.lcsim_b200_project_lanes.argtypes = [vp, C.POINTER(LaneDesc), vp]
     lib.lcsim_b200_guidance_cost.argtypes = [vp, i32, vp, i32, C.c_float, C.c_float, vp, vp, vp, vp]
     lib.lcsim_b200_plan_metrics.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.lcsim_b200_load_dirs.argtypes = [C.POINTER(C.c_char_p), i32, C.c_double, C.c_double, C.c_int32, i32, C.POINTER(vp)]
+    lib.lcsim_b200_scenarios_dims.argtypes = [vp, C.POINTER(C.c_int32)]
+    lib.lcsim_b200_scenarios_static.argtypes = [vp, C.POINTER(StaticHost)]
+    lib.lcsim_b200_scenarios_agent_id.argtypes = [vp]
+    lib.lcsim_b200_scenarios_agent_id.restype = vp
+    lib.lcsim_b200_scenarios_junction_id.argtypes = [vp]
+    lib.lcsim_b200_scenarios_junction_id.restype = vp
+    lib.lcsim_b200_scenarios_polylines.argtypes = [vp, C.POINTER(vp)]
+    lib.lcsim_b200_scenarios_polylines.restype = vp
+    lib.lcsim_b200_scenarios_error.argtypes = [vp]
+    lib.lcsim_b200_scenarios_error.restype = C.c_char_p
+    lib.lcsim_b200_scenarios_free.argtypes = [vp]
+    lib.lcsim_b200_scenarios_free.restype = None
     lib.lcsim_b200_views.argtypes = [vp, C.POINTER(StateViews)]
     lib.lcsim_b200_episode_stats.argtypes = [vp, vp, vp]
     lib.lcsim_b200_launch_count.argtypes = [vp]
@@ -199,6 +214,46 @@ def bind(path: str) -> C.CDLL:
     if lib.lcsim_b200_abi_version() != ABI_VERSION:
         raise NativeLibraryError(f"{path}: ABI version {lib.lcsim_b200_abi_version()} != {ABI_VERSION}")
     return lib
+
+
+def load_dirs(lib: C.CDLL, dirs, start: float = 0.0, interval: float = 0.1, total_steps: int = 91, n_threads: int = 0):
+    """lcsim_b200_load_dirs: scenario directories -> (packer.StaticBatch, [polyline centres per scenario], junction ids).
+    The arrays are copies; the native object is freed before returning."""
+    from .packer import StaticBatch
+
+    arr = (C.c_char_p * len(dirs))(*[os.fsencode(d) for d in dirs])
+    h = C.c_void_p()
+    rc = lib.lcsim_b200_load_dirs(arr, len(dirs), float(start), float(interval), int(total_steps), int(n_threads), C.byref(h))
+    try:
+        if rc != 0:
+            raise NativeLibraryError(f"lcsim_b200_load_dirs: {rc}: {lib.lcsim_b200_scenarios_error(h).decode()}")
+        dims = (C.c_int32 * 5)()
+        lib.lcsim_b200_scenarios_dims(h, dims)
+        S, A, T, E, P = (int(x) for x in dims)
+        sh = StaticHost()
+        lib.lcsim_b200_scenarios_static(h, C.byref(sh))
+        shapes = {"n_agents": (S,), "ads_index": (S,), "agent_type": (S, A), "length": (S, A), "width": (S, A), "dynamic": (S, A),
+                  "traj_len": (S, A), "depart_tick": (S, A), "wait_order": (S, A), "home_xy": (S, A, 2), "traj_xy": (S, A, T, 2),
+                  "traj_vel": (S, A, T, 2), "traj_h": (S, A, T), "n_edge": (S,), "edge_xy": (S, E, 2), "edge_dir": (S, E, 2),
+                  "origin": (S, 2), "edge_poly_id": (S, E)}
+
+        def take(ptr, shape, dt):
+            n = int(np.prod(shape))
+            buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(int(ptr))
+            return np.frombuffer(buf, dtype=dt).reshape(shape).copy()
+
+        kw = {name: take(getattr(sh, name), shapes[name], dt) for name, dt in STATIC_FIELDS}
+        kw["agent_id"] = take(lib.lcsim_b200_scenarios_agent_id(h), (S, A), np.int32)
+        n_poly_p = C.c_void_p()
+        poly_p = lib.lcsim_b200_scenarios_polylines(h, C.byref(n_poly_p))
+        n_poly = take(n_poly_p.value, (S,), np.int32)
+        poly = take(poly_p, (S, P, 3), np.float64)
+        junction = take(lib.lcsim_b200_scenarios_junction_id(h), (S,), np.int32)
+        sb = StaticBatch(S=S, A=A, T=T, E=E, start=float(start), interval=float(interval), total_steps=int(total_steps), **kw)
+        return sb, [poly[s, : n_poly[s]] for s in range(S)], junction
+    finally:
+        if h:
+            lib.lcsim_b200_scenarios_free(h)
 
 
 _LIB = None
