@@ -326,7 +326,7 @@ def pack(scenarios: Sequence[ScenarioArrays], start: float = 0.0, interval: floa
         b.edge_xy[i, :ne] = sc.edge_xy
         b.edge_dir[i, :ne] = sc.edge_dir
         st = np.asarray(sc.edge_poly_start, np.int64)
-        if len(st) > 1:
+        if len(st) > 1 and int(st[-1]) == ne:  # (tests build scenarios whose edge arrays were cut by hand)
             b.edge_poly_id[i, :ne] = np.repeat(np.arange(len(st) - 1, dtype=np.int32), np.diff(st))
         # origin of the fp32 filter frame: integer metres near the middle of everything
         allp = [sc.edge_xy] if ne else []
