@@ -249,6 +249,41 @@ typedef struct {
 int lcsim_b200_upload_polylines(lcsim_b200_engine* e, const int32_t* n_poly, const double* poly_xyh, int P);
 int lcsim_b200_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_desc* obs, void* stream);
 
+/* Encoder inputs for ALL listed agents of every scenario: what AgentEncoder.forward derives from the
+ * HeteroData in front of its attention layers (motion_diff/modules/agent_encoder.py:98-256), written from the engine's
+ * state so that the model needs no torch_cluster call.  Agent rows = slots of the active list.  Outputs (device,
+ * caller-owned, any may be NULL):
+ *   agent       [S][A_stride]         agent index of every row, -1 beyond n_active
+ *   x_a         [S][A_stride][H][6]   |motion|, angle(head, motion), |vel|, angle(head, vel), length, width (:153-166)
+ *   r_t         [S][A_stride][H-1][4] temporal edge (row, i) -> (row, H-1): |dpos|, angle(head_dst, dpos), wrap(dhead),
+ *               i - (H-1); r_t_valid [S][A_stride][H-1] says which exist (both steps valid, H-1-i <= time_span; :174-199)
+ *   a2a         CSR over target rows: a2a_offset [S][A_stride+1], a2a_src [S][cap_a2a] source rows ascending (radius_graph,
+ *               loop=False, d^2 < r^2, at most 300 per target; :233-242), a2a_feat [S][cap_a2a][3] = |d|,
+ *               angle(head_dst, d), wrap(head_src - head_dst) with d = pos_src - pos_dst (:243-255); n_a2a [S] edges found
+ *   pl2a        CSR over polyline centres: pl2a_offset [S][P+1], pl2a_agent [S][cap_pl2a] agent rows ascending (radius,
+ *               at most 300 per polyline; :202-216), pl2a_feat [S][cap_pl2a][3] = |d|, angle(head_a, d),
+ *               wrap(head_pl - head_a) with d = pos_pl - pos_a (:217-231); n_pl2a [S]
+ * Edges beyond a capacity are counted but not stored.  The neighbour arithmetic of the reference lives in torch_cluster
+ * (not vendored): restated from its call-site contract, see lcsim_b200_obs_desc. */
+typedef struct {
+    double a2a_radius, pl2a_radius; /* 50, 50 in motion_diff/configs/config.yml */
+    int32_t time_span; /* 10 */
+    int32_t cap_a2a, cap_pl2a; /* edge capacities per scenario */
+    int32_t* agent;
+    float* x_a;
+    float* r_t;
+    uint8_t* r_t_valid;
+    int32_t* a2a_offset;
+    int32_t* a2a_src;
+    float* a2a_feat;
+    int32_t* n_a2a;
+    int32_t* pl2a_offset;
+    int32_t* pl2a_agent;
+    float* pl2a_feat;
+    int32_t* n_pl2a;
+} lcsim_b200_encoder_desc;
+int lcsim_b200_build_encoder_inputs(lcsim_b200_engine* e, const lcsim_b200_encoder_desc* d, void* stream);
+
 /* One environment step for ALL S scenarios with HOST buffers: the batched form of
  * BicycleSingleEnv.step (lcsim/envs/gym_warpper.py:78-87).  actions_host [S][2] are the normalised
  * (acc, steer) in [-1, 1] of every scenario's ADS -> BicycleAction.init_with_normalized (x6.0, x0.3;

@@ -241,6 +241,31 @@ class BatchEngine:
         self._keep = eg
         return out
 
+    def build_encoder_inputs(self, a2a_radius: float = 50.0, pl2a_radius: float = 50.0, time_span: int = 10,
+                             cap_a2a: Optional[int] = None, cap_pl2a: Optional[int] = None, with_polys: bool = True):
+        """Encoder inputs of ALL listed agents (include/lcsim_b200.h lcsim_b200_encoder_desc): x_a, temporal edges and
+        the a2a / pl2a edge lists in CSR form with the reference's relation features.  Returns a dict of device tensors
+        written by one launch."""
+        b = self.backend
+        S, Ap, H = self.S, self.A_stride, native.H_STEPS
+        cap_a2a = Ap * 32 if cap_a2a is None else int(cap_a2a)
+        P = int(getattr(self, "P", 0)) if with_polys else 0
+        cap_pl2a = max(1, P) * 16 if cap_pl2a is None else int(cap_pl2a)
+        out = dict(agent=b.empty((S, Ap), np.int32), x_a=b.empty((S, Ap, H, 6), np.float32),
+                   r_t=b.empty((S, Ap, H - 1, 4), np.float32), r_t_valid=b.empty((S, Ap, H - 1), np.uint8),
+                   a2a_offset=b.empty((S, Ap + 1), np.int32), a2a_src=b.empty((S, cap_a2a), np.int32),
+                   a2a_feat=b.empty((S, cap_a2a, 3), np.float32), n_a2a=b.empty((S,), np.int32))
+        if with_polys and P:
+            out.update(pl2a_offset=b.empty((S, P + 1), np.int32), pl2a_agent=b.empty((S, cap_pl2a), np.int32),
+                       pl2a_feat=b.empty((S, cap_pl2a, 3), np.float32), n_pl2a=b.empty((S,), np.int32))
+        d = native.EncoderDesc()
+        d.a2a_radius, d.pl2a_radius, d.time_span = float(a2a_radius), float(pl2a_radius), int(time_span)
+        d.cap_a2a, d.cap_pl2a = cap_a2a, cap_pl2a
+        for k, v in out.items():
+            setattr(d, k, b.ptr(v))
+        self._check(self.lib.lcsim_b200_build_encoder_inputs(self._h, C.byref(d), b.stream()), "build_encoder_inputs")
+        return out
+
     # ------------------------------------------------------------------ lane-centreline projection (SURVEY A15)
     def upload_centrelines(self, points):
         """points: per scenario a tuple (xy_theta (N_s,3) float32, ids (N_s,) int32) — packer.centreline_points()."""

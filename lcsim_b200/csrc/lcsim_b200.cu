@@ -1553,7 +1553,7 @@ LCS_D void lcs_rel_feature(float ex, float ey, float eh, float nx, float ny, flo
     const float rx = nx - ex, ry = ny - ey;
     f[0] = sqrtf(rx * rx + ry * ry);
     const float hx = cosf(eh), hy = sinf(eh);
-    f[1] = atan2f(hx * ry - hy * rx, hx * rx + hy * ry);
+    f[1] = atan2f(hx * ry - hy * rx, (0.0f + hx * rx) + hy * ry); // the dot is a torch .sum(): accumulated from +0
     f[2] = lcs_wrap_f32(nh - eh);
 }
 // newest history entry of agent a as the float32 tensors the reference builds (junction.py:319-325)
@@ -1638,10 +1638,11 @@ static void lcs_obs_scenario_serial(const LcsParams& p, const LcsObsArgs& o, int
 
 #ifndef LCSIM_HOSTEMU
 // One CTA per scenario.  Candidates are compacted in index order with ballot-word prefix sums; the top-k by
-// distance is a rank select over the (<= LCS_OBS_CAP) candidates held in shared memory.
+// distance is a bitonic sort (warp shuffles for the short strides) of the (<= LCS_OBS_CAP) candidates in shared memory.
 __global__ void __launch_bounds__(128) lcs_obs_kernel(const LcsParams p, const LcsObsArgs o) {
     __shared__ float c_d[LCS_OBS_CAP], c_x[LCS_OBS_CAP], c_y[LCS_OBS_CAP], c_h[LCS_OBS_CAP];
     __shared__ int c_id[LCS_OBS_CAP];
+    __shared__ unsigned long long keys[LCS_OBS_CAP];
     __shared__ uint32_t words[4];
     __shared__ int s_count;
     const int s = blockIdx.x, tid = threadIdx.x;
@@ -1688,14 +1689,43 @@ __global__ void __launch_bounds__(128) lcs_obs_kernel(const LcsParams p, const L
         }
         const int found = s_count, m = found < LCS_OBS_CAP ? found : LCS_OBS_CAP;
         if (tid == 0 && n_out) n_out[s] = found;
-        // output position of candidate c: its index (ascending order) or its rank by (distance, index)
-        for (int c = tid; c < m; c += 128) {
-            int pos = c;
-            if (o.d.sort_by_distance) {
-                pos = 0;
-                const float dc = c_d[c];
-                for (int q = 0; q < m; q++) pos += (c_d[q] < dc || (c_d[q] == dc && q < c)) ? 1 : 0;
-            }
+        // output position of candidate c: its index (ascending order), or its rank by (distance, candidate index): the
+        // k nearest come from a bitonic sort of 64-bit keys (distance bits, index) in shared memory — strides below 32
+        // stay inside a warp and are exchanged with shuffles, the longer ones go through shared memory
+        if (o.d.sort_by_distance && m > 1) {
+            int n2 = 2;
+            while (n2 < m) n2 <<= 1; // <= LCS_OBS_CAP = 1024 = 8 keys per thread
+            for (int c = tid; c < n2; c += 128)
+                keys[c] = c < m ? ((unsigned long long)__float_as_uint(c_d[c]) << 32) | (unsigned)c : ~0ull; // d2 >= 0: bits order like values
+            __syncthreads();
+            for (int k = 2; k <= n2; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    if (j >= 32 || n2 < 128 * 2) { // partner in another warp's range (or a small problem): shared memory step
+                        for (int c = tid; c < n2; c += 128) {
+                            const int q = c ^ j;
+                            if (q > c) {
+                                const unsigned long long a = keys[c], b = keys[q];
+                                const bool up = (c & k) == 0;
+                                if ((a > b) == up) { keys[c] = b; keys[q] = a; }
+                            }
+                        }
+                        __syncthreads();
+                    } else { // j < 32: element c = e * 128 + tid, its partner lives in the same warp
+                        for (int c = tid; c < n2; c += 128) {
+                            unsigned long long a = keys[c];
+                            const unsigned long long b = __shfl_xor_sync(0xffffffffu, a, j);
+                            const bool lower = (c & j) == 0, up = (c & k) == 0;
+                            const bool take_min = lower == up;
+                            a = take_min ? (a < b ? a : b) : (a > b ? a : b);
+                            keys[c] = a;
+                        }
+                        __syncthreads();
+                    }
+                }
+        }
+        for (int r = tid; r < m; r += 128) {
+            const int c = (o.d.sort_by_distance && m > 1) ? (int)(keys[r] & 0xffffffffu) : r; // candidate at output position r
+            const int pos = r;
             if (pos < cap) {
                 if (idx_out) idx_out[(size_t)s * cap + pos] = c_id[c];
                 if (feat_out) {
@@ -1755,6 +1785,32 @@ extern "C" int lcsim_b200_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_d
     LCS_CUDA(e, cudaGetLastError());
 #else
     for (int s = 0; s < e->p.S; s++) lcs_obs_scenario_serial(e->p, o, s);
+#endif
+    return 0;
+}
+
+// ---- encoder inputs for all agents: lcsim_encoder.cuh -------------------------------------------------
+#include "lcsim_encoder.cuh"
+extern "C" int lcsim_b200_build_encoder_inputs(lcsim_b200_engine* e, const lcsim_b200_encoder_desc* d, void* stream) {
+    if (!e || !d) return LCSIM_B200_ERR_ARG;
+    if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "build_encoder_inputs before upload_static");
+    LCS_GUARD(e);
+    if (d->cap_a2a < 0 || d->cap_pl2a < 0 || !(d->a2a_radius > 0) || !(d->pl2a_radius > 0) || d->time_span < 0)
+        return lcs_fail(e, LCSIM_B200_ERR_ARG, "build_encoder_inputs: capacities >= 0, radii > 0, time_span >= 0");
+    if ((d->pl2a_offset || d->pl2a_agent || d->pl2a_feat || d->n_pl2a) && !e->poly)
+        return lcs_fail(e, LCSIM_B200_ERR_STATE, "build_encoder_inputs: polyline outputs requested before upload_polylines");
+    LceArgs o;
+    o.d = *d;
+    o.r2_a2a = (float)d->a2a_radius * (float)d->a2a_radius;
+    o.r2_pl2a = (float)d->pl2a_radius * (float)d->pl2a_radius;
+    o.poly = e->poly;
+    o.n_poly = e->n_poly;
+    o.P = e->poly ? e->P : 0;
+#ifndef LCSIM_HOSTEMU
+    lce_encoder_kernel<<<e->p.S, 128, sizeof(float) * 5 * e->p.Ap, (cudaStream_t)stream>>>(e->p, o);
+    LCS_CUDA(e, cudaGetLastError());
+#else
+    for (int s = 0; s < e->p.S; s++) lce_scenario_serial(e->p, o, s);
 #endif
     return 0;
 }
@@ -1831,18 +1887,51 @@ LCS_D void lcs_lane_store_inactive(const LcsParams& p, const LcsLaneArgs& o, int
 }
 
 #ifndef LCSIM_HOSTEMU
+// mbarrier / bulk-copy primitives (sm_90+): one thread arms the barrier with the byte count and issues a 1-D
+// cp.async.bulk global -> shared; the copy engine completes the transaction on the barrier; everybody waits on the parity
+LCS_D uint32_t lcs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+LCS_D void lcs_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lcs_smem_u32(bar)), "r"(count));
+}
+LCS_D void lcs_bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lcs_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(lcs_smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(lcs_smem_u32(bar))
+                 : "memory");
+}
+LCS_D void lcs_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nLCS_WAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra LCS_WAIT_%=;\n}\n" ::"r"(lcs_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 // One CTA per scenario, thread = active-list slot; the centreline points stream through shared memory in tiles of
-// LCS_LANE_TILE (coalesced float4 loads), every thread tests its query against the tile.  The K smallest distances
-// of a query live in a shared-memory column [K][threads] (conflict-free); a point enters only when it beats the
-// column's maximum, which is tracked in registers, so the O(K) maximum search runs ~K ln(N/K) times per query.
+// LCS_LANE_TILE, every thread tests its query against the tile.  BULK: the tiles are moved by the copy engine
+// (cp.async.bulk + mbarrier, two buffers: tile i+1 lands while tile i is scanned, no thread touches the data on its
+// way in); otherwise by coalesced float4 loads and stores of the CTA (LCSIM_B200_LANE_BULK=0).  The K smallest
+// distances of a query live in a shared-memory column [K][threads] (conflict-free); a point enters only when it beats
+// the column's maximum, which is tracked in registers, so the O(K) maximum search runs ~K ln(N/K) times per query.
+template <bool BULK>
 __global__ void __launch_bounds__(128) lcs_lane_kernel(const LcsParams p, const LcsLaneArgs o) {
-    extern __shared__ __align__(16) unsigned char lane_smem[];
-    float4* tile = (float4*)lane_smem;
-    float* hd = (float*)(tile + LCS_LANE_TILE); // [K][128]
+    extern __shared__ __align__(128) unsigned char lane_smem[];
+    __shared__ __align__(8) uint64_t full[2];
+    float4* tiles = (float4*)lane_smem; // [BULK ? 2 : 1][LCS_LANE_TILE]
+    float* hd = (float*)(tiles + (BULK ? 2 : 1) * LCS_LANE_TILE); // [K][128]
     int* hi = (int*)(hd + (size_t)o.K * 128);
     const int s = blockIdx.x, tid = threadIdx.x, K = o.K;
     const int n = o.n_pts[s], na = p.n_active[s];
     const float4* P = o.pts + (size_t)s * o.N;
+    const int ntiles = (n + LCS_LANE_TILE - 1) / LCS_LANE_TILE;
+    if (BULK) {
+        if (tid == 0) {
+            lcs_mbar_init(&full[0], 1);
+            lcs_mbar_init(&full[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    unsigned used[2] = {0, 0}; // how often each buffer has been filled (parity of its barrier)
     for (int a = tid; a < p.Ap; a += 128)
         if (a < p.A && p.status[(size_t)s * p.Ap + a] != LCS_ACTIVE) lcs_lane_store_inactive(p, o, s, a);
     for (int base = 0; base < na; base += 128) {
@@ -1855,22 +1944,42 @@ __global__ void __launch_bounds__(128) lcs_lane_kernel(const LcsParams p, const 
         }
         int bi = -1, hn = 0, hmax_q = 0;
         float bd2 = lcs_inf_f(), on_d2 = lcs_inf_f(), hmax = lcs_inf_f();
-        for (int t0 = 0; t0 < n; t0 += LCS_LANE_TILE) {
-            __syncthreads();
-            for (int k = tid; k < LCS_LANE_TILE && t0 + k < n; k += 128) tile[k] = P[t0 + k];
-            __syncthreads();
-            if (a < 0) continue;
-            const int m = min(LCS_LANE_TILE, n - t0);
-            for (int k = 0; k < m; k++) {
-                const float4 c = tile[k];
-                const float d2 = lcs_lane_d2(qx, qy, c.x, c.y);
-                if (d2 < bd2) { bd2 = d2; bi = t0 + k; }
-                if (d2 < on_d2 && d2 < 25.001f) // cheap pre-test, then the reference's exact gates
-                    if (sqrtf(d2) < 5.0f && fabsf(lcs_wrap_f32(qh - c.z)) < 0.2f) on_d2 = d2;
-                if (K > 0) {
-                    if (hn < K) {
-                        hd[hn * 128 + tid] = d2; hi[hn * 128 + tid] = t0 + k; hn++;
-                        if (hn == K) { // first full column: find its maximum
+        if (BULK && tid == 0)
+            for (int it = 0; it < 2 && it < ntiles; it++)
+                lcs_bulk_load(tiles + it * LCS_LANE_TILE, P + it * LCS_LANE_TILE,
+                              16u * (unsigned)min(LCS_LANE_TILE, n - it * LCS_LANE_TILE), &full[it]);
+        for (int it = 0; it < ntiles; it++) {
+            const int t0 = it * LCS_LANE_TILE, buf = BULK ? (it & 1) : 0;
+            const float4* tile = tiles + buf * LCS_LANE_TILE;
+            if (BULK) {
+                lcs_mbar_wait(&full[buf], used[buf] & 1);
+                used[buf]++;
+            } else {
+                __syncthreads();
+                for (int k = tid; k < LCS_LANE_TILE && t0 + k < n; k += 128) tiles[k] = P[t0 + k];
+                __syncthreads();
+            }
+            if (a >= 0) {
+                const int m = min(LCS_LANE_TILE, n - t0);
+                for (int k = 0; k < m; k++) {
+                    const float4 c = tile[k];
+                    const float d2 = lcs_lane_d2(qx, qy, c.x, c.y);
+                    if (d2 < bd2) { bd2 = d2; bi = t0 + k; }
+                    if (d2 < on_d2 && d2 < 25.001f) // cheap pre-test, then the reference's exact gates
+                        if (sqrtf(d2) < 5.0f && fabsf(lcs_wrap_f32(qh - c.z)) < 0.2f) on_d2 = d2;
+                    if (K > 0) {
+                        if (hn < K) {
+                            hd[hn * 128 + tid] = d2; hi[hn * 128 + tid] = t0 + k; hn++;
+                            if (hn == K) { // first full column: find its maximum
+                                hmax_q = 0;
+                                for (int q = 1; q < K; q++) {
+                                    const float dq = hd[q * 128 + tid], dm = hd[hmax_q * 128 + tid];
+                                    if (dq > dm || (dq == dm && hi[q * 128 + tid] > hi[hmax_q * 128 + tid])) hmax_q = q;
+                                }
+                                hmax = hd[hmax_q * 128 + tid];
+                            }
+                        } else if (d2 < hmax) {
+                            hd[hmax_q * 128 + tid] = d2; hi[hmax_q * 128 + tid] = t0 + k;
                             hmax_q = 0;
                             for (int q = 1; q < K; q++) {
                                 const float dq = hd[q * 128 + tid], dm = hd[hmax_q * 128 + tid];
@@ -1878,16 +1987,14 @@ __global__ void __launch_bounds__(128) lcs_lane_kernel(const LcsParams p, const 
                             }
                             hmax = hd[hmax_q * 128 + tid];
                         }
-                    } else if (d2 < hmax) {
-                        hd[hmax_q * 128 + tid] = d2; hi[hmax_q * 128 + tid] = t0 + k;
-                        hmax_q = 0;
-                        for (int q = 1; q < K; q++) {
-                            const float dq = hd[q * 128 + tid], dm = hd[hmax_q * 128 + tid];
-                            if (dq > dm || (dq == dm && hi[q * 128 + tid] > hi[hmax_q * 128 + tid])) hmax_q = q;
-                        }
-                        hmax = hd[hmax_q * 128 + tid];
                     }
                 }
+            }
+            if (BULK) {
+                __syncthreads(); // everybody is done with this buffer: the copy engine may refill it
+                if (tid == 0 && it + 2 < ntiles)
+                    lcs_bulk_load(tiles + buf * LCS_LANE_TILE, P + (it + 2) * LCS_LANE_TILE,
+                                  16u * (unsigned)min(LCS_LANE_TILE, n - (it + 2) * LCS_LANE_TILE), &full[buf]);
             }
         }
         if (a >= 0) {
@@ -1940,9 +2047,18 @@ extern "C" int lcsim_b200_project_lanes(lcsim_b200_engine* e, const lcsim_b200_l
     o.N = e->lane_N;
     o.K = d->heading_diff ? d->top_k : 0;
 #ifndef LCSIM_HOSTEMU
-    const size_t smem = sizeof(float4) * LCS_LANE_TILE + (size_t)o.K * 128 * 8;
-    if (smem > 48 * 1024) LCS_CUDA(e, cudaFuncSetAttribute(lcs_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lcs_lane_kernel<<<e->p.S, 128, smem, (cudaStream_t)stream>>>(e->p, o);
+    static const bool bulk = []() { // LCSIM_B200_LANE_BULK=0: tiles through the CTA's own loads / stores
+        const char* env = getenv("LCSIM_B200_LANE_BULK");
+        return !(env && env[0] == '0');
+    }();
+    const size_t smem = sizeof(float4) * LCS_LANE_TILE * (bulk ? 2 : 1) + (size_t)o.K * 128 * 8;
+    if (bulk) {
+        if (smem > 48 * 1024) LCS_CUDA(e, cudaFuncSetAttribute(lcs_lane_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lcs_lane_kernel<true><<<e->p.S, 128, smem, (cudaStream_t)stream>>>(e->p, o);
+    } else {
+        if (smem > 48 * 1024) LCS_CUDA(e, cudaFuncSetAttribute(lcs_lane_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lcs_lane_kernel<false><<<e->p.S, 128, smem, (cudaStream_t)stream>>>(e->p, o);
+    }
     LCS_CUDA(e, cudaGetLastError());
 #else
     const LcsParams& p = e->p;

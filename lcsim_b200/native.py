@@ -19,6 +19,7 @@ ROOT = os.path.dirname(_HERE)
 SRC = os.path.join(_HERE, "csrc", "lcsim_b200.cu")
 HDRS = [os.path.join(_HERE, "csrc", "lcsim_core.cuh"), os.path.join(_HERE, "csrc", "lcsim_city.cuh"),
         os.path.join(_HERE, "csrc", "lcsim_plan.cuh"), os.path.join(_HERE, "csrc", "lcsim_loader.hpp"),
+        os.path.join(_HERE, "csrc", "lcsim_encoder.cuh"),
         os.path.join(ROOT, "include", "lcsim_b200.h")]
 LIB_PATH = os.path.join(_HERE, "liblcsim_b200.so")
 
@@ -103,6 +104,13 @@ class ObsDesc(C.Structure):
                 ("n_nbr_poly", C.c_void_p), ("history", C.c_void_p), ("history_agent", C.c_void_p)]
 
 
+class EncoderDesc(C.Structure):
+    _fields_ = [("a2a_radius", C.c_double), ("pl2a_radius", C.c_double), ("time_span", C.c_int32), ("cap_a2a", C.c_int32),
+                ("cap_pl2a", C.c_int32)] + [(n, C.c_void_p) for n in (
+                    "agent", "x_a", "r_t", "r_t_valid", "a2a_offset", "a2a_src", "a2a_feat", "n_a2a", "pl2a_offset", "pl2a_agent",
+                    "pl2a_feat", "n_pl2a")]
+
+
 class RolloutOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("tick_log", "pose32", "status", "coll_count", "nearest_edge", "offroad", "stats")]
 
@@ -141,7 +149,7 @@ class CityViews(C.Structure):
 
 EXPORTS = ("lcsim_b200_abi_version", "lcsim_b200_create", "lcsim_b200_upload_static", "lcsim_b200_reset",
            "lcsim_b200_step", "lcsim_b200_step_masked", "lcsim_b200_rollout", "lcsim_b200_rollout_log", "lcsim_b200_rollout_host", "lcsim_b200_set_ref_trajectory", "lcsim_b200_rewards",
-           "lcsim_b200_env_step", "lcsim_b200_upload_polylines", "lcsim_b200_build_obs",
+           "lcsim_b200_env_step", "lcsim_b200_upload_polylines", "lcsim_b200_build_obs", "lcsim_b200_build_encoder_inputs",
            "lcsim_b200_upload_centrelines", "lcsim_b200_project_lanes", "lcsim_b200_guidance_cost",
            "lcsim_b200_plan_metrics", "lcsim_b200_load_dirs", "lcsim_b200_scenarios_dims", "lcsim_b200_scenarios_static",
            "lcsim_b200_scenarios_agent_id", "lcsim_b200_scenarios_junction_id", "lcsim_b200_scenarios_polylines",
@@ -172,6 +180,7 @@ def bind(path: str) -> C.CDLL:
     lib.lcsim_b200_env_step.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.lcsim_b200_upload_polylines.argtypes = [vp, vp, vp, i32]
     lib.lcsim_b200_build_obs.argtypes = [vp, C.POINTER(ObsDesc), vp]
+    lib.lcsim_b200_build_encoder_inputs.argtypes = [vp, C.POINTER(EncoderDesc), vp]
     lib.lcsim_b200_upload_centrelines.argtypes = [vp, vp, vp, vp, i32]
     lib.lcsim_b200_project_lanes.argtypes = [vp, C.POINTER(LaneDesc), vp]
     lib.lcsim_b200_guidance_cost.argtypes = [vp, i32, vp, i32, C.c_float, C.c_float, vp, vp, vp, vp]

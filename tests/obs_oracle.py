@@ -20,7 +20,7 @@ def rel_feature(ex, ey, eh, nx, ny, nh):
     rx, ry = (nx - ex).astype(F), (ny - ey).astype(F)
     dist = np.sqrt(rx * rx + ry * ry).astype(F)
     hx, hy = np.cos(eh).astype(F), np.sin(eh).astype(F)
-    ang = np.arctan2(hx * ry - hy * rx, hx * rx + hy * ry).astype(F)
+    ang = np.arctan2(hx * ry - hy * rx, (F(0) + hx * rx) + hy * ry).astype(F)  # torch .sum() accumulates from +0
     return np.stack([dist, ang, wrap_f32((nh - eh).astype(F))], axis=-1)
 
 
