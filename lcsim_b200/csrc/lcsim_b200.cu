@@ -57,16 +57,21 @@ struct alignas(16) float4 { float x, y, z, w; };
 // ------------------------------------------------------------------------------------ kernels
 
 // ---- the engine kernel ------------------------------------------------------------------------------------------
-// A launch covers n_ticks ticks of all S scenarios as a queue of work items, processed by a grid of persistent CTAs
-// (one thread per active-list slot):
+// A launch covers n_ticks ticks of all S scenarios as work items, one CTA per item (one thread per active-list slot):
 //   tick item   T(k, s): Engine.step for scenario s (engine.py:145-158: update -> check_departure_and_arrival ->
 //                        prepare_obs -> clock); leaves a snapshot of the new list in ring slot k % D
 //   metric item M(k, s): check_collision_all / check_offroads of that snapshot (manager.py:313-345); nothing a later
 //                        tick reads, so it is off the scenario's serial chain and runs whenever a CTA is free
-// Ticket order: T(0, 0..S-1), M(0, 0..S-1), T(1, ...), ...  T(k, s) needs T(k-1, s) and M(k-D, s) (its ring slot is
-// free again), M(k, s) needs T(k, s) and M(k-1, s): always SMALLER tickets.  Tickets are claimed by running CTAs (atomic counter),
-// so the item a CTA waits for was claimed by a CTA that already runs — forward progress holds for any grid size, with
-// or without other work on the GPU; nothing depends on the order in which the hardware dispatches blocks.
+// Dependencies: T(k, s) needs T(k-1, s) and M(k-D, s) (its ring slot is free again); M(k, s) needs T(k, s) and
+// M(k-1, s) (metric items of a scenario update the same per-agent outputs, and an agent that did not move keeps the
+// flag its previous metric item stored).
+// Scheduling is a READY QUEUE in device memory.  The CTA that completes an item updates the scenario's progress word
+// (items done / issued, one 64-bit compare-and-swap) and pushes the items that became runnable; a starting CTA pops the
+// next entry (one atomic counter; entry i is pushed exactly once and popped exactly once: #CTAs = #items) and waits
+// only if that entry has not been pushed yet, i.e. when fewer items are runnable than CTAs are resident.  An item is
+// pushed only when everything it depends on is complete, so a CTA that holds an item never waits for another CTA:
+// forward progress does not depend on the order in which the hardware dispatches blocks, on the grid fitting the
+// device, or on what else runs on the GPU; slots are never held by work that cannot proceed.
 #define LCS_TICK_PHASES(SYNC, FOR_T)                                                \
     FOR_T lcs_phase_update(p, sm, s, tid, TH);                                      \
     SYNC;                                                                           \
@@ -96,13 +101,54 @@ struct alignas(16) float4 { float x, y, z, w; };
     FOR_T { lcs_mc_stats(p, sm, s, tid, TH); lcs_me_stats(p, s, tid, sm.misc + 12, TH); }
 
 #ifndef LCSIM_HOSTEMU
-// waits until scenario's pair of counters (tick items done, metric items done) reached (want_t, want_m): one 8-byte load per poll
-LCS_D void lcs_wait_seq(const int32_t* pair, int want_t, int want_m) {
-    int vt, vm;
+// progress word of a scenario: four 16-bit counters
+//   bits  0-15  tick items done      bits 16-31  metric items done
+//   bits 32-47  tick items issued beyond T(0, s) (which the launch itself issues)      bits 48-63  metric items issued
+LCS_D unsigned long long lcs_atom_cas_acq_rel(unsigned long long* addr, unsigned long long cmp, unsigned long long val) {
+    unsigned long long old;
+    asm volatile("atom.acq_rel.gpu.global.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "l"(addr), "l"(cmp), "l"(val) : "memory");
+    return old;
+}
+// pops this CTA's item: entries 0 .. S-1 are the launch's own T(0, s); the others are awaited (acquire)
+LCS_D int lcs_queue_pop(const LcsParams& p) {
+    const int my = atomicAdd(p.q_head, 1);
+    if (my < p.S) return my;
+    int v;
     for (;;) {
-        asm volatile("ld.relaxed.gpu.global.v2.s32 {%0, %1}, [%2];" : "=r"(vt), "=r"(vm) : "l"(pair) : "memory");
-        if (vt >= want_t && vm >= want_m) break;
-        __nanosleep(100);
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.q_items + my) : "memory");
+        if (v >= 0) return v;
+        __nanosleep(64);
+    }
+}
+LCS_D void lcs_queue_push(const LcsParams& p, int item) {
+    const int at = p.S + atomicAdd(p.q_tail, 1); // (the first S entries are the launch's own items)
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.q_items + at), "r"(item) : "memory");
+}
+// called by one thread after the CTA's barrier: records the completion and pushes what became runnable
+LCS_D void lcs_queue_complete(const LcsParams& p, int s, bool metric) {
+    unsigned long long* w = p.q_state + s;
+    const unsigned D = (unsigned)p.snap_depth, n = (unsigned)p.n_ticks;
+    unsigned long long old = *(volatile unsigned long long*)w;
+    for (;;) {
+        unsigned td = (unsigned)(old & 0xffff), md = (unsigned)((old >> 16) & 0xffff);
+        unsigned ti = (unsigned)((old >> 32) & 0xffff) + 1, mi = (unsigned)((old >> 48) & 0xffff); // T(0, s) counts as issued
+        if (metric) md++; else td++;
+        // the next tick item: its predecessor is done and its snapshot slot is free again (metric item ti - D done)
+        const bool can_t = ti == td && ti < n && (!p.with_metrics || ti < md + D);
+        // the next metric item: its predecessor is done and its tick item is done
+        const bool can_m = p.with_metrics && mi == md && mi < td;
+        const unsigned long long nw = (unsigned long long)td | ((unsigned long long)md << 16) |
+                                      ((unsigned long long)(ti - 1 + (can_t ? 1 : 0)) << 32) | ((unsigned long long)(mi + (can_m ? 1 : 0)) << 48);
+        // acq_rel: this CTA's stores are published with the counter, and whatever the other completers of this
+        // scenario published before is visible here — and, through the release store of the push, to the popper
+        const unsigned long long seen = lcs_atom_cas_acq_rel(w, old, nw);
+        if (seen == old) {
+            const int per_tick = p.with_metrics ? 2 * p.S : p.S;
+            if (can_t) lcs_queue_push(p, (int)ti * per_tick + s); // the tick item first: it is the scenario's serial chain
+            if (can_m) lcs_queue_push(p, (int)mi * per_tick + p.S + s);
+            return;
+        }
+        old = seen;
     }
 }
 
@@ -199,39 +245,28 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
     extern __shared__ __align__(128) unsigned char lcs_smem_raw[];
     __shared__ int s_item;
     const int tid = threadIdx.x;
-    const int per_tick = p.with_metrics ? 2 * p.S : p.S, D = p.snap_depth;
-    // one item per CTA; the ticket is claimed when the CTA RUNS (not blockIdx): see the forward-progress argument above
-    if (tid == 0) s_item = atomicAdd(p.q_ticket, 1);
+    const int per_tick = p.with_metrics ? 2 * p.S : p.S;
+    long long t_wait = 0;
+    if (CLK && tid == 0) t_wait = clock64();
+    if (tid == 0) {
+        s_item = lcs_queue_pop(p);
+        // one acquire fence (it also drops this SM's stale L1 lines); the barrier hands the data to the whole CTA
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
     __syncthreads();
     const int item = s_item;
     const int k = item / per_tick, r = item - k * per_tick;
     const bool metric = r >= p.S;
     const int s = metric ? r - p.S : r;
-    long long t_wait = 0;
-    if (CLK && tid == 0) t_wait = clock64();
-    if (tid == 0) {
-        // the scenario's previous items (claimed earlier, hence running or done): wait for their release, then one
-        // acquire fence (it also drops this SM's stale L1 lines); the barrier hands the data to the whole CTA
-        // (metric items of a scenario run in order: they update the same per-agent outputs, and an agent that did not
-        // move keeps the flag its previous metric item stored)
-        if (!metric) {
-            if (k > 0) lcs_wait_seq(p.q_seq + 2 * s, k, p.with_metrics ? k - D + 1 : 0);
-        } else {
-            lcs_wait_seq(p.q_seq + 2 * s, k + 1, k);
-        }
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        if (CLK) p.dbg[(size_t)s * 16 + (metric ? 15 : 7)] = clock64() - t_wait; // cycles spent waiting for the dependencies
-    }
-    __syncthreads();
-    if (!(p.reset_mask && !p.reset_mask[s])) { // a masked-out scenario: nothing to do, but its items still count as done
+    if (CLK && tid == 0) p.dbg[(size_t)s * 16 + (metric ? 15 : 7)] = clock64() - t_wait; // cycles until the item was in hand
+    if (!(p.reset_mask && !p.reset_mask[s])) { // a masked-out scenario: nothing to do, but its items still complete
         if (!metric)
             lcs_item_tick<MAXT, CLK>(p, lcs_smem_raw, s, k);
         else
             lcs_item_metric<MAXT, CLK>(p, lcs_smem_raw, s, k);
     }
-    __syncthreads(); // every thread's stores precede the release (cumulativity through the barrier)
-    if (tid == 0)
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.q_seq + 2 * s + (metric ? 1 : 0)), "r"(k + 1) : "memory");
+    __syncthreads(); // every thread's stores precede the completion (cumulativity through the barrier)
+    if (tid == 0) lcs_queue_complete(p, s, metric);
 }
 #endif
 
@@ -243,7 +278,9 @@ static void lcs_launch(const LcsParams& p, int grid_cap, cudaStream_t stream) {
     const long long total = (long long)p.n_ticks * (p.with_metrics ? 2 : 1) * p.S;
     const int nblk = (int)total; // one CTA per item (n_ticks * 2 * S <= 2^31 - 1 is checked by the callers)
     (void)grid_cap;
-    cudaMemsetAsync(p.q_ticket, 0, sizeof(int32_t) * (2 + 2 * (size_t)p.S), stream); // ticket and the counter pairs are one block
+    // queue state of this launch: pop / push counters and progress words zero (one block), entries empty
+    cudaMemsetAsync(p.q_head, 0, 8 + sizeof(unsigned long long) * (size_t)p.S, stream);
+    cudaMemsetAsync(p.q_items, 0xFF, sizeof(int32_t) * (size_t)total, stream);
     if (p.dbg && Ap == 128 && p.mode == 0)
         lcs_engine_kernel<128, true><<<nblk, Ap, smem, stream>>>(p);
     else if (Ap <= 128)
@@ -596,6 +633,7 @@ struct lcsim_b200_engine {
     float* plan_sum = nullptr; // [S][plan_parts] partial sums of the guidance / metric kernels
     int32_t* plan_cnt = nullptr;
     int plan_parts = 0;
+    size_t q_cap = 0; // entries of p.q_items
     int device = 0;
     int grid_cap = 1; // CTAs of the engine kernel the device holds at once (occupancy x SMs)
     std::string err;
@@ -776,8 +814,11 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     LCS_ALLOC(e, p.grid_dim, S * 2);
     LCS_ALLOC(e, p.ge_xy, SE);
     LCS_ALLOC(e, p.ge_idx, SE);
-    LCS_ALLOC(e, p.q_ticket, 2 + 2 * S);
-    p.q_seq = p.q_ticket + 2; // 8-byte aligned pairs
+    LCS_ALLOC(e, p.q_head, 2 + 2 * S); // head, tail, then the S 64-bit progress words (one block: one memset per launch)
+    p.q_tail = p.q_head + 1;
+    p.q_state = (unsigned long long*)(p.q_head + 2);
+    e->q_cap = 2 * S * 128; // grown by lcs_launch_ticks when a longer launch asks for it
+    LCS_ALLOC(e, p.q_items, e->q_cap);
     if (p.with_metrics) {
         const size_t D = p.snap_depth;
         LCS_ALLOC(e, p.snap_hdr, D * S * 4);
@@ -1328,10 +1369,25 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     return 0;
 }
 
-static void lcs_launch_ticks(lcsim_b200_engine* e, LcsParams& q, int n_ticks, cudaStream_t st) {
-    q.n_ticks = n_ticks;
-    lcs_launch(q, e->grid_cap, st);
-    e->launches += 1;
+// launches of at most LCS_MAX_TICKS_PER_LAUNCH ticks (16-bit progress counters, bounded queue)
+#define LCS_MAX_TICKS_PER_LAUNCH 4096
+static int lcs_launch_ticks(lcsim_b200_engine* e, LcsParams& q, int n_ticks, cudaStream_t st, int log_base = 0) {
+    for (int done = 0; done < n_ticks;) {
+        const int n = std::min(n_ticks - done, LCS_MAX_TICKS_PER_LAUNCH);
+        const size_t need = (size_t)n * (q.with_metrics ? 2 : 1) * q.S;
+        if (need > e->q_cap) {
+            lcs_release(e, e->p.q_items);
+            LCS_ALLOC(e, e->p.q_items, need);
+            e->q_cap = need;
+        }
+        q.q_items = e->p.q_items;
+        q.n_ticks = n;
+        q.log_base = log_base + done;
+        lcs_launch(q, e->grid_cap, st);
+        e->launches += 1;
+        done += n;
+    }
+    return 0;
 }
 
 extern "C" int lcsim_b200_reset(lcsim_b200_engine* e, const uint8_t* reset_mask, void* stream) {
@@ -1388,9 +1444,10 @@ static int lcs_rollout(lcsim_b200_engine* e, int n_ticks, bool want_log, int32_t
     q.tick_log = want_log ? e->tick_log : nullptr;
     cudaStream_t us = (cudaStream_t)stream;
     if (q.dbg) { // phase clocks: one tick per launch, so that the stamps are those of the last tick
-        for (int k = 0; k < n_ticks; k++) lcs_launch_ticks(e, q, 1, us);
+        for (int k = 0; k < n_ticks; k++) lcs_launch_ticks(e, q, 1, us, k);
     } else {
-        lcs_launch_ticks(e, q, n_ticks, us);
+        int rc = lcs_launch_ticks(e, q, n_ticks, us);
+        if (rc) return rc;
     }
     LCS_CUDA(e, cudaGetLastError());
     if (log_out)
@@ -1906,12 +1963,32 @@ LCS_D void lcs_mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// sift-down of entry r in the max-heap of column `tid` ([K][128] layout), ordered by (distance, index)
+LCS_D void lcs_heap_sift(float* hd, int* hi, int tid, int K, int r) {
+    const float d = hd[r * 128 + tid];
+    const int ix = hi[r * 128 + tid];
+    for (;;) {
+        int c = 2 * r + 1;
+        if (c >= K) break;
+        float dc = hd[c * 128 + tid];
+        int ic = hi[c * 128 + tid];
+        if (c + 1 < K) {
+            const float d2 = hd[(c + 1) * 128 + tid];
+            const int i2 = hi[(c + 1) * 128 + tid];
+            if (d2 > dc || (d2 == dc && i2 > ic)) { c++; dc = d2; ic = i2; }
+        }
+        if (!(dc > d || (dc == d && ic > ix))) break;
+        hd[r * 128 + tid] = dc; hi[r * 128 + tid] = ic;
+        r = c;
+    }
+    hd[r * 128 + tid] = d; hi[r * 128 + tid] = ix;
+}
+
 // One CTA per scenario, thread = active-list slot; the centreline points stream through shared memory in tiles of
 // LCS_LANE_TILE, every thread tests its query against the tile.  BULK: the tiles are moved by the copy engine
 // (cp.async.bulk + mbarrier, two buffers: tile i+1 lands while tile i is scanned, no thread touches the data on its
 // way in); otherwise by coalesced float4 loads and stores of the CTA (LCSIM_B200_LANE_BULK=0).  The K smallest
-// distances of a query live in a shared-memory column [K][threads] (conflict-free); a point enters only when it beats
-// the column's maximum, which is tracked in registers, so the O(K) maximum search runs ~K ln(N/K) times per query.
+// distances of a query live in a shared-memory column [K][threads] (conflict-free) organised as a max-heap.
 template <bool BULK>
 __global__ void __launch_bounds__(128) lcs_lane_kernel(const LcsParams p, const LcsLaneArgs o) {
     extern __shared__ __align__(128) unsigned char lane_smem[];
@@ -1942,7 +2019,7 @@ __global__ void __launch_bounds__(128) lcs_lane_kernel(const LcsParams p, const 
             const double* ps = p.pose64 + 4 * ((size_t)s * p.Ap + a);
             qx = (float)ps[0]; qy = (float)ps[1]; qh = (float)ps[2];
         }
-        int bi = -1, hn = 0, hmax_q = 0;
+        int bi = -1, hn = 0;
         float bd2 = lcs_inf_f(), on_d2 = lcs_inf_f(), hmax = lcs_inf_f();
         if (BULK && tid == 0)
             for (int it = 0; it < 2 && it < ntiles; it++)
@@ -1968,24 +2045,19 @@ __global__ void __launch_bounds__(128) lcs_lane_kernel(const LcsParams p, const 
                     if (d2 < on_d2 && d2 < 25.001f) // cheap pre-test, then the reference's exact gates
                         if (sqrtf(d2) < 5.0f && fabsf(lcs_wrap_f32(qh - c.z)) < 0.2f) on_d2 = d2;
                     if (K > 0) {
+                        // the K smallest (distance, index) pairs as a binary MAX-heap in the thread's shared-memory column:
+                        // a point enters only when it beats the root, and then costs one sift-down (log2 K levels) — points
+                        // along a lane that approaches the query beat the current maximum one after the other
                         if (hn < K) {
                             hd[hn * 128 + tid] = d2; hi[hn * 128 + tid] = t0 + k; hn++;
-                            if (hn == K) { // first full column: find its maximum
-                                hmax_q = 0;
-                                for (int q = 1; q < K; q++) {
-                                    const float dq = hd[q * 128 + tid], dm = hd[hmax_q * 128 + tid];
-                                    if (dq > dm || (dq == dm && hi[q * 128 + tid] > hi[hmax_q * 128 + tid])) hmax_q = q;
-                                }
-                                hmax = hd[hmax_q * 128 + tid];
+                            if (hn == K) { // first full column: heapify
+                                for (int r0 = K / 2 - 1; r0 >= 0; r0--) lcs_heap_sift(hd, hi, tid, K, r0);
+                                hmax = hd[tid];
                             }
                         } else if (d2 < hmax) {
-                            hd[hmax_q * 128 + tid] = d2; hi[hmax_q * 128 + tid] = t0 + k;
-                            hmax_q = 0;
-                            for (int q = 1; q < K; q++) {
-                                const float dq = hd[q * 128 + tid], dm = hd[hmax_q * 128 + tid];
-                                if (dq > dm || (dq == dm && hi[q * 128 + tid] > hi[hmax_q * 128 + tid])) hmax_q = q;
-                            }
-                            hmax = hd[hmax_q * 128 + tid];
+                            hd[tid] = d2; hi[tid] = t0 + k;
+                            lcs_heap_sift(hd, hi, tid, K, 0);
+                            hmax = hd[tid];
                         }
                     }
                 }

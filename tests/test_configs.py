@@ -1,7 +1,8 @@
 """BASELINE.json configs[2] and configs[4] as parity cases (configs[0]/[1]: test_parity.py, configs[3]: test_city.py).
 
 configs[2] "RL env rollout: parallel waymo_ppo envs with observation + reward build": every scenario is one
-BicycleSingleEnv (lcsim/envs/gym_warpper.py:60-92, config lcsim/config/waymo_ppo.yml: reactive, total 90); each tick a
+BicycleSingleEnv (lcsim/envs/gym_warpper.py:60-92, config experiments/rl/configs/waymo_ppo.yml:10-41: reactive False,
+total 90; the reactive variant is run too); each tick a
 policy action per env goes in through lcsim_b200_env_step, reward terms / flags / route come back, the neighbour
 gather feeds the observation.  configs[4] "diffusion-controlled rollout": every plan_interval ticks the dynamic agents
 of every scenario receive new float32 (80, .) reference trajectories (Engine._plan_trajectory, engine.py:286-297 —
@@ -14,7 +15,7 @@ from lcsim_b200.batch import BatchEngine
 from oracle import oracle as orc
 from parity_util import compare_engine_with_oracle
 
-WAYMO_PPO_REWARD = {"forward": 2, "collision": 10, "offroad": 5, "smooth": 1, "destination": 1}  # waymo_ppo.yml:36-41
+WAYMO_PPO_REWARD = {"forward": 0.1, "collision": 10, "offroad": 5, "smooth": 2, "destination": 1}  # waymo_ppo.yml:36-41
 
 
 @pytest.fixture(scope="module", params=["hostemu", pytest.param("cuda", marks=pytest.mark.gpu)])
@@ -26,11 +27,12 @@ def backend(request):
     return NumpyEmuBackend()
 
 
-def test_rl_env_rollout_matches_oracle(backend):
+@pytest.mark.parametrize("reactive", [False, True])
+def test_rl_env_rollout_matches_oracle(backend, reactive):
     S = 6
-    sb = workload.synthetic_batch(400, S, 128, workers=1)
-    be = BatchEngine(sb, reactive=True, with_metrics=True, backend=backend)
-    o = orc.Oracle(sb, reactive=True)
+    sb = workload.synthetic_batch(400, S, 128, workers=1, total_steps=90)
+    be = BatchEngine(sb, reactive=reactive, with_metrics=True, backend=backend)
+    o = orc.Oracle(sb, reactive=reactive)
     rng = np.random.default_rng(3)
     out = np.zeros(S, native.ENV_OUT_DTYPE)
     ads = sb.ads_index

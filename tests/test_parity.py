@@ -68,13 +68,14 @@ def test_synthetic_batch_matches_oracle_every_tick(backend, synth8, reactive):
     be.close()
 
 
-@pytest.mark.parametrize("fused", ["0", "1"])
+@pytest.mark.parametrize("depth", ["1", "2", "4"])
 @pytest.mark.parametrize("reactive", [False, True])
-def test_fused_rollout_matches_oracle(backend, synth8, reactive, fused, monkeypatch):
-    """lcsim_b200_rollout_log: all ticks of a scenario in one launch.  The end state equals the oracle's after the
-    same number of steps, the per-tick log equals the oracle's per-tick sums, and a rollout split into uneven
-    chunks (1 + 17 + 73 ticks: per-tick kernel, then two fused launches) lands on bit-identical state."""
-    monkeypatch.setenv("LCSIM_B200_FUSED", fused)  # read by lcsim_b200_create: force the fused / per-tick form
+def test_rollout_launch_matches_oracle(backend, synth8, reactive, depth, monkeypatch):
+    """lcsim_b200_rollout_log: all ticks of all scenarios in ONE launch (tick items and metric items of a run-time ticket
+    queue, metric items lagging behind over a snapshot ring of the given depth).  The end state equals the oracle's
+    after the same number of steps, the per-tick log equals the oracle's per-tick sums, and a rollout split into
+    uneven chunks (1 + 17 + 73 ticks) lands on bit-identical state."""
+    monkeypatch.setenv("LCSIM_B200_SNAP_DEPTH", depth)  # read by lcsim_b200_create
     sb = synth8
     o = orc.Oracle(sb, reactive=reactive)
     want = np.zeros((91, sb.S, 4), np.int64)
