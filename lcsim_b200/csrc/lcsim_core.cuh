@@ -190,11 +190,11 @@ struct LcsParams {
     double* snap_rec; // [D][S][Ap][6] x, y, cos h, sin h, length, width of that agent
     int32_t* snap_fin; // [D][S][Ap] agents that left the list in this tick (dense)
     int32_t snap_depth; // D
-    // ---- ready queue of the engine kernel (lcsim_b200.cu): items are pushed when everything they depend on is complete
-    int32_t *q_head, *q_tail; // pop / push counters
-    int32_t* q_items; // [n_ticks * items per tick] entry i: the i-th pushed item, -1 until then
-    unsigned long long* q_state; // [S] progress word of every scenario (items done / issued)
-    int32_t log_base; // tick_log row of this launch's first tick (a long rollout is several launches)
+    // ---- work queue of the engine kernel: tickets are claimed at run time, in an order in which every item depends
+    // only on items with smaller tickets (tick k of scenario s on its tick k-1 and on the metric item of tick k-D;
+    // the metric item on its tick item) -> a running CTA can only wait for work that is already running or done
+    int32_t* q_ticket; // [1] next ticket
+    int32_t* q_seq; // [S][2] tick items / metric items of this launch completed for the scenario
     int32_t n_ticks; // ticks of this launch
     // ---- launch mode
     long long* dbg; // [S][16] phase clocks (instrumented instantiation of the tick kernel only)
@@ -1348,7 +1348,7 @@ LCS_D void lcs_phase_depart_fill(const LcsParams& p, LcsSmem& sm, int s, int tid
             st[6] += 1;
             p.tick[s] = sm.misc[4] + 1;
             if (p.tick_log) {
-                int32_t* lg = p.tick_log + ((size_t)(p.log_base + t.k) * p.S + s) * 4;
+                int32_t* lg = p.tick_log + ((size_t)t.k * p.S + s) * 4;
                 lg[0] = n;
                 lg[1] = n_new;
                 if (!p.with_metrics) lg[2] = lg[3] = 0;
@@ -1657,7 +1657,7 @@ LCS_D void lcs_mc_out(const LcsParams& p, LcsSmem& sm, int s, int tid, int a) {
 LCS_D void lcs_mc_stats(const LcsParams& p, LcsSmem& sm, int s, int tid, const LcsThread& t) {
     if (tid == 0 && p.mode == 0) {
         p.stats[(size_t)s * LCS_NSTAT + 2] += sm.misc[2];
-        if (p.tick_log) p.tick_log[((size_t)(p.log_base + t.k) * p.S + s) * 4 + 2] = sm.misc[2];
+        if (p.tick_log) p.tick_log[((size_t)t.k * p.S + s) * 4 + 2] = sm.misc[2];
     }
 }
 
@@ -1702,6 +1702,6 @@ LCS_D void lcs_me_search(const LcsParams& p, int s, int tid, const uint32_t* wor
 LCS_D void lcs_me_stats(const LcsParams& p, int s, int tid, const int32_t* cnt, const LcsThread& t) {
     if (tid == 0 && p.mode == 0) {
         p.stats[(size_t)s * LCS_NSTAT + 3] += cnt[1];
-        if (p.tick_log) p.tick_log[((size_t)(p.log_base + t.k) * p.S + s) * 4 + 3] = cnt[1];
+        if (p.tick_log) p.tick_log[((size_t)t.k * p.S + s) * 4 + 3] = cnt[1];
     }
 }
