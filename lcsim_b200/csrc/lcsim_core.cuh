@@ -692,17 +692,30 @@ LCS_D int lcs_nearest_edge(const LcsParams& p, int s, double qx, double qy, bool
 // point is no farther than U(C), so K(C) contains every point that can attain (or tie within the filter's error band)
 // the minimum.  The search is one header load and a contiguous run of 32-byte blocks, four in flight; the float32
 // filter / float64 tie-break logic is the one of the other searches.  Returns -2 when the query lies outside the grid.
-LCS_D int lcs_nearest_edge_cell(const LcsParams& p, int s, double qx, double qy, bool* offroad) {
+// begin: the cell's span in the scenario's list run (b, e); status -2 = no list for this query
+struct LcsCellQ {
+    float fqx, fqy;
+    int b, e; // e < 0: not available
+};
+LCS_D void lcs_edge_cell_begin(const LcsParams& p, int s, double qx, double qy, LcsCellQ& q) {
+    q.b = 0;
+    q.e = -1;
     const int W = p.cl_dim[2 * s], H = p.cl_dim[2 * s + 1];
-    if (W <= 0) return -2;
-    const float fqx = (float)(qx - p.origin[2 * s]), fqy = (float)(qy - p.origin[2 * s + 1]);
+    q.fqx = (float)(qx - p.origin[2 * s]);
+    q.fqy = (float)(qy - p.origin[2 * s + 1]);
+    if (W <= 0) return;
     const float gx0 = p.cl_geom[4 * s], gy0 = p.cl_geom[4 * s + 1], inv = p.cl_geom[4 * s + 2];
-    const float fx = floorf((fqx - gx0) * inv), fy = floorf((fqy - gy0) * inv);
-    if (!(fx >= 0.0f && fy >= 0.0f && fx < (float)W && fy < (float)H)) return -2;
+    const float fx = floorf((q.fqx - gx0) * inv), fy = floorf((q.fqy - gy0) * inv);
+    if (!(fx >= 0.0f && fy >= 0.0f && fx < (float)W && fy < (float)H)) return;
     const int cell = (int)fy * W + (int)fx;
     const int32_t* cs = p.cl_start + (size_t)s * (p.cl_nc + 1);
-    const int b = cs[cell], e = cs[cell + 1];
-    if (e <= b) return -2; // no edge point at all in this scenario
+    q.b = cs[cell];
+    q.e = cs[cell + 1];
+}
+LCS_D int lcs_edge_cell_finish(const LcsParams& p, int s, double qx, double qy, const LcsCellQ& q, bool* offroad) {
+    const float fqx = q.fqx, fqy = q.fqy;
+    const int b = q.b, e = q.e;
+    if (e <= b) return -2; // outside the grid, or no edge point at all in this scenario
     const size_t base = (size_t)p.cl_base[s];
     const lcs_f2* gp = p.cl_xy + base;
     float m = lcs_inf_f(), m2 = lcs_inf_f();
@@ -741,6 +754,12 @@ LCS_D int lcs_nearest_edge_cell(const LcsParams& p, int s, double qx, double qy,
     }
     *offroad = lcs_edge_side(p, s, qx, qy, best);
     return best;
+}
+
+LCS_D int lcs_nearest_edge_cell(const LcsParams& p, int s, double qx, double qy, bool* offroad) {
+    LcsCellQ q;
+    lcs_edge_cell_begin(p, s, qx, qy, q);
+    return lcs_edge_cell_finish(p, s, qx, qy, q, offroad);
 }
 
 // Nearest edge point with a HINT: `hint` is the original index of some edge point (the agent's nearest point of
@@ -1429,6 +1448,35 @@ LCS_D void lcs_push_pair(LcsSmem& sm, int cap, int i, int j, bool* overflow) {
 // it must be certainly in and its error interval must lie below every other possible partner's.  Otherwise
 // (rare: ties, partners on the edge of the corridor) the thread falls back to the float64 evaluation of every partner
 // of the list, in list order with the reference's strict <.
+#define LCS_LEAD_LIST 16 // private survivor list per thread (uint16 entries in the pair-queue area)
+// full float32 classification of partner slot j for ego slot tid: certainly out / possible (interval [d - e, d + e] of its
+// true distance, `sure` when certainly in); keeps the partner with the smallest upper end and the smallest lower end
+// among the others
+LCS_D void lcs_lead_classify(const LcsSmem& sm, int tid, int j, const lcs_f4 me, float c32, float s32, float hl, float hw, float& h1,
+                             float& l1, float& lo2, int& j1, bool& sure1) {
+    const lcs_f4 ot = sm.crec[j];
+    const float dx = ot.x - me.x, dy = ot.y - me.y;
+    const float rxx = dx * c32 + dy * s32, ryy = dy * c32 - dx * s32;
+    // error of rx, ry and of the corner extents: coordinate rounding (slack) + float32 trig / arithmetic
+    const float e = ot.w + me.w + 3e-6f * (fabsf(dx) + fabsf(dy)) + 2e-5f;
+    // every corner lies within the other's half diagonal (ot.z) of its centre; a partner whose interval lies above both
+    // h1 and lo2 changes neither
+    if (fabsf(ryy) > hw + ot.z + e || rxx < hl - e || rxx - ot.z - hl - e > fmaxf(h1, lo2)) return;
+    const lcs_f4 o2 = sm.crec2[j];
+    const float cr = o2.x * c32 + o2.y * s32, sr = o2.y * c32 - o2.x * s32; // cos / sin of the relative heading
+    const float ex = fabsf(o2.z * cr) + fabsf(o2.w * sr), ey = fabsf(o2.z * sr) + fabsf(o2.w * cr);
+    const float xmin = rxx - ex, ymax = ryy + ey, ymin = ryy - ey;
+    if (ymax < -hw - e || ymin > hw + e || xmin < hl - e) return; // certainly not a lead vehicle
+    const bool sure = ymax >= -hw + e && ymin <= hw - e && xmin >= hl + e;
+    const float d = xmin - hl, lo = d - e, hi = d + e;
+    if (hi < h1) {
+        if (j1 >= 0) lo2 = fminf(lo2, l1);
+        h1 = hi; l1 = lo; j1 = j; sure1 = sure;
+    } else {
+        lo2 = fminf(lo2, lo);
+    }
+}
+
 LCS_D void lcs_phase_lead(const LcsParams& p, LcsSmem& sm, int s, int tid) {
     const int n_new = sm.misc[1];
     if (tid >= n_new) return;
@@ -1444,9 +1492,8 @@ LCS_D void lcs_phase_lead(const LcsParams& p, LcsSmem& sm, int s, int tid) {
     // First test, four partners per step on the coordinate arrays: the centre must lie in the corridor widened by the
     // largest bounding radius of the list and not behind the ego (conservative: rmax, emax bound every partner's radius
     // and error).  A partner whose CENTRE lies well inside the corridor and whose whole circle is ahead of the ego is
-    // certainly a lead candidate no farther than rx - hl: `bound` (the smallest such value + emax) prunes everybody
-    // whose circle starts beyond it — they can neither win nor touch the winner's error interval.  The few survivors
-    // go through the full classification.
+    // certainly a lead candidate no farther than rx - hl: `bound` (the smallest such value + emax so far) prunes everybody
+    // whose circle starts beyond it — they can neither win nor touch the winner's error interval.
     const float* sx = sm.soa;
     const float* sy = sm.soa + LCS_SOA_Y(p.Ap);
     const float rmax = lcs_i2f(sm.misc[14]), wmax = lcs_i2f(sm.misc[15]);
@@ -1455,7 +1502,12 @@ LCS_D void lcs_phase_lead(const LcsParams& p, LcsSmem& sm, int s, int tid) {
     const float emax = 52.0f * wmax + 1.2e-4f;
     const float cy = hw + rmax + emax, cx = hl - emax, cy_in = hw - emax, cx_in = hl + rmax + emax;
     const float off = rmax + hl + emax;
+    // pass 1 (no divergence): the running bound, and the partners that can matter under it go to the thread's private
+    // list (a column of shared memory) — classifying them inside this loop would make the warp walk the classification
+    // for the union of its lanes' survivors
     float bound = lcs_inf_f();
+    uint16_t* list = (uint16_t*)sm.queue; // [LCS_LEAD_LIST][Ap]
+    int nl = 0;
     for (int j4 = 0; j4 < n_new; j4 += 4) {
         const lcs_f4 X = *(const lcs_f4*)(sx + j4), Y = *(const lcs_f4*)(sy + j4);
         float rx[4], ry[4];
@@ -1477,28 +1529,18 @@ LCS_D void lcs_phase_lead(const LcsParams& p, LcsSmem& sm, int s, int tid) {
             m &= m - 1;
             const int j = j4 + r;
             if (j >= n_new || j == tid) continue;
-            const lcs_f4 ot = sm.crec[j];
-            const float dx = ot.x - me.x, dy = ot.y - me.y;
-            const float rxx = dx * c32 + dy * s32, ryy = dy * c32 - dx * s32;
-            // error of rx, ry and of the corner extents: coordinate rounding (slack) + float32 trig / arithmetic
-            const float e = ot.w + me.w + 3e-6f * (fabsf(dx) + fabsf(dy)) + 2e-5f;
-            // every corner lies within the other's half diagonal (ot.z) of its centre; a partner whose interval lies
-            // above both h1 and lo2 changes neither
-            if (fabsf(ryy) > hw + ot.z + e || rxx < hl - e || rxx - ot.z - hl - e > fmaxf(h1, lo2)) continue;
-            const lcs_f4 o2 = sm.crec2[j];
-            const float cr = o2.x * c32 + o2.y * s32, sr = o2.y * c32 - o2.x * s32; // cos / sin of the relative heading
-            const float ex = fabsf(o2.z * cr) + fabsf(o2.w * sr), ey = fabsf(o2.z * sr) + fabsf(o2.w * cr);
-            const float xmin = rxx - ex, ymax = ryy + ey, ymin = ryy - ey;
-            if (ymax < -hw - e || ymin > hw + e || xmin < hl - e) continue; // certainly not a lead vehicle
-            const bool sure = ymax >= -hw + e && ymin <= hw - e && xmin >= hl + e;
-            const float d = xmin - hl, lo = d - e, hi = d + e;
-            if (hi < h1) {
-                if (j1 >= 0) lo2 = fminf(lo2, l1);
-                h1 = hi; l1 = lo; j1 = j; sure1 = sure;
-            } else {
-                lo2 = fminf(lo2, lo);
-            }
+            if (nl < LCS_LEAD_LIST)
+                list[nl++ * p.Ap + tid] = (uint16_t)j;
+            else
+                lcs_lead_classify(sm, tid, j, me, c32, s32, hl, hw, h1, l1, lo2, j1, sure1); // (list full: rare)
         }
+    }
+    // pass 2: the listed partners, every lane on its own list
+    for (int k = 0; k < nl; k++) {
+        const int j = list[k * p.Ap + tid];
+        const float dx = sm.crec[j].x - me.x, dy = sm.crec[j].y - me.y;
+        if (dx * c32 + dy * s32 - off > bound) continue; // listed before the bound tightened
+        lcs_lead_classify(sm, tid, j, me, c32, s32, hl, hw, h1, l1, lo2, j1, sure1);
     }
     const size_t ia = (size_t)s * p.Ap + sm.act2[tid];
     double dis = lcs_inf_d(), vl = 0.0;
@@ -1685,18 +1727,32 @@ LCS_D void lcs_me_flags(const LcsParams& p, int s, int tid, uint32_t* words, int
 }
 // Part 2: the searches run on DENSE lanes: thread k takes the k-th slot that needs one (a warp pays for the longest
 // search among its lanes whatever their number)
-LCS_D void lcs_me_search(const LcsParams& p, int s, int tid, const uint32_t* words, int32_t* cnt, const LcsThread& t) {
-    if (tid >= cnt[0]) return;
+struct LcsEdgeJob { // one edge search of thread k = the k-th slot that needs one
+    double qx, qy;
+    size_t ia;
+    LcsCellQ q;
+    bool on;
+};
+// begin: query and the header loads of its candidate list
+LCS_D void lcs_me_search_begin(const LcsParams& p, int s, int tid, const uint32_t* words, const int32_t* cnt, const LcsThread& t,
+                               LcsEdgeJob& job) {
+    job.on = tid < cnt[0];
+    if (!job.on) return;
     const size_t q = lcs_snap_base(p, t.snap, s) + lcs_select(words, (p.Ap + 31) >> 5, tid);
     const int a = p.snap_agent[q] & (LCS_SNAP_MOVED - 1);
-    const size_t ia = (size_t)s * p.Ap + a;
-    const double qx = p.snap_rec[6 * q], qy = p.snap_rec[6 * q + 1];
+    job.ia = (size_t)s * p.Ap + a;
+    job.qx = p.snap_rec[6 * q];
+    job.qy = p.snap_rec[6 * q + 1];
+    lcs_edge_cell_begin(p, s, job.qx, job.qy, job.q);
+}
+LCS_D void lcs_me_search_finish(const LcsParams& p, int s, int32_t* cnt, const LcsEdgeJob& job) {
+    if (!job.on) return;
     bool off = false;
-    int k = lcs_nearest_edge_cell(p, s, qx, qy, &off);
-    if (k == -2) k = lcs_nearest_edge_hint(p, s, qx, qy, p.edge_hint[ia], &off); // outside the lists' grid
-    p.nearest_edge[ia] = k;
-    p.edge_hint[ia] = k;
-    p.offroad[ia] = off ? 1 : 0;
+    int k = lcs_edge_cell_finish(p, s, job.qx, job.qy, job.q, &off);
+    if (k == -2) k = lcs_nearest_edge_hint(p, s, job.qx, job.qy, p.edge_hint[job.ia], &off); // outside the lists' grid
+    p.nearest_edge[job.ia] = k;
+    p.edge_hint[job.ia] = k;
+    p.offroad[job.ia] = off ? 1 : 0;
     if (off) lcs_atomic_add(&cnt[1], 1);
 }
 LCS_D void lcs_me_stats(const LcsParams& p, int s, int tid, const int32_t* cnt, const LcsThread& t) {
