@@ -1569,20 +1569,24 @@ LCS_D void lcs_last_pose_f32(const LcsParams& p, size_t ia, float* x, float* y, 
     *y = (float)r[1];
     *h = (float)r[4];
 }
-// one row of the (N,11,6) history stack: list slot `slot`, shift-register position k
-LCS_D void lcs_history_cell(const LcsParams& p, const LcsObsArgs& o, int s, int slot, int k) {
-    float* out = o.d.history + (((size_t)s * p.Ap + slot) * LCS_H + k) * 6;
+// one row of the (N,11,6) history stack: list slot `slot`, all 11 shift-register positions (the slot's agent, ring head
+// and count are read once)
+LCS_D void lcs_history_row(const LcsParams& p, const LcsObsArgs& o, int s, int slot) {
+    float* out = o.d.history + ((size_t)s * p.Ap + slot) * LCS_H * 6;
     const int a = slot < p.n_active[s] ? p.active[(size_t)s * p.Ap + slot] : -1;
-    if (k == 0 && o.d.history_agent) o.d.history_agent[(size_t)s * p.Ap + slot] = a;
+    if (o.d.history_agent) o.d.history_agent[(size_t)s * p.Ap + slot] = a;
     if (a < 0) {
-        for (int c = 0; c < 6; c++) out[c] = 0.f;
+        for (int c = 0; c < LCS_H * 6; c++) out[c] = 0.f;
         return;
     }
     const size_t ia = (size_t)s * p.Ap + a;
     const int head = p.ring_head[ia], cnt = p.ring_count[ia];
-    const double* r = p.ring + (ia * LCS_H + (head + k) % LCS_H) * 5;
-    for (int c = 0; c < 5; c++) out[c] = (float)r[c];
-    out[5] = k >= LCS_H - cnt ? 1.f : 0.f;
+    for (int k = 0; k < LCS_H; k++) {
+        const int slot_k = head + k >= LCS_H ? head + k - LCS_H : head + k;
+        const double* r = p.ring + (ia * LCS_H + slot_k) * 5;
+        for (int c = 0; c < 5; c++) out[6 * k + c] = (float)r[c];
+        out[6 * k + 5] = k >= LCS_H - cnt ? 1.f : 0.f;
+    }
 }
 
 #ifdef LCSIM_HOSTEMU
@@ -1636,8 +1640,7 @@ static void lcs_obs_scenario_serial(const LcsParams& p, const LcsObsArgs& o, int
         }
     }
     if (o.d.history)
-        for (int slot = 0; slot < p.Ap; slot++)
-            for (int k = 0; k < LCS_H; k++) lcs_history_cell(p, o, s, slot, k);
+        for (int slot = 0; slot < p.Ap; slot++) lcs_history_row(p, o, s, slot);
 }
 #endif
 
@@ -1748,7 +1751,7 @@ __global__ void __launch_bounds__(128) lcs_obs_kernel(const LcsParams p, const L
         __syncthreads();
     }
     if (o.d.history)
-        for (int c = tid; c < p.Ap * LCS_H; c += 128) lcs_history_cell(p, o, s, c / LCS_H, c % LCS_H);
+        for (int slot = tid; slot < p.Ap; slot += 128) lcs_history_row(p, o, s, slot);
 }
 #endif
 

@@ -59,7 +59,7 @@ LCS_D void lcs_atomic_max(int* p, int v) { atomicMax(p, v); }
 
 // host emulation only: counters of the fast / fallback paths (tests read them to see how often a shortcut applies)
 #ifdef LCSIM_HOSTEMU
-static long long lcs_dbg_count[8]; // 0 window ok, 1 window rejected, 2 blob (no window), 3 lead decided, 4 lead fallback, 5 lead none
+static long long lcs_dbg_count[8]; // 0 window ok, 1 window rejected, 2 blob (no window), 3 lead decided, 4 lead fallback, 5 lead none, 6 cursor tie-break pass
 #define LCS_COUNT(i) (lcs_dbg_count[i]++)
 #else
 #define LCS_COUNT(i) ((void)0)
@@ -543,17 +543,25 @@ LCS_D int lcs_scan_finish(const LcsParams& p, int s, int a, int len, double qx, 
     const float eta = lcs_filter_eta(p.eta_pts[s], fqx, fqy, sc.m);
     const float thr = lcs_filter_thr(sc.m, eta);
     if (sc.m2 > thr) return sc.j;
+    LCS_COUNT(6);
     const double* t64 = p.traj_xy + ((size_t)s * p.Ap + a) * p.T * 2;
-    const lcs_f2* tf2 = p.tf_xy;
+    const lcs_f8* tf = (const lcs_f8*)(p.tf_xy + lcs_tf_index(p, s, 0, a));
     double bd = lcs_inf_d();
     int best = sc.j;
-    for (int k = 0; k < len; k++) {
-        const lcs_f2 pt = tf2[lcs_tf_index(p, s, k, a)];
-        const float dx = pt.x - fqx, dy = pt.y - fqy;
-        const float d = dx * dx + dy * dy;
-        if (d <= thr) {
-            const double e = lcs_norm2_axis(lcs_dsub(t64[2 * k], qx), lcs_dsub(t64[2 * k + 1], qy));
-            if (e < bd) { bd = e; best = k; }
+    // near-tie (common for parked agents whose logged points jitter inside a few centimetres): the row once more, four
+    // points per load (it is in L1 from the scan), float64 on the points inside the band, first minimum wins
+    const int n4 = (len + 3) >> 2;
+    for (int k4 = 0; k4 < n4; k4++) {
+        const lcs_f8 v = lcs_ld32(tf + k4);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int k = 4 * k4 + r;
+            const float dx = v.v[2 * r] - fqx, dy = v.v[2 * r + 1] - fqy;
+            const float d = dx * dx + dy * dy;
+            if (d <= thr && k < len) {
+                const double e = lcs_norm2_axis(lcs_dsub(t64[2 * k], qx), lcs_dsub(t64[2 * k + 1], qy));
+                if (e < bd) { bd = e; best = k; }
+            }
         }
     }
     return best;
@@ -1270,8 +1278,8 @@ LCS_D int lcs_phase_init(const LcsParams& p, LcsSmem& sm, int s, int tid, LcsThr
     int a = -1;
     if (p.mode == 1)
         lcs_reset_agent(p, s, tid);
-    else if (tid < n_old)
-        a = p.active[(size_t)s * p.Ap + tid];
+    else
+        a = p.active[(size_t)s * p.Ap + tid]; // -1 beyond the list (lcs_phase_publish): no need to wait for n_active
     sm.act[tid] = a;
     return a;
 }
@@ -1678,10 +1686,13 @@ LCS_D int lcs_mc_load(const LcsParams& p, LcsSmem& sm, int s, int tid, const Lcs
     }
     sm.cnt[tid] = 0;
     sm.act2[tid] = tid;
+    // the slot's record is loaded whether or not the slot is listed (stale but in bounds beyond the list): the loads
+    // go out together with the header's instead of after it
+    const int a = p.snap_agent[base + tid] & (LCS_SNAP_MOVED - 1);
+    const double* rp = p.snap_rec + 6 * (base + tid);
+    const double r[6] = {rp[0], rp[1], rp[2], rp[3], rp[4], rp[5]};
     if (tid < n_fin) p.coll_count[(size_t)s * p.Ap + p.snap_fin[base + tid]] = 0; // left the list: outputs reset
     if (tid >= n_new) return -1;
-    const int a = p.snap_agent[base + tid] & (LCS_SNAP_MOVED - 1);
-    const double* r = p.snap_rec + 6 * (base + tid);
     lcs_store_ex(sm, tid, r[0], r[1], 0.0, r[2], r[3], r[4], r[5], 0.0);
     lcs_make_crec(p, s, r[0], r[1], r[2], r[3], r[4], r[5], &sm.crec[tid], &sm.crec2[tid]);
     // coordinates once more as doubled float arrays (collision filter), largest bounding radius of the list
