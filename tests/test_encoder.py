@@ -79,6 +79,7 @@ def test_encoder_inputs_capacity_and_batch(backend):
 
     sb, centres = workload.synthetic_batch(70, 3, 48, workers=1, with_centres=True)
     be = BatchEngine(sb, backend=backend)
+    be.upload_polylines([c[:5] for c in centres])  # a second upload replaces the first (and frees its buffers)
     be.upload_polylines(centres)
     be.rollout(12)
     tn = be.backend.to_numpy
