@@ -196,6 +196,10 @@ struct LcsParams {
     int32_t* q_ticket; // [1] next ticket
     int32_t* q_seq; // [S][2] tick items / metric items of this launch completed for the scenario
     int32_t n_ticks; // ticks of this launch
+    // fused launch: every tick item is followed by the scenario's metric item in the same CTA (no second ticket, no
+    // dependency wait; the CTA re-reads the snapshot it wrote).  Used for single-tick launches, where there is no chain
+    // of ticks to keep short; LCSIM_B200_FUSE=1 / 0 forces it on / off for every launch.
+    int32_t fuse;
     // ---- launch mode
     long long* dbg; // [S][16] phase clocks (instrumented instantiation of the tick kernel only)
     int32_t mode; // 0 = step, 1 = reset
