@@ -335,6 +335,8 @@ def bench_batch(ctx: Ctx, kind: str, steps: int, warmup: int, traffic=(None, Non
         obs_bytes_env_tick = 12.0 * P + 16.0 * (K_A + K_P)  # polyline-centre read + edge/feature writes
         extra.update(k_agents=K_A, k_polys=K_P, polyline_centres=P)
 
+        obs_buf, rew_buf = [None], [None]  # written in place every tick (no allocation inside the loop)
+
         def one_rollout(timed=False):
             be.reset()
             if timed:
@@ -342,8 +344,8 @@ def bench_batch(ctx: Ctx, kind: str, steps: int, warmup: int, traffic=(None, Non
                 a.record()
             for k in range(90):
                 be.step(act_agent, act_type, act_data[k])
-                be.build_obs(k_agents=K_A, k_polys=K_P, sort_by_distance=True)
-                be.rewards(coef=WAYMO_PPO_REWARD)
+                obs_buf[0] = be.build_obs(k_agents=K_A, k_polys=K_P, sort_by_distance=True, out=obs_buf[0])
+                rew_buf[0] = be.rewards(coef=WAYMO_PPO_REWARD, out=rew_buf[0])
             if timed:
                 b.record()
                 kev.append((a, b))
@@ -427,20 +429,21 @@ def bench_batch(ctx: Ctx, kind: str, steps: int, warmup: int, traffic=(None, Non
             h2d, d2h = 90 * S * 16, 90 * h_out.numel() + 64
             cnt, ret = [0], [0.0]
 
+            be.set_env_obs(k_agents=K_A, k_polys=K_P, sort_by_distance=True)  # env_step builds it behind every tick
+            h_act_ptrs = [h_acts[k] for k in range(90)]
+
             def step_e2e():
                 for _ in range(R):
                     be.reset()
                     for k in range(90):
-                        be.env_step(h_acts[k], h_out, coef=WAYMO_PPO_REWARD, sync=False)
-                        be.build_obs(k_agents=K_A, k_polys=K_P, sort_by_distance=True)
-                        torch.cuda.current_stream(dev).synchronize()
+                        be.env_step(h_act_ptrs[k], h_out, coef=WAYMO_PPO_REWARD, sync=True)  # returns after the stream sync
                         ret[0] += float(out_np["reward"][0])  # the host consumes the result
                     h_stats.copy_(be.episode_stats(), non_blocking=True)
                     torch.cuda.current_stream(dev).synchronize()
                     cnt[0] += int(h_stats[0])
-            what = ("per tick: lcsim_b200_env_step (pinned H2D of every env's ADS action, tick, reward kernel, D2H of "
-                    "reward/terms/route/flags) + lcsim_b200_build_obs (device tensors for the encoder), stream sync and "
-                    "host read every tick; per rollout D2H of the statistics")
+            what = ("per tick ONE call lcsim_b200_env_step with the observation registered by lcsim_b200_set_env_obs: pinned "
+                    "H2D of every env's ADS action, tick, reward kernel next to the observation build (device tensors for "
+                    "the encoder), D2H of reward/terms/route/flags, stream sync, host read; per rollout D2H of the statistics")
         else:
             # plans arrive in pinned HOST memory (the reference hands numpy arrays to set_ref_trajectory), go H2D, and the
             # rollout ends with the read-back of rollout_host

@@ -299,6 +299,12 @@ typedef struct {
 } lcsim_b200_env_out;
 int lcsim_b200_env_step(lcsim_b200_engine* e, const double* actions_host, const double* coef6,
                         lcsim_b200_env_out* out_host, int sync, void* stream);
+/* Registers the observation build of env_step: BicycleSingleEnv.step returns the observation with the reward
+ * (gym_warpper.py:78-92 -> Engine.get_step_return, engine.py:160-201), so after this call every lcsim_b200_env_step
+ * also runs lcsim_b200_build_obs(obs) behind its tick (on an engine-owned side stream, concurrently with the reward
+ * kernel; joined before the D2H copy, so a sync != 0 covers it).  The descriptor is copied; its device output buffers
+ * stay caller-owned and must outlive the registration.  obs == NULL removes it. */
+int lcsim_b200_set_env_obs(lcsim_b200_engine* e, const lcsim_b200_obs_desc* obs);
 
 /* Lane-centreline projection.  The centreline points are Junction.roadgraph_points restricted to
  * the centreline types 1|2 (junction/junction.py:186-253 <- lane/lane.py:108-124: the 0.5 m-resampled lane

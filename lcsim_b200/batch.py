@@ -169,17 +169,27 @@ class BatchEngine:
         self._keep = (sc, ag, xy, vel, hd)
 
     # ------------------------------------------------------------------ rewards / route
-    def rewards(self, agent=None, coef: Optional[dict] = None):
+    def _coef6(self, coef: Optional[dict]):
+        """host (6,) float64 array of the reward coefficients (cached per dict: the per-tick calls pass the same one)"""
+        if coef is None:
+            return None
+        key = tuple(float(coef.get(k, 0.0)) for k in native.REWARD_KEYS)
+        hit = getattr(self, "_coef_cache", None)
+        if hit is None or hit[0] != key:
+            hit = self._coef_cache = (key, np.asarray(key, np.float64))
+        return hit[1]
+
+    def rewards(self, agent=None, coef: Optional[dict] = None, out: Optional[dict] = None):
         """Engine._compute_rewards + get_route for one agent per scenario (None = the ADS).
-        Returns dict(terms (S,6), terminated (S,), truncated (S,), route (S,10,2), reward (S,))."""
+        Returns dict(terms (S,6), terminated (S,), truncated (S,), route (S,10,2), reward (S,)); ``out`` = a dict returned
+        by an earlier call is written in place (a per-tick loop then allocates nothing)."""
         b = self.backend
-        out = dict(terms=b.empty((self.S, native.N_REWARD_TERMS), np.float64), terminated=b.empty((self.S,), np.uint8),
-                   truncated=b.empty((self.S,), np.uint8), route=b.empty((self.S, native.ROUTE_LEN, 2), np.float64),
-                   reward=b.empty((self.S,), np.float64))
+        if out is None:
+            out = dict(terms=b.empty((self.S, native.N_REWARD_TERMS), np.float64), terminated=b.empty((self.S,), np.uint8),
+                       truncated=b.empty((self.S,), np.uint8), route=b.empty((self.S, native.ROUTE_LEN, 2), np.float64),
+                       reward=b.empty((self.S,), np.float64))
         ag = None if agent is None else b.to_device(agent, np.int32)
-        cf = None
-        if coef is not None:
-            cf = np.asarray([float(coef.get(k, 0.0)) for k in native.REWARD_KEYS], np.float64)
+        cf = self._coef6(coef)
         self._check(self.lib.lcsim_b200_rewards(
             self._h, None if ag is None else b.ptr(ag), None if cf is None else cf.ctypes.data,
             b.ptr(out["reward"]), b.ptr(out["terms"]), b.ptr(out["terminated"]), b.ptr(out["truncated"]),
@@ -197,9 +207,7 @@ class BatchEngine:
         def host_ptr(x):
             return x.ctypes.data if isinstance(x, np.ndarray) else int(x.data_ptr())
 
-        cf = None
-        if coef is not None:
-            cf = np.asarray([float(coef.get(k, 0.0)) for k in native.REWARD_KEYS], np.float64)
+        cf = self._coef6(coef)
         self._check(self.lib.lcsim_b200_env_step(self._h, None if actions is None else host_ptr(actions),
                                                  None if cf is None else cf.ctypes.data, host_ptr(out), int(sync),
                                                  self.backend.stream()), "env_step")
@@ -218,27 +226,55 @@ class BatchEngine:
         self._check(self.lib.lcsim_b200_upload_polylines(self._h, n.ctypes.data, arr.ctypes.data, P), "upload_polylines")
         self.P = P
 
-    def build_obs(self, k_agents: int = 32, k_polys: int = 64, radius: float = 50.0, sort_by_distance: bool = False,
-                  ego=None, with_polys: bool = True, with_history: bool = True):
-        """Ego-centric neighbour gather + history stack (include/lcsim_b200.h lcsim_b200_obs_desc).  Returns a dict of
-        device tensors written in place by one launch."""
+    def _obs_desc(self, k_agents, k_polys, radius, sort_by_distance, ego, with_polys, with_history, out):
         b = self.backend
-        out = dict(nbr_agent=b.empty((self.S, k_agents), np.int32), nbr_agent_feat=b.empty((self.S, k_agents, 3), np.float32),
-                   n_nbr_agent=b.empty((self.S,), np.int32))
-        if with_polys:
-            out.update(nbr_poly=b.empty((self.S, k_polys), np.int32), nbr_poly_feat=b.empty((self.S, k_polys, 3), np.float32),
-                       n_nbr_poly=b.empty((self.S,), np.int32))
-        if with_history:
-            out.update(history=b.empty((self.S, self.A_stride, native.H_STEPS, 6), np.float32),
-                       history_agent=b.empty((self.S, self.A_stride), np.int32))
+        if out is None:
+            out = dict(nbr_agent=b.empty((self.S, k_agents), np.int32), nbr_agent_feat=b.empty((self.S, k_agents, 3), np.float32),
+                       n_nbr_agent=b.empty((self.S,), np.int32))
+            if with_polys:
+                out.update(nbr_poly=b.empty((self.S, k_polys), np.int32), nbr_poly_feat=b.empty((self.S, k_polys, 3), np.float32),
+                           n_nbr_poly=b.empty((self.S,), np.int32))
+            if with_history:
+                out.update(history=b.empty((self.S, self.A_stride, native.H_STEPS, 6), np.float32),
+                           history_agent=b.empty((self.S, self.A_stride), np.int32))
         d = native.ObsDesc()
         eg = None if ego is None else b.to_device(ego, np.int32)
         d.ego = None if eg is None else b.ptr(eg)
         d.radius, d.k_agents, d.k_polys, d.sort_by_distance = float(radius), int(k_agents), int(k_polys), int(sort_by_distance)
         for k, v in out.items():
             setattr(d, k, b.ptr(v))
+        return d, out, eg
+
+    def build_obs(self, k_agents: int = 32, k_polys: int = 64, radius: float = 50.0, sort_by_distance: bool = False,
+                  ego=None, with_polys: bool = True, with_history: bool = True, out: Optional[dict] = None):
+        """Ego-centric neighbour gather + history stack (include/lcsim_b200.h lcsim_b200_obs_desc).  Returns a dict of
+        device tensors written in place by one launch; ``out`` = the dict of an earlier call with the same arguments is
+        reused (nothing is allocated, the descriptor is kept)."""
+        b = self.backend
+        key = (k_agents, k_polys, radius, sort_by_distance, with_polys, with_history)
+        hit = getattr(self, "_obs_cache", None)
+        if out is not None and ego is None and hit is not None and hit[0] == key and hit[2] is out:
+            d, eg = hit[1], None
+        else:
+            d, out, eg = self._obs_desc(k_agents, k_polys, radius, sort_by_distance, ego, with_polys, with_history, out)
+            if ego is None:
+                self._obs_cache = (key, d, out)
         self._check(self.lib.lcsim_b200_build_obs(self._h, C.byref(d), b.stream()), "build_obs")
         self._keep = eg
+        return out
+
+    def set_env_obs(self, k_agents: int = 32, k_polys: int = 64, radius: float = 50.0, sort_by_distance: bool = False,
+                    ego=None, with_polys: bool = True, with_history: bool = True, enable: bool = True):
+        """Registers the observation that every later :meth:`env_step` builds behind its tick (BicycleSingleEnv.step
+        returns the observation together with the reward, gym_warpper.py:78-92).  Returns the dict of device tensors the
+        engine keeps writing; ``enable=False`` removes the registration."""
+        if not enable:
+            self._check(self.lib.lcsim_b200_set_env_obs(self._h, None), "set_env_obs")
+            self._env_obs = None
+            return None
+        d, out, eg = self._obs_desc(k_agents, k_polys, radius, sort_by_distance, ego, with_polys, with_history, None)
+        self._check(self.lib.lcsim_b200_set_env_obs(self._h, C.byref(d)), "set_env_obs")
+        self._env_obs = (out, eg)  # the engine holds raw pointers into these
         return out
 
     def build_encoder_inputs(self, a2a_radius: float = 50.0, pl2a_radius: float = 50.0, time_span: int = 10,

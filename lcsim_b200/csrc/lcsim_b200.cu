@@ -210,9 +210,31 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
     if (tid == 0) s_item = atomicAdd(p.q_ticket, 1);
     __syncthreads();
     const int item = s_item;
-    const int k = item / per_tick, r = item - k * per_tick;
-    const bool metric = r >= p.S;
-    const int s = metric ? r - p.S : r;
+    int k = item / per_tick, r = item - k * per_tick;
+    bool metric = r >= p.S;
+    int s = metric ? r - p.S : r;
+    if (p.order && per_tick == 2 * p.S && item >= p.S) {
+        // experiment orders (LCSIM_B200_ORDER), metric items one tick behind their tick items: T(0, .), then rounds
+        // q = 1 .. n-1 holding T(q, .) and M(q-1, .), then M(n-1, .).  order 1 interleaves a round as T(q, s), M(q-1, s)
+        // pairs, order 2 keeps the round as two blocks T(q, .) | M(q-1, .).  In both, an item's dependencies were
+        // claimed about 2 S tickets earlier (needs snap_depth >= 2; order 2 wants 3).  Measured at S=1024: order 1 is
+        // SLOWER than the plain order (replay 2.76e9 vs 2.90e9, reactive 0.82e9 vs 1.08e9) - see profiles/NOTES_r2.md.
+        const int u = item - p.S, q = u / per_tick + 1, v = u - (q - 1) * per_tick;
+        if (q < p.n_ticks) {
+            if (p.order == 1) {
+                s = v >> 1;
+                metric = v & 1;
+            } else {
+                metric = v >= p.S;
+                s = metric ? v - p.S : v;
+            }
+            k = metric ? q - 1 : q;
+        } else {
+            s = v;
+            metric = true;
+            k = p.n_ticks - 1;
+        }
+    }
     long long t_wait = 0;
     if (CLK && tid == 0) t_wait = clock64();
     if (tid == 0) {
@@ -607,6 +629,9 @@ struct lcsim_b200_engine {
     int plan_parts = 0;
     int device = 0;
     int grid_cap = 1; // CTAs of the engine kernel the device holds at once (occupancy x SMs)
+    bool env_obs_on = false; // set_env_obs: env_step builds this observation behind its tick
+    lcsim_b200_obs_desc env_obs;
+    void *obs_stream = nullptr, *ev_tick = nullptr, *ev_obs = nullptr; // side stream + fork / join events of that build
     int fuse_mode = 2; // LCSIM_B200_FUSE: 0 = never, 1 = every launch, default = single-tick launches (LcsParams::fuse)
     std::string err;
 };
@@ -683,6 +708,11 @@ extern "C" int64_t lcsim_b200_launch_count(const lcsim_b200_engine* e) { return 
 extern "C" void lcsim_b200_destroy(lcsim_b200_engine* e) {
     if (!e) return;
     for (void* q : e->allocs) cudaFree(q);
+#ifndef LCSIM_HOSTEMU
+    if (e->ev_tick) cudaEventDestroy((cudaEvent_t)e->ev_tick);
+    if (e->ev_obs) cudaEventDestroy((cudaEvent_t)e->ev_obs);
+    if (e->obs_stream) cudaStreamDestroy((cudaStream_t)e->obs_stream);
+#endif
     delete e;
 }
 
@@ -789,6 +819,11 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     LCS_ALLOC(e, p.q_ticket, 2 + 2 * S);
     p.q_seq = p.q_ticket + 2; // 8-byte aligned pairs
     p.fuse = 0;
+    {
+        const char* om = getenv("LCSIM_B200_ORDER"); // experiments: 0 = plain ticket order of the rollout launch
+        p.order = om ? std::min(2, std::max(0, atoi(om))) : 0;
+        if (p.snap_depth < 2) p.order = 0; // T(k, s) would wait for M(k-1, s), whose ticket follows it
+    }
     {
         const char* fm = getenv("LCSIM_B200_FUSE");
         e->fuse_mode = !fm ? 2 : atoi(fm) ? 1 : 0;
@@ -1516,6 +1551,35 @@ extern "C" int lcsim_b200_rewards(lcsim_b200_engine* e, const int32_t* agent, co
     return 0;
 }
 
+static int lcs_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_desc* obs, void* stream);
+
+extern "C" int lcsim_b200_set_env_obs(lcsim_b200_engine* e, const lcsim_b200_obs_desc* obs) {
+    if (!e) return LCSIM_B200_ERR_ARG;
+    if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "set_env_obs before upload_static");
+    LCS_GUARD(e);
+    e->env_obs_on = false;
+    if (!obs) return 0;
+    if (obs->k_agents < 0 || obs->k_polys < 0 || obs->k_agents > 1024 || obs->k_polys > 1024 || !(obs->radius > 0))
+        return lcs_fail(e, LCSIM_B200_ERR_ARG, "set_env_obs: k_agents/k_polys must be in [0,1024], radius > 0");
+    if ((obs->nbr_poly || obs->nbr_poly_feat) && !e->poly)
+        return lcs_fail(e, LCSIM_B200_ERR_STATE, "set_env_obs: polyline outputs requested before upload_polylines");
+#ifndef LCSIM_HOSTEMU
+    if (!e->obs_stream) {
+        cudaStream_t st2;
+        cudaEvent_t a, b;
+        LCS_CUDA(e, cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+        e->obs_stream = st2;
+        LCS_CUDA(e, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        e->ev_tick = a;
+        LCS_CUDA(e, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        e->ev_obs = b;
+    }
+#endif
+    e->env_obs = *obs;
+    e->env_obs_on = true;
+    return 0;
+}
+
 extern "C" int lcsim_b200_env_step(lcsim_b200_engine* e, const double* actions_host, const double* coef6,
                                    lcsim_b200_env_out* out_host, int sync, void* stream) {
     if (!e || !out_host) return LCSIM_B200_ERR_ARG;
@@ -1537,11 +1601,23 @@ extern "C" int lcsim_b200_env_step(lcsim_b200_engine* e, const double* actions_h
     r.env = e->env_out;
     r.s_tab0 = e->s_tab0;
 #ifndef LCSIM_HOSTEMU
+    if (e->env_obs_on) { // the observation of the new state, next to the reward kernel (both only read the tick's results)
+        LCS_CUDA(e, cudaEventRecord((cudaEvent_t)e->ev_tick, st));
+        LCS_CUDA(e, cudaStreamWaitEvent((cudaStream_t)e->obs_stream, (cudaEvent_t)e->ev_tick, 0));
+        int rc = lcs_build_obs(e, &e->env_obs, e->obs_stream);
+        if (rc) return rc;
+        LCS_CUDA(e, cudaEventRecord((cudaEvent_t)e->ev_obs, (cudaStream_t)e->obs_stream));
+    }
     lcs_rewards_kernel<<<(q.S + 3) / 4, 128, 0, st>>>(e->p, r);
     LCS_CUDA(e, cudaGetLastError());
+    if (e->env_obs_on) LCS_CUDA(e, cudaStreamWaitEvent(st, (cudaEvent_t)e->ev_obs, 0));
     LCS_CUDA(e, cudaMemcpyAsync(out_host, e->env_out, sizeof(lcsim_b200_env_out) * q.S, cudaMemcpyDeviceToHost, st));
     if (sync) LCS_CUDA(e, cudaStreamSynchronize(st));
 #else
+    if (e->env_obs_on) {
+        int rc = lcs_build_obs(e, &e->env_obs, stream);
+        if (rc) return rc;
+    }
     for (int s = 0; s < q.S; s++) lcs_rewards_one(e->p, r, s, 0, 1);
     memcpy(out_host, e->env_out, sizeof(lcsim_b200_env_out) * q.S);
 #endif
@@ -1664,12 +1740,20 @@ __global__ void __launch_bounds__(128) lcs_obs_kernel(const LcsParams p, const L
     __shared__ uint32_t words[4];
     __shared__ int s_count;
     const int s = blockIdx.x, tid = threadIdx.x;
+    // grid (S, 3): the agent list, the polyline list and the history stack of a scenario are independent pieces of
+    // work, one CTA each (blockIdx.y)
+    if (blockIdx.y == 2) {
+        if (o.d.history)
+            for (int c = tid; c < p.Ap * LCS_H; c += 128) lcs_history_cell(p, o, s, c / LCS_H, c % LCS_H);
+        return;
+    }
     const int e = o.d.ego ? o.d.ego[s] : p.ads_index[s];
     const size_t ie = (size_t)s * p.Ap + e;
     const bool ego_active = p.status[ie] == LCS_ACTIVE;
     float ex = 0, ey = 0, eh = 0;
     if (ego_active) lcs_last_pose_f32(p, ie, &ex, &ey, &eh);
-    for (int which = 0; which < 2; which++) {
+    {
+        const int which = blockIdx.y;
         const int cap = which == 0 ? o.d.k_agents : o.d.k_polys;
         int32_t* idx_out = which == 0 ? o.d.nbr_agent : o.d.nbr_poly;
         float* feat_out = which == 0 ? o.d.nbr_agent_feat : o.d.nbr_poly_feat;
@@ -1758,10 +1842,7 @@ __global__ void __launch_bounds__(128) lcs_obs_kernel(const LcsParams p, const L
             if (feat_out)
                 for (int c = 0; c < 3; c++) feat_out[((size_t)s * cap + k) * 3 + c] = 0.f;
         }
-        __syncthreads();
     }
-    if (o.d.history)
-        for (int c = tid; c < p.Ap * LCS_H; c += 128) lcs_history_cell(p, o, s, c / LCS_H, c % LCS_H);
 }
 #endif
 
@@ -1788,6 +1869,9 @@ extern "C" int lcsim_b200_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_d
     if (!e || !obs) return LCSIM_B200_ERR_ARG;
     if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "build_obs before upload_static");
     LCS_GUARD(e);
+    return lcs_build_obs(e, obs, stream);
+}
+static int lcs_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_desc* obs, void* stream) {
     if (obs->k_agents < 0 || obs->k_polys < 0 || obs->k_agents > LCS_OBS_CAP || obs->k_polys > LCS_OBS_CAP || !(obs->radius > 0))
         return lcs_fail(e, LCSIM_B200_ERR_ARG, "build_obs: k_agents/k_polys must be in [0,%d], radius > 0", LCS_OBS_CAP);
     if ((obs->nbr_poly || obs->nbr_poly_feat) && !e->poly)
@@ -1799,7 +1883,7 @@ extern "C" int lcsim_b200_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_d
     o.n_poly = e->n_poly;
     o.P = e->P;
 #ifndef LCSIM_HOSTEMU
-    lcs_obs_kernel<<<e->p.S, 128, 0, (cudaStream_t)stream>>>(e->p, o);
+    lcs_obs_kernel<<<dim3(e->p.S, 3), 128, 0, (cudaStream_t)stream>>>(e->p, o);
     LCS_CUDA(e, cudaGetLastError());
 #else
     for (int s = 0; s < e->p.S; s++) lcs_obs_scenario_serial(e->p, o, s);

@@ -200,6 +200,9 @@ struct LcsParams {
     // dependency wait; the CTA re-reads the snapshot it wrote).  Used for single-tick launches, where there is no chain
     // of ticks to keep short; LCSIM_B200_FUSE=1 / 0 forces it on / off for every launch.
     int32_t fuse;
+    // ticket order of a multi-tick launch with metric items: 0 = T(k, .) then M(k, .); 1 = interleaved, M one tick behind:
+    // T(k, 0), M(k-1, 0), T(k, 1), M(k-1, 1), ... (every dependency of an item lies two slot generations back)
+    int32_t order;
     // ---- launch mode
     long long* dbg; // [S][16] phase clocks (instrumented instantiation of the tick kernel only)
     int32_t mode; // 0 = step, 1 = reset
@@ -387,6 +390,20 @@ LCS_D lcs_f8 lcs_ld32(const lcs_f8* q) {
     lcs_f8 r;
     // not volatile: the scheduler must be free to issue several of these before the first use
     asm("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(q));
+    return r;
+#endif
+}
+
+// The same load for data that is read once per search and never again soon (candidate lists: 3.5 GB of them at
+// S=1024): L2 evict-first, so that these lines do not push the per-tick state (13 MB, re-read every tick) out of L2.
+LCS_D lcs_f8 lcs_ld32_stream(const lcs_f8* q) {
+#if defined(LCSIM_HOSTEMU) || !defined(LCS_STREAM_EF)
+    return lcs_ld32(q);
+#else
+    lcs_f8 r;
+    asm("ld.global.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
                  : "l"(q));
     return r;
@@ -736,7 +753,7 @@ LCS_D int lcs_edge_cell_finish(const LcsParams& p, int s, double qx, double qy, 
         lcs_f8 v[4];
 #pragma unroll
         for (int r = 0; r < 4; r++)
-            if (k0 + 4 * r < e) v[r] = lcs_ld32((const lcs_f8*)(gp + k0 + 4 * r));
+            if (k0 + 4 * r < e) v[r] = lcs_ld32_stream((const lcs_f8*)(gp + k0 + 4 * r));
 #pragma unroll
         for (int r = 0; r < 4; r++)
             if (k0 + 4 * r < e) {
@@ -1159,7 +1176,20 @@ LCS_D void lcs_update_pre(const LcsParams& p, int s, int a, LcsUpd& u) {
         // pristine float64 trajectory and a fresh observation: the waypoint comes as one replay record
         const bool use_rec = p.wp_rec && !p.stale_valid[ia] && !p.traj_f32[ia];
         if (use_rec) {
+#if defined(LCSIM_HOSTEMU) || !defined(LCS_STREAM_EF)
             const LcsWpRec r = p.wp_rec[ia * p.T + (len == 1 ? cursor : cursor + 1)];
+#else
+            LcsWpRec r; // read once per rollout: L2 evict-first
+            {
+                const LcsWpRec* rp = p.wp_rec + ia * p.T + (len == 1 ? cursor : cursor + 1);
+                long long w7;
+                asm("ld.global.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.h), "=d"(r.v) : "l"(rp));
+                asm("ld.global.L2::evict_first.v4.b64 {%0,%1,%2,%3}, [%4];"
+                    : "=l"(*(long long*)&r.ch), "=l"(*(long long*)&r.sh), "=l"(*(long long*)&r.vn), "=l"(w7)
+                    : "l"((const char*)rp + 32));
+                r.canon = (int32_t)(w7 & 0xffffffffll);
+            }
+#endif
             if (!p.reactive) {
                 // StateExpert -> STATE action -> Trajectory.next(new xy): all of it is in the record
                 u.x = r.x; u.y = r.y; u.h = r.h; u.v = r.v; u.ch = r.ch; u.sh = r.sh; u.qx = r.x; u.qy = r.y;

@@ -92,3 +92,34 @@ def test_build_obs_argument_errors(backend):
     with pytest.raises(native.NativeLibraryError, match="k_agents"):
         be.build_obs(k_agents=5000, with_polys=False)
     be.close()
+
+
+def test_env_step_builds_registered_observation(backend):
+    """set_env_obs: every env_step leaves the observation of the NEW state in the registered tensors — the same bytes a
+    separate build_obs writes after that tick; out= reuses the tensors of an earlier build_obs call."""
+    raws = [synth.make_raw_scenario(260 + i, 64) for i in range(3)]
+    scs = [packer.scenario_from_raw(r) for r in raws]
+    sb = packer.pack(scs)
+    centres = [packer.polyline_centres(sc.lanes) for sc in scs]
+    be = BatchEngine(sb, reactive=False, with_metrics=True, backend=backend)
+    be.upload_polylines(centres)
+    tn = be.backend.to_numpy
+    kw = dict(k_agents=8, k_polys=24, radius=50.0, sort_by_distance=True)
+    reg = be.set_env_obs(**kw)
+    out = np.zeros(sb.S, native.ENV_OUT_DTYPE)
+    rng = np.random.default_rng(5)
+    sep = None
+    for tick in range(25):
+        be.env_step(rng.uniform(-0.5, 0.5, (sb.S, 2)), out, sync=True)
+        got = {k: tn(v).copy() for k, v in reg.items()}
+        sep = be.build_obs(out=sep, **kw)
+        be.sync()
+        for k, v in sep.items():
+            np.testing.assert_array_equal(got[k], tn(v), err_msg=f"{k} at tick {tick}")
+    assert (got["n_nbr_poly"] > 0).any()
+    be.set_env_obs(enable=False)
+    before = {k: tn(v).copy() for k, v in reg.items()}
+    be.env_step(None, out, sync=True)
+    for k, v in reg.items():
+        np.testing.assert_array_equal(before[k], tn(v))  # no longer written
+    be.close()
