@@ -7,6 +7,7 @@
 #include "../../include/lcsim_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -745,8 +746,10 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     *out = e; // returned even on failure below so the caller can read last_error and destroy
     e->device = d->device;
     {
+        // reactive mode: metric items run one tick behind (order 2 below) over a ring of 3 snapshots: measured 1.110e9
+        // vs 1.073e9 agent-steps/s at S=1024 (log-replay: 2.85e9 vs 2.90e9, so it keeps the plain order and 2 snapshots)
         const char* env = getenv("LCSIM_B200_SNAP_DEPTH");
-        p.snap_depth = env ? std::min(LCS_SNAP_MAX, std::max(1, atoi(env))) : 2;
+        p.snap_depth = env ? std::min(LCS_SNAP_MAX, std::max(1, atoi(env))) : (p.reactive ? 3 : 2);
         if (!p.with_metrics) p.snap_depth = 1;
     }
     p.n_ticks = 1;
@@ -821,7 +824,7 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     p.fuse = 0;
     {
         const char* om = getenv("LCSIM_B200_ORDER"); // experiments: 0 = plain ticket order of the rollout launch
-        p.order = om ? std::min(2, std::max(0, atoi(om))) : 0;
+        p.order = om ? std::min(2, std::max(0, atoi(om))) : (p.reactive ? 2 : 0);
         if (p.snap_depth < 2) p.order = 0; // T(k, s) would wait for M(k-1, s), whose ticket follows it
     }
     {
@@ -876,18 +879,46 @@ float lcs_round_down_f32(double x) {
     return f;
 }
 
+// Allocator of the large zero-initialised staging arrays: calloc hands out untouched zero pages and the vector's
+// value-initialisation is a no-op, so a gigabyte of staging costs nothing until the (threaded) per-scenario
+// preparation writes it.  Only for trivially copyable element types whose zero value is all-zero bytes.
+template <typename Tp>
+struct LcsZeroAlloc {
+    using value_type = Tp;
+    LcsZeroAlloc() = default;
+    template <typename U>
+    LcsZeroAlloc(const LcsZeroAlloc<U>&) {}
+    Tp* allocate(size_t n) {
+        void* q = calloc(n ? n : 1, sizeof(Tp));
+        if (!q) throw std::bad_alloc();
+        return (Tp*)q;
+    }
+    void deallocate(Tp* q, size_t) { free(q); }
+    template <typename U>
+    void construct(U*) {} // the bytes are zero already
+    template <typename U, typename... Args>
+    void construct(U* q, Args&&... args) { ::new ((void*)q) U(std::forward<Args>(args)...); }
+    template <typename U>
+    bool operator==(const LcsZeroAlloc<U>&) const { return true; }
+    template <typename U>
+    bool operator!=(const LcsZeroAlloc<U>&) const { return false; }
+};
+template <typename Tp>
+using LcsZeroVec = std::vector<Tp, LcsZeroAlloc<Tp>>;
+
 struct Staging {
     std::vector<int32_t> depart_sorted, depart_tick, wait_order, traj_len, ge_idx, grid_dim, grid_start, home_edge;
     std::vector<uint8_t> dynamic;
-    std::vector<double> length, width, home_xy, traj_xy, traj_vel, traj_h, s_tab, edge_xy, edge_dir;
+    std::vector<double> length, width, home_xy;
+    LcsZeroVec<double> traj_xy, traj_vel, traj_h, s_tab, edge_xy, edge_dir;
     std::vector<lcs_f2> tf_xy, ge_xy;
-    std::vector<float> tf_rho;
+    LcsZeroVec<float> tf_rho;
     std::vector<uint8_t> traj_blob;
     std::vector<float> cl_geom;
     std::vector<int32_t> cl_dim;
     std::vector<std::vector<int32_t>> cl_start, cl_idx; // per scenario
     std::vector<std::vector<lcs_f2>> cl_xy;
-    std::vector<LcsWpRec> wp_rec;
+    LcsZeroVec<LcsWpRec> wp_rec;
     std::vector<float> grid_geom, eta;
 };
 
@@ -914,6 +945,19 @@ double np_sum_rec(const double* a, int64_t n) {
 }
 
 } // namespace
+
+// LCSIM_B200_UPLOAD_TIMES=1: phase times of upload_static on stderr
+struct LcsStopwatch {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    LcsStopwatch() : on(getenv("LCSIM_B200_UPLOAD_TIMES") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[lcsim_b200 upload] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 static void lcs_parallel_range(int n, const std::function<void(int, int)>& fn) {
     int nt = (int)std::thread::hardware_concurrency();
@@ -951,6 +995,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
             prev = dtk;
         }
     }
+    LcsStopwatch sw;
     Staging g;
     g.depart_tick.assign(SA, 0x7fffffff);
     g.wait_order.assign(SA, 0);
@@ -960,24 +1005,20 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     g.length.assign(SA, 0.0);
     g.width.assign(SA, 0.0);
     g.home_xy.assign(SA * 2, 0.0);
-    g.traj_xy.assign(SAT * 2, 0.0);
-    g.traj_vel.assign(SAT * 2, 0.0);
-    g.traj_h.assign(SAT, 0.0);
-    g.s_tab.assign(SAT, 0.0);
-    if (e->wp_rec) {
-        LcsWpRec z;
-        memset(&z, 0, sizeof z);
-        g.wp_rec.assign(SAT, z);
-    }
+    g.traj_xy.resize(SAT * 2); // zero pages (LcsZeroAlloc), first touched by the threads below
+    g.traj_vel.resize(SAT * 2);
+    g.traj_h.resize(SAT);
+    g.s_tab.resize(SAT);
+    if (e->wp_rec) g.wp_rec.resize(SAT);
     lcs_f2 far;
     far.x = LCS_FAR;
     far.y = LCS_FAR;
     g.tf_xy.assign(SA * p.Tp, far);
-    g.tf_rho.assign(SA * p.Tp, 0.f);
+    g.tf_rho.resize(SA * p.Tp);
     g.traj_blob.assign(SA, 0);
     const size_t Ed = (size_t)p.E;
-    g.edge_xy.assign((size_t)S * Ed * 2, 0.0);
-    g.edge_dir.assign((size_t)S * Ed * 2, 0.0);
+    g.edge_xy.resize((size_t)S * Ed * 2);
+    g.edge_dir.resize((size_t)S * Ed * 2);
     g.ge_xy.assign((size_t)S * Ed, far);
     g.ge_idx.assign((size_t)S * Ed, 0);
     g.grid_geom.assign((size_t)S * 4, 0.f);
@@ -997,6 +1038,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     const float cell = e->desc.grid_cell > 0 ? e->desc.grid_cell : 4.0f;
     std::vector<std::vector<int32_t>> cell_starts(S);
 
+    sw.lap("staging alloc");
     lcs_parallel_range(S, [&](int s0, int s1) {
         std::vector<double> seg(T);
         std::vector<char> live;
@@ -1179,36 +1221,54 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
                 // K(box) = points with mindist(point, box) <= U(box) + 1 cm, U(box) = min over points of maxdist(point, box).
                 // For a box inside a larger one, K(box) is a subset of K(larger) and so is the point that attains
                 // U(box): the fine cells are therefore built from the list of their 8 x 8 block, not from all points.
-                auto select = [&](double x0, double x1, double y0, double y1, const std::vector<int>& from, std::vector<int>& out) {
+                // Three levels (8 x 8 blocks, 2 x 2 blocks, cells); every level keeps its points' coordinates in
+                // contiguous arrays, so both passes of a selection are plain streaming loops.
+                struct Lvl {
+                    std::vector<int> idx;
+                    std::vector<double> x, y;
+                };
+                auto select = [&](double x0, double x1, double y0, double y1, const Lvl& from, Lvl& out) {
+                    const size_t n = from.idx.size();
+                    const double *fxp = from.x.data(), *fyp = from.y.data();
                     double U2 = 1e300; // squared distance to the farthest corner, minimised over the points
-                    for (int q : from) {
-                        const double fx = std::max(px[q] - x0, x1 - px[q]), fy = std::max(py[q] - y0, y1 - py[q]);
+                    for (size_t k = 0; k < n; k++) {
+                        const double fx = std::max(fxp[k] - x0, x1 - fxp[k]), fy = std::max(fyp[k] - y0, y1 - fyp[k]);
                         U2 = std::min(U2, fx * fx + fy * fy);
                     }
                     const double U = std::sqrt(U2) + 0.01, lim = U * U;
-                    out.clear();
-                    for (int q : from) {
-                        const double nx = std::max(std::max(x0 - px[q], px[q] - x1), 0.0), ny = std::max(std::max(y0 - py[q], py[q] - y1), 0.0);
-                        if (nx * nx + ny * ny <= lim) out.push_back(q);
+                    out.idx.clear();
+                    out.x.clear();
+                    out.y.clear();
+                    for (size_t k = 0; k < n; k++) {
+                        const double nx = std::max(std::max(x0 - fxp[k], fxp[k] - x1), 0.0), ny = std::max(std::max(y0 - fyp[k], fyp[k] - y1), 0.0);
+                        if (nx * nx + ny * ny <= lim) {
+                            out.idx.push_back(from.idx[k]);
+                            out.x.push_back(fxp[k]);
+                            out.y.push_back(fyp[k]);
+                        }
                     }
                 };
-                std::vector<int> all(np_), coarse, fine;
-                for (size_t q = 0; q < np_; q++) all[q] = (int)q;
-                const int CB = 8;
-                std::vector<std::vector<int>> row_lists((cw + CB - 1) / CB);
+                auto box = [&](int bx0, int bx1, int by0, int by1, const Lvl& from, Lvl& out) { // cells [bx0, bx1) x [by0, by1)
+                    select((double)cx0 + (double)bx0 * cl_cell - infl, (double)cx0 + (double)bx1 * cl_cell + infl,
+                           (double)cy0 + (double)by0 * cl_cell - infl, (double)cy0 + (double)by1 * cl_cell + infl, from, out);
+                };
+                Lvl all, fine;
+                all.idx.resize(np_);
+                for (size_t q = 0; q < np_; q++) all.idx[q] = (int)q;
+                all.x = px;
+                all.y = py;
+                const int CB = 8, MB = 2;
+                std::vector<Lvl> row_lists((cw + CB - 1) / CB), mid_lists((cw + MB - 1) / MB);
                 for (int cyy = 0; cyy < ch && cxy.size() <= ((size_t)4 << 20); cyy++) {
                     if (cyy % CB == 0) // the coarse blocks of this band of rows
-                        for (int bx = 0; bx * CB < cw; bx++) {
-                            const int xe = std::min(cw, (bx + 1) * CB), ye = std::min(ch, cyy + CB);
-                            select((double)cx0 + (double)(bx * CB) * cl_cell - infl, (double)cx0 + (double)xe * cl_cell + infl,
-                                   (double)cy0 + (double)cyy * cl_cell - infl, (double)cy0 + (double)ye * cl_cell + infl, all, row_lists[bx]);
-                        }
+                        for (int bx = 0; bx * CB < cw; bx++) box(bx * CB, std::min(cw, (bx + 1) * CB), cyy, std::min(ch, cyy + CB), all, row_lists[bx]);
+                    if (cyy % MB == 0) // the 2 x 2 blocks of this pair of rows, each from its coarse block
+                        for (int mx = 0; mx * MB < cw; mx++)
+                            box(mx * MB, std::min(cw, (mx + 1) * MB), cyy, std::min(ch, cyy + MB), row_lists[mx * MB / CB], mid_lists[mx]);
                     for (int cxx = 0; cxx < cw; cxx++) {
-                        select((double)cx0 + (double)cxx * cl_cell - infl, (double)cx0 + (double)(cxx + 1) * cl_cell + infl,
-                               (double)cy0 + (double)cyy * cl_cell - infl, (double)cy0 + (double)(cyy + 1) * cl_cell + infl,
-                               row_lists[cxx / CB], fine);
+                        box(cxx, cxx + 1, cyy, cyy + 1, mid_lists[cxx / MB], fine);
                         cst[(size_t)cyy * cw + cxx] = (int32_t)cxy.size();
-                        for (int q : fine) { // ascending original index (keep[] is sorted)
+                        for (int q : fine.idx) { // ascending original index (keep[] is sorted)
                             cxy.push_back(pts[q]);
                             cidx.push_back(keep[q]);
                         }
@@ -1230,6 +1290,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
             }
         }
     });
+    sw.lap("per-scenario preparation");
     int GC = 2;
     for (int s = 0; s < S; s++) GC = std::max<int>(GC, (int)cell_starts[s].size());
     g.grid_start.assign((size_t)S * GC, 0);
@@ -1263,27 +1324,28 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
             }
         }
     }
-    // candidate lists: concatenate the scenarios' runs
+    // candidate lists: the scenarios' runs go to the device one after the other, straight from the vectors the
+    // threads filled (no host-side concatenation: that was a single-threaded 3.5 GB copy at S=1024)
     {
         int nc = 1;
         for (int s = 0; s < S; s++) nc = std::max<int>(nc, (int)g.cl_start[s].size() - 1);
-        std::vector<int32_t> cstart((size_t)S * (nc + 1), 0);
+        LcsZeroVec<int32_t> cstart((size_t)S * (nc + 1));
         std::vector<long long> cbase(S, 0);
         size_t total = 0;
         for (int s = 0; s < S; s++) {
             cbase[s] = (long long)total;
-            const std::vector<int32_t>& c = g.cl_start[s];
-            for (size_t k = 0; k < (size_t)nc + 1; k++) cstart[(size_t)s * (nc + 1) + k] = c.empty() ? 0 : c[std::min(k, c.size() - 1)];
             total += g.cl_xy[s].size();
         }
-        std::vector<lcs_f2> cxy(std::max<size_t>(total, 4), far);
-        std::vector<int32_t> cidx(std::max<size_t>(total, 4), 0);
-        for (int s = 0; s < S; s++) {
-            std::copy(g.cl_xy[s].begin(), g.cl_xy[s].end(), cxy.begin() + cbase[s]);
-            std::copy(g.cl_idx[s].begin(), g.cl_idx[s].end(), cidx.begin() + cbase[s]);
-            std::vector<lcs_f2>().swap(g.cl_xy[s]);
-            std::vector<int32_t>().swap(g.cl_idx[s]);
-        }
+        lcs_parallel_range(S, [&](int s0, int s1) {
+            for (int s = s0; s < s1; s++) {
+                const std::vector<int32_t>& c = g.cl_start[s];
+                int32_t* dst = cstart.data() + (size_t)s * (nc + 1);
+                if (c.empty()) continue;
+                std::copy(c.begin(), c.end(), dst);
+                for (size_t k = c.size(); k < (size_t)nc + 1; k++) dst[k] = c.back();
+            }
+        });
+        sw.lap("candidate lists: offsets");
         p.cl_nc = nc;
         lcs_release(e, p.cl_geom); // a second upload replaces the first one's lists
         lcs_release(e, p.cl_dim);
@@ -1296,15 +1358,41 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
         LCS_ALLOC(e, p.cl_dim, (size_t)S * 2);
         LCS_ALLOC(e, p.cl_start, cstart.size());
         LCS_ALLOC(e, p.cl_base, S);
-        LCS_ALLOC(e, p.cl_xy, cxy.size());
-        LCS_ALLOC(e, p.cl_idx, cidx.size());
+        {
+            // (no memset of the two big arrays: every entry is written below; total == 0 keeps 4 far points)
+            void *qx = nullptr, *qi = nullptr;
+            const size_t n = std::max<size_t>(total, 4);
+            if (cudaMalloc(&qx, n * sizeof(lcs_f2)) != cudaSuccess || cudaMalloc(&qi, n * sizeof(int32_t)) != cudaSuccess) {
+                if (qx) cudaFree(qx);
+                return lcs_fail(e, LCSIM_B200_ERR_NOMEM, "cudaMalloc(%zu bytes) for the candidate lists failed", n * 12);
+            }
+            e->allocs.push_back(qx);
+            e->allocs.push_back(qi);
+            p.cl_xy = (const lcs_f2*)qx;
+            p.cl_idx = (const int32_t*)qi;
+            if (total == 0) {
+                const lcs_f2 f4[4] = {far, far, far, far};
+                LCS_CUDA(e, cudaMemcpy(qx, f4, sizeof f4, cudaMemcpyHostToDevice));
+                LCS_CUDA(e, cudaMemset(qi, 0, 4 * sizeof(int32_t)));
+            }
+        }
         LCS_CUDA(e, cudaMemcpy((void*)p.cl_geom, g.cl_geom.data(), g.cl_geom.size() * sizeof(float), cudaMemcpyHostToDevice));
         LCS_CUDA(e, cudaMemcpy((void*)p.cl_dim, g.cl_dim.data(), g.cl_dim.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         LCS_CUDA(e, cudaMemcpy((void*)p.cl_start, cstart.data(), cstart.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         LCS_CUDA(e, cudaMemcpy((void*)p.cl_base, cbase.data(), cbase.size() * sizeof(long long), cudaMemcpyHostToDevice));
-        LCS_CUDA(e, cudaMemcpy((void*)p.cl_xy, cxy.data(), cxy.size() * sizeof(lcs_f2), cudaMemcpyHostToDevice));
-        LCS_CUDA(e, cudaMemcpy((void*)p.cl_idx, cidx.data(), cidx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        for (int s = 0; s < S; s++) {
+            const size_t n = g.cl_xy[s].size();
+            if (!n) continue;
+            LCS_CUDA(e, cudaMemcpyAsync((void*)(p.cl_xy + cbase[s]), g.cl_xy[s].data(), n * sizeof(lcs_f2), cudaMemcpyHostToDevice, 0));
+            LCS_CUDA(e, cudaMemcpyAsync((void*)(p.cl_idx + cbase[s]), g.cl_idx[s].data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, 0));
+        }
+        LCS_CUDA(e, cudaDeviceSynchronize());
+        for (int s = 0; s < S; s++) {
+            std::vector<lcs_f2>().swap(g.cl_xy[s]);
+            std::vector<int32_t>().swap(g.cl_idx[s]);
+        }
         e->cand_entries = (int64_t)total;
+        sw.lap("candidate lists: device");
     }
     p.GC = GC;
     LCS_ALLOC(e, p.grid_start, (size_t)S * GC);
@@ -1371,6 +1459,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     }
     LCS_CUDA(e, cudaMemset(p.traj_f32, 0, SA));
     LCS_CUDA(e, cudaMemset(p.stale_valid, 0, SA));
+    sw.lap("other arrays: device");
     e->uploaded = true;
     int rc = lcsim_b200_reset(e, nullptr, nullptr);
     if (rc) return rc;
@@ -2393,33 +2482,38 @@ __global__ void __launch_bounds__(1024) lcc_scan_tiles(int32_t* data, int n, int
     if (base + 1 < n) data[base + 1] = excl + a;
     if (tid == 1023) tile_sum[blockIdx.x] = excl + a + b;
 }
-__global__ void __launch_bounds__(1024) lcc_scan_sums(int32_t* tile_sum, int n_tiles, int32_t* total) {
-    __shared__ int32_t buf[1024];
-    __shared__ int32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < n_tiles; base += 1024) { // chunks of 1024 tile sums, one after the other
-        const int i = base + threadIdx.x;
-        const int32_t own = i < n_tiles ? tile_sum[i] : 0;
-        buf[threadIdx.x] = own;
-        __syncthreads();
-        for (int d = 1; d < 1024; d <<= 1) { // inclusive Hillis-Steele
-            const int32_t o = threadIdx.x >= d ? buf[threadIdx.x - d] : 0;
-            __syncthreads();
-            buf[threadIdx.x] += o;
-            __syncthreads();
-        }
-        if (i < n_tiles) tile_sum[i] = carry + buf[threadIdx.x] - own;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += buf[1023];
-        __syncthreads();
+// second pass: element i gets the sum of the tiles in front of its own; every block adds those tile sums up itself
+// (a city has ~100 tiles, a block of 256 elements lies inside one tile), so there is no kernel for the scan of the
+// tile sums between the two passes.  Block 0 also writes the grand total.
+__global__ void __launch_bounds__(256) lcc_scan_add(int32_t* data, int n, const int32_t* tile_sum, int n_tiles, int32_t* copy, int32_t* total) {
+    __shared__ int32_t part[8];
+    __shared__ int32_t s_off;
+    const int tile = blockIdx.x * 256 / LCC_SCAN_TILE, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int upto = (blockIdx.x == 0 && total) ? n_tiles : tile; // block 0 sums everything (tile == 0 contributes nothing to it)
+    int32_t acc = 0, acc_all = 0;
+    for (int j = threadIdx.x; j < upto; j += 256) {
+        const int32_t v = tile_sum[j];
+        acc_all += v;
+        if (j < tile) acc += v;
     }
-    if (threadIdx.x == 0 && total) *total = carry;
-}
-__global__ void lcc_scan_add(int32_t* data, int n, const int32_t* tile_sum, int32_t* copy) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool want_total = blockIdx.x == 0 && total;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        acc_all += __shfl_xor_sync(0xffffffffu, acc_all, d);
+    }
+    if (lane == 0) part[w] = want_total ? acc_all : acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t t = 0;
+        for (int k = 0; k < 8; k++) t += part[k];
+        if (want_total) *total = t;
+        s_off = want_total ? 0 : t; // block 0 lies in tile 0: nothing in front of it
+    }
+    __syncthreads();
+    const int i = blockIdx.x * 256 + threadIdx.x;
     if (i < n) {
-        const int32_t v = data[i] + tile_sum[i / LCC_SCAN_TILE];
+        const int32_t v = data[i] + s_off;
         data[i] = v;
         if (copy) copy[i] = v; // the scatter's cursor array, written in the same pass
     }
@@ -2430,7 +2524,8 @@ __global__ void lcc_scan_add(int32_t* data, int n, const int32_t* tile_sum, int3
 struct lcsim_b200_city {
     LccP c;
     std::vector<void*> allocs;
-    int32_t* tile_sum = nullptr;
+    int32_t* tile_sum = nullptr; // [3][tile_cap]
+    size_t tile_cap = 0;
     int with_metrics = 1;
     int device = 0;
     bool fresh_reset = false;
@@ -2439,18 +2534,26 @@ struct lcsim_b200_city {
 #ifndef LCSIM_HOSTEMU
     cudaGraphExec_t tick_graph = nullptr; // one tick's launch sequence, captured once (LCSIM_B200_CITY_GRAPH=0: off)
     int use_graph = 1;
+    // the part of a tick behind the new active list forks into independent branches (lane buckets + observations |
+    // collision cells + SAT | off-road): side streams and fork / join events (LCSIM_B200_CITY_FORK=0: one stream)
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_upd = nullptr, ev_list = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
+    int use_fork = 1;
 #endif
     std::string err;
 };
 
-static void lcc_scan(lcsim_b200_city* e, int32_t* data, int n, int32_t* total, int32_t* copy, cudaStream_t st) {
+// which: the scan's own tile-sum scratch (0 = list ranks, 1 = lane buckets, 2 = collision cells; the last two run on
+// concurrent branches of the tick)
+static void lcc_scan(lcsim_b200_city* e, int which, int32_t* data, int n, int32_t* total, int32_t* copy, cudaStream_t st) {
 #ifndef LCSIM_HOSTEMU
     const int tiles = (n + LCC_SCAN_TILE - 1) / LCC_SCAN_TILE;
-    lcc_scan_tiles<<<tiles, 1024, 0, st>>>(data, n, e->tile_sum);
-    lcc_scan_sums<<<1, 1024, 0, st>>>(e->tile_sum, tiles, total);
-    lcc_scan_add<<<(n + 255) / 256, 256, 0, st>>>(data, n, e->tile_sum, copy);
-    e->launches += 3;
+    int32_t* ts = e->tile_sum + (size_t)which * e->tile_cap;
+    lcc_scan_tiles<<<tiles, 1024, 0, st>>>(data, n, ts);
+    lcc_scan_add<<<(n + 255) / 256, 256, 0, st>>>(data, n, ts, tiles, copy, total);
+    e->launches += 2;
 #else
+    (void)which;
     int32_t acc = 0;
     for (int i = 0; i < n; i++) {
         const int32_t v = data[i];
@@ -2498,6 +2601,14 @@ extern "C" void lcsim_b200_city_destroy(lcsim_b200_city* e) {
     if (e->tick_graph) cudaGraphExecDestroy(e->tick_graph);
 #endif
     for (void* q : e->allocs) cudaFree(q);
+#ifndef LCSIM_HOSTEMU
+    for (int k = 0; k < 3; k++) {
+        if (e->ev_side[k]) cudaEventDestroy(e->ev_side[k]);
+        if (e->side[k]) cudaStreamDestroy(e->side[k]);
+    }
+    if (e->ev_upd) cudaEventDestroy(e->ev_upd);
+    if (e->ev_list) cudaEventDestroy(e->ev_list);
+#endif
     delete e;
 }
 
@@ -2613,7 +2724,23 @@ extern "C" int lcsim_b200_city_create(const lcsim_b200_city_static* st, int devi
     LCC_TRY(lcc_alloc(e, &c.cell_agent, N));
     LCC_TRY(lcc_alloc(e, &c.cell_rec, (size_t)N * 8));
     const int max_scan = std::max(std::max(N, NL + 1), c.n_cells + 1);
-    LCC_TRY(lcc_alloc(e, &e->tile_sum, max_scan / 2048 + 2));
+    e->tile_cap = (size_t)max_scan / 2048 + 2;
+    LCC_TRY(lcc_alloc(e, &e->tile_sum, 3 * e->tile_cap));
+#ifndef LCSIM_HOSTEMU
+    {
+        const char* env = getenv("LCSIM_B200_CITY_FORK");
+        e->use_fork = !(env && env[0] == '0');
+        bool ok = true;
+        if (e->use_fork) {
+            for (int k = 0; k < 3 && ok; k++)
+                ok = cudaStreamCreateWithFlags(&e->side[k], cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&e->ev_side[k], cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&e->ev_upd, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&e->ev_list, cudaEventDisableTiming) == cudaSuccess;
+            if (!ok) return lcc_fail(e, LCSIM_B200_ERR_CUDA, "city: side streams / events could not be created");
+        }
+    }
+#endif
     int rc = lcsim_b200_city_reset(e, nullptr);
     if (rc) return rc;
     if (cudaDeviceSynchronize() != cudaSuccess) return lcc_fail(e, LCSIM_B200_ERR_CUDA, "reset failed");
@@ -2622,33 +2749,73 @@ extern "C" int lcsim_b200_city_create(const lcsim_b200_city_static* st, int devi
 
 // arrivals/departures -> (lane buckets) -> observations -> metrics: the part of a tick after the update, which is
 // also everything Engine.reset does after re-initialising the agents
-static void lcc_prepare(lcsim_b200_city* e, LccP& c, bool swap_lanes, cudaStream_t st) {
+// `after_update`: the caller recorded e->ev_upd on st behind the last kernel that READS the lane buckets / cells of the
+// previous tick, so the branches may clear their counters from there on (tick); otherwise they start behind the list.
+static void lcc_prepare(lcsim_b200_city* e, LccP& c, bool swap_lanes, bool after_update, cudaStream_t st) {
     const int N = c.N;
+#ifndef LCSIM_HOSTEMU
+    const bool fork = e->use_fork;
+    cudaStream_t sa = fork ? e->side[0] : st, sb = fork ? e->side[1] : st, sc = fork ? e->side[2] : st;
+    if (fork) {
+        if (!after_update) cudaEventRecord(e->ev_upd, st);
+        if (swap_lanes) cudaStreamWaitEvent(sa, e->ev_upd, 0);
+        if (c.with_metrics) cudaStreamWaitEvent(sb, e->ev_upd, 0);
+    }
+#else
+    cudaStream_t sa = st, sb = st, sc = st;
+    (void)after_update;
+#endif
+    if (swap_lanes) cudaMemsetAsync(c.lane_start, 0, sizeof(int32_t) * (c.NL + 1), sa);
+    if (c.with_metrics) cudaMemsetAsync(c.cell_start, 0, sizeof(int32_t) * (c.n_cells + 1), sb);
+    // ---- the new active list (main stream)
     LCC_RUN(lcc_pop_count, c, N, st);
     cudaMemcpyAsync(c.rank, c.fin, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, st);
-    lcc_scan(e, c.rank, N, c.scal + LCC_N_ARR, nullptr, st);
+    lcc_scan(e, 0, c.rank, N, c.scal + LCC_N_ARR, nullptr, st);
     LCC_RUN(lcc_place, c, N, st);
     LCC_RUN(lcc_place_end, c, 1, st);
-    if (swap_lanes) { // Lane.prepare: agents <- new_agents (lane.py:171-175)
-        cudaMemsetAsync(c.lane_start, 0, sizeof(int32_t) * (c.NL + 1), st);
-        LCC_RUN(lcc_bucket_count, c, 2 * N, st);
-        lcc_scan(e, c.lane_start, c.NL + 1, nullptr, c.lane_cur, st);
-        LCC_RUN(lcc_bucket_scatter, c, 2 * N, st);
-        LCC_RUN(lcc_bucket_end, c, 1, st);
+    e->launches += 3;
+#ifndef LCSIM_HOSTEMU
+    if (fork) {
+        cudaEventRecord(e->ev_list, st);
+        cudaStreamWaitEvent(sa, e->ev_list, 0);
+        if (c.with_metrics) {
+            cudaStreamWaitEvent(sb, e->ev_list, 0);
+            cudaStreamWaitEvent(sc, e->ev_list, 0);
+        }
+    }
+#endif
+    // ---- branch A: Lane.prepare (agents <- new_agents, lane.py:171-175) and the observations
+    if (swap_lanes) {
+        LCC_RUN(lcc_bucket_count, c, 2 * N, sa);
+        lcc_scan(e, 1, c.lane_start, c.NL + 1, nullptr, c.lane_cur, sa);
+        LCC_RUN(lcc_bucket_scatter, c, 2 * N, sa);
+        LCC_RUN(lcc_bucket_end, c, 1, sa);
         e->launches += 3;
     }
-    LCC_RUN(lcc_observe, c, N, st);
-    e->launches += 4;
+    LCC_RUN(lcc_observe, c, N, sa);
+    e->launches += 1;
     if (c.with_metrics) {
-        cudaMemsetAsync(c.cell_start, 0, sizeof(int32_t) * (c.n_cells + 1), st);
-        LCC_RUN(lcc_cell_count, c, N, st);
-        lcc_scan(e, c.cell_start, c.n_cells + 1, nullptr, c.cell_cur, st);
-        LCC_RUN(lcc_cell_scatter, c, N, st);
-        LCC_RUN(lcc_collide, c, N, st);
-        LCC_RUN(lcc_offroad, c, N, st);
+        // ---- branch B: collision cells + SAT; branch C: off-road
+        LCC_RUN(lcc_cell_count, c, N, sb);
+        lcc_scan(e, 2, c.cell_start, c.n_cells + 1, nullptr, c.cell_cur, sb);
+        LCC_RUN(lcc_cell_scatter, c, N, sb);
+        LCC_RUN(lcc_collide, c, N, sb);
+        LCC_RUN(lcc_offroad, c, N, sc);
         e->launches += 4;
     }
     cudaMemcpyAsync(c.active, c.active2, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, st);
+#ifndef LCSIM_HOSTEMU
+    if (fork) { // join
+        cudaEventRecord(e->ev_side[0], sa);
+        cudaStreamWaitEvent(st, e->ev_side[0], 0);
+        if (c.with_metrics) {
+            cudaEventRecord(e->ev_side[1], sb);
+            cudaStreamWaitEvent(st, e->ev_side[1], 0);
+            cudaEventRecord(e->ev_side[2], sc);
+            cudaStreamWaitEvent(st, e->ev_side[2], 0);
+        }
+    }
+#endif
 }
 
 extern "C" int lcsim_b200_city_reset(lcsim_b200_city* e, void* stream) {
@@ -2663,7 +2830,7 @@ extern "C" int lcsim_b200_city_reset(lcsim_b200_city* e, void* stream) {
     LCC_RUN(lcc_reset_agent, c, c.N, st);
     e->launches += 1;
     // Engine.reset (engine.py:139-143) never calls lane_manager.prepare(): the departed agents stay pending
-    lcc_prepare(e, c, false, st);
+    lcc_prepare(e, c, false, false, st);
     if (cudaGetLastError() != cudaSuccess) return lcc_fail(e, LCSIM_B200_ERR_CUDA, "city reset launch failed");
     return 0;
 }
@@ -2678,7 +2845,10 @@ static void lcc_tick(lcsim_b200_city* e, LccP& c, cudaStream_t st) {
     }
     LCC_RUN(lcc_update_serial, c, 1, st);
     LCC_RUN(lcc_commit_v, c, c.N, st);
-    lcc_prepare(e, c, true, st);
+#ifndef LCSIM_HOSTEMU
+    if (e->use_fork) cudaEventRecord(e->ev_upd, st);
+#endif
+    lcc_prepare(e, c, true, true, st);
     LCC_RUN(lcc_tick_end, c, 1, st);
     e->launches += 4 + LCC_READER_ROUNDS;
 }

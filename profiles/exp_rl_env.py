@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scenarios", type=int, default=512)
     ap.add_argument("--n", type=int, default=200)
+    ap.add_argument("--quick", action="store_true", help="30 warm ticks, then 8 ticks of step / build_obs / rewards and exit (ncu launch list)")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -46,6 +47,16 @@ def main():
                       "n_nbr_poly_mean": float(o["n_nbr_poly"].float().mean()), "n_nbr_poly_max": int(o["n_nbr_poly"].max()),
                       "P": int(be.P), "n_active_mean": float(be.n_active.float().mean())}), flush=True)
 
+    if args.quick:
+        ob = rw = None
+        for _ in range(8):
+            be.step(act_agent, act_type, act_data)
+            ob = be.build_obs(k_agents=32, k_polys=64, sort_by_distance=True, out=ob)
+            rw = be.rewards(coef=coef, out=rw)
+        torch.cuda.synchronize()
+        be.close()
+        return
+
     def measure(name, fn, n=args.n):
         for _ in range(5):
             fn()
@@ -62,10 +73,20 @@ def main():
         print(json.dumps({"what": name, "device_us_per_call": a.elapsed_time(b) * 1e3 / n, "host_enqueue_us_per_call": (t1 - t0) * 1e6 / n,
                           "wall_us_per_call": (t2 - t0) * 1e6 / n}), flush=True)
 
+    bufs = [None, None]
+
     def tick():
         be.step(act_agent, act_type, act_data)
-        be.build_obs(k_agents=32, k_polys=64, sort_by_distance=True)
-        be.rewards(coef=coef)
+        bufs[0] = be.build_obs(k_agents=32, k_polys=64, sort_by_distance=True, out=bufs[0])
+        bufs[1] = be.rewards(coef=coef, out=bufs[1])
+
+    ob, rw = [None], [None]
+
+    def obs_reuse():
+        ob[0] = be.build_obs(k_agents=32, k_polys=64, sort_by_distance=True, out=ob[0])
+
+    def rew_reuse():
+        rw[0] = be.rewards(coef=coef, out=rw[0])
 
     measure("step", lambda: be.step(act_agent, act_type, act_data), 60)
     be.reset()
@@ -76,6 +97,8 @@ def main():
     measure("build_obs(no history, no polys)", lambda: be.build_obs(k_agents=32, k_polys=64, sort_by_distance=True, with_history=False, with_polys=False))
     measure("build_obs(unsorted)", lambda: be.build_obs(k_agents=32, k_polys=64, sort_by_distance=False))
     measure("rewards", lambda: be.rewards(coef=coef))
+    measure("build_obs(all, out= reused)", obs_reuse)
+    measure("rewards(out= reused)", rew_reuse)
     be.reset()
     measure("tick = step + build_obs + rewards", tick, 60)
     h_acts = torch.zeros(S, 2, dtype=torch.float64).pin_memory()
