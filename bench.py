@@ -326,16 +326,17 @@ def bench_batch(ctx: Ctx, kind: str, steps: int, warmup: int, traffic=(None, Non
         rng = np.random.default_rng(1 + ctx.rank)
         acts = torch.from_numpy(np.stack([rng.uniform(-0.3, 0.3, (N_TICKS, S)), rng.uniform(-0.2, 0.2, (N_TICKS, S))],
                                          axis=-1)).contiguous().to(dev)
-        act_agent = torch.from_numpy(sb.ads_index.reshape(S, 1).astype(np.int32)).to(dev)
-        act_type = torch.full((S, 1), native.ACT_BICYCLE, dtype=torch.int32, device=dev)
-        act_data = torch.zeros(N_TICKS, S, 1, 5, dtype=torch.float64, device=dev)
-        act_data[..., 0, 0], act_data[..., 0, 1] = acts[..., 0] * 6.0, acts[..., 1] * 0.3
         K_A, K_P = 32, 64
         P = int(be.P)
         obs_bytes_env_tick = 12.0 * P + 16.0 * (K_A + K_P)  # polyline-centre read + edge/feature writes
         extra.update(k_agents=K_A, k_polys=K_P, polyline_centres=P)
 
-        obs_buf, rew_buf = [None], [None]  # written in place every tick (no allocation inside the loop)
+        # device-resident arm: lcsim_b200_env_step_device (actions and result records stay in HBM) with the observation
+        # registered once (lcsim_b200_set_env_obs): per tick ONE call = tick items | metric items + reward kernel beside
+        # the observation build
+        be.set_env_obs(k_agents=K_A, k_polys=K_P, sort_by_distance=True)
+        acts_k = [acts[k].contiguous() for k in range(90)]
+        env_buf = [None]
 
         def one_rollout(timed=False):
             be.reset()
@@ -343,9 +344,7 @@ def bench_batch(ctx: Ctx, kind: str, steps: int, warmup: int, traffic=(None, Non
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
             for k in range(90):
-                be.step(act_agent, act_type, act_data[k])
-                obs_buf[0] = be.build_obs(k_agents=K_A, k_polys=K_P, sort_by_distance=True, out=obs_buf[0])
-                rew_buf[0] = be.rewards(coef=WAYMO_PPO_REWARD, out=rew_buf[0])
+                env_buf[0] = be.env_step_device(acts_k[k], env_buf[0], coef=WAYMO_PPO_REWARD)
             if timed:
                 b.record()
                 kev.append((a, b))
@@ -394,7 +393,7 @@ def bench_batch(ctx: Ctx, kind: str, steps: int, warmup: int, traffic=(None, Non
         "roofline": _roofline(agent_steps_rank / max(n_step_launches, 1), launch_ms, bpa,
                               "lcs_engine_kernel (one launch = %s)" % ("91 ticks" if kind in ("replay", "reactive") else
                                                                        "the ticks between two re-plans" if kind == "replan" else
-                                                                       "90 x (tick + obs + rewards kernels)"),
+                                                                       "90 x (tick items, metric items, obs and rewards kernels)"),
                               *(traffic if kind == "replay" else (None, None))),
         "episode": shard.rates(total), **extra,
     }

@@ -299,6 +299,10 @@ typedef struct {
 } lcsim_b200_env_out;
 int lcsim_b200_env_step(lcsim_b200_engine* e, const double* actions_host, const double* coef6,
                         lcsim_b200_env_out* out_host, int sync, void* stream);
+/* The same step with DEVICE buffers (a policy that lives on the GPU): actions_dev [S][2] float64 or NULL, out_dev [S]
+ * records; nothing is copied and the call never waits for the stream. */
+int lcsim_b200_env_step_device(lcsim_b200_engine* e, const double* actions_dev, const double* coef6,
+                               lcsim_b200_env_out* out_dev, void* stream);
 /* Registers the observation build of env_step: BicycleSingleEnv.step returns the observation with the reward
  * (gym_warpper.py:78-92 -> Engine.get_step_return, engine.py:160-201), so after this call every lcsim_b200_env_step
  * also runs lcsim_b200_build_obs(obs) behind its tick (on an engine-owned side stream, concurrently with the reward

@@ -213,6 +213,23 @@ class BatchEngine:
                                                  self.backend.stream()), "env_step")
         self._keep = (actions, out)
 
+    def env_step_device(self, actions, out=None, coef: Optional[dict] = None):
+        """:meth:`env_step` with DEVICE buffers (lcsim_b200_env_step_device): actions (S,2) float64 device tensor or None,
+        out a device uint8 tensor of S * ENV_OUT_DTYPE.itemsize bytes (allocated when None; reuse it).  Nothing is copied
+        or waited for; a registered observation (:meth:`set_env_obs`) is built beside the metric items."""
+        b = self.backend
+        if out is None:
+            out = b.empty((self.S * native.ENV_OUT_DTYPE.itemsize,), np.uint8)
+        a = None if actions is None else b.to_device(actions, np.float64)
+        self._check(self.lib.lcsim_b200_env_step_device(self._h, None if a is None else b.ptr(a), self._coef6_ptr(coef),
+                                                        b.ptr(out), b.stream()), "env_step_device")
+        self._keep = (a, out)
+        return out
+
+    def _coef6_ptr(self, coef):
+        cf = self._coef6(coef)
+        return None if cf is None else cf.ctypes.data
+
     # ------------------------------------------------------------------ observation builder (SURVEY A10)
     def upload_polylines(self, centres):
         """centres: list of (P_s,3) arrays (x, y, heading) per scenario — packer.polyline_centres()."""

@@ -206,14 +206,15 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
     __shared__ int s_item;
     const int tid = threadIdx.x;
     const bool fused = p.with_metrics && p.fuse; // tick items followed by their metric items
-    const int per_tick = p.with_metrics && !fused ? 2 * p.S : p.S, D = p.snap_depth;
+    const int only = p.only;
+    const int per_tick = p.with_metrics && !fused && !only ? 2 * p.S : p.S, D = p.snap_depth;
     // one item per CTA; the ticket is claimed when the CTA RUNS (not blockIdx): see the forward-progress argument above
     if (tid == 0) s_item = atomicAdd(p.q_ticket, 1);
     __syncthreads();
     const int item = s_item;
     int k = item / per_tick, r = item - k * per_tick;
-    bool metric = r >= p.S;
-    int s = metric ? r - p.S : r;
+    bool metric = r >= p.S || only == 2;
+    int s = r >= p.S ? r - p.S : r;
     if (p.order && per_tick == 2 * p.S && item >= p.S) {
         // experiment orders (LCSIM_B200_ORDER), metric items one tick behind their tick items: T(0, .), then rounds
         // q = 1 .. n-1 holding T(q, .) and M(q-1, .), then M(n-1, .).  order 1 interleaves a round as T(q, s), M(q-1, s)
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
     }
     long long t_wait = 0;
     if (CLK && tid == 0) t_wait = clock64();
-    if (tid == 0) {
+    if (tid == 0 && !only) {
         // the scenario's previous items (claimed earlier, hence running or done): wait for their release, then one
         // acquire fence (it also drops this SM's stale L1 lines); the barrier hands the data to the whole CTA
         // (metric items of a scenario run in order: they update the same per-agent outputs, and an agent that did not
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
         if (metric || fused) lcs_item_metric<MAXT, CLK>(p, lcs_smem_raw, s, k);
     }
     __syncthreads(); // every thread's stores precede the release (cumulativity through the barrier)
-    if (tid == 0) {
+    if (tid == 0 && !only) {
         if (fused)
             asm volatile("st.release.gpu.global.v2.s32 [%0], {%1, %1};" ::"l"(p.q_seq + 2 * s), "r"(k + 1) : "memory");
         else
@@ -272,7 +273,7 @@ static void lcs_launch(const LcsParams& p, int grid_cap, cudaStream_t stream) {
 #ifndef LCSIM_HOSTEMU
     const int Ap = p.Ap;
     const size_t smem = lcs_smem_bytes(Ap);
-    const long long total = (long long)p.n_ticks * (p.with_metrics && !p.fuse ? 2 : 1) * p.S;
+    const long long total = (long long)p.n_ticks * (p.with_metrics && !p.fuse && !p.only ? 2 : 1) * p.S;
     const int nblk = (int)total; // one CTA per item (n_ticks * 2 * S <= 2^31 - 1 is checked by the callers)
     (void)grid_cap;
     cudaMemsetAsync(p.q_ticket, 0, sizeof(int32_t) * (2 + 2 * (size_t)p.S), stream); // ticket and the counter pairs are one block
@@ -630,6 +631,7 @@ struct lcsim_b200_engine {
     int plan_parts = 0;
     int device = 0;
     int grid_cap = 1; // CTAs of the engine kernel the device holds at once (occupancy x SMs)
+    int env_split = 1; // LCSIM_B200_ENV_SPLIT=0: env_step keeps the fused single-tick launch when an observation is registered
     bool env_obs_on = false; // set_env_obs: env_step builds this observation behind its tick
     lcsim_b200_obs_desc env_obs;
     void *obs_stream = nullptr, *ev_tick = nullptr, *ev_obs = nullptr; // side stream + fork / join events of that build
@@ -826,6 +828,10 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
         const char* om = getenv("LCSIM_B200_ORDER"); // experiments: 0 = plain ticket order of the rollout launch
         p.order = om ? std::min(2, std::max(0, atoi(om))) : (p.reactive ? 2 : 0);
         if (p.snap_depth < 2) p.order = 0; // T(k, s) would wait for M(k-1, s), whose ticket follows it
+    }
+    {
+        const char* sp = getenv("LCSIM_B200_ENV_SPLIT");
+        e->env_split = !(sp && sp[0] == '0');
     }
     {
         const char* fm = getenv("LCSIM_B200_FUSE");
@@ -1467,10 +1473,11 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     return 0;
 }
 
-static void lcs_launch_ticks(lcsim_b200_engine* e, LcsParams& q, int n_ticks, cudaStream_t st) {
+static void lcs_launch_ticks(lcsim_b200_engine* e, LcsParams& q, int n_ticks, cudaStream_t st, int only = 0) {
     q.n_ticks = n_ticks;
+    q.only = q.with_metrics ? only : 0;
     // (the phase-clock runs launch tick by tick to time the items of a rollout: they stay split)
-    q.fuse = q.with_metrics && (e->fuse_mode == 1 || (e->fuse_mode == 2 && n_ticks == 1 && !q.dbg)) ? 1 : 0;
+    q.fuse = !q.only && q.with_metrics && (e->fuse_mode == 1 || (e->fuse_mode == 2 && n_ticks == 1 && !q.dbg)) ? 1 : 0;
     lcs_launch(q, e->grid_cap, st);
     e->launches += 1;
 }
@@ -1669,46 +1676,75 @@ extern "C" int lcsim_b200_set_env_obs(lcsim_b200_engine* e, const lcsim_b200_obs
     return 0;
 }
 
+static int lcs_env_step(lcsim_b200_engine* e, const double* actions, const double* coef6, lcsim_b200_env_out* out, bool host,
+                        int sync, void* stream);
 extern "C" int lcsim_b200_env_step(lcsim_b200_engine* e, const double* actions_host, const double* coef6,
                                    lcsim_b200_env_out* out_host, int sync, void* stream) {
     if (!e || !out_host) return LCSIM_B200_ERR_ARG;
     if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "env_step before upload_static");
     LCS_GUARD(e);
+    return lcs_env_step(e, actions_host, coef6, out_host, true, sync, stream);
+}
+extern "C" int lcsim_b200_env_step_device(lcsim_b200_engine* e, const double* actions_dev, const double* coef6,
+                                          lcsim_b200_env_out* out_dev, void* stream) {
+    if (!e || !out_dev) return LCSIM_B200_ERR_ARG;
+    if (!e->uploaded) return lcs_fail(e, LCSIM_B200_ERR_STATE, "env_step_device before upload_static");
+    LCS_GUARD(e);
+    return lcs_env_step(e, actions_dev, coef6, out_dev, false, 0, stream);
+}
+// host = true: actions / out are host buffers (copied through the engine's staging blocks); false: device buffers, used in place
+static int lcs_env_step(lcsim_b200_engine* e, const double* actions_host, const double* coef6, lcsim_b200_env_out* out_host, bool host,
+                        int sync, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LcsParams q = e->p;
     q.mode = 0;
     q.K = 0;
-    if (actions_host) {
+    if (actions_host && host) {
         LCS_CUDA(e, cudaMemcpyAsync(e->env_act, actions_host, sizeof(double) * 2 * q.S, cudaMemcpyHostToDevice, st));
         q.ads_action = e->env_act;
+    } else if (actions_host) {
+        q.ads_action = actions_host;
     }
-    lcs_launch_ticks(e, q, 1, st);
     LcsRewardArgs r;
     memset(&r, 0, sizeof r);
     r.has_coef = coef6 != nullptr;
     if (coef6) memcpy(r.coef, coef6, sizeof r.coef);
-    r.env = e->env_out;
+    r.env = host ? e->env_out : out_host;
     r.s_tab0 = e->s_tab0;
 #ifndef LCSIM_HOSTEMU
-    if (e->env_obs_on) { // the observation of the new state, next to the reward kernel (both only read the tick's results)
+    if (e->env_obs_on && q.with_metrics && !q.dbg && e->env_split) {
+        // the observation needs the tick items only (history ring, list, poses): the launch is split into its tick
+        // items and its metric items, and the observation build runs beside the metric items and the reward kernel
+        lcs_launch_ticks(e, q, 1, st, 1);
         LCS_CUDA(e, cudaEventRecord((cudaEvent_t)e->ev_tick, st));
         LCS_CUDA(e, cudaStreamWaitEvent((cudaStream_t)e->obs_stream, (cudaEvent_t)e->ev_tick, 0));
         int rc = lcs_build_obs(e, &e->env_obs, e->obs_stream);
         if (rc) return rc;
         LCS_CUDA(e, cudaEventRecord((cudaEvent_t)e->ev_obs, (cudaStream_t)e->obs_stream));
+        lcs_launch_ticks(e, q, 1, st, 2);
+    } else {
+        lcs_launch_ticks(e, q, 1, st);
+        if (e->env_obs_on) { // beside the reward kernel only
+            LCS_CUDA(e, cudaEventRecord((cudaEvent_t)e->ev_tick, st));
+            LCS_CUDA(e, cudaStreamWaitEvent((cudaStream_t)e->obs_stream, (cudaEvent_t)e->ev_tick, 0));
+            int rc = lcs_build_obs(e, &e->env_obs, e->obs_stream);
+            if (rc) return rc;
+            LCS_CUDA(e, cudaEventRecord((cudaEvent_t)e->ev_obs, (cudaStream_t)e->obs_stream));
+        }
     }
     lcs_rewards_kernel<<<(q.S + 3) / 4, 128, 0, st>>>(e->p, r);
     LCS_CUDA(e, cudaGetLastError());
     if (e->env_obs_on) LCS_CUDA(e, cudaStreamWaitEvent(st, (cudaEvent_t)e->ev_obs, 0));
-    LCS_CUDA(e, cudaMemcpyAsync(out_host, e->env_out, sizeof(lcsim_b200_env_out) * q.S, cudaMemcpyDeviceToHost, st));
+    if (host) LCS_CUDA(e, cudaMemcpyAsync(out_host, e->env_out, sizeof(lcsim_b200_env_out) * q.S, cudaMemcpyDeviceToHost, st));
     if (sync) LCS_CUDA(e, cudaStreamSynchronize(st));
 #else
+    lcs_launch_ticks(e, q, 1, st);
     if (e->env_obs_on) {
         int rc = lcs_build_obs(e, &e->env_obs, stream);
         if (rc) return rc;
     }
     for (int s = 0; s < q.S; s++) lcs_rewards_one(e->p, r, s, 0, 1);
-    memcpy(out_host, e->env_out, sizeof(lcsim_b200_env_out) * q.S);
+    if (host) memcpy(out_host, e->env_out, sizeof(lcsim_b200_env_out) * q.S);
 #endif
     return 0;
 }
@@ -1820,20 +1856,23 @@ static void lcs_obs_scenario_serial(const LcsParams& p, const LcsObsArgs& o, int
 #endif
 
 #ifndef LCSIM_HOSTEMU
-// One CTA per scenario.  Candidates are compacted in index order with ballot-word prefix sums; the top-k by
-// distance is a bitonic sort (warp shuffles for the short strides) of the (<= LCS_OBS_CAP) candidates in shared memory.
+// grid (S, 4): the agent list (y = 0), the polyline list (y = 1) and the two halves of the history stack (y = 2, 3) of
+// a scenario are independent pieces of work, one CTA each.  Candidates are compacted in index order with ballot-word
+// prefix sums (one barrier per 128 candidates: the flag words are double-buffered and every thread carries the running
+// count itself); the top-k by distance is a bitonic sort of the (<= LCS_OBS_CAP) candidates' 64-bit keys (distance
+// bits, candidate index) in shared memory, in which all steps with a stride below 32 of a stage run in registers with
+// warp shuffles (one load, one store and one barrier for the five of them).
 __global__ void __launch_bounds__(128) lcs_obs_kernel(const LcsParams p, const LcsObsArgs o) {
     __shared__ float c_d[LCS_OBS_CAP], c_x[LCS_OBS_CAP], c_y[LCS_OBS_CAP], c_h[LCS_OBS_CAP];
     __shared__ int c_id[LCS_OBS_CAP];
     __shared__ unsigned long long keys[LCS_OBS_CAP];
-    __shared__ uint32_t words[4];
-    __shared__ int s_count;
+    __shared__ uint32_t words[2][4];
     const int s = blockIdx.x, tid = threadIdx.x;
-    // grid (S, 3): the agent list, the polyline list and the history stack of a scenario are independent pieces of
-    // work, one CTA each (blockIdx.y)
-    if (blockIdx.y == 2) {
-        if (o.d.history)
-            for (int c = tid; c < p.Ap * LCS_H; c += 128) lcs_history_cell(p, o, s, c / LCS_H, c % LCS_H);
+    if (blockIdx.y >= 2) {
+        if (o.d.history) {
+            const int cells = p.Ap * LCS_H, half = (cells + 1) / 2, c0 = blockIdx.y == 2 ? 0 : half, c1 = blockIdx.y == 2 ? half : cells;
+            for (int c = c0 + tid; c < c1; c += 128) lcs_history_cell(p, o, s, c / LCS_H, c % LCS_H);
+        }
         return;
     }
     const int e = o.d.ego ? o.d.ego[s] : p.ads_index[s];
@@ -1841,96 +1880,90 @@ __global__ void __launch_bounds__(128) lcs_obs_kernel(const LcsParams p, const L
     const bool ego_active = p.status[ie] == LCS_ACTIVE;
     float ex = 0, ey = 0, eh = 0;
     if (ego_active) lcs_last_pose_f32(p, ie, &ex, &ey, &eh);
-    {
-        const int which = blockIdx.y;
-        const int cap = which == 0 ? o.d.k_agents : o.d.k_polys;
-        int32_t* idx_out = which == 0 ? o.d.nbr_agent : o.d.nbr_poly;
-        float* feat_out = which == 0 ? o.d.nbr_agent_feat : o.d.nbr_poly_feat;
-        int32_t* n_out = which == 0 ? o.d.n_nbr_agent : o.d.n_nbr_poly;
-        const int n = !ego_active ? 0 : (which == 0 ? p.n_active[s] : (o.poly ? o.n_poly[s] : 0));
-        if (tid == 0) s_count = 0;
-        __syncthreads();
-        for (int j0 = 0; j0 < n; j0 += 128) {
-            const int j = j0 + tid;
-            bool hit = false;
-            float x = 0, y = 0, h = 0, d2 = 0;
-            int id = -1;
-            if (j < n) {
-                if (which == 0) {
-                    id = p.active[(size_t)s * p.Ap + j];
-                    if (id != e) lcs_last_pose_f32(p, (size_t)s * p.Ap + id, &x, &y, &h);
-                } else {
-                    id = j;
-                    const float* q = o.poly + ((size_t)s * o.P + j) * 3;
-                    x = q[0]; y = q[1]; h = q[2];
-                }
-                const float dx = x - ex, dy = y - ey;
-                d2 = lcs_fadd(lcs_fmul(dx, dx), lcs_fmul(dy, dy)); // unfused, like torch
-                hit = !(which == 0 && id == e) && d2 < o.r2;
+    const int which = blockIdx.y;
+    const int cap = which == 0 ? o.d.k_agents : o.d.k_polys;
+    int32_t* idx_out = which == 0 ? o.d.nbr_agent : o.d.nbr_poly;
+    float* feat_out = which == 0 ? o.d.nbr_agent_feat : o.d.nbr_poly_feat;
+    int32_t* n_out = which == 0 ? o.d.n_nbr_agent : o.d.n_nbr_poly;
+    if (!idx_out && !feat_out && !n_out) return; // nothing asked of this list
+    const int n = !ego_active ? 0 : (which == 0 ? p.n_active[s] : (o.poly ? o.n_poly[s] : 0));
+    int found = 0; // running count, the same in every thread
+    for (int j0 = 0, it = 0; j0 < n; j0 += 128, it ^= 1) {
+        const int j = j0 + tid;
+        bool hit = false;
+        float x = 0, y = 0, h = 0, d2 = 0;
+        int id = -1;
+        if (j < n) {
+            if (which == 0) {
+                id = p.active[(size_t)s * p.Ap + j];
+                if (id != e) lcs_last_pose_f32(p, (size_t)s * p.Ap + id, &x, &y, &h);
+            } else {
+                id = j;
+                const float* q = o.poly + ((size_t)s * o.P + j) * 3;
+                x = q[0]; y = q[1]; h = q[2];
             }
-            lcs_set_flag(words, tid, hit);
-            __syncthreads();
-            const int base = s_count, pos = base + lcs_prefix(words, tid);
-            if (hit && pos < LCS_OBS_CAP) {
-                c_d[pos] = d2; c_x[pos] = x; c_y[pos] = y; c_h[pos] = h; c_id[pos] = id;
-            }
-            __syncthreads();
-            if (tid == 0) s_count = base + lcs_total(words, 4);
-            __syncthreads();
+            const float dx = x - ex, dy = y - ey;
+            d2 = lcs_fadd(lcs_fmul(dx, dx), lcs_fmul(dy, dy)); // unfused, like torch
+            hit = !(which == 0 && id == e) && d2 < o.r2;
         }
-        const int found = s_count, m = found < LCS_OBS_CAP ? found : LCS_OBS_CAP;
-        if (tid == 0 && n_out) n_out[s] = found;
-        // output position of candidate c: its index (ascending order), or its rank by (distance, candidate index): the
-        // k nearest come from a bitonic sort of 64-bit keys (distance bits, index) in shared memory — strides below 32
-        // stay inside a warp and are exchanged with shuffles, the longer ones go through shared memory
-        if (o.d.sort_by_distance && m > 1) {
-            int n2 = 2;
-            while (n2 < m) n2 <<= 1; // <= LCS_OBS_CAP = 1024 = 8 keys per thread
-            for (int c = tid; c < n2; c += 128)
-                keys[c] = c < m ? ((unsigned long long)__float_as_uint(c_d[c]) << 32) | (unsigned)c : ~0ull; // d2 >= 0: bits order like values
-            __syncthreads();
-            for (int k = 2; k <= n2; k <<= 1)
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    if (j >= 32 || n2 < 128 * 2) { // partner in another warp's range (or a small problem): shared memory step
-                        for (int c = tid; c < n2; c += 128) {
-                            const int q = c ^ j;
-                            if (q > c) {
-                                const unsigned long long a = keys[c], b = keys[q];
-                                const bool up = (c & k) == 0;
-                                if ((a > b) == up) { keys[c] = b; keys[q] = a; }
-                            }
-                        }
-                        __syncthreads();
-                    } else { // j < 32: element c = e * 128 + tid, its partner lives in the same warp
-                        for (int c = tid; c < n2; c += 128) {
-                            unsigned long long a = keys[c];
-                            const unsigned long long b = __shfl_xor_sync(0xffffffffu, a, j);
-                            const bool lower = (c & j) == 0, up = (c & k) == 0;
-                            const bool take_min = lower == up;
-                            a = take_min ? (a < b ? a : b) : (a > b ? a : b);
-                            keys[c] = a;
-                        }
-                        __syncthreads();
+        lcs_set_flag(words[it], tid, hit);
+        __syncthreads(); // (the next iteration writes the other buffer; nobody is more than one barrier ahead)
+        const int pos = found + lcs_prefix(words[it], tid);
+        if (hit && pos < LCS_OBS_CAP) {
+            c_d[pos] = d2; c_x[pos] = x; c_y[pos] = y; c_h[pos] = h; c_id[pos] = id;
+        }
+        found += lcs_total(words[it], 4);
+    }
+    const int m = found < LCS_OBS_CAP ? found : LCS_OBS_CAP;
+    if (tid == 0 && n_out) n_out[s] = found;
+    __syncthreads();
+    // output position of candidate c: its index (ascending order), or its rank by (distance, candidate index)
+    const bool sorted = o.d.sort_by_distance && m > 1;
+    if (sorted) {
+        int n2 = 128;
+        while (n2 < m) n2 <<= 1; // 128 .. LCS_OBS_CAP = 1024: 1 .. 8 keys per thread, element c = r * 128 + tid
+        for (int c = tid; c < n2; c += 128)
+            keys[c] = c < m ? ((unsigned long long)__float_as_uint(c_d[c]) << 32) | (unsigned)c : ~0ull; // d2 >= 0: bits order like values
+        __syncthreads();
+        for (int k = 2; k <= n2; k <<= 1) {
+            int j = k >> 1;
+            for (; j >= 32; j >>= 1) { // partner in another warp's range: through shared memory
+                for (int c = tid; c < n2; c += 128) {
+                    const int q = c ^ j;
+                    if (q > c) {
+                        const unsigned long long a = keys[c], b = keys[q];
+                        const bool up = (c & k) == 0;
+                        if ((a > b) == up) { keys[c] = b; keys[q] = a; }
                     }
                 }
-        }
-        for (int r = tid; r < m; r += 128) {
-            const int c = (o.d.sort_by_distance && m > 1) ? (int)(keys[r] & 0xffffffffu) : r; // candidate at output position r
-            const int pos = r;
-            if (pos < cap) {
-                if (idx_out) idx_out[(size_t)s * cap + pos] = c_id[c];
-                if (feat_out) {
-                    float f[3];
-                    lcs_rel_feature(ex, ey, eh, c_x[c], c_y[c], c_h[c], f);
-                    for (int k = 0; k < 3; k++) feat_out[((size_t)s * cap + pos) * 3 + k] = f[k];
-                }
+                __syncthreads();
             }
+            for (int c = tid; c < n2; c += 128) { // the remaining strides stay inside the warp: registers + shuffles
+                unsigned long long a = keys[c];
+                const bool up = (c & k) == 0;
+                for (int jj = j; jj > 0; jj >>= 1) {
+                    const unsigned long long b = __shfl_xor_sync(0xffffffffu, a, jj);
+                    const bool take_min = ((c & jj) == 0) == up;
+                    a = take_min ? (a < b ? a : b) : (a > b ? a : b);
+                }
+                keys[c] = a;
+            }
+            __syncthreads();
         }
-        for (int k = m + tid; k < cap; k += 128) {
-            if (idx_out) idx_out[(size_t)s * cap + k] = -1;
-            if (feat_out)
-                for (int c = 0; c < 3; c++) feat_out[((size_t)s * cap + k) * 3 + c] = 0.f;
+    }
+    for (int r = tid; r < m && r < cap; r += 128) {
+        const int c = sorted ? (int)(keys[r] & 0xffffffffu) : r; // candidate at output position r
+        if (idx_out) idx_out[(size_t)s * cap + r] = c_id[c];
+        if (feat_out) {
+            float f[3];
+            lcs_rel_feature(ex, ey, eh, c_x[c], c_y[c], c_h[c], f);
+            for (int k = 0; k < 3; k++) feat_out[((size_t)s * cap + r) * 3 + k] = f[k];
         }
+    }
+    for (int k = m + tid; k < cap; k += 128) {
+        if (idx_out) idx_out[(size_t)s * cap + k] = -1;
+        if (feat_out)
+            for (int c = 0; c < 3; c++) feat_out[((size_t)s * cap + k) * 3 + c] = 0.f;
     }
 }
 #endif
@@ -1972,7 +2005,7 @@ static int lcs_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_desc* obs, v
     o.n_poly = e->n_poly;
     o.P = e->P;
 #ifndef LCSIM_HOSTEMU
-    lcs_obs_kernel<<<dim3(e->p.S, 3), 128, 0, (cudaStream_t)stream>>>(e->p, o);
+    lcs_obs_kernel<<<dim3(e->p.S, 4), 128, 0, (cudaStream_t)stream>>>(e->p, o);
     LCS_CUDA(e, cudaGetLastError());
 #else
     for (int s = 0; s < e->p.S; s++) lcs_obs_scenario_serial(e->p, o, s);

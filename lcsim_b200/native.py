@@ -149,7 +149,7 @@ class CityViews(C.Structure):
 
 EXPORTS = ("lcsim_b200_abi_version", "lcsim_b200_create", "lcsim_b200_upload_static", "lcsim_b200_reset",
            "lcsim_b200_step", "lcsim_b200_step_masked", "lcsim_b200_rollout", "lcsim_b200_rollout_log", "lcsim_b200_rollout_host", "lcsim_b200_set_ref_trajectory", "lcsim_b200_rewards",
-           "lcsim_b200_env_step", "lcsim_b200_set_env_obs", "lcsim_b200_upload_polylines", "lcsim_b200_build_obs", "lcsim_b200_build_encoder_inputs",
+           "lcsim_b200_env_step", "lcsim_b200_env_step_device", "lcsim_b200_set_env_obs", "lcsim_b200_upload_polylines", "lcsim_b200_build_obs", "lcsim_b200_build_encoder_inputs",
            "lcsim_b200_upload_centrelines", "lcsim_b200_project_lanes", "lcsim_b200_guidance_cost",
            "lcsim_b200_plan_metrics", "lcsim_b200_load_dirs", "lcsim_b200_scenarios_dims", "lcsim_b200_scenarios_static",
            "lcsim_b200_scenarios_agent_id", "lcsim_b200_scenarios_junction_id", "lcsim_b200_scenarios_polylines",
@@ -179,6 +179,7 @@ def bind(path: str) -> C.CDLL:
     lib.lcsim_b200_rewards.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.lcsim_b200_env_step.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.lcsim_b200_set_env_obs.argtypes = [vp, C.POINTER(ObsDesc)]
+    lib.lcsim_b200_env_step_device.argtypes = [vp, vp, vp, vp, vp]
     lib.lcsim_b200_upload_polylines.argtypes = [vp, vp, vp, i32]
     lib.lcsim_b200_build_obs.argtypes = [vp, C.POINTER(ObsDesc), vp]
     lib.lcsim_b200_build_encoder_inputs.argtypes = [vp, C.POINTER(EncoderDesc), vp]

@@ -111,10 +111,17 @@ def main():
         torch.cuda.current_stream(dev).synchronize()
 
     measure("e2e tick = env_step + build_obs + sync", env_tick, 60)
-    if hasattr(be, "set_env_obs"):
-        be.reset()
-        be.set_env_obs(k_agents=32, k_polys=64, sort_by_distance=True)
-        measure("e2e tick = env_step (obs registered, sync inside)", lambda: be.env_step(h_acts, h_out, coef=coef, sync=True), 60)
+    be.reset()
+    be.set_env_obs(k_agents=32, k_polys=64, sort_by_distance=True)
+    measure("e2e tick = env_step (obs registered, sync inside)", lambda: be.env_step(h_acts, h_out, coef=coef, sync=True), 60)
+    be.reset()
+    d_acts = h_acts.to(dev)
+    d_out = [None]
+
+    def dev_tick():
+        d_out[0] = be.env_step_device(d_acts, d_out[0], coef=coef)
+
+    measure("device tick = env_step_device (obs registered)", dev_tick, 60)
     be.close()
 
 

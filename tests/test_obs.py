@@ -106,11 +106,19 @@ def test_env_step_builds_registered_observation(backend):
     tn = be.backend.to_numpy
     kw = dict(k_agents=8, k_polys=24, radius=50.0, sort_by_distance=True)
     reg = be.set_env_obs(**kw)
-    out = np.zeros(sb.S, native.ENV_OUT_DTYPE)
+    # a second engine without a registered observation: its env_step is the fused single-tick launch, while the first
+    # one's is split into tick items | metric items with the observation build beside the latter
+    be2 = BatchEngine(sb, reactive=False, with_metrics=True, backend=backend)
+    out, out2 = np.zeros(sb.S, native.ENV_OUT_DTYPE), np.zeros(sb.S, native.ENV_OUT_DTYPE)
     rng = np.random.default_rng(5)
     sep = None
     for tick in range(25):
-        be.env_step(rng.uniform(-0.5, 0.5, (sb.S, 2)), out, sync=True)
+        act = rng.uniform(-0.5, 0.5, (sb.S, 2))
+        be.env_step(act, out, coef=dict(forward=0.1, collision=10, offroad=5), sync=True)
+        be2.env_step(act, out2, coef=dict(forward=0.1, collision=10, offroad=5), sync=True)
+        assert out.tobytes() == out2.tobytes()
+        for nm in ("pose64", "status", "coll_count", "nearest_edge", "offroad", "active", "stats"):
+            np.testing.assert_array_equal(tn(getattr(be, nm)), tn(getattr(be2, nm)), err_msg=f"{nm} at tick {tick}")
         got = {k: tn(v).copy() for k, v in reg.items()}
         sep = be.build_obs(out=sep, **kw)
         be.sync()
@@ -123,3 +131,22 @@ def test_env_step_builds_registered_observation(backend):
     for k, v in reg.items():
         np.testing.assert_array_equal(before[k], tn(v))  # no longer written
     be.close()
+    be2.close()
+
+
+def test_env_step_device_equals_host_form(backend):
+    """lcsim_b200_env_step_device: same records as the host-buffer form, written to a device buffer."""
+    sb = workload.synthetic_batch(310, 3, 48, workers=1)
+    a, b = BatchEngine(sb, backend=backend), BatchEngine(sb, backend=backend)
+    tn = a.backend.to_numpy
+    out = np.zeros(sb.S, native.ENV_OUT_DTYPE)
+    rng = np.random.default_rng(9)
+    dev = None
+    for _ in range(15):
+        act = rng.uniform(-1, 1, (sb.S, 2))
+        a.env_step(act, out, coef=dict(forward=1.0, smooth=2.0), sync=True)
+        dev = b.env_step_device(act, dev, coef=dict(forward=1.0, smooth=2.0))
+        b.sync()
+        assert tn(dev).tobytes() == out.tobytes()
+    a.close()
+    b.close()
