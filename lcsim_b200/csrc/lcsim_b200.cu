@@ -631,7 +631,7 @@ struct lcsim_b200_engine {
     int plan_parts = 0;
     int device = 0;
     int grid_cap = 1; // CTAs of the engine kernel the device holds at once (occupancy x SMs)
-    int env_split = 1; // LCSIM_B200_ENV_SPLIT=0: env_step keeps the fused single-tick launch when an observation is registered
+    int env_split = 0; // LCSIM_B200_ENV_SPLIT=1: env_step splits its launch into tick items | metric items when an observation is registered
     bool env_obs_on = false; // set_env_obs: env_step builds this observation behind its tick
     lcsim_b200_obs_desc env_obs;
     void *obs_stream = nullptr, *ev_tick = nullptr, *ev_obs = nullptr; // side stream + fork / join events of that build
@@ -830,8 +830,10 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
         if (p.snap_depth < 2) p.order = 0; // T(k, s) would wait for M(k-1, s), whose ticket follows it
     }
     {
+        // measured at 512 envs: the split costs a launch more than the overlap returns (device tick 90.9 us split vs
+        // 86.4 us fused, e2e 117 vs 112 us), so it is off unless LCSIM_B200_ENV_SPLIT=1
         const char* sp = getenv("LCSIM_B200_ENV_SPLIT");
-        e->env_split = !(sp && sp[0] == '0');
+        e->env_split = sp && sp[0] == '1';
     }
     {
         const char* fm = getenv("LCSIM_B200_FUSE");
@@ -2487,10 +2489,10 @@ extern "C" void* lcsim_b200_debug_clocks(lcsim_b200_engine* e) { return e ? (voi
 // 2048-element tiles, scan of the tile sums by one block, offset add.  n <= 2048 * 2048.
 #ifndef LCSIM_HOSTEMU
 #define LCC_SCAN_TILE 2048
-__global__ void __launch_bounds__(1024) lcc_scan_tiles(int32_t* data, int n, int32_t* tile_sum) {
+__global__ void __launch_bounds__(1024) lcc_scan_tiles(const int32_t* in, int32_t* data, int n, int32_t* tile_sum) {
     __shared__ int32_t warp_sum[32];
     const int tid = threadIdx.x, base = blockIdx.x * LCC_SCAN_TILE + 2 * tid;
-    const int a = base < n ? data[base] : 0, b = base + 1 < n ? data[base + 1] : 0;
+    const int a = base < n ? in[base] : 0, b = base + 1 < n ? in[base + 1] : 0;
     int v = a + b;
     const int lane = tid & 31, w = tid >> 5;
 #pragma unroll
@@ -2578,18 +2580,19 @@ struct lcsim_b200_city {
 
 // which: the scan's own tile-sum scratch (0 = list ranks, 1 = lane buckets, 2 = collision cells; the last two run on
 // concurrent branches of the tick)
-static void lcc_scan(lcsim_b200_city* e, int which, int32_t* data, int n, int32_t* total, int32_t* copy, cudaStream_t st) {
+// in: the values (may be `data` itself: in place)
+static void lcc_scan(lcsim_b200_city* e, int which, const int32_t* in, int32_t* data, int n, int32_t* total, int32_t* copy, cudaStream_t st) {
 #ifndef LCSIM_HOSTEMU
     const int tiles = (n + LCC_SCAN_TILE - 1) / LCC_SCAN_TILE;
     int32_t* ts = e->tile_sum + (size_t)which * e->tile_cap;
-    lcc_scan_tiles<<<tiles, 1024, 0, st>>>(data, n, ts);
+    lcc_scan_tiles<<<tiles, 1024, 0, st>>>(in, data, n, ts);
     lcc_scan_add<<<(n + 255) / 256, 256, 0, st>>>(data, n, ts, tiles, copy, total);
     e->launches += 2;
 #else
     (void)which;
     int32_t acc = 0;
     for (int i = 0; i < n; i++) {
-        const int32_t v = data[i];
+        const int32_t v = in[i];
         data[i] = acc;
         if (copy) copy[i] = acc;
         acc += v;
@@ -2800,13 +2803,19 @@ static void lcc_prepare(lcsim_b200_city* e, LccP& c, bool swap_lanes, bool after
 #endif
     if (swap_lanes) cudaMemsetAsync(c.lane_start, 0, sizeof(int32_t) * (c.NL + 1), sa);
     if (c.with_metrics) cudaMemsetAsync(c.cell_start, 0, sizeof(int32_t) * (c.n_cells + 1), sb);
-    // ---- the new active list (main stream)
-    LCC_RUN(lcc_pop_count, c, N, st);
-    cudaMemcpyAsync(c.rank, c.fin, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, st);
-    lcc_scan(e, 0, c.rank, N, c.scal + LCC_N_ARR, nullptr, st);
+    // ---- the new active list (main stream); in a tick the pop test ran with the speed commit (lcc_commit_pop)
+    if (!after_update) {
+        LCC_RUN(lcc_pop_count, c, N, st);
+        e->launches += 1;
+    }
+    lcc_scan(e, 0, c.fin, c.rank, N, c.scal + LCC_N_ARR, nullptr, st);
+#ifndef LCSIM_HOSTEMU
+    lcc_place_all_k<<<(N + 255) / 256, 256, 0, st>>>(c, N); // + lcc_place_end by its last block
+#else
     LCC_RUN(lcc_place, c, N, st);
     LCC_RUN(lcc_place_end, c, 1, st);
-    e->launches += 3;
+#endif
+    e->launches += 1;
 #ifndef LCSIM_HOSTEMU
     if (fork) {
         cudaEventRecord(e->ev_list, st);
@@ -2820,23 +2829,23 @@ static void lcc_prepare(lcsim_b200_city* e, LccP& c, bool swap_lanes, bool after
     // ---- branch A: Lane.prepare (agents <- new_agents, lane.py:171-175) and the observations
     if (swap_lanes) {
         LCC_RUN(lcc_bucket_count, c, 2 * N, sa);
-        lcc_scan(e, 1, c.lane_start, c.NL + 1, nullptr, c.lane_cur, sa);
+        lcc_scan(e, 1, c.lane_start, c.lane_start, c.NL + 1, nullptr, c.lane_cur, sa);
         LCC_RUN(lcc_bucket_scatter, c, 2 * N, sa);
-        LCC_RUN(lcc_bucket_end, c, 1, sa);
-        e->launches += 3;
+        e->launches += 2; // (lcc_bucket_end is the first line of lcc_observe)
     }
     LCC_RUN(lcc_observe, c, N, sa);
     e->launches += 1;
     if (c.with_metrics) {
         // ---- branch B: collision cells + SAT; branch C: off-road
         LCC_RUN(lcc_cell_count, c, N, sb);
-        lcc_scan(e, 2, c.cell_start, c.n_cells + 1, nullptr, c.cell_cur, sb);
+        lcc_scan(e, 2, c.cell_start, c.cell_start, c.n_cells + 1, nullptr, c.cell_cur, sb);
         LCC_RUN(lcc_cell_scatter, c, N, sb);
         LCC_RUN(lcc_collide, c, N, sb);
         LCC_RUN(lcc_offroad, c, N, sc);
         e->launches += 4;
     }
-    cudaMemcpyAsync(c.active, c.active2, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, st);
+    LCC_RUN(lcc_finish, c, N, st); // list <- new list; a tick also advances the clock here
+    e->launches += 1;
 #ifndef LCSIM_HOSTEMU
     if (fork) { // join
         cudaEventRecord(e->ev_side[0], sa);
@@ -2877,13 +2886,12 @@ static void lcc_tick(lcsim_b200_city* e, LccP& c, cudaStream_t st) {
         LCC_RUN(lcc_update_round, cr, c.N, st);
     }
     LCC_RUN(lcc_update_serial, c, 1, st);
-    LCC_RUN(lcc_commit_v, c, c.N, st);
+    LCC_RUN(lcc_commit_pop, c, c.N, st);
 #ifndef LCSIM_HOSTEMU
     if (e->use_fork) cudaEventRecord(e->ev_upd, st);
 #endif
     lcc_prepare(e, c, true, true, st);
-    LCC_RUN(lcc_tick_end, c, 1, st);
-    e->launches += 4 + LCC_READER_ROUNDS;
+    e->launches += 3 + LCC_READER_ROUNDS;
 }
 
 extern "C" int lcsim_b200_city_step(lcsim_b200_city* e, int n_ticks, void* stream) {

@@ -49,7 +49,8 @@ struct LccP {
     double* cell_rec; // [N][8] collision records in cell order
     int32_t mode; // 1 = reset
 };
-enum { LCC_N_ACTIVE = 0, LCC_WAIT_PTR, LCC_TICK, LCC_N_ENT, LCC_N_ARR, LCC_M_POP, LCC_LC_REQUIRED, LCC_LC_ERROR, LCC_N_OLD, LCC_N_PENDING };
+enum { LCC_N_ACTIVE = 0, LCC_WAIT_PTR, LCC_TICK, LCC_N_ENT, LCC_N_ARR, LCC_M_POP, LCC_LC_REQUIRED, LCC_LC_ERROR, LCC_N_OLD, LCC_N_PENDING,
+       LCC_SYNC /* blocks of lcc_place_k that are done */ };
 
 #ifndef LCSIM_HOSTEMU
 #define LCC_KERNEL(name)                                          \
@@ -433,6 +434,13 @@ LCS_D void lcc_pop_count(const LccP& c, int j) {
     if (c.depart_tick[c.wait_order[p]] <= tick && (p + 1 == c.N || c.depart_tick[c.wait_order[p + 1]] > tick)) c.scal[LCC_M_POP] = j + 1;
 }
 LCC_KERNEL(lcc_pop_count)
+// one launch for two independent per-index jobs of a tick: the speed commit of list slot i and the pop test of waiting
+// offset i
+LCS_D void lcc_commit_pop(const LccP& c, int i) {
+    lcc_commit_v(c, i);
+    lcc_pop_count(c, i);
+}
+LCC_KERNEL(lcc_commit_pop)
 // thread i: list slot i and, independently, popped waiting entry i
 LCS_D void lcc_place(const LccP& c, int i) {
     const int n = c.scal[LCC_N_ACTIVE], n_arr = c.scal[LCC_N_ARR], m = c.scal[LCC_M_POP], wp = c.scal[LCC_WAIT_PTR];
@@ -476,6 +484,30 @@ LCS_D void lcc_place_end(const LccP& c, int i) {
     c.stats[5] += m;
 }
 LCC_KERNEL(lcc_place_end)
+#ifndef LCSIM_HOSTEMU
+// lcc_place for every index, then lcc_place_end by the block that finishes last (its threads' reads of the old counters
+// are over by then: every block passed its barrier before it took a ticket)
+__global__ void lcc_place_all_k(const LccP c, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lcc_place(c, i);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(&c.scal[LCC_SYNC], 1);
+        if (done == (int)gridDim.x - 1) {
+            c.scal[LCC_SYNC] = 0;
+            __threadfence();
+            lcc_place_end(c, 0);
+        }
+    }
+}
+#endif
+// end of a tick on the main branch: the new list becomes the list, the clock advances
+LCS_D void lcc_finish(const LccP& c, int i) {
+    c.active[i] = c.active2[i];
+    if (i == 0 && c.mode == 0) c.scal[LCC_TICK] += 1;
+}
+LCC_KERNEL(lcc_finish)
 
 // ------------------------------------------------------------------ lane buckets = Lane.prepare (lane.py:171-175)
 LCS_D void lcc_bucket_count(const LccP& c, int e) {
@@ -522,6 +554,7 @@ LCS_D bool lcc_first_agent(const LccP& c, int lane, double* ks, int* agent) {
 
 // ------------------------------------------------------------------ prepare_obs, LaneIDM branch (agent.py:198-243)
 LCS_D void lcc_observe(const LccP& c, int i) {
+    if (i == 0 && c.mode == 0) c.scal[LCC_N_ENT] = 0; // (lcc_bucket_end) the pending lane entries were all bucketed
     if (i >= c.scal[LCC_N_ACTIVE]) return;
     const int a = c.active2[i];
     const int lane = c.lane[a];
@@ -590,29 +623,35 @@ LCS_D void lcc_cell_scatter(const LccP& c, int i) {
     r[6] = (double)a;
 }
 LCC_KERNEL(lcc_cell_scatter)
-LCS_D void lcc_collide(const LccP& c, int i) {
-    if (i >= c.scal[LCC_N_ACTIVE]) return;
-    const int a = c.active2[i];
+// thread e: the e-th entry of the cell table (cell order: its own 64-byte record and its neighbours' come from the
+// same few lines); the trigonometry runs only for pairs whose bounding circles touch
+LCS_D void lcc_collide(const LccP& c, int e0) {
+    if (e0 >= c.scal[LCC_N_ACTIVE]) return;
+    const double* me = c.cell_rec + 8 * (size_t)e0;
+    const double mx = me[0], my = me[1], mh = me[2], mL = me[3], mW = me[4], ra = me[5];
+    const int a = (int)me[6];
     double ea[8], eb[8];
-    {
-        double sh, ch;
-        lcs_sincos(c.h[a], &sh, &ch);
-        ea[0] = c.xy[2 * a]; ea[1] = c.xy[2 * a + 1]; ea[2] = 0.0; ea[3] = ch; ea[4] = sh; ea[5] = c.length[a]; ea[6] = c.width[a]; ea[7] = c.h[a];
-    }
-    const double ra = 0.5 * sqrt(ea[5] * ea[5] + ea[6] * ea[6]);
-    const int cell = lcc_cell_of(c, a), cx = cell % c.cell_w, cy = cell / c.cell_w;
+    bool have_ea = false;
+    int cx = (int)floor(lcs_dmul(lcs_dsub(mx, c.cell_x0), c.cell_inv)), cy = (int)floor(lcs_dmul(lcs_dsub(my, c.cell_y0), c.cell_inv));
+    cx = cx < 0 ? 0 : (cx >= c.cell_w ? c.cell_w - 1 : cx);
+    cy = cy < 0 ? 0 : (cy >= c.cell_h ? c.cell_h - 1 : cy);
     const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx < c.cell_w - 1 ? cx + 1 : c.cell_w - 1;
     int cnt = 0;
     for (int y = cy - 1; y <= cy + 1; y++) {
         if (y < 0 || y >= c.cell_h) continue;
         const int b0 = c.cell_start[y * c.cell_w + x0], b1 = c.cell_start[y * c.cell_w + x1 + 1];
         for (int e = b0; e < b1; e++) {
+            if (e == e0) continue;
             const double* r = c.cell_rec + 8 * (size_t)e;
-            const double dx = r[0] - ea[0], dy = r[1] - ea[1];
+            const double dx = r[0] - mx, dy = r[1] - my;
             const double rr = (ra + r[5]) * 1.000001 + 1e-6; // bounding circles apart: the SAT cannot overlap
             if (dx * dx + dy * dy > rr * rr) continue;
-            if ((int)r[6] == a) continue;
             double sh, ch;
+            if (!have_ea) {
+                lcs_sincos(mh, &sh, &ch);
+                ea[0] = mx; ea[1] = my; ea[2] = 0.0; ea[3] = ch; ea[4] = sh; ea[5] = mL; ea[6] = mW; ea[7] = mh;
+                have_ea = true;
+            }
             lcs_sincos(r[2], &sh, &ch);
             eb[0] = r[0]; eb[1] = r[1]; eb[2] = 0.0; eb[3] = ch; eb[4] = sh; eb[5] = r[3]; eb[6] = r[4]; eb[7] = r[2];
             if (lcs_collide(ea, eb)) cnt++;

@@ -105,10 +105,18 @@ def test_env_step_builds_registered_observation(backend):
     be.upload_polylines(centres)
     tn = be.backend.to_numpy
     kw = dict(k_agents=8, k_polys=24, radius=50.0, sort_by_distance=True)
-    reg = be.set_env_obs(**kw)
     # a second engine without a registered observation: its env_step is the fused single-tick launch, while the first
     # one's is split into tick items | metric items with the observation build beside the latter
+    os.environ["LCSIM_B200_ENV_SPLIT"] = "1"  # (read at create; the default is the fused launch)
+    try:
+        be_split = BatchEngine(sb, reactive=False, with_metrics=True, backend=backend)
+    finally:
+        del os.environ["LCSIM_B200_ENV_SPLIT"]
+    be_split.upload_polylines(centres)
+    be.close()
+    be = be_split
     be2 = BatchEngine(sb, reactive=False, with_metrics=True, backend=backend)
+    reg = be.set_env_obs(**kw)
     out, out2 = np.zeros(sb.S, native.ENV_OUT_DTYPE), np.zeros(sb.S, native.ENV_OUT_DTYPE)
     rng = np.random.default_rng(5)
     sep = None
@@ -147,6 +155,8 @@ def test_env_step_device_equals_host_form(backend):
         a.env_step(act, out, coef=dict(forward=1.0, smooth=2.0), sync=True)
         dev = b.env_step_device(act, dev, coef=dict(forward=1.0, smooth=2.0))
         b.sync()
-        assert tn(dev).tobytes() == out.tobytes()
+        got = np.frombuffer(tn(dev).tobytes(), native.ENV_OUT_DTYPE)
+        for f in ("reward", "terms", "route", "terminated", "truncated", "finished"):  # (the pad bytes are not written)
+            np.testing.assert_array_equal(got[f], out[f], err_msg=f)
     a.close()
     b.close()
