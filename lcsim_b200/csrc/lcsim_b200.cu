@@ -206,7 +206,11 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
     __shared__ int s_item;
     const int tid = threadIdx.x;
     const bool fused = p.with_metrics && p.fuse; // tick items followed by their metric items
+#ifdef LCS_NO_ONLY // experiment build: the split single-tick launches compiled out
+    const int only = 0;
+#else
     const int only = p.only;
+#endif
     const int per_tick = p.with_metrics && !fused && !only ? 2 * p.S : p.S, D = p.snap_depth;
     // one item per CTA; the ticket is claimed when the CTA RUNS (not blockIdx): see the forward-progress argument above
     if (tid == 0) s_item = atomicAdd(p.q_ticket, 1);
@@ -2762,6 +2766,10 @@ extern "C" int lcsim_b200_city_create(const lcsim_b200_city_static* st, int devi
     const int max_scan = std::max(std::max(N, NL + 1), c.n_cells + 1);
     e->tile_cap = (size_t)max_scan / 2048 + 2;
     LCC_TRY(lcc_alloc(e, &e->tile_sum, 3 * e->tile_cap));
+    {
+        const char* ord = getenv("LCSIM_B200_CITY_ORDER");
+        c.by_agent = !(ord && ord[0] == 's');
+    }
 #ifndef LCSIM_HOSTEMU
     {
         const char* env = getenv("LCSIM_B200_CITY_FORK");

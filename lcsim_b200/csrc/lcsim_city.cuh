@@ -48,9 +48,36 @@ struct LccP {
     int32_t *cell_start, *cell_cur, *cell_agent; // [n_cells+1], [n_cells+1], [N]
     double* cell_rec; // [N][8] collision records in cell order
     int32_t mode; // 1 = reset
+    // 1: the per-agent kernels map thread -> AGENT index (its slot from slot_of) instead of thread -> list slot: every
+    // per-agent array is then read and written coalesced (the list order is the order of departures, i.e. random
+    // against the agent index: a slot-ordered warp touches 32 sectors per array).  LCSIM_B200_CITY_ORDER=slot: 0
+    int32_t by_agent;
 };
 enum { LCC_N_ACTIVE = 0, LCC_WAIT_PTR, LCC_TICK, LCC_N_ENT, LCC_N_ARR, LCC_M_POP, LCC_LC_REQUIRED, LCC_LC_ERROR, LCC_N_OLD, LCC_N_PENDING,
        LCC_SYNC /* blocks of lcc_place_k that are done */ };
+// thread t of a per-agent kernel -> (agent, slot) or false when it has none
+LCS_D bool lcc_member(const LccP& c, int t, int* a, int* i) {
+    if (c.by_agent) {
+        *a = t;
+        *i = c.slot_of[t];
+        return *i >= 0;
+    }
+    if (t >= c.scal[LCC_N_ACTIVE]) return false;
+    *i = t;
+    *a = c.active[t];
+    return true;
+}
+// the same after lcc_place (the new list is active2 until the end of the tick)
+LCS_D bool lcc_member2(const LccP& c, int t, int* a) {
+    if (c.by_agent) {
+        *a = t;
+        return c.slot_of[t] >= 0;
+    }
+    if (t >= c.scal[LCC_N_ACTIVE]) return false;
+    *a = c.active2[t];
+    return true;
+}
+
 
 #ifndef LCSIM_HOSTEMU
 #define LCC_KERNEL(name)                                          \
@@ -325,13 +352,10 @@ LCS_D void lcc_finalize(const LccP& c, int i, int a, double acc) {
 }
 // slot i of the active list: manager.py:105-115 -> LaneIDM.get_action (idm_policy.py:53-90).  Agents whose action
 // needs no live read of another agent are finished here; the others leave (acc, whom to read) for the rounds.
-LCS_D void lcc_update(const LccP& c, int i) {
-    const int n = c.scal[LCC_N_ACTIVE];
-    if (i >= n) {
-        c.fin[i] = 0;
-        return;
-    }
-    const int a = c.active[i];
+LCS_D void lcc_update(const LccP& c, int t) {
+    if (t >= c.scal[LCC_N_ACTIVE]) c.fin[t] = 0; // (t as a slot beyond the list)
+    int a, i;
+    if (!lcc_member(c, t, &a, &i)) return;
     const int lane = c.lane[a];
     const double* idm = c.idm + 5 * (size_t)a;
     const bool lv = c.lead_valid[a] != 0;
@@ -384,8 +408,7 @@ LCS_D void lcc_update(const LccP& c, int i) {
 }
 LCC_KERNEL(lcc_update)
 // reader of slot i: ahead_a.runtime.v is this tick's value if that agent precedes it in the list, else last tick's
-LCS_D bool lcc_reader_step(const LccP& c, int i, int round, bool serial) {
-    const int a = c.active[i];
+LCS_D bool lcc_reader_step(const LccP& c, int i, int a, int round, bool serial) {
     if (c.done_round[a] != 0x7fffffff) return false;
     const int x = c.rd_ahead[a];
     const int sx = c.slot_of[x];
@@ -401,9 +424,11 @@ LCS_D bool lcc_reader_step(const LccP& c, int i, int round, bool serial) {
     c.done_round[a] = round;
     return true;
 }
-LCS_D void lcc_update_round(const LccP& c, int i) {
-    if (c.scal[LCC_N_PENDING] == 0 || i >= c.scal[LCC_N_ACTIVE]) return;
-    if (lcc_reader_step(c, i, c.mode /* round number travels in mode */, false)) lcs_atomic_add(&c.scal[LCC_N_PENDING], -1);
+LCS_D void lcc_update_round(const LccP& c, int t) {
+    if (c.scal[LCC_N_PENDING] == 0) return;
+    int a, i;
+    if (!lcc_member(c, t, &a, &i)) return;
+    if (lcc_reader_step(c, i, a, c.mode /* round number travels in mode */, false)) lcs_atomic_add(&c.scal[LCC_N_PENDING], -1);
 }
 LCC_KERNEL(lcc_update_round)
 // whatever dependency chain is longer than the rounds: one thread, list order (normally no work at all)
@@ -411,12 +436,12 @@ LCS_D void lcc_update_serial(const LccP& c, int unused) {
     if (c.scal[LCC_N_PENDING] == 0) return;
     const int n = c.scal[LCC_N_ACTIVE];
     for (int i = 0; i < n; i++)
-        if (lcc_reader_step(c, i, 0x7ffffffe, true)) c.scal[LCC_N_PENDING] -= 1; // list order: predecessors are finished
+        if (lcc_reader_step(c, i, c.active[i], 0x7ffffffe, true)) c.scal[LCC_N_PENDING] -= 1; // list order: predecessors are finished
 }
 LCC_KERNEL(lcc_update_serial)
-LCS_D void lcc_commit_v(const LccP& c, int i) {
-    if (i >= c.scal[LCC_N_ACTIVE]) return;
-    const int a = c.active[i];
+LCS_D void lcc_commit_v(const LccP& c, int t) {
+    int a, i;
+    if (!lcc_member(c, t, &a, &i)) return;
     c.v[a] = c.v2[a];
 }
 LCC_KERNEL(lcc_commit_v)
@@ -555,8 +580,8 @@ LCS_D bool lcc_first_agent(const LccP& c, int lane, double* ks, int* agent) {
 // ------------------------------------------------------------------ prepare_obs, LaneIDM branch (agent.py:198-243)
 LCS_D void lcc_observe(const LccP& c, int i) {
     if (i == 0 && c.mode == 0) c.scal[LCC_N_ENT] = 0; // (lcc_bucket_end) the pending lane entries were all bucketed
-    if (i >= c.scal[LCC_N_ACTIVE]) return;
-    const int a = c.active2[i];
+    int a;
+    if (!lcc_member2(c, i, &a)) return;
     const int lane = c.lane[a];
     const double s = c.s[a], len_a = c.length[a];
     double ks;
@@ -606,14 +631,15 @@ LCS_D int lcc_cell_of(const LccP& c, int a) {
     return cy * c.cell_w + cx;
 }
 LCS_D void lcc_cell_count(const LccP& c, int i) {
-    if (i < c.scal[LCC_N_ACTIVE]) lcs_atomic_add(&c.cell_start[lcc_cell_of(c, c.active2[i])], 1);
+    int a;
+    if (lcc_member2(c, i, &a)) lcs_atomic_add(&c.cell_start[lcc_cell_of(c, a)], 1);
 }
 LCC_KERNEL(lcc_cell_count)
 // slot -> its cell, as a 64-byte record {x, y, heading, length, width, bounding radius, agent}: the collision kernel
 // then reads its candidates from three contiguous runs (the three cells of a grid row are neighbours in the table)
 LCS_D void lcc_cell_scatter(const LccP& c, int i) {
-    if (i >= c.scal[LCC_N_ACTIVE]) return;
-    const int a = c.active2[i];
+    int a;
+    if (!lcc_member2(c, i, &a)) return;
     const int e = lcs_atomic_add(&c.cell_cur[lcc_cell_of(c, a)], 1);
     c.cell_agent[e] = a;
     double* r = c.cell_rec + 8 * (size_t)e;
@@ -664,8 +690,8 @@ LCC_KERNEL(lcc_collide)
 // Agent.is_offroad (agent.py:482-494) -> Road.check_offroad (road.py:342-362, raw nodes) /
 // Junction.check_offroad (junction.py:365-385, resampled): first-index argmin, side by the 2-D cross product
 LCS_D void lcc_offroad(const LccP& c, int i) {
-    if (i >= c.scal[LCC_N_ACTIVE]) return;
-    const int a = c.active2[i];
+    int a;
+    if (!lcc_member2(c, i, &a)) return;
     const int es = c.lane_eset[c.lane[a]];
     const int b = c.eset_start[es], e = c.eset_start[es + 1];
     const double px = c.xy[2 * a], py = c.xy[2 * a + 1];

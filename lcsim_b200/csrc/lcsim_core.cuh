@@ -24,6 +24,9 @@ LCS_D double lcs_dmul(double a, double b) { return a * b; } // built with -ffp-c
 LCS_D double lcs_dadd(double a, double b) { return a + b; }
 LCS_D double lcs_dsub(double a, double b) { return a - b; }
 LCS_D double lcs_dfma(double a, double b, double c) { return fma(a, b, c); }
+#define LCS_DM static inline
+#define LCS_ST_STREAM(ptr, v) (*(ptr) = (v))
+#define LCS_LD_STREAM(ptr) (*(ptr))
 LCS_D void lcs_sincos(double a, double* s, double* c) { *s = sin(a); *c = cos(a); }
 LCS_D float lcs_fmul(float a, float b) { return a * b; }
 LCS_D float lcs_fadd(float a, float b) { return a + b; }
@@ -44,7 +47,23 @@ LCS_D double lcs_dmul(double a, double b) { return __dmul_rn(a, b); }
 LCS_D double lcs_dadd(double a, double b) { return __dadd_rn(a, b); }
 LCS_D double lcs_dsub(double a, double b) { return __dsub_rn(a, b); }
 LCS_D double lcs_dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
-LCS_D void lcs_sincos(double a, double* s, double* c) { sincos(a, s, c); }
+// streaming hints for data that is written and not read again by the rollout (history ring, float32 pose copy) or read
+// exactly once (the snapshot a metric item consumes): evict-first in L2, so that the per-tick state stays resident
+#ifdef LCS_CS_HINTS
+#define LCS_ST_STREAM(ptr, v) __stcs((ptr), (v))
+#define LCS_LD_STREAM(ptr) __ldcs(ptr)
+#else
+#define LCS_ST_STREAM(ptr, v) (*(ptr) = (v))
+#define LCS_LD_STREAM(ptr) (*(ptr))
+#endif
+// LCS_NOINLINE_MATH (experiment build): the long float64 sequences (sincos, wrap_angle, sqrt) exist once in the kernel
+// instead of at every call site (the engine kernel is 200 KB of code against a 32 KB instruction cache per SM)
+#ifdef LCS_NOINLINE_MATH
+#define LCS_DM __device__ __noinline__
+#else
+#define LCS_DM __device__ __forceinline__
+#endif
+LCS_DM void lcs_sincos(double a, double* s, double* c) { sincos(a, s, c); }
 LCS_D float lcs_fmul(float a, float b) { return __fmul_rn(a, b); }
 LCS_D float lcs_fadd(float a, float b) { return __fadd_rn(a, b); }
 LCS_D int lcs_popc(uint32_t x) { return __popc(x); }
@@ -266,7 +285,7 @@ LCS_D void lcs_smem_carve(LcsSmem& sm, unsigned char* base, int Ap) {
 
 // reference: utils/polygon.py:191-192 wrap_angle = (a + pi) % (2*pi) - pi with the floored
 // modulo of Python/NumPy.  fmod is exact in IEEE arithmetic on both sides.
-LCS_D double lcs_wrap_angle(double a) {
+LCS_DM double lcs_wrap_angle(double a) {
     const double two_pi = 2 * LCS_PI;
     const double t = lcs_dadd(a, LCS_PI);
     double r;
@@ -292,7 +311,7 @@ LCS_D double lcs_wrap_angle(double a) {
 // two-term dot product the way BLAS evaluates np.dot / np.matmul / 1-D np.linalg.norm: a0*b0 then fma
 LCS_D double lcs_dot2(double a0, double b0, double a1, double b1) { return lcs_dfma(a1, b1, lcs_dmul(a0, b0)); }
 // np.linalg.norm over a trailing axis of length 2 (unfused)
-LCS_D double lcs_norm2_axis(double dx, double dy) { return sqrt(lcs_dadd(lcs_dmul(dx, dx), lcs_dmul(dy, dy))); }
+LCS_DM double lcs_norm2_axis(double dx, double dy) { return sqrt(lcs_dadd(lcs_dmul(dx, dx), lcs_dmul(dy, dy))); }
 // np.linalg.norm of a 1-D 2-vector (BLAS ddot)
 LCS_D double lcs_norm2_vec(double dx, double dy) { return sqrt(lcs_dot2(dx, dx, dy, dy)); }
 LCS_D double lcs_pymax(double a, double b) { return b > a ? b : a; }
@@ -401,8 +420,9 @@ LCS_D lcs_f8 lcs_ld32(const lcs_f8* q) {
 
 // The same load for data that is read once per search and never again soon (candidate lists: 3.5 GB of them at
 // S=1024): L2 evict-first, so that these lines do not push the per-tick state (13 MB, re-read every tick) out of L2.
+// Measured at S=1024 against a build with -DLCS_NO_STREAM_EF: log-replay 2.97e9 vs 2.91e9, reactive 1.137e9 vs 1.107e9.
 LCS_D lcs_f8 lcs_ld32_stream(const lcs_f8* q) {
-#if defined(LCSIM_HOSTEMU) || !defined(LCS_STREAM_EF)
+#if defined(LCSIM_HOSTEMU) || defined(LCS_NO_STREAM_EF)
     return lcs_ld32(q);
 #else
     lcs_f8 r;
@@ -1006,16 +1026,16 @@ LCS_D bool lcs_policy_waypoint(const LcsParams& p, size_t ia, int cursor, int le
 LCS_D void lcs_ring_push_at(const LcsParams& p, size_t ia, int head, int c, double x, double y, double h, double v, double ch,
                             double sh, bool f32) {
     double* r = p.ring + (ia * LCS_H + head) * 5;
-    r[0] = x;
-    r[1] = y;
+    LCS_ST_STREAM(r + 0, x);
+    LCS_ST_STREAM(r + 1, y);
     if (f32) { // runtime.v / heading are np.float32 after a STATE action read from a float32 re-plan
-        r[2] = (double)((float)v * cosf((float)h));
-        r[3] = (double)((float)v * sinf((float)h));
+        LCS_ST_STREAM(r + 2, (double)((float)v * cosf((float)h)));
+        LCS_ST_STREAM(r + 3, (double)((float)v * sinf((float)h)));
     } else {
-        r[2] = lcs_dmul(v, ch);
-        r[3] = lcs_dmul(v, sh);
+        LCS_ST_STREAM(r + 2, lcs_dmul(v, ch));
+        LCS_ST_STREAM(r + 3, lcs_dmul(v, sh));
     }
-    r[4] = h;
+    LCS_ST_STREAM(r + 4, h);
     p.ring_head[ia] = head + 1 == LCS_H ? 0 : head + 1;
     if (c < LCS_H) p.ring_count[ia] = c + 1;
 }
@@ -1073,7 +1093,11 @@ LCS_D void lcs_store_pose(const LcsParams& p, int s, size_t ia, double x, double
     p32.y = (float)(y - p.origin[2 * s + 1]);
     p32.z = (float)h;
     p32.w = (float)v;
+#if defined(LCS_CS_HINTS) && !defined(LCSIM_HOSTEMU)
+    __stcs((float4*)&p.pose32[ia], make_float4(p32.x, p32.y, p32.z, p32.w));
+#else
     p.pose32[ia] = p32;
+#endif
 }
 
 // Agent.__init__ / Engine.reset for agent a (agent.py:106-171, engine.py:132-143)
@@ -1179,7 +1203,7 @@ LCS_D void lcs_update_pre(const LcsParams& p, int s, int a, LcsUpd& u) {
         // pristine float64 trajectory and a fresh observation: the waypoint comes as one replay record
         const bool use_rec = p.wp_rec && !p.stale_valid[ia] && !p.traj_f32[ia];
         if (use_rec) {
-#if defined(LCSIM_HOSTEMU) || !defined(LCS_STREAM_EF)
+#if defined(LCSIM_HOSTEMU) || defined(LCS_NO_STREAM_EF)
             const LcsWpRec r = p.wp_rec[ia * p.T + (len == 1 ? cursor : cursor + 1)];
 #else
             LcsWpRec r; // read once per rollout: L2 evict-first
@@ -1727,7 +1751,7 @@ LCS_D int lcs_mc_load(const LcsParams& p, LcsSmem& sm, int s, int tid, const Lcs
     // go out together with the header's instead of after it
     const int a = p.snap_agent[base + tid] & (LCS_SNAP_MOVED - 1);
     const double* rp = p.snap_rec + 6 * (base + tid);
-    const double r[6] = {rp[0], rp[1], rp[2], rp[3], rp[4], rp[5]};
+    const double r[6] = {LCS_LD_STREAM(rp), LCS_LD_STREAM(rp + 1), LCS_LD_STREAM(rp + 2), LCS_LD_STREAM(rp + 3), LCS_LD_STREAM(rp + 4), LCS_LD_STREAM(rp + 5)};
     if (tid < n_fin) p.coll_count[(size_t)s * p.Ap + p.snap_fin[base + tid]] = 0; // left the list: outputs reset
     if (tid >= n_new) return -1;
     lcs_store_ex(sm, tid, r[0], r[1], 0.0, r[2], r[3], r[4], r[5], 0.0);
