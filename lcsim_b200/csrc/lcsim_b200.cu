@@ -467,7 +467,7 @@ LCS_D void lcs_scan_lanes(const LcsParams& p, int s, int a, int len, LcsScan& sc
     }
 #endif
 }
-LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s, int lane, int nlanes) {
+LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s, int lane, int nlanes, double* stage = nullptr) {
     const int a = r.agent ? r.agent[s] : p.ads_index[s];
     const size_t ia = (size_t)s * p.Ap + a;
     double terms[6] = {0, 0, 0, 0, 0, 0};
@@ -568,8 +568,28 @@ LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s, in
             }
         }
     }
+#ifndef LCSIM_HOSTEMU
+    if (r.env && stage) {
+        // the 224-byte record leaves the warp as ONE coalesced store (28 lanes x 8 bytes): the record may live in the
+        // caller's pinned host memory, where 30 scalar stores of one lane would be 30 small PCIe writes
+        static_assert(sizeof(lcsim_b200_env_out) == 28 * sizeof(double), "env_out layout");
+        if (lane == 0) {
+            lcsim_b200_env_out* o = (lcsim_b200_env_out*)stage;
+            o->reward = rew;
+            for (int k = 0; k < 6; k++) o->terms[k] = terms[k];
+            for (int k = 0; k < LCS_ROUTE * 2; k++) o->route[k / 2][k % 2] = finished ? 0.0 : route[k]; // engine.py:189-192
+            o->terminated = (collision || off) ? 1 : 0;
+            o->truncated = truncated ? 1 : 0;
+            o->finished = finished ? 1 : 0;
+            for (int k = 0; k < 5; k++) o->pad[k] = 0;
+        }
+        __syncwarp();
+        if (lane < 28) ((double*)(r.env + s))[lane] = stage[lane];
+        __syncwarp();
+    }
+#endif
     if (lane != 0) return;
-    if (r.env) {
+    if (r.env && !stage) {
         lcsim_b200_env_out* o = r.env + s;
         o->reward = rew;
         for (int k = 0; k < 6; k++) o->terms[k] = terms[k];
@@ -588,8 +608,9 @@ LCS_D void lcs_rewards_one(const LcsParams& p, const LcsRewardArgs& r, int s, in
 }
 #ifndef LCSIM_HOSTEMU
 __global__ void lcs_rewards_kernel(const LcsParams p, const LcsRewardArgs r) {
+    __shared__ double stage[4][28]; // one env_out record per warp
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (s < p.S) lcs_rewards_one(p, r, s, threadIdx.x & 31, 32);
+    if (s < p.S) lcs_rewards_one(p, r, s, threadIdx.x & 31, 32, stage[threadIdx.x >> 5]);
 }
 __global__ void lcs_stats_kernel(const int64_t* stats, int S, int64_t* out) {
     __shared__ long long acc[LCS_NSTAT];
@@ -635,6 +656,7 @@ struct lcsim_b200_engine {
     int plan_parts = 0;
     int device = 0;
     int grid_cap = 1; // CTAs of the engine kernel the device holds at once (occupancy x SMs)
+    int env_zerocopy = 1; // LCSIM_B200_ENV_ZEROCOPY
     int env_split = 0; // LCSIM_B200_ENV_SPLIT=1: env_step splits its launch into tick items | metric items when an observation is registered
     bool env_obs_on = false; // set_env_obs: env_step builds this observation behind its tick
     lcsim_b200_obs_desc env_obs;
@@ -836,6 +858,8 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     {
         // measured at 512 envs: the split costs a launch more than the overlap returns (device tick 90.9 us split vs
         // 86.4 us fused, e2e 117 vs 112 us), so it is off unless LCSIM_B200_ENV_SPLIT=1
+        const char* zc = getenv("LCSIM_B200_ENV_ZEROCOPY");
+        if (zc) e->env_zerocopy = atoi(zc);
         const char* sp = getenv("LCSIM_B200_ENV_SPLIT");
         e->env_split = sp && sp[0] == '1';
     }
@@ -1698,6 +1722,17 @@ extern "C" int lcsim_b200_env_step_device(lcsim_b200_engine* e, const double* ac
     LCS_GUARD(e);
     return lcs_env_step(e, actions_dev, coef6, out_dev, false, 0, stream);
 }
+// device alias of a pinned (page-locked, mapped) host buffer, or null: kernels can then read / write the caller's
+// buffer across PCIe directly and the staging copy is not needed
+static void* lcs_pinned_alias(const void* host) {
+#ifndef LCSIM_HOSTEMU
+    cudaPointerAttributes at;
+    if (host && cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
+    cudaGetLastError();
+#endif
+    (void)host;
+    return nullptr;
+}
 // host = true: actions / out are host buffers (copied through the engine's staging blocks); false: device buffers, used in place
 static int lcs_env_step(lcsim_b200_engine* e, const double* actions_host, const double* coef6, lcsim_b200_env_out* out_host, bool host,
                         int sync, void* stream) {
@@ -1705,17 +1740,21 @@ static int lcs_env_step(lcsim_b200_engine* e, const double* actions_host, const 
     LcsParams q = e->p;
     q.mode = 0;
     q.K = 0;
-    if (actions_host && host) {
+    // pinned host buffers (LCSIM_B200_ENV_ZEROCOPY: 1 = results, 2 = results and actions, 0 = never): the reward kernel
+    // writes the records into the caller's buffer / the tick reads the actions from it, no staging copy on the stream
+    lcsim_b200_env_out* out_alias = host && e->env_zerocopy >= 1 ? (lcsim_b200_env_out*)lcs_pinned_alias(out_host) : nullptr;
+    const double* act_alias = host && actions_host && e->env_zerocopy >= 2 ? (const double*)lcs_pinned_alias(actions_host) : nullptr;
+    if (actions_host && host && !act_alias) {
         LCS_CUDA(e, cudaMemcpyAsync(e->env_act, actions_host, sizeof(double) * 2 * q.S, cudaMemcpyHostToDevice, st));
         q.ads_action = e->env_act;
     } else if (actions_host) {
-        q.ads_action = actions_host;
+        q.ads_action = act_alias ? act_alias : actions_host;
     }
     LcsRewardArgs r;
     memset(&r, 0, sizeof r);
     r.has_coef = coef6 != nullptr;
     if (coef6) memcpy(r.coef, coef6, sizeof r.coef);
-    r.env = host ? e->env_out : out_host;
+    r.env = !host ? out_host : out_alias ? out_alias : e->env_out;
     r.s_tab0 = e->s_tab0;
 #ifndef LCSIM_HOSTEMU
     if (e->env_obs_on && q.with_metrics && !q.dbg && e->env_split) {
@@ -1741,7 +1780,7 @@ static int lcs_env_step(lcsim_b200_engine* e, const double* actions_host, const 
     lcs_rewards_kernel<<<(q.S + 3) / 4, 128, 0, st>>>(e->p, r);
     LCS_CUDA(e, cudaGetLastError());
     if (e->env_obs_on) LCS_CUDA(e, cudaStreamWaitEvent(st, (cudaEvent_t)e->ev_obs, 0));
-    if (host) LCS_CUDA(e, cudaMemcpyAsync(out_host, e->env_out, sizeof(lcsim_b200_env_out) * q.S, cudaMemcpyDeviceToHost, st));
+    if (host && !out_alias) LCS_CUDA(e, cudaMemcpyAsync(out_host, e->env_out, sizeof(lcsim_b200_env_out) * q.S, cudaMemcpyDeviceToHost, st));
     if (sync) LCS_CUDA(e, cudaStreamSynchronize(st));
 #else
     lcs_launch_ticks(e, q, 1, st);

@@ -114,6 +114,7 @@ def main():
     be.reset()
     be.set_env_obs(k_agents=32, k_polys=64, sort_by_distance=True)
     measure("e2e tick = env_step (obs registered, sync inside)", lambda: be.env_step(h_acts, h_out, coef=coef, sync=True), 60)
+    print(json.dumps({"what": "LCSIM_B200_ENV_ZEROCOPY", "value": os.environ.get("LCSIM_B200_ENV_ZEROCOPY", "default (1)")}), flush=True)
     be.reset()
     d_acts = h_acts.to(dev)
     d_out = [None]

@@ -160,3 +160,36 @@ def test_env_step_device_equals_host_form(backend):
             np.testing.assert_array_equal(got[f], out[f], err_msg=f)
     a.close()
     b.close()
+
+
+@pytest.mark.gpu
+def test_env_step_pinned_buffers_written_in_place():
+    """Pinned host buffers are used in place (no staging copy): same records as with pageable buffers, for results only
+    (LCSIM_B200_ENV_ZEROCOPY=1, the default) and for results + actions (=2)."""
+    import torch
+
+    sb = workload.synthetic_batch(330, 5, 64, workers=1)
+    ref = BatchEngine(sb, device=0)
+    out_ref = np.zeros(sb.S, native.ENV_OUT_DTYPE)
+    engines = []
+    for mode in ("1", "2"):
+        os.environ["LCSIM_B200_ENV_ZEROCOPY"] = mode
+        try:
+            engines.append(BatchEngine(sb, device=0))
+        finally:
+            del os.environ["LCSIM_B200_ENV_ZEROCOPY"]
+    pinned = [torch.zeros(sb.S * native.ENV_OUT_DTYPE.itemsize, dtype=torch.uint8).pin_memory() for _ in engines]
+    act_pin = torch.zeros(sb.S, 2, dtype=torch.float64).pin_memory()
+    rng = np.random.default_rng(3)
+    coef = dict(forward=0.1, collision=10, offroad=5, smooth=2, destination=1)
+    for _ in range(20):
+        act = rng.uniform(-1, 1, (sb.S, 2))
+        act_pin.copy_(torch.from_numpy(act))
+        ref.env_step(act, out_ref, coef=coef, sync=True)
+        for be, buf in zip(engines, pinned):
+            be.env_step(act_pin, buf, coef=coef, sync=True)
+            got = buf.numpy().view(native.ENV_OUT_DTYPE)
+            for f in ("reward", "terms", "route", "terminated", "truncated", "finished"):
+                np.testing.assert_array_equal(got[f], out_ref[f], err_msg=f)
+    for be in engines + [ref]:
+        be.close()
