@@ -612,18 +612,33 @@ __global__ void lcs_rewards_kernel(const LcsParams p, const LcsRewardArgs r) {
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s < p.S) lcs_rewards_one(p, r, s, threadIdx.x & 31, 32, stage[threadIdx.x >> 5]);
 }
-__global__ void lcs_stats_kernel(const int64_t* stats, int S, int64_t* out) {
-    __shared__ long long acc[LCS_NSTAT];
-    if (threadIdx.x < LCS_NSTAT) acc[threadIdx.x] = 0;
-    __syncthreads();
+// S x 8 int64 -> 8 sums: one block of 1024 threads, a thread reads whole 64-byte rows, warp shuffles, one barrier
+__global__ void __launch_bounds__(1024) lcs_stats_kernel(const int64_t* stats, int S, int64_t* out) {
+    __shared__ long long part[32][LCS_NSTAT];
     long long loc[LCS_NSTAT];
     for (int k = 0; k < LCS_NSTAT; k++) loc[k] = 0;
-    for (int s = threadIdx.x; s < S; s += blockDim.x)
-        for (int k = 0; k < LCS_NSTAT; k++) loc[k] += stats[(size_t)s * LCS_NSTAT + k];
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        const longlong2* row = (const longlong2*)(stats + (size_t)s * LCS_NSTAT);
+#pragma unroll
+        for (int k = 0; k < LCS_NSTAT / 2; k++) {
+            const longlong2 v = row[k];
+            loc[2 * k] += v.x;
+            loc[2 * k + 1] += v.y;
+        }
+    }
+#pragma unroll
     for (int k = 0; k < LCS_NSTAT; k++)
-        if (loc[k]) atomicAdd((unsigned long long*)&acc[k], (unsigned long long)loc[k]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) loc[k] += __shfl_xor_sync(0xffffffffu, loc[k], d);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0)
+        for (int k = 0; k < LCS_NSTAT; k++) part[w][k] = loc[k];
     __syncthreads();
-    if (threadIdx.x < LCS_NSTAT) out[threadIdx.x] = acc[threadIdx.x];
+    if (threadIdx.x < LCS_NSTAT) {
+        long long t = 0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); q++) t += part[q][threadIdx.x];
+        out[threadIdx.x] = t;
+    }
 }
 #endif
 
@@ -1605,7 +1620,7 @@ extern "C" int lcsim_b200_rollout_host(lcsim_b200_engine* e, const uint8_t* rese
     rc = lcs_rollout(e, n_ticks, out->tick_log != nullptr, nullptr, stream);
     if (rc) return rc;
 #ifndef LCSIM_HOSTEMU
-    if (out->stats) lcs_stats_kernel<<<1, 256, 0, st>>>(p.stats, p.S, (int64_t*)e->env_act); // env_act doubles as 64-byte scratch
+    if (out->stats) lcs_stats_kernel<<<1, 1024, 0, st>>>(p.stats, p.S, (int64_t*)e->env_act); // env_act doubles as 64-byte scratch
 #else
     if (out->stats)
         for (int k = 0; k < LCS_NSTAT; k++) {
@@ -2506,7 +2521,7 @@ extern "C" int lcsim_b200_episode_stats(lcsim_b200_engine* e, int64_t* stats_dev
     if (!e || !stats_device) return LCSIM_B200_ERR_ARG;
     LCS_GUARD(e);
 #ifndef LCSIM_HOSTEMU
-    lcs_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(e->p.stats, e->p.S, stats_device);
+    lcs_stats_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(e->p.stats, e->p.S, stats_device);
     LCS_CUDA(e, cudaGetLastError());
 #else
     for (int k = 0; k < LCS_NSTAT; k++) {
