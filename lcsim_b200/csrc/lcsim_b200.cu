@@ -211,28 +211,42 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
 #else
     const int only = p.only;
 #endif
-    const int per_tick = p.with_metrics && !fused && !only ? 2 * p.S : p.S, D = p.snap_depth;
+    const int D = p.snap_depth;
     // one item per CTA; the ticket is claimed when the CTA RUNS (not blockIdx): see the forward-progress argument above
     if (tid == 0) s_item = atomicAdd(p.q_ticket, 1);
     __syncthreads();
-    const int item = s_item;
+    int item = s_item;
+    // Scenario groups (multi-tick launches of more scenarios than the device holds CTAs): tickets run group-major —
+    // the whole rollout of scenarios [0, G), then of [G, 2G), ... — so that the state a tick touches stays the size of one
+    // group (L2-resident) instead of growing with S.  Groups are independent, inside a group the order is the usual one.
+    int s0 = 0, Sg = p.S;
+    const int mult = p.with_metrics && !fused && !only ? 2 : 1;
+    if (p.group > 0 && p.group < p.S && p.n_ticks > 1) {
+        const int per_group = p.n_ticks * mult * p.group, n_groups = (p.S + p.group - 1) / p.group;
+        int g = item / per_group;
+        if (g > n_groups - 1) g = n_groups - 1; // the last group may be smaller: it takes what is left
+        item -= g * per_group;
+        s0 = g * p.group;
+        Sg = p.S - s0 < p.group ? p.S - s0 : p.group;
+    }
+    const int per_tick = mult * Sg;
     int k = item / per_tick, r = item - k * per_tick;
-    bool metric = r >= p.S || only == 2;
-    int s = r >= p.S ? r - p.S : r;
-    if (p.order && per_tick == 2 * p.S && item >= p.S) {
+    bool metric = r >= Sg || only == 2;
+    int s = r >= Sg ? r - Sg : r;
+    if (p.order && mult == 2 && item >= Sg) {
         // experiment orders (LCSIM_B200_ORDER), metric items one tick behind their tick items: T(0, .), then rounds
         // q = 1 .. n-1 holding T(q, .) and M(q-1, .), then M(n-1, .).  order 1 interleaves a round as T(q, s), M(q-1, s)
         // pairs, order 2 keeps the round as two blocks T(q, .) | M(q-1, .).  In both, an item's dependencies were
         // claimed about 2 S tickets earlier (needs snap_depth >= 2; order 2 wants 3).  Measured at S=1024: order 1 is
         // SLOWER than the plain order (replay 2.76e9 vs 2.90e9, reactive 0.82e9 vs 1.08e9) - see profiles/NOTES_r2.md.
-        const int u = item - p.S, q = u / per_tick + 1, v = u - (q - 1) * per_tick;
+        const int u = item - Sg, q = u / per_tick + 1, v = u - (q - 1) * per_tick;
         if (q < p.n_ticks) {
             if (p.order == 1) {
                 s = v >> 1;
                 metric = v & 1;
             } else {
-                metric = v >= p.S;
-                s = metric ? v - p.S : v;
+                metric = v >= Sg;
+                s = metric ? v - Sg : v;
             }
             k = metric ? q - 1 : q;
         } else {
@@ -241,6 +255,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
             k = p.n_ticks - 1;
         }
     }
+    s += s0;
     long long t_wait = 0;
     if (CLK && tid == 0) t_wait = clock64();
     if (tid == 0 && !only) {
@@ -869,6 +884,10 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
         const char* om = getenv("LCSIM_B200_ORDER"); // experiments: 0 = plain ticket order of the rollout launch
         p.order = om ? std::min(2, std::max(0, atoi(om))) : (p.reactive ? 2 : 0);
         if (p.snap_depth < 2) p.order = 0; // T(k, s) would wait for M(k-1, s), whose ticket follows it
+        // ticket groups: log-replay runs batches beyond one generation of CTAs group by group (S=4096: 2.55e9 -> see
+        // profiles/NOTES_r2.md); the reactive mode gains from MORE scenarios per wave (1.14e9 at 1024, 1.30e9 at 4096)
+        const char* gm = getenv("LCSIM_B200_GROUP");
+        p.group = gm ? std::max(0, atoi(gm)) : (p.reactive ? 0 : e->grid_cap);
     }
     {
         // measured at 512 envs: the split costs a launch more than the overlap returns (device tick 90.9 us split vs

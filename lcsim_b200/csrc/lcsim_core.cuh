@@ -222,6 +222,8 @@ struct LcsParams {
     // ticket order of a multi-tick launch with metric items: 0 = T(k, .) then M(k, .); 1 = interleaved, M one tick behind:
     // T(k, 0), M(k-1, 0), T(k, 1), M(k-1, 1), ... (every dependency of an item lies two slot generations back)
     int32_t order;
+    // scenarios per ticket group of a multi-tick launch (0 = one group): see lcs_engine_kernel
+    int32_t group;
     // single-tick launch split in two (env_step: the observation build overlaps the metric items): 1 = tick items only
     // (the snapshot is still published), 2 = metric items only (of the tick the previous launch ran); no tickets wait
     int32_t only;
