@@ -142,6 +142,10 @@ __device__ LCS_ITEM_INLINE void lcs_item_tick(const LcsParams& p, unsigned char*
         STAMP(); // 2: scan done
         if (a >= 0) th.fin = lcs_update_post(p, sm, s, a, u, sc);
     } else {
+        if (p.mode == 1) { // reset launch
+            lcs_ring_clear(p, s);
+            __syncthreads();
+        }
         lcs_phase_update(p, sm, s, tid, th);
     }
     __syncthreads();

@@ -1102,6 +1102,16 @@ LCS_D void lcs_store_pose(const LcsParams& p, int s, size_t ia, double x, double
 #endif
 }
 
+#ifndef LCSIM_HOSTEMU
+// reset launch: the history rings of a scenario (Ap x 11 x 5 doubles, contiguous) cleared by the whole CTA with 16-byte
+// stores — per-thread loops over the agent's own row were 55 stores of 8 bytes at a stride of 440 bytes per lane,
+// i.e. partial-sector writes: ~40 us of the 87 us reset launch at S=1024.  The caller puts a barrier behind it.
+LCS_D void lcs_ring_clear(const LcsParams& p, int s) {
+    double2* r = (double2*)(p.ring + (size_t)s * p.Ap * LCS_H * 5); // Ap is a multiple of 32: the block is 16-byte aligned
+    const int n2 = p.Ap * LCS_H * 5 / 2;
+    for (int k = threadIdx.x; k < n2; k += blockDim.x) r[k] = make_double2(0.0, 0.0);
+}
+#endif
 // Agent.__init__ / Engine.reset for agent a (agent.py:106-171, engine.py:132-143)
 LCS_D void lcs_reset_agent(const LcsParams& p, int s, int a) {
     const size_t ia = (size_t)s * p.Ap + a;
@@ -1117,7 +1127,9 @@ LCS_D void lcs_reset_agent(const LcsParams& p, int s, int a) {
     p.nearest_edge[ia] = -1;
     p.edge_hint[ia] = p.home_edge[ia];
     p.offroad[ia] = 0;
+#ifdef LCSIM_HOSTEMU // (device: the CTA clears the scenario's whole ring with coalesced stores first, lcs_ring_clear)
     for (int k = 0; k < LCS_H * 5; k++) p.ring[ia * LCS_H * 5 + k] = 0.0;
+#endif
     if (a >= p.n_agents[s]) { // padding agents: inert but defined
         lcs_store_pose(p, s, ia, 0.0, 0.0, 0.0, 0.0);
         return;
