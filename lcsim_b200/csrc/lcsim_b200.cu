@@ -1939,21 +1939,28 @@ static void lcs_obs_scenario_serial(const LcsParams& p, const LcsObsArgs& o, int
 #endif
 
 #ifndef LCSIM_HOSTEMU
-// grid (S, 4): the agent list (y = 0), the polyline list (y = 1) and the two halves of the history stack (y = 2, 3) of
-// a scenario are independent pieces of work, one CTA each.  Candidates are compacted in index order with ballot-word
-// prefix sums (one barrier per 128 candidates: the flag words are double-buffered and every thread carries the running
-// count itself); the top-k by distance is a bitonic sort of the (<= LCS_OBS_CAP) candidates' 64-bit keys (distance
-// bits, candidate index) in shared memory, in which all steps with a stride below 32 of a stage run in registers with
-// warp shuffles (one load, one store and one barrier for the five of them).
+// grid (S, 2 + LCS_OBS_HIST): the agent list (y = 0), the polyline list (y = 1) and LCS_OBS_HIST slices of the history
+// stack (y >= 2) of a scenario are independent pieces of work, one CTA each.  Candidates are compacted in index order
+// with ballot-word prefix sums (one barrier per 128 candidates: the flag words are double-buffered and every thread
+// carries the running count itself).  The k nearest (k <= 128) are SELECTED, not sorted out of everything: a four-pass
+// radix select over the distance bits finds the k-th smallest distance (256-bin histograms in shared memory), the
+// candidates below it plus the first ties in index order are compacted, and only those k keys (distance bits, candidate
+// index) go through a bitonic sort — one key per thread, strides below 32 in registers with warp shuffles.  Sorting all
+// m candidates (203 polyline centres on average, 512 keys padded) made the kernel issue-bound: 21 us of its 27.
+// Larger k sort everything (the general path).
+#define LCS_OBS_HIST 4
 __global__ void __launch_bounds__(128) lcs_obs_kernel(const LcsParams p, const LcsObsArgs o) {
-    __shared__ float c_d[LCS_OBS_CAP], c_x[LCS_OBS_CAP], c_y[LCS_OBS_CAP], c_h[LCS_OBS_CAP];
+    __shared__ float c_d[LCS_OBS_CAP];
     __shared__ int c_id[LCS_OBS_CAP];
     __shared__ unsigned long long keys[LCS_OBS_CAP];
-    __shared__ uint32_t words[2][4];
+    __shared__ uint32_t words[2][2][4];
+    __shared__ int hist[256];
+    __shared__ int s_sel[2]; // radix select: chosen bin, elements still wanted inside it
     const int s = blockIdx.x, tid = threadIdx.x;
     if (blockIdx.y >= 2) {
         if (o.d.history) {
-            const int cells = p.Ap * LCS_H, half = (cells + 1) / 2, c0 = blockIdx.y == 2 ? 0 : half, c1 = blockIdx.y == 2 ? half : cells;
+            const int cells = p.Ap * LCS_H, part = (cells + LCS_OBS_HIST - 1) / LCS_OBS_HIST, c0 = (blockIdx.y - 2) * part;
+            const int c1 = c0 + part < cells ? c0 + part : cells;
             for (int c = c0 + tid; c < c1; c += 128) lcs_history_cell(p, o, s, c / LCS_H, c % LCS_H);
         }
         return;
@@ -1974,39 +1981,95 @@ __global__ void __launch_bounds__(128) lcs_obs_kernel(const LcsParams p, const L
     for (int j0 = 0, it = 0; j0 < n; j0 += 128, it ^= 1) {
         const int j = j0 + tid;
         bool hit = false;
-        float x = 0, y = 0, h = 0, d2 = 0;
+        float d2 = 0;
         int id = -1;
         if (j < n) {
+            float x = 0, y = 0, h = 0;
             if (which == 0) {
                 id = p.active[(size_t)s * p.Ap + j];
                 if (id != e) lcs_last_pose_f32(p, (size_t)s * p.Ap + id, &x, &y, &h);
             } else {
                 id = j;
                 const float* q = o.poly + ((size_t)s * o.P + j) * 3;
-                x = q[0]; y = q[1]; h = q[2];
+                x = q[0]; y = q[1];
             }
             const float dx = x - ex, dy = y - ey;
             d2 = lcs_fadd(lcs_fmul(dx, dx), lcs_fmul(dy, dy)); // unfused, like torch
             hit = !(which == 0 && id == e) && d2 < o.r2;
         }
-        lcs_set_flag(words[it], tid, hit);
+        lcs_set_flag(words[it][0], tid, hit);
         __syncthreads(); // (the next iteration writes the other buffer; nobody is more than one barrier ahead)
-        const int pos = found + lcs_prefix(words[it], tid);
+        const int pos = found + lcs_prefix(words[it][0], tid);
         if (hit && pos < LCS_OBS_CAP) {
-            c_d[pos] = d2; c_x[pos] = x; c_y[pos] = y; c_h[pos] = h; c_id[pos] = id;
+            c_d[pos] = d2; c_id[pos] = id;
         }
-        found += lcs_total(words[it], 4);
+        found += lcs_total(words[it][0], 4);
     }
     const int m = found < LCS_OBS_CAP ? found : LCS_OBS_CAP;
     if (tid == 0 && n_out) n_out[s] = found;
     __syncthreads();
     // output position of candidate c: its index (ascending order), or its rank by (distance, candidate index)
     const bool sorted = o.d.sort_by_distance && m > 1;
+    int n_sort = m; // keys to sort (in keys[0 .. n_sort))
+    if (sorted && cap <= 128 && m > cap) {
+        // ---- radix select of the cap-th smallest distance (d2 >= 0: the bits order like the values)
+        uint32_t prefix = 0;
+        int want = cap;
+        for (int pass = 3; pass >= 0; pass--) {
+            for (int b = tid; b < 256; b += 128) hist[b] = 0;
+            __syncthreads();
+            for (int c = tid; c < m; c += 128) {
+                const uint32_t bits = __float_as_uint(c_d[c]);
+                if (pass == 3 || (bits >> (8 * (pass + 1))) == prefix) atomicAdd(&hist[(bits >> (8 * pass)) & 255u], 1);
+            }
+            __syncthreads();
+            if (tid < 32) { // lane l owns bins 8 l .. 8 l + 7: the bin in which the running count reaches `want`
+                int cnt[8], sum = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) { cnt[q] = hist[8 * tid + q]; sum += cnt[q]; }
+                int incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o2 = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (tid >= d) incl += o2;
+                }
+                int before = incl - sum;
+                if (before < want && want <= incl) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (before < want && want <= before + cnt[q]) { s_sel[0] = 8 * tid + q; s_sel[1] = want - before; }
+                        before += cnt[q];
+                    }
+                }
+            }
+            __syncthreads();
+            prefix = (prefix << 8) | (uint32_t)s_sel[0];
+            want = s_sel[1];
+        }
+        // ---- compaction in candidate (= source index) order: everything below the threshold, and the first `want` ties
+        int n_lt = 0, n_eq = 0;
+        for (int c0 = 0, it = 0; c0 < m; c0 += 128, it ^= 1) {
+            const int c = c0 + tid;
+            const uint32_t bits = c < m ? __float_as_uint(c_d[c]) : 0xffffffffu;
+            const bool lt = c < m && bits < prefix, eq = c < m && bits == prefix;
+            lcs_set_flag(words[it][0], tid, lt);
+            lcs_set_flag(words[it][1], tid, eq);
+            __syncthreads();
+            const int pl = n_lt + lcs_prefix(words[it][0], tid), pe = n_eq + lcs_prefix(words[it][1], tid);
+            if (lt || (eq && pe < want)) keys[pl + (pe < want ? pe : want)] = ((unsigned long long)bits << 32) | (unsigned)c;
+            n_lt += lcs_total(words[it][0], 4);
+            n_eq += lcs_total(words[it][1], 4);
+        }
+        n_sort = cap;
+        __syncthreads();
+    } else if (sorted) {
+        for (int c = tid; c < m; c += 128) keys[c] = ((unsigned long long)__float_as_uint(c_d[c]) << 32) | (unsigned)c;
+        __syncthreads();
+    }
     if (sorted) {
         int n2 = 128;
-        while (n2 < m) n2 <<= 1; // 128 .. LCS_OBS_CAP = 1024: 1 .. 8 keys per thread, element c = r * 128 + tid
-        for (int c = tid; c < n2; c += 128)
-            keys[c] = c < m ? ((unsigned long long)__float_as_uint(c_d[c]) << 32) | (unsigned)c : ~0ull; // d2 >= 0: bits order like values
+        while (n2 < n_sort) n2 <<= 1; // 128 .. LCS_OBS_CAP = 1024: 1 .. 8 keys per thread, element c = r * 128 + tid
+        for (int c = n_sort + tid; c < n2; c += 128) keys[c] = ~0ull;
         __syncthreads();
         for (int k = 2; k <= n2; k <<= 1) {
             int j = k >> 1;
@@ -2036,10 +2099,17 @@ __global__ void __launch_bounds__(128) lcs_obs_kernel(const LcsParams p, const L
     }
     for (int r = tid; r < m && r < cap; r += 128) {
         const int c = sorted ? (int)(keys[r] & 0xffffffffu) : r; // candidate at output position r
-        if (idx_out) idx_out[(size_t)s * cap + r] = c_id[c];
+        const int id = c_id[c];
+        if (idx_out) idx_out[(size_t)s * cap + r] = id;
         if (feat_out) {
-            float f[3];
-            lcs_rel_feature(ex, ey, eh, c_x[c], c_y[c], c_h[c], f);
+            float x, y, h, f[3];
+            if (which == 0) {
+                lcs_last_pose_f32(p, (size_t)s * p.Ap + id, &x, &y, &h);
+            } else {
+                const float* q = o.poly + ((size_t)s * o.P + id) * 3;
+                x = q[0]; y = q[1]; h = q[2];
+            }
+            lcs_rel_feature(ex, ey, eh, x, y, h, f);
             for (int k = 0; k < 3; k++) feat_out[((size_t)s * cap + r) * 3 + k] = f[k];
         }
     }
@@ -2088,7 +2158,7 @@ static int lcs_build_obs(lcsim_b200_engine* e, const lcsim_b200_obs_desc* obs, v
     o.n_poly = e->n_poly;
     o.P = e->P;
 #ifndef LCSIM_HOSTEMU
-    lcs_obs_kernel<<<dim3(e->p.S, 4), 128, 0, (cudaStream_t)stream>>>(e->p, o);
+    lcs_obs_kernel<<<dim3(e->p.S, 2 + LCS_OBS_HIST), 128, 0, (cudaStream_t)stream>>>(e->p, o);
     LCS_CUDA(e, cudaGetLastError());
 #else
     for (int s = 0; s < e->p.S; s++) lcs_obs_scenario_serial(e->p, o, s);

@@ -98,6 +98,16 @@ def main():
     measure("build_obs(unsorted)", lambda: be.build_obs(k_agents=32, k_polys=64, sort_by_distance=False))
     measure("rewards", lambda: be.rewards(coef=coef))
     measure("build_obs(all, out= reused)", obs_reuse)
+    for name, kw in (("agents only", dict(with_polys=False, with_history=False)), ("agents + polys", dict(with_history=False)),
+                     ("agents + history", dict(with_polys=False)), ("agents + polys unsorted", dict(with_history=False, sort_by_distance=False))):
+        args_ = dict(k_agents=32, k_polys=64, sort_by_distance=True)
+        args_.update(kw)
+        buf = [be.build_obs(**args_)]
+
+        def part(args_=args_, buf=buf):
+            buf[0] = be.build_obs(out=buf[0], **args_)
+
+        measure("build_obs(" + name + ", out= reused)", part)
     measure("rewards(out= reused)", rew_reuse)
     be.reset()
     measure("tick = step + build_obs + rewards", tick, 60)

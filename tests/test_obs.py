@@ -37,8 +37,8 @@ def test_polyline_centres_match_reference(path):
     np.testing.assert_array_equal(c[:, 2].astype(np.float32), np.arctan2(ref[:, 4], ref[:, 3]))
 
 
-@pytest.mark.parametrize("sort", [False, True])
-def test_neighbour_gather_and_history(backend, sort):
+@pytest.mark.parametrize("sort,KA,KP", [(False, 16, 48), (True, 16, 48), (True, 8, 160), (True, 64, 128)])
+def test_neighbour_gather_and_history(backend, sort, KA, KP):
     raws = [synth.make_raw_scenario(200 + i, 128) for i in range(3)]
     scs = [packer.scenario_from_raw(r) for r in raws]
     sb = packer.pack(scs)
@@ -47,7 +47,8 @@ def test_neighbour_gather_and_history(backend, sort):
     be.upload_polylines(centres)
     o = orc.Oracle(sb, reactive=True)
     tn = be.backend.to_numpy
-    KA, KP = 16, 48  # small caps so that both the cap and the top-k cut are exercised
+    # small caps so that both the cap and the top-k cut are exercised: k <= 128 takes the radix select + small sort,
+    # k > 128 the sort of all candidates
     for tick in range(60):
         be.step()
         o.step()
