@@ -1867,8 +1867,9 @@ LCS_D void lcs_last_pose_f32(const LcsParams& p, size_t ia, float* x, float* y, 
 }
 // one cell of the (N,11,6) history stack: list slot `slot`, shift-register position k (thread per cell: consecutive
 // threads write consecutive 24-byte cells; one thread per row was measured 1.6x slower)
-LCS_D void lcs_history_cell(const LcsParams& p, const LcsObsArgs& o, int s, int slot, int k) {
-    float* out = o.d.history + (((size_t)s * p.Ap + slot) * LCS_H + k) * 6;
+LCS_D void lcs_history_cell(const LcsParams& p, const LcsObsArgs& o, int s, int slot, int k, float* stage = nullptr) {
+    // stage: where the six values go instead of their place in the tensor (the kernel stages a tile in shared memory)
+    float* out = stage ? stage : o.d.history + (((size_t)s * p.Ap + slot) * LCS_H + k) * 6;
     const int a = slot < p.n_active[s] ? p.active[(size_t)s * p.Ap + slot] : -1;
     if (k == 0 && o.d.history_agent) o.d.history_agent[(size_t)s * p.Ap + slot] = a;
     if (a < 0) {
@@ -1959,9 +1960,28 @@ __global__ void __launch_bounds__(128) lcs_obs_kernel(const LcsParams p, const L
     const int s = blockIdx.x, tid = threadIdx.x;
     if (blockIdx.y >= 2) {
         if (o.d.history) {
+            // 128 cells at a time: the values go to a tile in shared memory and leave as whole 16-byte pieces of the
+            // (contiguous) output — six 4-byte stores per thread at a stride of 24 bytes were 144 partial-sector writes
+            // per warp instead of 24 sectors, and the L2 write rate was the kernel's limit (20 us of 27)
+            float* tile = (float*)keys; // [128][6]
             const int cells = p.Ap * LCS_H, part = (cells + LCS_OBS_HIST - 1) / LCS_OBS_HIST, c0 = (blockIdx.y - 2) * part;
             const int c1 = c0 + part < cells ? c0 + part : cells;
-            for (int c = c0 + tid; c < c1; c += 128) lcs_history_cell(p, o, s, c / LCS_H, c % LCS_H);
+            float* base = o.d.history + (size_t)s * cells * 6; // 16-byte aligned: cells * 6 floats is a multiple of 4
+            for (int b0 = c0; b0 < c1; b0 += 128) {
+                const int c = b0 + tid, nb = c1 - b0 < 128 ? c1 - b0 : 128;
+                if (c < c1) lcs_history_cell(p, o, s, c / LCS_H, c % LCS_H, tile + 6 * tid);
+                __syncthreads();
+                const int f0 = b0 * 6, f1 = f0 + nb * 6; // floats [f0, f1) of the scenario's block
+                // head and tail up to the 16-byte boundaries as scalars, the middle as float4
+                const int a0 = (f0 + 3) & ~3, a1 = f1 & ~3;
+                for (int f = f0 + tid; f < (a0 < f1 ? a0 : f1); f += 128) base[f] = tile[f - f0];
+                for (int f = a0 + 4 * tid; f + 3 < a1 + 0 && f < a1; f += 4 * 128) {
+                    const float4 v = make_float4(tile[f - f0], tile[f - f0 + 1], tile[f - f0 + 2], tile[f - f0 + 3]);
+                    *(float4*)(base + f) = v;
+                }
+                for (int f = (a1 > a0 ? a1 : a0) + tid; f < f1; f += 128) base[f] = tile[f - f0];
+                __syncthreads();
+            }
         }
         return;
     }
