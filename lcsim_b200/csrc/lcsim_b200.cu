@@ -2038,17 +2038,9 @@ __global__ void __launch_bounds__(128) lcs_obs_kernel(const LcsParams p, const L
         for (int pass = 3; pass >= 0; pass--) {
             for (int b = tid; b < 256; b += 128) hist[b] = 0;
             __syncthreads();
-            for (int c0 = 0; c0 < m; c0 += 128) {
-                // one atomic per distinct bin of a warp: neighbours' distances share their leading bytes, so plain
-                // atomics pile up on one or two bins (hundreds of serialised updates in the first passes)
-                const int c = c0 + tid;
-                unsigned bin = 256u + (tid & 31); // not counted: a value of its own
-                if (c < m) {
-                    const uint32_t bits = __float_as_uint(c_d[c]);
-                    if (pass == 3 || (bits >> (8 * (pass + 1))) == prefix) bin = (bits >> (8 * pass)) & 255u;
-                }
-                const unsigned grp = __match_any_sync(0xffffffffu, bin);
-                if (bin < 256u && (tid & 31) == __ffs(grp) - 1) atomicAdd(&hist[bin], __popc(grp));
+            for (int c = tid; c < m; c += 128) {
+                const uint32_t bits = __float_as_uint(c_d[c]);
+                if (pass == 3 || (bits >> (8 * (pass + 1))) == prefix) atomicAdd(&hist[(bits >> (8 * pass)) & 255u], 1);
             }
             __syncthreads();
             if (tid < 32) { // lane l owns bins 8 l .. 8 l + 7: the bin in which the running count reaches `want`
