@@ -264,7 +264,7 @@ LCS_D double lcc_car_follow(const double* idm, double self_v, double target_v, d
         const double t = lcs_dadd(lcs_dmul(self_v, 2.0 /* headway, idm_policy.py:35 */), lcc_div(lcs_dmul(self_v, lcs_dsub(self_v, ahead_v)), den));
         const double s_star = lcs_dadd(gap, lcs_pymax(t, 0.0));
         const double r1 = lcc_div(self_v, target_v), r2 = lcc_div(s_star, distance);
-        acc = lcs_dmul(ma, lcs_dsub(lcs_dsub(1.0, pow(r1, 4.0)), lcs_dmul(r2, r2)));
+        acc = lcs_dmul(ma, lcs_dsub(lcs_dsub(1.0, lcs_pow4(r1)), lcs_dmul(r2, r2)));
     }
     return lcs_pymax(mb, lcs_pymin(ma, acc));
 }
