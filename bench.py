@@ -442,7 +442,8 @@ def bench_batch(ctx: Ctx, kind: str, steps: int, warmup: int, traffic=(None, Non
                     cnt[0] += int(h_stats[0])
             what = ("per tick ONE call lcsim_b200_env_step with the observation registered by lcsim_b200_set_env_obs: pinned "
                     "H2D of every env's ADS action, tick, reward kernel next to the observation build (device tensors for "
-                    "the encoder), D2H of reward/terms/route/flags, stream sync, host read; per rollout D2H of the statistics")
+                    "the encoder), reward/terms/route/flags written by the reward kernel straight into the pinned host "
+                    "buffer (224 B per env across PCIe), stream sync, host read; per rollout D2H of the statistics")
         else:
             # plans arrive in pinned HOST memory (the reference hands numpy arrays to set_ref_trajectory), go H2D, and the
             # rollout ends with the read-back of rollout_host
