@@ -260,6 +260,9 @@ def measure_traffic(args):
     return fallback
 
 
+_BATCH_CACHE: dict = {}
+
+
 def bench_batch(ctx: Ctx, kind: str, steps: int, warmup: int, traffic=(None, None)):
     """replay / reactive / replan / rl_env on a BatchEngine; returns the workload's record"""
     import numpy as np
@@ -272,8 +275,13 @@ def bench_batch(ctx: Ctx, kind: str, steps: int, warmup: int, traffic=(None, Non
     R = max(1, args.rollouts_per_step // (3 if kind != "replay" else 1))  # rollouts per step
     reactive = kind == "reactive"
     t_init = time.time()
-    sb = workload.synthetic_batch(ctx.rank * S + (0 if kind in ("replay", "reactive") else 100000), S, args.agents,
-                                  workers=max(1, min(32, (os.cpu_count() or 1) // ctx.world)), with_centres=kind == "rl_env")
+    # (log-replay and reactive run the same batch: generated once per process, `init_s` of the second is its upload)
+    key = (ctx.rank * S + (0 if kind in ("replay", "reactive") else 100000), S, args.agents, kind == "rl_env")
+    if key not in _BATCH_CACHE:
+        _BATCH_CACHE.clear()
+        _BATCH_CACHE[key] = workload.synthetic_batch(key[0], S, args.agents, workers=max(1, min(32, (os.cpu_count() or 1) // ctx.world)),
+                                                     with_centres=kind == "rl_env")
+    sb = _BATCH_CACHE[key]
     if kind == "rl_env":
         sb, centres = sb
     be = BatchEngine(sb, reactive=reactive, with_metrics=not args.no_metrics, device=ctx.local, grid_cell=args.grid_cell)
