@@ -291,8 +291,16 @@ class BatchEngine:
             return None
         d, out, eg = self._obs_desc(k_agents, k_polys, radius, sort_by_distance, ego, with_polys, with_history, None)
         self._check(self.lib.lcsim_b200_set_env_obs(self._h, C.byref(d)), "set_env_obs")
-        self._env_obs = (out, eg)  # the engine holds raw pointers into these
+        self._env_obs = (out, eg, d)  # the engine holds raw pointers into these
         return out
+
+    def build_env_obs(self):
+        """Builds the registered observation now (after a reset, where no env_step ran); returns its tensors."""
+        reg = getattr(self, "_env_obs", None)
+        if reg is None:
+            raise native.NativeLibraryError("build_env_obs: no observation registered (set_env_obs)")
+        self._check(self.lib.lcsim_b200_build_obs(self._h, C.byref(reg[2]), self.backend.stream()), "build_obs")
+        return reg[0]
 
     def build_encoder_inputs(self, a2a_radius: float = 50.0, pl2a_radius: float = 50.0, time_span: int = 10,
                              cap_a2a: Optional[int] = None, cap_pl2a: Optional[int] = None, with_polys: bool = True):

@@ -178,14 +178,18 @@ class BicycleVectorEnv:
         self._out = np.zeros(self.num_envs, native.ENV_OUT_DTYPE)
         self.scene_encoder = None  # callable(engine, neighbour tensors) -> (S,128); zeros without a model
         self.obs_neighbours = obs_neighbours  # kwargs of BatchEngine.build_obs, or None: no neighbour gather
+        # the gather is registered once: every env_step then leaves the observation of the new state in these tensors
+        self._nb = self._be.set_env_obs(**obs_neighbours) if obs_neighbours is not None else None
+        self._nb_fresh = False
 
     def _obs(self):
         fin = self._out["finished"].astype(bool)
         route = self._out["route"].copy()
         route[fin] = 0.0  # engine.py:189-192
         emb = np.zeros((self.num_envs, 128))
-        if self.obs_neighbours is not None:
-            nb = self._be.build_obs(**self.obs_neighbours)
+        if self._nb is not None:
+            nb = self._nb if self._nb_fresh else self._be.build_env_obs()  # (after a reset no env_step built it)
+            self._nb_fresh = False
             if self.scene_encoder is not None:
                 emb = np.asarray(self.scene_encoder(self.engine, nb))
                 emb[fin] = 0.0
@@ -212,6 +216,7 @@ class BicycleVectorEnv:
     def step(self, actions):
         actions = np.ascontiguousarray(actions, np.float64).reshape(self.num_envs, 2)
         self._be.env_step(actions, self._out, coef=self.reward_config, sync=True)
+        self._nb_fresh = True
         for s in range(self.num_envs):
             self.engine._time[s] += self.engine.step_interval
             self.engine._step_count[s] += 1

@@ -139,3 +139,29 @@ def test_vector_env_matches_reference(dataset, backend):
     check_step(c, 1, {"route": obs["route"][1], "scene_emb": obs["scene_emb"][1]}, reward[1], terminated[1], truncated[1],
                {"rewards": {key: v[1] for key, v in info["rewards"].items()}})
     env.close()
+
+
+def test_vector_env_observation_tensors(dataset, backend):
+    """obs_neighbours registers the gather once (lcsim_b200_set_env_obs): after reset and after every step the scene
+    encoder hook receives the tensors of the CURRENT state — the same bytes a fresh build_obs call produces."""
+    kw = dict(k_agents=8, k_polys=16, radius=50.0, sort_by_distance=True, with_polys=False)
+    env = BicycleVectorEnv(make_config(dataset, 3, backend), obs_neighbours=kw)
+    tn = env._be.backend.to_numpy
+    seen = []
+
+    def encoder(engine, nb):
+        seen.append({k: tn(v).copy() for k, v in nb.items()})
+        return np.ones((3, 128))
+
+    env.scene_encoder = encoder
+    rng = np.random.default_rng(2)
+    obs, _ = env.reset()
+    for k in range(12):
+        if k:
+            obs, *_ = env.step(rng.uniform(-1, 1, (3, 2)))
+        assert len(seen) == k + 1 and obs["scene_emb"].shape == (3, 128)
+        fresh = env._be.build_obs(**kw)
+        env._be.sync()
+        for name, v in fresh.items():
+            np.testing.assert_array_equal(seen[-1][name], tn(v), err_msg=f"{name} at step {k}")
+    env.close()
