@@ -2648,6 +2648,8 @@ extern "C" int lcsim_b200_episode_stats(lcsim_b200_engine* e, int64_t* stats_dev
 
 #ifdef LCSIM_HOSTEMU
 extern "C" long long* lcsim_hostemu_counters(void) { return lcs_dbg_count; }
+extern "C" double lcsim_hostemu_pow4(double x) { return lcs_pow4(x); } // test hook (tests/test_numerics.py)
+extern "C" double lcsim_hostemu_wrap_angle(double a) { return lcs_wrap_angle(a); }
 #endif
 // not part of the public ABI: device pointer of the phase-clock buffer ([S][16] int64) or NULL
 extern "C" void* lcsim_b200_debug_clocks(lcsim_b200_engine* e) { return e ? (void*)e->p.dbg : nullptr; }
