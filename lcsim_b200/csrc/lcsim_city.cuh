@@ -85,6 +85,13 @@ LCS_D bool lcc_member2(const LccP& c, int t, int* a) {
         const int i = blockIdx.x * blockDim.x + threadIdx.x;      \
         if (i < n) name(c, i);                                    \
     }
+// the same with a floor on the resident blocks per SM (a register cap): a kernel bound by the latency of its
+// dependent loads wants all of its blocks resident at once, not one and a third waves of them
+#define LCC_KERNEL_LB(name, minb)                                                     \
+    __global__ void __launch_bounds__(256, minb) name##_k(const LccP c, int n) {      \
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;                          \
+        if (i < n) name(c, i);                                                        \
+    }
 #define LCC_RUN(name, c, n, st)                                                                  \
     do {                                                                                         \
         if ((n) > 0) name##_k<<<((n) + 255) / 256, 256, 0, st>>>(c, n);                          \
@@ -93,6 +100,7 @@ LCS_D double lcc_div(double a, double b) { return __ddiv_rn(a, b); }
 LCS_D void atomicAdd_i64(int64_t* p, int64_t v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
 #else
 #define LCC_KERNEL(name)
+#define LCC_KERNEL_LB(name, minb)
 #define LCC_RUN(name, c, n, st)                          \
     do {                                                 \
         for (int _i = 0; _i < (n); _i++) name(c, _i);    \
@@ -406,7 +414,14 @@ LCS_D void lcc_update(const LccP& c, int t) {
         lcs_atomic_add(&c.scal[LCC_N_PENDING], 1);
     }
 }
+#ifndef LCC_UPDATE_MINB
+#define LCC_UPDATE_MINB 0
+#endif
+#if LCC_UPDATE_MINB > 0
+LCC_KERNEL_LB(lcc_update, LCC_UPDATE_MINB)
+#else
 LCC_KERNEL(lcc_update)
+#endif
 // reader of slot i: ahead_a.runtime.v is this tick's value if that agent precedes it in the list, else last tick's
 LCS_D bool lcc_reader_step(const LccP& c, int i, int a, int round, bool serial) {
     if (c.done_round[a] != 0x7fffffff) return false;
@@ -686,7 +701,14 @@ LCS_D void lcc_collide(const LccP& c, int e0) {
     c.coll_count[a] = cnt;
     if (cnt) atomicAdd_i64(&c.stats[2], cnt);
 }
+#ifndef LCC_COLLIDE_MINB
+#define LCC_COLLIDE_MINB 0
+#endif
+#if LCC_COLLIDE_MINB > 0
+LCC_KERNEL_LB(lcc_collide, LCC_COLLIDE_MINB)
+#else
 LCC_KERNEL(lcc_collide)
+#endif
 // Agent.is_offroad (agent.py:482-494) -> Road.check_offroad (road.py:342-362, raw nodes) /
 // Junction.check_offroad (junction.py:365-385, resampled): first-index argmin, side by the 2-D cross product
 LCS_D void lcc_offroad(const LccP& c, int i) {
