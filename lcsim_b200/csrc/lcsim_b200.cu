@@ -260,6 +260,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
         }
     }
     s += s0;
+    if (p.perm && p.n_ticks > 1) s = p.perm[s];
     long long t_wait = 0;
     if (CLK && tid == 0) t_wait = clock64();
     if (tid == 0 && !only) {
@@ -1533,6 +1534,21 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     }
     LCS_CUDA(e, cudaMemset(p.traj_f32, 0, SA));
     LCS_CUDA(e, cudaMemset(p.stale_valid, 0, SA));
+    {
+        // ticket order of the rollout launches: scenarios by decreasing weight (agent-steps of their trajectories)
+        const char* pm = getenv("LCSIM_B200_PERM");
+        lcs_release(e, p.perm);
+        if (!(pm && pm[0] == '0') && S > 1) {
+            std::vector<long long> w(S, 0);
+            for (int s = 0; s < S; s++)
+                for (int a = 0; a < st->n_agents[s]; a++) w[s] += st->traj_len[(size_t)s * A + a];
+            std::vector<int32_t> perm(S);
+            for (int s = 0; s < S; s++) perm[s] = s;
+            std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return w[a] > w[b]; });
+            LCS_ALLOC(e, p.perm, S);
+            LCS_CUDA(e, cudaMemcpy((void*)p.perm, perm.data(), sizeof(int32_t) * S, cudaMemcpyHostToDevice));
+        }
+    }
     sw.lap("other arrays: device");
     e->uploaded = true;
     int rc = lcsim_b200_reset(e, nullptr, nullptr);

@@ -138,17 +138,20 @@ def test_city_20k_properties():
 @pytest.mark.parametrize("reactive", [False, True])
 def test_ticket_orders_and_ring_depths_agree(reactive):
     """The schedule of the rollout launch must not show in the results: every ticket order (plain, interleaved pairs,
-    metric items one tick behind), every depth of the snapshot ring and every grouping of the scenarios leaves the same bytes after a 91-tick rollout of
+    metric items one tick behind), every depth of the snapshot ring, every grouping of the scenarios and the heaviest-first permutation leave the same bytes after a 91-tick rollout of
     256 scenarios, with the per-tick log identical too."""
     sb = workload.synthetic_batch(5000, 256, 128, workers=min(16, os.cpu_count() or 1))
     ref_state, ref_log = None, None
-    for order, depth, group in (("0", "2", "0"), ("1", "2", "0"), ("2", "3", "0"), ("2", "2", "100"), ("0", "4", "0"), ("1", "3", "64"),
-                                ("0", "2", "100"), ("2", "3", "255")):  # groups: scenarios per ticket group (100 + 100 + 56, ...)
-        os.environ["LCSIM_B200_ORDER"], os.environ["LCSIM_B200_SNAP_DEPTH"], os.environ["LCSIM_B200_GROUP"] = order, depth, group
+    # (order, ring depth, scenarios per ticket group (100 + 100 + 56, ...), heaviest scenarios first)
+    for order, depth, group, perm in (("0", "2", "0", "0"), ("1", "2", "0", "1"), ("2", "3", "0", "1"), ("2", "2", "100", "0"), ("0", "4", "0", "1"),
+                                      ("1", "3", "64", "1"), ("0", "2", "100", "1"), ("2", "3", "255", "0")):
+        env = {"LCSIM_B200_ORDER": order, "LCSIM_B200_SNAP_DEPTH": depth, "LCSIM_B200_GROUP": group, "LCSIM_B200_PERM": perm}
+        os.environ.update(env)
         try:
             be = BatchEngine(sb, reactive=reactive, with_metrics=True, device=0)
         finally:
-            del os.environ["LCSIM_B200_ORDER"], os.environ["LCSIM_B200_SNAP_DEPTH"], os.environ["LCSIM_B200_GROUP"]
+            for k in env:
+                del os.environ[k]
         tn = be.backend.to_numpy
         log = tn(be.rollout(91, log=True)).copy()
         state = {k: tn(getattr(be, k)).copy() for k in KEYS}
@@ -156,6 +159,6 @@ def test_ticket_orders_and_ring_depths_agree(reactive):
         if ref_state is None:
             ref_state, ref_log = state, log
             continue
-        np.testing.assert_array_equal(log, ref_log, err_msg=f"tick log, order {order} depth {depth} group {group}")
+        np.testing.assert_array_equal(log, ref_log, err_msg=f"tick log, order {order} depth {depth} group {group} perm {perm}")
         for k, v in state.items():
-            np.testing.assert_array_equal(v, ref_state[k], err_msg=f"{k}, order {order} depth {depth} group {group}")
+            np.testing.assert_array_equal(v, ref_state[k], err_msg=f"{k}, order {order} depth {depth} group {group} perm {perm}")
