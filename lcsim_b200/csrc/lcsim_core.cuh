@@ -225,7 +225,7 @@ struct LcsParams {
     // scenarios per ticket group of a multi-tick launch (0 = one group): see lcs_engine_kernel
     int32_t group;
     // position in the ticket order -> scenario (heaviest scenarios first: their tick items are the long ones of a wave and
-    // their chain is the critical path of the rollout), or null = identity.  LCSIM_B200_PERM=0 disables it.
+    // their chain is the critical path of the rollout), or null = identity.  Experiment, LCSIM_B200_PERM=1 (measured: no gain).
     const int32_t* perm;
     // single-tick launch split in two (env_step: the observation build overlaps the metric items): 1 = tick items only
     // (the snapshot is still published), 2 = metric items only (of the tick the previous launch ran); no tickets wait
