@@ -166,9 +166,7 @@ __device__ LCS_ITEM_INLINE void lcs_item_tick(const LcsParams& p, unsigned char*
     }
 }
 template <int MAXT, bool CLK>
-// part: 0 = the whole metric item; 1 = its collision half, 2 = its edge-search half (single-tick launches of few
-// scenarios run the two halves in different CTAs, LcsParams::fuse == 2)
-__device__ LCS_ITEM_INLINE void lcs_item_metric(const LcsParams& p, unsigned char* smem_raw, int s, int k, int part) {
+__device__ LCS_ITEM_INLINE void lcs_item_metric(const LcsParams& p, unsigned char* smem_raw, int s, int k) {
     const int tid = threadIdx.x;
     LcsSmem sm;
     lcs_smem_carve(sm, smem_raw, p.Ap);
@@ -180,33 +178,28 @@ __device__ LCS_ITEM_INLINE void lcs_item_metric(const LcsParams& p, unsigned cha
     STAMP(); // 8
     if (tid < 3) sm.misc[12 + tid] = 0; // edge-search counters, largest radius (float bits)
     __syncthreads();
-    int ag = -1;
-    if (part != 2) ag = lcs_mc_load(p, sm, s, tid, th);
-    if (part != 1) lcs_me_flags(p, s, tid, sm.mask, sm.misc + 12, th);
+    const int ag = lcs_mc_load(p, sm, s, tid, th);
+    lcs_me_flags(p, s, tid, sm.mask, sm.misc + 12, th);
     __syncthreads();
     STAMP(); // 9: load
-    if (part != 2) lcs_phase_collision_filter(p, sm, s, tid);
+    lcs_phase_collision_filter(p, sm, s, tid);
     if (CLK) {
         __syncthreads();
         STAMP(); // 10: collision filter
     }
     // (issuing the list-header loads in front of the collision loop was measured: the registers they hold across the
     // loop cost more than the latency they hide, 2.77e9 vs 2.89e9)
-    if (part != 1) {
-        LcsEdgeJob job;
-        lcs_me_search_begin(p, s, tid, sm.mask, sm.misc + 12, th, job);
-        lcs_me_search_finish(p, s, sm.misc + 12, job);
-    }
+    LcsEdgeJob job;
+    lcs_me_search_begin(p, s, tid, sm.mask, sm.misc + 12, th, job);
+    lcs_me_search_finish(p, s, sm.misc + 12, job);
     __syncthreads();
     STAMP(); // 11 (10 without CLK): edge search
-    if (part != 2) { // (part is the same for the whole CTA: the barriers are uniform)
-        lcs_phase_collision_drain(p, sm, s, tid);
-        __syncthreads();
-        lcs_mc_out(p, sm, s, tid, ag);
-        __syncthreads();
-        lcs_mc_stats(p, sm, s, tid, th);
-    }
-    if (part != 1) lcs_me_stats(p, s, tid, sm.misc + 12, th);
+    lcs_phase_collision_drain(p, sm, s, tid);
+    __syncthreads();
+    lcs_mc_out(p, sm, s, tid, ag);
+    __syncthreads();
+    lcs_mc_stats(p, sm, s, tid, th);
+    lcs_me_stats(p, s, tid, sm.misc + 12, th);
     STAMP(); // 12: drain + out
 }
 #undef STAMP
@@ -217,10 +210,6 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
     __shared__ int s_item;
     const int tid = threadIdx.x;
     const bool fused = p.with_metrics && p.fuse; // tick items followed by their metric items
-    // fuse == 2 (single-tick launches of at most half a generation of scenarios): the CTA of a tick item continues with
-    // the COLLISION half of the metric item, the edge-search half runs in a second CTA that waits for the tick item —
-    // the launch lasts tick + max(halves) instead of tick + both
-    const bool fsplit = fused && p.fuse == 2;
 #ifdef LCS_NO_ONLY // experiment build: the split single-tick launches compiled out
     const int only = 0;
 #else
@@ -235,7 +224,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
     // the whole rollout of scenarios [0, G), then of [G, 2G), ... — so that the state a tick touches stays the size of one
     // group (L2-resident) instead of growing with S.  Groups are independent, inside a group the order is the usual one.
     int s0 = 0, Sg = p.S;
-    const int mult = p.with_metrics && (!fused || fsplit) && !only ? 2 : 1;
+    const int mult = p.with_metrics && !fused && !only ? 2 : 1;
     if (p.group > 0 && p.group < p.S && p.n_ticks > 1) {
         const int per_group = p.n_ticks * mult * p.group, n_groups = (p.S + p.group - 1) / p.group;
         int g = item / per_group;
@@ -280,7 +269,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
         // (metric items of a scenario run in order: they update the same per-agent outputs, and an agent that did not
         // move keeps the flag its previous metric item stored)
         if (!metric) {
-            if (k > 0) lcs_wait_seq(p.q_seq + 2 * s, k, p.with_metrics ? (fused && !fsplit ? k : k - D + 1) : 0);
+            if (k > 0) lcs_wait_seq(p.q_seq + 2 * s, k, p.with_metrics ? (fused ? k : k - D + 1) : 0);
         } else {
             lcs_wait_seq(p.q_seq + 2 * s, k + 1, k);
         }
@@ -291,14 +280,10 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? LCS_MIN_CTAS : 1)) lcs_en
     if (!(p.reset_mask && !p.reset_mask[s])) { // a masked-out scenario: nothing to do, but its items still count as done
         if (!metric) lcs_item_tick<MAXT, CLK>(p, lcs_smem_raw, s, k);
         if (fused) __syncthreads(); // the snapshot this CTA wrote is read back by other threads of it
-        if (fsplit && !metric && tid == 0) // the tick item is complete: the edge-search CTA of this scenario may go
-            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.q_seq + 2 * s), "r"(k + 1) : "memory");
-        if (metric || fused) lcs_item_metric<MAXT, CLK>(p, lcs_smem_raw, s, k, fsplit ? (metric ? 2 : 1) : 0);
-    } else if (fsplit && !metric && tid == 0) {
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.q_seq + 2 * s), "r"(k + 1) : "memory");
+        if (metric || fused) lcs_item_metric<MAXT, CLK>(p, lcs_smem_raw, s, k);
     }
     __syncthreads(); // every thread's stores precede the release (cumulativity through the barrier)
-    if (tid == 0 && !only && !fsplit) {
+    if (tid == 0 && !only) {
         if (fused)
             asm volatile("st.release.gpu.global.v2.s32 [%0], {%1, %1};" ::"l"(p.q_seq + 2 * s), "r"(k + 1) : "memory");
         else
@@ -312,7 +297,7 @@ static void lcs_launch(const LcsParams& p, int grid_cap, cudaStream_t stream) {
 #ifndef LCSIM_HOSTEMU
     const int Ap = p.Ap;
     const size_t smem = lcs_smem_bytes(Ap);
-    const long long total = (long long)p.n_ticks * (p.with_metrics && (!p.fuse || p.fuse == 2) && !p.only ? 2 : 1) * p.S;
+    const long long total = (long long)p.n_ticks * (p.with_metrics && !p.fuse && !p.only ? 2 : 1) * p.S;
     const int nblk = (int)total; // one CTA per item (n_ticks * 2 * S <= 2^31 - 1 is checked by the callers)
     (void)grid_cap;
     cudaMemsetAsync(p.q_ticket, 0, sizeof(int32_t) * (2 + 2 * (size_t)p.S), stream); // ticket and the counter pairs are one block
@@ -706,7 +691,6 @@ struct lcsim_b200_engine {
     int plan_parts = 0;
     int device = 0;
     int grid_cap = 1; // CTAs of the engine kernel the device holds at once (occupancy x SMs)
-    int fuse_split = 1; // LCSIM_B200_FUSE_SPLIT=0: single-tick launches keep tick + whole metric item in one CTA
     int env_zerocopy = 1; // LCSIM_B200_ENV_ZEROCOPY
     int env_split = 0; // LCSIM_B200_ENV_SPLIT=1: env_step splits its launch into tick items | metric items when an observation is registered
     bool env_obs_on = false; // set_env_obs: env_step builds this observation behind its tick
@@ -913,8 +897,6 @@ extern "C" int lcsim_b200_create(const lcsim_b200_batch_desc* d, lcsim_b200_engi
     {
         // measured at 512 envs: the split costs a launch more than the overlap returns (device tick 90.9 us split vs
         // 86.4 us fused, e2e 117 vs 112 us), so it is off unless LCSIM_B200_ENV_SPLIT=1
-        const char* fs = getenv("LCSIM_B200_FUSE_SPLIT");
-        if (fs) e->fuse_split = atoi(fs) != 0;
         const char* zc = getenv("LCSIM_B200_ENV_ZEROCOPY");
         if (zc) e->env_zerocopy = atoi(zc);
         const char* sp = getenv("LCSIM_B200_ENV_SPLIT");
@@ -1582,8 +1564,6 @@ static void lcs_launch_ticks(lcsim_b200_engine* e, LcsParams& q, int n_ticks, cu
     q.only = q.with_metrics ? only : 0;
     // (the phase-clock runs launch tick by tick to time the items of a rollout: they stay split)
     q.fuse = !q.only && q.with_metrics && (e->fuse_mode == 1 || (e->fuse_mode == 2 && n_ticks == 1 && !q.dbg)) ? 1 : 0;
-    // few scenarios: the two halves of the metric item side by side (both CTAs of every scenario resident at once)
-    if (q.fuse && n_ticks == 1 && e->fuse_split && 2 * q.S <= e->grid_cap) q.fuse = 2;
     lcs_launch(q, e->grid_cap, st);
     e->launches += 1;
 }
