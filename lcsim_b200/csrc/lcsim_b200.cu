@@ -1105,7 +1105,10 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     g.cl_start.resize(S);
     g.cl_idx.resize(S);
     g.cl_xy.resize(S);
-    float cl_cell = 2.0f; // LCSIM_B200_CAND_CELL: cell of the candidate lists in metres, 0 = no lists (hinted search only)
+    // LCSIM_B200_CAND_CELL: cell of the candidate lists in metres, 0 = no lists (hinted search only).  Measured at S=1024
+    // (log-replay / reactive, profiles/NOTES_r2.md): 3 m 2.81e9 / 1.08e9, 2 m 2.95e9 / 1.12e9, 1.5 m 3.02e9 / 1.136e9, 1.25 m
+    // 3.04e9 / 1.148e9 (upload 2.8 s instead of 2.2), 1 m 2.32e9 / 1.03e9 (the 192 x 192 cap no longer covers the maps)
+    float cl_cell = 1.5f;
     {
         const char* env = getenv("LCSIM_B200_CAND_CELL");
         if (env) cl_cell = (float)atof(env);
@@ -1467,6 +1470,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
             std::vector<int32_t>().swap(g.cl_idx[s]);
         }
         e->cand_entries = (int64_t)total;
+        if (sw.on) fprintf(stderr, "[lcsim_b200 upload] candidate lists: %.1f MB (%lld entries, cell %.2f m)\n", total * 12.0 / 1e6, (long long)total, cl_cell);
         sw.lap("candidate lists: device");
     }
     p.GC = GC;
