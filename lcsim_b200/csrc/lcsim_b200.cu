@@ -7,6 +7,7 @@
 #include "../../include/lcsim_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -1117,6 +1118,8 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
     std::vector<std::vector<int32_t>> cell_starts(S);
 
     sw.lap("staging alloc");
+    std::atomic<long long> dbg_ns[4]; // LCSIM_B200_UPLOAD_TIMES: thread time of the list builder's levels (coarse, 2 x 2, cells)
+    for (auto& v : dbg_ns) v = 0;
     lcs_parallel_range(S, [&](int s0, int s1) {
         std::vector<double> seg(T);
         std::vector<char> live;
@@ -1299,13 +1302,13 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
                 // K(box) = points with mindist(point, box) <= U(box) + 1 cm, U(box) = min over points of maxdist(point, box).
                 // For a box inside a larger one, K(box) is a subset of K(larger) and so is the point that attains
                 // U(box): the fine cells are therefore built from the list of their 8 x 8 block, not from all points.
-                // Three levels (8 x 8 blocks, 2 x 2 blocks, cells); every level keeps its points' coordinates in
+                // Four levels (32 x 32 blocks, 8 x 8 blocks, 2 x 2 blocks, cells); every level keeps its points' coordinates in
                 // contiguous arrays, so both passes of a selection are plain streaming loops.
                 struct Lvl {
                     std::vector<int> idx;
                     std::vector<double> x, y;
                 };
-                auto select = [&](double x0, double x1, double y0, double y1, const Lvl& from, Lvl& out) {
+                auto select = [&](double x0, double x1, double y0, double y1, const Lvl& from, Lvl& out, bool want_xy) {
                     const size_t n = from.idx.size();
                     const double *fxp = from.x.data(), *fyp = from.y.data();
                     double U2 = 1e300; // squared distance to the farthest corner, minimised over the points
@@ -1321,30 +1324,47 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
                         const double nx = std::max(std::max(x0 - fxp[k], fxp[k] - x1), 0.0), ny = std::max(std::max(y0 - fyp[k], fyp[k] - y1), 0.0);
                         if (nx * nx + ny * ny <= lim) {
                             out.idx.push_back(from.idx[k]);
-                            out.x.push_back(fxp[k]);
-                            out.y.push_back(fyp[k]);
+                            if (want_xy) { // (the cells' own lists are only read as indices)
+                                out.x.push_back(fxp[k]);
+                                out.y.push_back(fyp[k]);
+                            }
                         }
                     }
                 };
-                auto box = [&](int bx0, int bx1, int by0, int by1, const Lvl& from, Lvl& out) { // cells [bx0, bx1) x [by0, by1)
+                auto box = [&](int bx0, int bx1, int by0, int by1, const Lvl& from, Lvl& out, bool want_xy = true) { // cells [bx0, bx1) x [by0, by1)
                     select((double)cx0 + (double)bx0 * cl_cell - infl, (double)cx0 + (double)bx1 * cl_cell + infl,
-                           (double)cy0 + (double)by0 * cl_cell - infl, (double)cy0 + (double)by1 * cl_cell + infl, from, out);
+                           (double)cy0 + (double)by0 * cl_cell - infl, (double)cy0 + (double)by1 * cl_cell + infl, from, out, want_xy);
                 };
                 Lvl all, fine;
                 all.idx.resize(np_);
                 for (size_t q = 0; q < np_; q++) all.idx[q] = (int)q;
                 all.x = px;
                 all.y = py;
-                const int CB = 8, MB = 2;
-                std::vector<Lvl> row_lists((cw + CB - 1) / CB), mid_lists((cw + MB - 1) / MB);
+                const int TB = 32, CB = 8, MB = 2; // four levels: 32 x 32 blocks, 8 x 8, 2 x 2, cells (each nested in the one before)
+                std::vector<Lvl> top_lists((cw + TB - 1) / TB), row_lists((cw + CB - 1) / CB), mid_lists((cw + MB - 1) / MB);
+                cxy.reserve(np_ * 96); // ~5 MB per scenario at 1.5 m cells: no re-allocation on the way
+                cidx.reserve(np_ * 96);
+                auto tnow = [] { return std::chrono::steady_clock::now(); };
+                auto t0 = tnow();
                 for (int cyy = 0; cyy < ch && cxy.size() <= ((size_t)4 << 20); cyy++) {
-                    if (cyy % CB == 0) // the coarse blocks of this band of rows
-                        for (int bx = 0; bx * CB < cw; bx++) box(bx * CB, std::min(cw, (bx + 1) * CB), cyy, std::min(ch, cyy + CB), all, row_lists[bx]);
+                    if (cyy % CB == 0) { // the coarse blocks of this band of rows
+                        if (sw.on) t0 = tnow();
+                        if (cyy % TB == 0)
+                            for (int tx = 0; tx * TB < cw; tx++) box(tx * TB, std::min(cw, (tx + 1) * TB), cyy, std::min(ch, cyy + TB), all, top_lists[tx]);
+                        for (int bx = 0; bx * CB < cw; bx++)
+                            box(bx * CB, std::min(cw, (bx + 1) * CB), cyy, std::min(ch, cyy + CB), top_lists[bx * CB / TB], row_lists[bx]);
+                        if (sw.on) dbg_ns[0] += std::chrono::duration_cast<std::chrono::nanoseconds>(tnow() - t0).count();
+                    }
+                    if (sw.on) t0 = tnow();
                     if (cyy % MB == 0) // the 2 x 2 blocks of this pair of rows, each from its coarse block
                         for (int mx = 0; mx * MB < cw; mx++)
                             box(mx * MB, std::min(cw, (mx + 1) * MB), cyy, std::min(ch, cyy + MB), row_lists[mx * MB / CB], mid_lists[mx]);
+                    if (sw.on) {
+                        dbg_ns[1] += std::chrono::duration_cast<std::chrono::nanoseconds>(tnow() - t0).count();
+                        t0 = tnow();
+                    }
                     for (int cxx = 0; cxx < cw; cxx++) {
-                        box(cxx, cxx + 1, cyy, cyy + 1, mid_lists[cxx / MB], fine);
+                        box(cxx, cxx + 1, cyy, cyy + 1, mid_lists[cxx / MB], fine, false);
                         cst[(size_t)cyy * cw + cxx] = (int32_t)cxy.size();
                         for (int q : fine.idx) { // ascending original index (keep[] is sorted)
                             cxy.push_back(pts[q]);
@@ -1355,6 +1375,7 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
                             cidx.push_back(0);
                         }
                     }
+                    if (sw.on) dbg_ns[2] += std::chrono::duration_cast<std::chrono::nanoseconds>(tnow() - t0).count();
                 }
                 cst[(size_t)cw * ch] = (int32_t)cxy.size();
                 if (cxy.size() > (size_t)4 << 20) {
@@ -1368,6 +1389,9 @@ extern "C" int lcsim_b200_upload_static(lcsim_b200_engine* e, const lcsim_b200_s
             }
         }
     });
+    if (sw.on)
+        fprintf(stderr, "[lcsim_b200 upload] list builder, thread time: 8x8 blocks %.0f ms, 2x2 blocks %.0f ms, cells %.0f ms\n",
+                dbg_ns[0] / 1e6, dbg_ns[1] / 1e6, dbg_ns[2] / 1e6);
     sw.lap("per-scenario preparation");
     int GC = 2;
     for (int s = 0; s < S; s++) GC = std::max<int>(GC, (int)cell_starts[s].size());
