@@ -1967,7 +1967,8 @@ static void lcs_obs_scenario_serial(const LcsParams& p, const LcsObsArgs& o, int
         std::vector<int> order(cand.size());
         for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
         if (o.d.sort_by_distance)
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cand[a] < cand[b]; });
+            // by distance, ties in source order (the device sorts keys of (distance bits, candidate index))
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cand[a].first < cand[b].first; });
         if (n_out) n_out[s] = (int)cand.size();
         for (int k = 0; k < cap; k++) {
             const bool have = k < (int)order.size();
